@@ -1,0 +1,243 @@
+"""ctypes binding of the flat C ABI in include/dvp_mvs.h.
+
+`Engine` drives any shared library that exports that ABI under a prefix:
+  * prefix "dvp_"  -> dvp_mvs_b200/libdvp_mvs.so, the product (hand-written sm_100a CUDA);
+  * prefix "ref_"  -> oracle/_ref/libapd_ref.so, the reference's own APD.cu compiled unmodified
+                      (TEST INFRASTRUCTURE; only tests/, bench.py --impl reference and smoke() load it).
+There is no CPU fallback: if the CUDA library is missing, importing the product engine raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+from .synth import CAMERA_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(_HERE, "libdvp_mvs.so")
+REFERENCE_LIB = os.path.join(os.path.dirname(_HERE), "oracle", "_ref", "libapd_ref.so")
+
+FIRST_INIT, REFINE_INIT, REFINE_ITER = 0, 1, 2
+WEAK, STRONG, UNKNOWN = 0, 1, 2
+
+
+class Params(C.Structure):
+    """Mirror of dvp_params == reference PatchMatchParams (main.h:86-112)."""
+    _fields_ = [
+        ("max_iterations", C.c_int32), ("num_images", C.c_int32), ("sigma_spatial", C.c_float),
+        ("sigma_color", C.c_float), ("top_k", C.c_int32), ("depth_min", C.c_float), ("depth_max", C.c_float),
+        ("geom_consistency", C.c_int32), ("strong_radius", C.c_int32), ("strong_increment", C.c_int32),
+        ("weak_radius", C.c_int32), ("weak_increment", C.c_int32), ("use_APD", C.c_int32),
+        ("use_edge", C.c_int32), ("use_limit", C.c_int32), ("use_label", C.c_int32), ("use_detail", C.c_int32),
+        ("use_radius", C.c_int32), ("weak_peak_radius", C.c_int32), ("rotate_time", C.c_int32),
+        ("ransac_threshold", C.c_float), ("geom_factor", C.c_float), ("state", C.c_int32),
+    ]
+
+    def copy(self) -> "Params":
+        p = Params()
+        C.memmove(C.byref(p), C.byref(self), C.sizeof(Params))
+        return p
+
+
+class Inputs(C.Structure):
+    _fields_ = [
+        ("images", C.c_void_p), ("depths", C.c_void_p), ("cameras", C.c_void_p), ("planes", C.c_void_p),
+        ("selected_views", C.c_void_p), ("weak_info", C.c_void_p), ("edge", C.c_void_p), ("label", C.c_void_p),
+        ("radius", C.c_void_p), ("seed", C.c_uint64),
+    ]
+
+
+BUF = dict(planes=0, costs=1, selected=2, weak=3, radius=4, view_weight=5, rand=6, fit_planes=7, edge_neigh=8,
+           candidate=9, nearest_strong=10, weak_reliable=11, neighbours_map=12, neighbours=13, label_boundary=14,
+           complex=15)
+BUF_DTYPE = dict(planes=np.float32, costs=np.float32, selected=np.uint32, weak=np.uint8, radius=np.int32,
+                 view_weight=np.uint8, rand=np.uint32, fit_planes=np.float32, edge_neigh=np.int16,
+                 candidate=np.int16, nearest_strong=np.int16, weak_reliable=np.uint8, neighbours_map=np.int32,
+                 neighbours=np.int16, label_boundary=np.int16, complex=np.float32)
+STAGES = ["K1_INIT_RANDOM_STATES", "K2_GEN_EDGE_INFORM", "K3_FIND_NEAREST_STRONG", "K4_GEN_NEIGHBOURS",
+          "K5_NEIGHBOUR_UPDATE", "K6_RANDOM_INITIALIZATION", "K7_BLACK_STRONG", "K8_RED_STRONG",
+          "K9_RANSAC_FIT_PLANE", "K10_BLACK_WEAK", "K11_RED_WEAK", "K12_DEPTH_NORMAL", "K13_BLACK_FILTER",
+          "K14_RED_FILTER", "K15_DEPTH_TO_WEAK", "K16_LOCAL_REFINE"]
+STAGE = {n: i for i, n in enumerate(STAGES)}
+STATUS = {0: "DVP_OK", -1: "DVP_ERR_ARG", -2: "DVP_ERR_CUDA", -3: "DVP_ERR_STATE", -4: "DVP_ERR_UNSUPPORTED"}
+
+ABI_SYMBOLS = ["version", "default_params", "create", "destroy", "upload", "run", "run_stage", "download",
+               "buffer_bytes", "get_buffer", "set_buffer", "last_run_times", "weak_count", "last_cuda_error", "stream"]
+PRODUCT_ONLY_SYMBOLS = ["upload_device"]
+
+
+class DvpError(RuntimeError):
+    pass
+
+
+def load_library(path: str, prefix: str):
+    if not os.path.exists(path):
+        raise DvpError(
+            f"{path} not found: the CUDA library must be built first "
+            f"(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    f = lambda n: getattr(lib, prefix + n)
+    f("version").restype = C.c_char_p
+    f("default_params").argtypes = [C.POINTER(Params)]; f("default_params").restype = None
+    f("create").argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Params)]; f("create").restype = C.c_void_p
+    f("destroy").argtypes = [C.c_void_p]; f("destroy").restype = None
+    f("upload").argtypes = [C.c_void_p, C.POINTER(Inputs), C.POINTER(Params)]; f("upload").restype = C.c_int
+    f("run").argtypes = [C.c_void_p, C.c_int]; f("run").restype = C.c_int
+    f("run_stage").argtypes = [C.c_void_p, C.c_int, C.c_int]; f("run_stage").restype = C.c_int
+    f("download").argtypes = [C.c_void_p] + [C.c_void_p] * 4; f("download").restype = C.c_int
+    f("buffer_bytes").argtypes = [C.c_void_p, C.c_int]; f("buffer_bytes").restype = C.c_size_t
+    f("get_buffer").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]; f("get_buffer").restype = C.c_int
+    f("set_buffer").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]; f("set_buffer").restype = C.c_int
+    f("last_run_times").argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    f("last_run_times").restype = C.c_int
+    f("weak_count").argtypes = [C.c_void_p]; f("weak_count").restype = C.c_int
+    f("last_cuda_error").argtypes = [C.c_void_p]; f("last_cuda_error").restype = C.c_int
+    f("stream").argtypes = [C.c_void_p]; f("stream").restype = C.c_void_p
+    if prefix == "dvp_":
+        f("upload_device").argtypes = [C.c_void_p, C.POINTER(Inputs), C.POINTER(Params)]; f("upload_device").restype = C.c_int
+    return lib
+
+
+def default_params(lib=None, prefix="dvp_") -> Params:
+    p = Params()
+    if lib is not None:
+        getattr(lib, prefix + "default_params")(C.byref(p))
+        return p
+    # reference defaults (main.h:86-112), used when no library is loaded (CPU-only host logic/tests)
+    p.max_iterations, p.num_images, p.sigma_spatial, p.sigma_color, p.top_k = 3, 5, 5.0, 3.0, 4
+    p.depth_min, p.depth_max, p.geom_consistency = 0.0, 1.0, 0
+    p.strong_radius, p.strong_increment, p.weak_radius, p.weak_increment = 5, 2, 5, 5
+    p.use_APD, p.use_edge, p.use_limit, p.use_label, p.use_detail, p.use_radius = 1, 1, 1, 1, 0, 1
+    p.weak_peak_radius, p.rotate_time, p.ransac_threshold, p.geom_factor, p.state = 2, 4, 0.005, 0.2, FIRST_INIT
+    return p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _carr(a, dtype, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+class Engine:
+    """One PatchMatch context (one reference view on one GPU)."""
+
+    def __init__(self, width: int, height: int, num_src: int, params: Params, device: int = 0,
+                 impl: str = "product", lib_path: str | None = None):
+        self.prefix = "dvp_" if impl == "product" else "ref_"
+        self.impl = impl
+        path = lib_path or (PRODUCT_LIB if impl == "product" else REFERENCE_LIB)
+        self.lib = load_library(path, self.prefix)
+        self.W, self.H, self.S, self.N = width, height, num_src, width * height
+        self.params = params.copy()
+        self.params.num_images = num_src + 1
+        self._f = lambda n: getattr(self.lib, self.prefix + n)
+        self.ctx = self._f("create")(device, width, height, num_src, C.byref(self.params))
+        if not self.ctx:
+            raise DvpError(f"{self.prefix}create failed (device {device}, {width}x{height}, S={num_src})")
+        self._keep = None
+
+    def version(self) -> str:
+        return self._f("version")().decode()
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise DvpError(f"{self.prefix}{what} -> {STATUS.get(rc, rc)} (cudaError {self._f('last_cuda_error')(self.ctx)})")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self._f("destroy")(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, images, cameras, planes, depths=None, selected_views=None, weak_info=None, edge=None,
+               label=None, radius=None, seed=0x5EED, params: Params | None = None):
+        S, H, W = self.S, self.H, self.W
+        if params is not None:
+            self.params = params.copy()
+            self.params.num_images = S + 1
+        keep = dict(
+            images=_carr(images, np.float32, (S + 1, H, W)),
+            depths=_carr(depths, np.float32, (S + 1, H, W)),
+            cameras=_carr(cameras, CAMERA_DTYPE, (S + 1,)),
+            planes=_carr(planes, np.float32, (H, W, 4)),
+            selected_views=_carr(selected_views, np.uint32, (H, W)),
+            weak_info=_carr(weak_info, np.uint8, (H, W)),
+            edge=_carr(edge, np.uint8, (H, W)),
+            label=_carr(label, np.int32, (H, W)),
+            radius=_carr(radius, np.int32, (H, W)),
+        )
+        inp = Inputs(*[_ptr(keep[k]) for k in ("images", "depths", "cameras", "planes", "selected_views",
+                                                  "weak_info", "edge", "label", "radius")], int(seed))
+        self._keep = keep
+        self._check(self._f("upload")(self.ctx, C.byref(inp), C.byref(self.params)), "upload")
+
+    def upload_raw(self, inp: Inputs, device: bool = False):
+        fn = self._f("upload_device") if device else self._f("upload")
+        self._check(fn(self.ctx, C.byref(inp), C.byref(self.params)), "upload_device" if device else "upload")
+
+    def run(self, sync: bool = True, mode: int | None = None):
+        arg = (1 if sync else 0) if mode is None else mode
+        self._check(self._f("run")(self.ctx, arg), "run")
+
+    def run_stage(self, stage, iteration: int = 0):
+        sid = STAGE[stage] if isinstance(stage, str) else int(stage)
+        self._check(self._f("run_stage")(self.ctx, sid, iteration), f"run_stage({stage})")
+
+    def last_run_times(self):
+        total = C.c_float(); per = (C.c_float * 16)(); n = C.c_int()
+        self._check(self._f("last_run_times")(self.ctx, C.byref(total), per, C.byref(n)), "last_run_times")
+        return float(total.value), [float(x) for x in per], int(n.value)
+
+    def weak_count(self) -> int:
+        return int(self._f("weak_count")(self.ctx))
+
+    def get(self, name: str) -> np.ndarray:
+        nbytes = int(self._f("buffer_bytes")(self.ctx, BUF[name]))
+        dt = np.dtype(BUF_DTYPE[name])
+        out = np.empty(nbytes // dt.itemsize, dtype=dt)
+        if nbytes:
+            self._check(self._f("get_buffer")(self.ctx, BUF[name], _ptr(out), nbytes), f"get_buffer({name})")
+        return self._shape(name, out)
+
+    def set(self, name: str, arr: np.ndarray):
+        a = np.ascontiguousarray(arr, dtype=BUF_DTYPE[name])
+        nbytes = int(self._f("buffer_bytes")(self.ctx, BUF[name]))
+        if a.nbytes != nbytes:
+            raise ValueError(f"{name}: expected {nbytes} bytes, got {a.nbytes}")
+        if nbytes:
+            self._check(self._f("set_buffer")(self.ctx, BUF[name], _ptr(a), nbytes), f"set_buffer({name})")
+
+    def _shape(self, name, a):
+        H, W = self.H, self.W
+        shp = dict(planes=(H, W, 4), fit_planes=(H, W, 4), costs=(H, W), selected=(H, W), weak=(H, W), radius=(H, W),
+                   view_weight=(H, W, 32), rand=(H, W, 6), edge_neigh=(H, W, 8, 2), candidate=(H, W, 4, 8, 2),
+                   nearest_strong=(H, W, 2), weak_reliable=(H, W), neighbours_map=(H, W),
+                   neighbours=(-1, 12, 2), label_boundary=(-1, 8, 2), complex=(-1,))[name]
+        return a.reshape(shp)
+
+    def download(self):
+        H, W = self.H, self.W
+        planes = np.empty((H, W, 4), np.float32); weak = np.empty((H, W), np.uint8)
+        sel = np.empty((H, W), np.uint32); rad = np.empty((H, W), np.int32)
+        self._check(self._f("download")(self.ctx, _ptr(planes), _ptr(weak), _ptr(sel), _ptr(rad)), "download")
+        return planes, weak, sel, rad
+
+    def snapshot(self, names=("planes", "costs", "selected", "weak", "radius", "view_weight", "rand", "fit_planes")):
+        return {n: self.get(n) for n in names}
+
+    def restore(self, snap: dict):
+        for n, a in snap.items():
+            self.set(n, a)

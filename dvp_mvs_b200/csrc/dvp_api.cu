@@ -1,0 +1,470 @@
+// dvp_api.cu — host side of the flat C ABI declared in include/dvp_mvs.h: context, device memory and
+// texture set-up (replaces APD::CudaSpaceInitialization / SetDataPassHelperInCuda / ~APD, reference
+// APD.cpp:989-1043, 1497-1613, 1670-1704) and the RunPatchMatch launch sequence (reference APD.cu:4406-4532).
+//
+// Differences from the reference's host code, none of which changes results:
+//  * one context = one device + one non-blocking stream; no cudaDeviceSynchronize between kernels
+//    (the reference synchronises the whole device after each of its 11 + 5*iters launches);
+//  * parameters travel as a __grid_constant__ kernel argument instead of a device-resident pointer bundle;
+//  * buffers are allocated once per context and reused across uploads (multi-pass / multi-view reuse);
+//  * `selected_views` carries one zeroed padding row on each side so the reference's out-of-bounds
+//    4-neighbour reads at the image border are defined (they read 0).
+#include "dvp_common.cuh"
+#include "dvp_launch.h"
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <new>
+
+namespace dvp { cudaError_t launch_edge_inform(const KArgs& a, cudaStream_t st); }
+
+using namespace dvp;
+
+struct dvp_ctx {
+	int device = 0;
+	int W = 0, H = 0, S = 0, N = 0;
+	dvp_params prm;
+	cudaStream_t stream = nullptr;
+	bool uploaded = false;
+	unsigned long long seed = 0;
+	int weak_count = 0;
+	int weak_capacity = 0;
+	int last_err = 0;
+	// textures
+	cudaArray_t img_arr[DVP_MAX_IMAGES] = {nullptr};
+	cudaArray_t dep_arr[DVP_MAX_IMAGES] = {nullptr};
+	cudaTextureObject_t img_tex[DVP_MAX_IMAGES] = {0};
+	cudaTextureObject_t dep_tex[DVP_MAX_IMAGES] = {0};
+	cudaTextureObject_t* d_img_tex = nullptr;
+	cudaTextureObject_t* d_dep_tex = nullptr;
+	float* ref_img = nullptr;
+	dvp_camera* cams = nullptr;
+	dvp_camera ref_cam;
+	ViewConst* views = nullptr;
+	float4* planes = nullptr;
+	float4* fit_planes = nullptr;
+	float* costs = nullptr;
+	uint32_t* selected_alloc = nullptr;
+	uint32_t* selected = nullptr;
+	uint8_t* weak = nullptr;
+	int32_t* radius = nullptr;
+	uint8_t* view_weight = nullptr;
+	uint32_t* rng = nullptr;
+	uint8_t* edge = nullptr;
+	short2* edge_neigh = nullptr;
+	int32_t* label = nullptr;
+	short2* candidate = nullptr;
+	short2* nearest_strong = nullptr;
+	uint8_t* weak_reliable = nullptr;
+	int32_t* neighbours_map = nullptr;
+	short2* neighbours = nullptr;
+	short2* label_boundary = nullptr;
+	float* complex_ = nullptr;
+	// host staging
+	std::vector<int32_t> h_i32;
+	std::vector<uint8_t> h_u8;
+	// timing
+	static const int kMaxLaunch = 16 + 5 * 64;
+	cudaEvent_t ev[2 * (16 + 5 * 64) + 2] = {nullptr};
+	int ev_stage[16 + 5 * 64] = {0};
+	int n_timed = 0;
+	bool timed_valid = false;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->last_err = (int)e_; \
+	fprintf(stderr, "[dvp] %s failed: %s (%s:%d)\n", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return DVP_ERR_CUDA; } } while (0)
+
+namespace {
+
+template <typename T> cudaError_t zalloc(T** p, size_t count) {
+	if (count == 0) count = 1;
+	cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+	if (e != cudaSuccess) return e;
+	return cudaMemset(*p, 0, count * sizeof(T));
+}
+
+KArgs make_args(const dvp_ctx* c) {
+	KArgs a;
+	memset(&a, 0, sizeof(a));
+	a.W = c->W; a.H = c->H; a.S = c->S; a.N = c->N;
+	a.prm = c->prm; a.ref = c->ref_cam;
+	a.tex_img = c->d_img_tex; a.tex_depth = c->d_dep_tex; a.ref_img = c->ref_img;
+	a.cams = c->cams; a.views = c->views;
+	a.planes = c->planes; a.fit_planes = c->fit_planes; a.costs = c->costs; a.selected = c->selected;
+	a.weak = c->weak; a.radius = c->radius; a.view_weight = c->view_weight; a.rng = c->rng;
+	a.edge = c->edge; a.edge_neigh = c->edge_neigh; a.label = c->label; a.candidate = c->candidate;
+	a.nearest_strong = c->nearest_strong; a.weak_reliable = c->weak_reliable; a.neighbours_map = c->neighbours_map;
+	a.neighbours = c->neighbours; a.label_boundary = c->label_boundary; a.complex_ = c->complex_;
+	a.scratch = nullptr; a.weak_count = c->weak_count;
+	return a;
+}
+
+int make_texture(dvp_ctx* ctx, cudaArray_t* arr, cudaTextureObject_t* tex, const float* src, cudaMemcpyKind kind) {
+	cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+	if (!*arr) CK(cudaMallocArray(arr, &desc, ctx->W, ctx->H));
+	CK(cudaMemcpy2DToArrayAsync(*arr, 0, 0, src, ctx->W * sizeof(float), ctx->W * sizeof(float), ctx->H, kind, ctx->stream));
+	if (!*tex) {
+		// hardware bilinear filter, unnormalised coordinates, clamp addressing: what the reference's texture
+		// objects do in effect (it asks for wrap, which degrades to clamp with unnormalised coordinates)
+		cudaResourceDesc res; memset(&res, 0, sizeof(res));
+		res.resType = cudaResourceTypeArray; res.res.array.array = *arr;
+		cudaTextureDesc td; memset(&td, 0, sizeof(td));
+		td.addressMode[0] = cudaAddressModeClamp; td.addressMode[1] = cudaAddressModeClamp;
+		td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+		CK(cudaCreateTextureObject(tex, &res, &td, nullptr));
+	}
+	return DVP_OK;
+}
+
+struct BufDesc { void* ptr; size_t bytes; };
+BufDesc buf_desc(dvp_ctx* c, int id) {
+	const size_t N = (size_t)c->N, wc = (size_t)c->weak_count;
+	switch (id) {
+	case DVP_BUF_PLANES: return {c->planes, N * 16};
+	case DVP_BUF_COSTS: return {c->costs, N * 4};
+	case DVP_BUF_SELECTED: return {c->selected, N * 4};
+	case DVP_BUF_WEAK: return {c->weak, N};
+	case DVP_BUF_RADIUS: return {c->radius, N * 4};
+	case DVP_BUF_VIEW_WEIGHT: return {c->view_weight, N * DVP_MAX_IMAGES};
+	case DVP_BUF_RAND: return {c->rng, N * 24};
+	case DVP_BUF_FIT_PLANES: return {c->fit_planes, N * 16};
+	case DVP_BUF_EDGE_NEIGH: return {c->edge_neigh, N * DVP_EDGE_NEIGH_NUM * 4};
+	case DVP_BUF_CANDIDATE: return {c->candidate, N * DVP_LAB_BOUNDARY_NUM * DVP_NUM_IMAGES * 4};
+	case DVP_BUF_NEAREST_STRONG: return {c->nearest_strong, N * 4};
+	case DVP_BUF_WEAK_RELIABLE: return {c->weak_reliable, N};
+	case DVP_BUF_NEIGHBOURS_MAP: return {c->neighbours_map, N * 4};
+	case DVP_BUF_NEIGHBOURS: return {c->neighbours, wc * DVP_NEIGHBOUR_NUM * 4};
+	case DVP_BUF_LABEL_BOUNDARY: return {c->label_boundary, wc * DVP_LAB_BOUNDARY_NUM * 4};
+	case DVP_BUF_COMPLEX: return {c->complex_, wc * 4};
+	default: return {nullptr, 0};
+	}
+}
+
+cudaError_t launch_stage(dvp_ctx* c, const KArgs& a, int stage, int iter) {
+	cudaStream_t st = c->stream;
+	switch (stage) {
+	case DVP_K1_INIT_RANDOM_STATES: return launch_init_rng(a, c->seed, st);
+	case DVP_K2_GEN_EDGE_INFORM: return launch_edge_inform(a, st);
+	case DVP_K3_FIND_NEAREST_STRONG: return launch_nearest_strong(a, st);
+	case DVP_K4_GEN_NEIGHBOURS: return launch_gen_neighbours(a, st);
+	case DVP_K5_NEIGHBOUR_UPDATE: return launch_neighbour_update(a, st);
+	case DVP_K6_RANDOM_INITIALIZATION: return launch_random_init(a, st);
+	case DVP_K7_BLACK_STRONG: return launch_strong_sweep(a, iter, 0, st);
+	case DVP_K8_RED_STRONG: return launch_strong_sweep(a, iter, 1, st);
+	case DVP_K9_RANSAC_FIT_PLANE: return launch_ransac_fit(a, st);
+	case DVP_K10_BLACK_WEAK: return launch_weak_sweep(a, iter, 0, st);
+	case DVP_K11_RED_WEAK: return launch_weak_sweep(a, iter, 1, st);
+	case DVP_K12_DEPTH_NORMAL: return launch_depth_normal(a, st);
+	case DVP_K13_BLACK_FILTER: return launch_filter(a, 0, st);
+	case DVP_K14_RED_FILTER: return launch_filter(a, 1, st);
+	case DVP_K15_DEPTH_TO_WEAK: return launch_depth_to_weak(a, st);
+	case DVP_K16_LOCAL_REFINE: return launch_local_refine(a, st);
+	default: return cudaErrorInvalidValue;
+	}
+}
+
+int upload_common(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params, bool from_device) {
+	if (!ctx || !in || !in->images || !in->cameras || !in->planes) return DVP_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	if (params) ctx->prm = *params;
+	if (ctx->prm.num_images != ctx->S + 1) return DVP_ERR_ARG;
+	if (ctx->prm.geom_consistency && !in->depths) return DVP_ERR_ARG;
+	if (!ctx->prm.use_edge) return DVP_ERR_UNSUPPORTED;  // the ACMH-style branch (APD.cu:2142-2460) is never enabled by main.cpp
+	const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	const size_t N = (size_t)ctx->N;
+	cudaStream_t st = ctx->stream;
+	ctx->seed = in->seed;
+	for (int i = 0; i <= ctx->S; ++i) {
+		int r = make_texture(ctx, &ctx->img_arr[i], &ctx->img_tex[i], in->images + (size_t)i * N, kind);
+		if (r) return r;
+		if (in->depths) {
+			r = make_texture(ctx, &ctx->dep_arr[i], &ctx->dep_tex[i], in->depths + (size_t)i * N, kind);
+			if (r) return r;
+		}
+	}
+	CK(cudaMemcpyAsync(ctx->ref_img, in->images, N * 4, kind, st));
+	CK(cudaMemcpyAsync(ctx->d_img_tex, ctx->img_tex, sizeof(ctx->img_tex), cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->d_dep_tex, ctx->dep_tex, sizeof(ctx->dep_tex), cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->cams, in->cameras, sizeof(dvp_camera) * (ctx->S + 1), kind, st));
+	if (from_device) CK(cudaMemcpyAsync(&ctx->ref_cam, in->cameras, sizeof(dvp_camera), cudaMemcpyDeviceToHost, st));
+	else ctx->ref_cam = in->cameras[0];
+	CK(launch_setup_views(ctx->cams, ctx->views, ctx->S, st));
+	CK(cudaMemcpyAsync(ctx->planes, in->planes, N * 16, kind, st));
+	CK(cudaMemsetAsync(ctx->fit_planes, 0, N * 16, st));
+	if (in->selected_views) CK(cudaMemcpyAsync(ctx->selected, in->selected_views, N * 4, kind, st));
+	else CK(cudaMemsetAsync(ctx->selected, 0, N * 4, st));
+	if (in->edge) CK(cudaMemcpyAsync(ctx->edge, in->edge, N, kind, st)); else CK(cudaMemsetAsync(ctx->edge, 0, N, st));
+	if (in->label) CK(cudaMemcpyAsync(ctx->label, in->label, N * 4, kind, st)); else CK(cudaMemsetAsync(ctx->label, 0, N * 4, st));
+
+	// pixel states, neighbours map, radius (APD.cpp:1169-1204, 1647-1667).  These need a host pass over the
+	// state map (the reference does the same on the host); device-resident callers provide host copies too.
+	int weak_count = 0;
+	const bool have_weak = ctx->prm.use_APD && in->weak_info;
+	if (from_device && (have_weak || in->radius)) {
+		// device-resident state maps: bring the (small, 1 B/px) state map to the host for the prefix count
+		ctx->h_u8.resize(N);
+		if (have_weak) CK(cudaMemcpyAsync(ctx->h_u8.data(), in->weak_info, N, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+	}
+	const uint8_t* wh = have_weak ? (from_device ? ctx->h_u8.data() : in->weak_info) : nullptr;
+	if (have_weak) {
+		ctx->h_i32.assign(N, 0);
+		for (size_t i = 0; i < N; ++i) if (wh[i] == DVP_WEAK) ctx->h_i32[i] = weak_count++;
+		CK(cudaMemcpyAsync(ctx->weak, in->weak_info, N, kind, st));
+		CK(cudaMemcpyAsync(ctx->neighbours_map, ctx->h_i32.data(), N * 4, cudaMemcpyHostToDevice, st));
+		CK(cudaStreamSynchronize(st));  // h_i32 is reused below
+	} else {
+		CK(cudaMemsetAsync(ctx->weak, DVP_STRONG, N, st));
+		CK(cudaMemsetAsync(ctx->neighbours_map, 0, N * 4, st));
+	}
+	ctx->weak_count = weak_count;
+	if (weak_count > ctx->weak_capacity) {
+		cudaFree(ctx->neighbours); cudaFree(ctx->label_boundary); cudaFree(ctx->complex_);
+		ctx->neighbours = nullptr; ctx->label_boundary = nullptr; ctx->complex_ = nullptr;
+		CK(zalloc(&ctx->neighbours, (size_t)weak_count * DVP_NEIGHBOUR_NUM));
+		CK(zalloc(&ctx->label_boundary, (size_t)weak_count * DVP_LAB_BOUNDARY_NUM));
+		CK(zalloc(&ctx->complex_, (size_t)weak_count));
+		ctx->weak_capacity = weak_count;
+	}
+	{
+		// radius map; UNKNOWN pixels are reset to strong_radius (APD.cpp:1663-1666)
+		if (from_device && in->radius) {
+			CK(cudaMemcpyAsync(ctx->radius, in->radius, N * 4, kind, st));
+			if (have_weak) {
+				ctx->h_i32.resize(N);
+				CK(cudaMemcpyAsync(ctx->h_i32.data(), in->radius, N * 4, cudaMemcpyDeviceToHost, st));
+				CK(cudaStreamSynchronize(st));
+				bool any = false;
+				for (size_t i = 0; i < N; ++i) if (wh[i] == DVP_UNKNOWN && ctx->h_i32[i] != ctx->prm.strong_radius) { ctx->h_i32[i] = ctx->prm.strong_radius; any = true; }
+				if (any) { CK(cudaMemcpyAsync(ctx->radius, ctx->h_i32.data(), N * 4, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
+			}
+		} else {
+			ctx->h_i32.resize(N);
+			if (in->radius) memcpy(ctx->h_i32.data(), in->radius, N * 4);
+			else for (size_t i = 0; i < N; ++i) ctx->h_i32[i] = ctx->prm.strong_radius;
+			if (have_weak) for (size_t i = 0; i < N; ++i) if (wh[i] == DVP_UNKNOWN) ctx->h_i32[i] = ctx->prm.strong_radius;
+			CK(cudaMemcpyAsync(ctx->radius, ctx->h_i32.data(), N * 4, cudaMemcpyHostToDevice, st));
+			CK(cudaStreamSynchronize(st));
+		}
+	}
+	CK(configure_strong_kernels(ctx->S));
+	CK(configure_weak_kernels(ctx->S));
+	CK(cudaStreamSynchronize(st));
+	ctx->uploaded = true;
+	ctx->timed_valid = false;
+	return DVP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dvp_version(void) { return "dvp_mvs_b200 0.1 sm_100a"; }
+
+void dvp_default_params(dvp_params* p) {
+	if (!p) return;
+	// reference defaults, main.h:86-112
+	p->max_iterations = 3; p->num_images = 5; p->sigma_spatial = 5.0f; p->sigma_color = 3.0f; p->top_k = 4;
+	p->depth_min = 0.0f; p->depth_max = 1.0f; p->geom_consistency = 0; p->strong_radius = 5; p->strong_increment = 2;
+	p->weak_radius = 5; p->weak_increment = 5; p->use_APD = 1; p->use_edge = 1; p->use_limit = 1; p->use_label = 1;
+	p->use_detail = 0; p->use_radius = 1; p->weak_peak_radius = 2; p->rotate_time = 4; p->ransac_threshold = 0.005f;
+	p->geom_factor = 0.2f; p->state = DVP_FIRST_INIT;
+}
+
+dvp_ctx* dvp_create(int device, int width, int height, int num_src, const dvp_params* params) {
+	if (!params || width <= 0 || height <= 0 || width > 32767 || height > 32767 || num_src < 1 || num_src + 1 > DVP_MAX_IMAGES) return nullptr;
+	if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+	dvp_ctx* c = new (std::nothrow) dvp_ctx();
+	if (!c) return nullptr;
+	c->device = device; c->W = width; c->H = height; c->S = num_src; c->N = width * height; c->prm = *params;
+	const size_t N = (size_t)c->N;
+	bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && zalloc(&c->d_img_tex, DVP_MAX_IMAGES) == cudaSuccess;
+	ok = ok && zalloc(&c->d_dep_tex, DVP_MAX_IMAGES) == cudaSuccess;
+	ok = ok && zalloc(&c->ref_img, N) == cudaSuccess;
+	ok = ok && zalloc(&c->cams, (size_t)num_src + 1) == cudaSuccess;
+	ok = ok && zalloc(&c->views, (size_t)num_src) == cudaSuccess;
+	ok = ok && zalloc(&c->planes, N) == cudaSuccess;
+	ok = ok && zalloc(&c->fit_planes, N) == cudaSuccess;
+	ok = ok && zalloc(&c->costs, N) == cudaSuccess;
+	ok = ok && zalloc(&c->selected_alloc, N + 2 * (size_t)width + 2) == cudaSuccess;
+	ok = ok && zalloc(&c->weak, N) == cudaSuccess;
+	ok = ok && zalloc(&c->radius, N) == cudaSuccess;
+	ok = ok && zalloc(&c->view_weight, N * DVP_MAX_IMAGES) == cudaSuccess;
+	ok = ok && zalloc(&c->rng, N * 6) == cudaSuccess;
+	ok = ok && zalloc(&c->edge, N) == cudaSuccess;
+	ok = ok && zalloc(&c->edge_neigh, N * DVP_EDGE_NEIGH_NUM) == cudaSuccess;
+	ok = ok && zalloc(&c->label, N) == cudaSuccess;
+	const int cand_views = num_src > DVP_NUM_IMAGES ? num_src : DVP_NUM_IMAGES;
+	ok = ok && zalloc(&c->candidate, (N + 1) * DVP_LAB_BOUNDARY_NUM * cand_views) == cudaSuccess;
+	ok = ok && zalloc(&c->nearest_strong, N) == cudaSuccess;
+	ok = ok && zalloc(&c->weak_reliable, N) == cudaSuccess;
+	ok = ok && zalloc(&c->neighbours_map, N) == cudaSuccess;
+	ok = ok && zalloc(&c->neighbours, 1) == cudaSuccess;
+	ok = ok && zalloc(&c->label_boundary, 1) == cudaSuccess;
+	ok = ok && zalloc(&c->complex_, 1) == cudaSuccess;
+	for (size_t i = 0; ok && i < sizeof(c->ev) / sizeof(c->ev[0]); ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+	if (!ok) {
+		fprintf(stderr, "[dvp] dvp_create: allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+		dvp_destroy(c);
+		return nullptr;
+	}
+	c->selected = c->selected_alloc + width + 1;
+	return c;
+}
+
+void dvp_destroy(dvp_ctx* c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	for (int i = 0; i < DVP_MAX_IMAGES; ++i) {
+		if (c->img_tex[i]) cudaDestroyTextureObject(c->img_tex[i]);
+		if (c->dep_tex[i]) cudaDestroyTextureObject(c->dep_tex[i]);
+		if (c->img_arr[i]) cudaFreeArray(c->img_arr[i]);
+		if (c->dep_arr[i]) cudaFreeArray(c->dep_arr[i]);
+	}
+	cudaFree(c->d_img_tex); cudaFree(c->d_dep_tex); cudaFree(c->ref_img); cudaFree(c->cams); cudaFree(c->views);
+	cudaFree(c->planes); cudaFree(c->fit_planes); cudaFree(c->costs); cudaFree(c->selected_alloc); cudaFree(c->weak);
+	cudaFree(c->radius); cudaFree(c->view_weight); cudaFree(c->rng); cudaFree(c->edge); cudaFree(c->edge_neigh);
+	cudaFree(c->label); cudaFree(c->candidate); cudaFree(c->nearest_strong); cudaFree(c->weak_reliable);
+	cudaFree(c->neighbours_map); cudaFree(c->neighbours); cudaFree(c->label_boundary); cudaFree(c->complex_);
+	for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int dvp_upload(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params) { return upload_common(ctx, in, params, false); }
+int dvp_upload_device(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params) { return upload_common(ctx, in, params, true); }
+
+int dvp_run_stage(dvp_ctx* ctx, int stage, int iter) {
+	if (!ctx) return DVP_ERR_ARG;
+	if (!ctx->uploaded) return DVP_ERR_STATE;
+	if (stage < 0 || stage >= DVP_STAGE_COUNT) return DVP_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	const KArgs a = make_args(ctx);
+	cudaError_t e = launch_stage(ctx, a, stage, iter);
+	if (e == cudaErrorNotSupported) return DVP_ERR_UNSUPPORTED;
+	CK(e);
+	CK(cudaStreamSynchronize(ctx->stream));
+	return DVP_OK;
+}
+
+int dvp_run(dvp_ctx* ctx, int sync) {
+	if (!ctx) return DVP_ERR_ARG;
+	if (!ctx->uploaded) return DVP_ERR_STATE;
+	if (ctx->prm.max_iterations > 64) return DVP_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	const KArgs a = make_args(ctx);
+	cudaStream_t st = ctx->stream;
+	int n = 0;
+	ctx->timed_valid = false;
+	auto go = [&](int stage, int iter) -> int {
+		CK(cudaEventRecord(ctx->ev[2 * n], st));
+		cudaError_t e = launch_stage(ctx, a, stage, iter);
+		if (e == cudaErrorNotSupported) return DVP_ERR_UNSUPPORTED;
+		CK(e);
+		CK(cudaEventRecord(ctx->ev[2 * n + 1], st));
+		ctx->ev_stage[n] = stage;
+		++n;
+		return DVP_OK;
+	};
+	int r;
+	for (int s = DVP_K1_INIT_RANDOM_STATES; s <= DVP_K6_RANDOM_INITIALIZATION; ++s) if ((r = go(s, 0))) return r;
+	for (int it = 0; it < ctx->prm.max_iterations; ++it)
+		for (int s = DVP_K7_BLACK_STRONG; s <= DVP_K11_RED_WEAK; ++s) if ((r = go(s, it))) return r;
+	for (int s = DVP_K12_DEPTH_NORMAL; s <= DVP_K16_LOCAL_REFINE; ++s) if ((r = go(s, 0))) return r;
+	ctx->n_timed = n;
+	ctx->timed_valid = true;
+	if (sync) CK(cudaStreamSynchronize(st));
+	return DVP_OK;
+}
+
+int dvp_last_run_times(dvp_ctx* ctx, float* total_ms, float* per_stage_ms, int* launches) {
+	if (!ctx) return DVP_ERR_ARG;
+	if (!ctx->timed_valid) return DVP_ERR_STATE;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (per_stage_ms) for (int i = 0; i < DVP_STAGE_COUNT; ++i) per_stage_ms[i] = 0.f;
+	float sum = 0.f;
+	for (int i = 0; i < ctx->n_timed; ++i) {
+		float ms = 0.f;
+		CK(cudaEventElapsedTime(&ms, ctx->ev[2 * i], ctx->ev[2 * i + 1]));
+		if (per_stage_ms) per_stage_ms[ctx->ev_stage[i]] += ms;
+		sum += ms;
+	}
+	if (total_ms) {
+		// wall time on the stream from the first launch to the end of the last one
+		float ms = 0.f;
+		CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2 * (ctx->n_timed - 1) + 1]));
+		*total_ms = ms;
+	}
+	(void)sum;
+	if (launches) {
+		// kernels launched by one dvp_run: K2 is two kernels when use_edge, the rest one each
+		*launches = ctx->n_timed + (ctx->prm.use_edge ? 1 : 0);
+	}
+	return DVP_OK;
+}
+
+int dvp_download(dvp_ctx* ctx, float* planes, uint8_t* weak_info, uint32_t* selected_views, int32_t* radius) {
+	if (!ctx) return DVP_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	const size_t N = (size_t)ctx->N;
+	cudaStream_t st = ctx->stream;
+	if (planes) CK(cudaMemcpyAsync(planes, ctx->planes, N * 16, cudaMemcpyDeviceToHost, st));
+	if (weak_info) CK(cudaMemcpyAsync(weak_info, ctx->weak, N, cudaMemcpyDeviceToHost, st));
+	if (selected_views) CK(cudaMemcpyAsync(selected_views, ctx->selected, N * 4, cudaMemcpyDeviceToHost, st));
+	if (radius) CK(cudaMemcpyAsync(radius, ctx->radius, N * 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	return DVP_OK;
+}
+
+size_t dvp_buffer_bytes(dvp_ctx* ctx, int buffer) { return ctx ? buf_desc(ctx, buffer).bytes : 0; }
+
+int dvp_get_buffer(dvp_ctx* ctx, int buffer, void* dst, size_t bytes) {
+	if (!ctx || !dst) return DVP_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	BufDesc b = buf_desc(ctx, buffer);
+	if (!b.ptr || bytes != b.bytes) return DVP_ERR_ARG;
+	if (bytes == 0) return DVP_OK;
+	if (buffer == DVP_BUF_RAND) {
+		uint32_t* tmp = nullptr;
+		CK(cudaMalloc((void**)&tmp, bytes));
+		const KArgs a = make_args(ctx);
+		CK(launch_rng_export(a, tmp, ctx->stream));
+		CK(cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		cudaFree(tmp);
+		return DVP_OK;
+	}
+	CK(cudaMemcpyAsync(dst, b.ptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return DVP_OK;
+}
+
+int dvp_set_buffer(dvp_ctx* ctx, int buffer, const void* src, size_t bytes) {
+	if (!ctx || !src) return DVP_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	BufDesc b = buf_desc(ctx, buffer);
+	if (!b.ptr || bytes != b.bytes) return DVP_ERR_ARG;
+	if (bytes == 0) return DVP_OK;
+	if (buffer == DVP_BUF_RAND) {
+		uint32_t* tmp = nullptr;
+		CK(cudaMalloc((void**)&tmp, bytes));
+		CK(cudaMemcpyAsync(tmp, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+		const KArgs a = make_args(ctx);
+		CK(launch_rng_import(a, tmp, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		cudaFree(tmp);
+		return DVP_OK;
+	}
+	CK(cudaMemcpyAsync(b.ptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return DVP_OK;
+}
+
+int dvp_weak_count(dvp_ctx* ctx) { return ctx ? ctx->weak_count : -1; }
+int dvp_last_cuda_error(dvp_ctx* ctx) { return ctx ? ctx->last_err : 0; }
+void* dvp_stream(dvp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+}  // extern "C"

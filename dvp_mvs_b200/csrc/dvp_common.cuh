@@ -1,0 +1,175 @@
+// dvp_common.cuh — shared device-side types and small math for the B200-native PatchMatch engine.
+//
+// Parity note (applies to every file in csrc/): results must match the reference kernels bit for bit
+// on race-free stages.  The reference is built with `--use_fast_math` (CMakeLists.txt:21), so this
+// library is built with the same flag and arithmetic that decides anything is written either in the
+// same expression shape as the reference (so nvcc contracts/approximates identically) or with explicit
+// intrinsics (__fmaf_rn / __fmul_rn / __fadd_rn, rcp/sqrt/ex2.approx.ftz via inline PTX) wherever the
+// computation was restructured (hoisting, warp cooperation).  The explicit forms were read off the
+// SASS of the reference build (oracle/_ref).
+#pragma once
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+#include <stdint.h>
+#include "../../include/dvp_mvs.h"
+
+#ifndef DVP_MIN
+#define DVP_MIN(a, b) ((a) > (b) ? (b) : (a))  // same definition as OpenCV's MIN (cvdef.h) used by the reference
+#define DVP_MAX(a, b) ((a) < (b) ? (b) : (a))
+#endif
+
+namespace dvp {
+
+constexpr int kMaxImages = DVP_MAX_IMAGES;
+constexpr int kHoistAxis = 6;                        // samples per patch axis when radius is a multiple of 5
+constexpr int kHoistSamples = kHoistAxis * kHoistAxis;
+
+// Per-source-view constants hoisted out of ComputeHomography (reference APD.cu:679-707 recomputes them on
+// every NCC call).  Filled on the device by k_setup_views so FMA contraction matches the reference.
+struct ViewConst {
+	float R_rel[9];   // src.R * ref.R^T
+	float t_rel[3];   // src.R * (C_ref - C_src)
+	float sK[9];      // source intrinsics
+	float sR[9];      // source rotation
+	float st[3];      // source translation
+	float sc[3];      // source centre
+	float R_c[9];     // ref.R * src.R^T   (GenerateRandomNormal_YZL, APD.cu:541-542)
+	float pad;
+};
+
+// Everything a kernel needs, passed by value as a __grid_constant__ parameter (the reference re-reads
+// helper->params->x through two pointer hops inside its inner loops).
+struct KArgs {
+	int W, H, S;       // S = number of source views
+	int N;
+	dvp_params prm;
+	dvp_camera ref;    // reference camera (cameras[0])
+	// textures
+	const cudaTextureObject_t* tex_img;    // [1+S] device array of texture objects (linear filter, clamp)
+	const cudaTextureObject_t* tex_depth;  // [1+S] or null
+	const float* ref_img;                  // [N] pitched-linear copy of image 0 (exact texel reads)
+	const dvp_camera* cams;                // [1+S]
+	const ViewConst* views;                // [S]  (index = src_idx-1)
+	float4* planes;
+	float4* fit_planes;
+	float* costs;
+	uint32_t* selected;   // padded allocation: index -W-1 .. N+W valid
+	uint8_t* weak;
+	int32_t* radius;
+	uint8_t* view_weight; // [N][32]
+	uint32_t* rng;        // SoA: 6 planes of N words {d, v0..v4}
+	uint8_t* edge;
+	short2* edge_neigh;   // [N][8]
+	int32_t* label;
+	short2* candidate;    // [N][4][8]
+	short2* nearest_strong;
+	uint8_t* weak_reliable;
+	int32_t* neighbours_map;
+	short2* neighbours;     // [weak_count][12]
+	short2* label_boundary; // [weak_count][8]
+	float* complex_;        // [weak_count]
+	float* scratch;         // per-pixel spill area for large S (cost arrays)
+	int weak_count;
+};
+
+// ---- approximate MUFU ops exactly as the reference build emits them -----------------------------------
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// ---- RNG: cuRAND XORWOW, stored as 6 SoA planes --------------------------------------------------------
+struct Rng {
+	curandStateXORWOW_t st;
+	__device__ __forceinline__ void load(const uint32_t* rng, int N, int idx) {
+		st.d = rng[idx];
+		st.v[0] = rng[N + idx]; st.v[1] = rng[2 * N + idx]; st.v[2] = rng[3 * N + idx];
+		st.v[3] = rng[4 * N + idx]; st.v[4] = rng[5 * N + idx];
+		st.boxmuller_flag = 0; st.boxmuller_flag_double = 0; st.boxmuller_extra = 0.f; st.boxmuller_extra_double = 0.0;
+	}
+	__device__ __forceinline__ void store(uint32_t* rng, int N, int idx) const {
+		rng[idx] = st.d;
+		rng[N + idx] = st.v[0]; rng[2 * N + idx] = st.v[1]; rng[3 * N + idx] = st.v[2];
+		rng[4 * N + idx] = st.v[3]; rng[5 * N + idx] = st.v[4];
+	}
+	__device__ __forceinline__ float uniform() { return curand_uniform(&st); }
+	__device__ __forceinline__ unsigned int next() { return curand(&st); }
+};
+
+// ---- small geometry helpers; expression shapes follow the reference so contraction is identical ------
+// reference APD.cu:372-377
+__device__ __forceinline__ void get_3d_point(const dvp_camera& cam, int px, int py, float depth, float* X) {
+	X[0] = depth * (px - cam.K[2]) / cam.K[0];
+	X[1] = depth * (py - cam.K[5]) / cam.K[4];
+	X[2] = depth;
+}
+// reference APD.cu:386-398
+__device__ __forceinline__ float4 get_view_direction(const dvp_camera& cam, int px, int py, float depth) {
+	float X[3];
+	get_3d_point(cam, px, py, depth, X);
+	float norm = sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2]);
+	float4 v;
+	v.x = X[0] / norm; v.y = X[1] / norm; v.z = X[2] / norm; v.w = 0;
+	return v;
+}
+// reference APD.cu:400-405
+__device__ __forceinline__ float get_distance2origin(const dvp_camera& cam, int px, int py, float depth, const float4 n) {
+	float X[3];
+	get_3d_point(cam, px, py, depth, X);
+	return -(n.x * X[0] + n.y * X[1] + n.z * X[2]);
+}
+// reference APD.cu:419-422
+__device__ __forceinline__ float depth_from_plane(const dvp_camera& cam, const float4 pl, int px, int py) {
+	return -pl.w * cam.K[0] / ((px - cam.K[2]) * pl.x + (cam.K[0] / cam.K[4]) * (py - cam.K[5]) * pl.y + cam.K[0] * pl.z);
+}
+// reference APD.cu:750-758 (camera -> world: R^T n)
+__device__ __forceinline__ float4 normal_to_world(const dvp_camera& cam, float4 pl) {
+	float4 o;
+	o.x = cam.R[0] * pl.x + cam.R[3] * pl.y + cam.R[6] * pl.z;
+	o.y = cam.R[1] * pl.x + cam.R[4] * pl.y + cam.R[7] * pl.z;
+	o.z = cam.R[2] * pl.x + cam.R[5] * pl.y + cam.R[8] * pl.z;
+	o.w = pl.w;
+	return o;
+}
+// reference APD.cu:760-768 (world -> reference camera: R n)
+__device__ __forceinline__ float4 normal_to_refcam(const dvp_camera& cam, float4 pl) {
+	float4 o;
+	o.x = cam.R[0] * pl.x + cam.R[1] * pl.y + cam.R[2] * pl.z;
+	o.y = cam.R[3] * pl.x + cam.R[4] * pl.y + cam.R[5] * pl.z;
+	o.z = cam.R[6] * pl.x + cam.R[7] * pl.y + cam.R[8] * pl.z;
+	o.w = pl.w;
+	return o;
+}
+// reference APD.cu:331-338
+__device__ __forceinline__ void normalize3(float4* v) {
+	const float n2 = v->x * v->x + v->y * v->y + v->z * v->z;
+	const float inv = rsqrtf(n2);
+	v->x *= inv; v->y *= inv; v->z *= inv;
+}
+// reference APD.cu:467-487
+__device__ __forceinline__ float3 point_to_world(float x, float y, float depth, const float* K, const float* R, const float* c) {
+	float3 pX, t;
+	pX.x = depth * (x - K[2]) / K[0];
+	pX.y = depth * (y - K[5]) / K[4];
+	pX.z = depth;
+	t.x = R[0] * pX.x + R[3] * pX.y + R[6] * pX.z;
+	t.y = R[1] * pX.x + R[4] * pX.y + R[7] * pX.z;
+	t.z = R[2] * pX.x + R[5] * pX.y + R[8] * pX.z;
+	pX.x = t.x + c[0]; pX.y = t.y + c[1]; pX.z = t.z + c[2];
+	return pX;
+}
+// reference APD.cu:489-499
+__device__ __forceinline__ void project_on_camera(const float3 P, const float* K, const float* R, const float* t, float2& pt, float& depth) {
+	float3 tmp;
+	tmp.x = R[0] * P.x + R[1] * P.y + R[2] * P.z + t[0];
+	tmp.y = R[3] * P.x + R[4] * P.y + R[5] * P.z + t[1];
+	tmp.z = R[6] * P.x + R[7] * P.y + R[8] * P.z + t[2];
+	depth = K[6] * tmp.x + K[7] * tmp.y + K[8] * tmp.z;
+	pt.x = (K[0] * tmp.x + K[1] * tmp.y + K[2] * tmp.z) / depth;
+	pt.y = (K[3] * tmp.x + K[4] * tmp.y + K[5] * tmp.z) / depth;
+}
+
+__device__ __forceinline__ int is_set(uint32_t v, int n) { return (v >> n) & 1; }
+// reference APD.cu:186-189 — clears bit n AND every lower bit (bug B1, reproduced on purpose)
+__device__ __forceinline__ void unset_bit_ref(uint32_t* v, int n) { (*v) &= (uint32_t)(0xFFFFFFFEu << n); }
+
+}  // namespace dvp

@@ -1,0 +1,168 @@
+// dvp_kernels_prep.cu — K2 GenEdgeInform, K3 FindNearestStrongPoint, K5 NeigbourUpdate and the RNG
+// exchange helpers (reference APD.cu:3731-3890, 4159-4193, 3713-3729).
+#include "dvp_common.cuh"
+#include "dvp_launch.h"
+
+namespace dvp {
+
+__constant__ int c_dir8[8][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, 1}, {-1, 1}, {1, -1}};
+
+// ------------------------------------------------------------------------------------------------------
+// K2 part (b): nearest edge pixel along each of 8 rays (APD.cu:3803-3824).
+// The reference walks an unbounded ray from every pixel (O(N * max(W,H)) reads).  The answer for pixel q
+// along direction d is "the closest edge pixel strictly ahead of q on q's line", so one backwards sweep
+// per line produces all answers on that line in O(length): 8N reads in total.  One thread per (direction, line).
+__global__ void __launch_bounds__(128) k_edge_neigh_sweep(const __grid_constant__ KArgs a) {
+	const int W = a.W, H = a.H;
+	const int n_diag = W + H - 1;
+	const int counts[8] = {W, W, H, H, n_diag, n_diag, n_diag, n_diag};
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	int d = 0;
+	while (d < 8 && t >= counts[d]) { t -= counts[d]; ++d; }
+	if (d >= 8) return;
+	const int dx = c_dir8[d][0], dy = c_dir8[d][1];
+	// far end of the line in direction +d
+	int x, y;
+	if (dx == 0) { x = t; y = (dy > 0) ? H - 1 : 0; }
+	else if (dy == 0) { y = t; x = (dx > 0) ? W - 1 : 0; }
+	else {
+		const int ex = (dx > 0) ? W - 1 : 0, ey = (dy > 0) ? H - 1 : 0;
+		if (t < W) { x = t; y = ey; }
+		else { const int k = t - W; x = ex; y = (ey == 0) ? k + 1 : k; }
+	}
+	short2 last = make_short2(-1, -1);
+	while (x >= 0 && x < W && y >= 0 && y < H) {
+		const int q = y * W + x;
+		a.edge_neigh[(size_t)q * DVP_EDGE_NEIGH_NUM + d] = last;
+		if (a.edge[q]) last = make_short2((short)x, (short)y);
+		x -= dx; y -= dy;
+	}
+}
+
+// K2 parts (c), (d), (e): per-pixel edge density, label-region boundaries, demotions (APD.cu:3826-3889).
+__global__ void __launch_bounds__(256) k_edge_inform_pixel(const __grid_constant__ KArgs a) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	const int W = a.W, H = a.H;
+	if (x >= W || y >= H) return;
+	const int center = x + y * W;
+	uint8_t state = a.weak[center];
+	if (a.prm.use_edge) {
+		if (state == DVP_WEAK) {
+			const int radius = a.prm.strong_radius;
+			int edge_pix = 0, tot_pix = 0;
+			for (int i = -radius; i <= radius; i++)
+				for (int j = -radius; j <= radius; j++) {
+					const int nx = x + i, ny = y + j;
+					if (nx < 0 || nx >= W || ny < 0 || ny >= H) continue;
+					if (a.edge[ny * W + nx]) edge_pix++;
+					tot_pix++;
+				}
+			const float density = 1.0f * edge_pix / tot_pix;
+			a.complex_[a.neighbours_map[center]] = 1.0f / (1.0f + exp(-25.0 * (density - 0.35)));
+		}
+		if (a.prm.state == DVP_REFINE_INIT && a.prm.use_detail && a.edge[center]) {
+			if (state != DVP_STRONG) { state = DVP_UNKNOWN; a.weak[center] = DVP_UNKNOWN; }
+		}
+	}
+	if (a.prm.use_label && state == DVP_WEAK) {
+		const int center_label = a.label[center];
+		if (center_label > 0) {
+			short2* lab_bound = a.label_boundary + (size_t)a.neighbours_map[center] * DVP_LAB_BOUNDARY_NUM;
+			for (int i = 0; i < DVP_LAB_BOUNDARY_NUM; i++) {
+				const int dx = c_dir8[i][0], dy = c_dir8[i][1];
+				int nx = x + dx, ny = y + dy;
+				int last_x = -1, last_y = -1;
+				while (true) {
+					if (nx < 0 || nx >= W || ny < 0 || ny >= H) break;
+					const int next_label = a.label[nx + ny * W];
+					if (next_label == center_label) { last_x = nx; last_y = ny; }
+					else if (next_label == -1) break;
+					nx += dx; ny += dy;
+				}
+				lab_bound[i] = make_short2((short)last_x, (short)last_y);
+			}
+		}
+		if (a.prm.state == DVP_REFINE_INIT && a.prm.use_detail && center_label == 0) {
+			if (state != DVP_STRONG) a.weak[center] = DVP_UNKNOWN;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K3 FindNearestStrongPoint (APD.cu:4159-4193): first STRONG pixel on growing square rings, radius <= 100,
+// scan order x-major then y inside each ring (the tie order is part of the result).
+__global__ void __launch_bounds__(256) k_nearest_strong(const __grid_constant__ KArgs a) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	const int W = a.W, H = a.H;
+	if (x >= W || y >= H) return;
+	const int center = x + y * W;
+	short2 out = make_short2(-1, -1);
+	if (a.weak[center] == DVP_WEAK) {
+		const int max_radius = 100;
+		bool found = false;
+		for (int r = 0; r <= max_radius && !found; ++r) {
+			for (int dx = -r; dx <= r && !found; ++dx) {
+				const int nx = x + dx;
+				if (nx < 0 || nx >= W) continue;
+				const bool full_col = (dx == -r || dx == r);
+				// on the two outer columns every y of the ring qualifies, otherwise only y = -r and y = +r
+				for (int dy = -r; dy <= r; dy += (full_col ? 1 : (r > 0 ? 2 * r : 1))) {
+					const int ny = y + dy;
+					if (ny < 0 || ny >= H) continue;
+					if (a.weak[nx + ny * W] == DVP_STRONG) { out = make_short2((short)nx, (short)ny); found = true; break; }
+				}
+			}
+		}
+	}
+	a.nearest_strong[center] = out;
+}
+
+// K5 NeigbourUpdate (APD.cu:3713-3729)
+__global__ void __launch_bounds__(256) k_neighbour_update(const __grid_constant__ KArgs a) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.N) return;
+	if (a.weak[i] != DVP_WEAK) return;
+	if (a.weak_reliable[i] != 1) a.weak[i] = DVP_UNKNOWN;
+}
+
+__global__ void k_rng_export(const __grid_constant__ KArgs a, uint32_t* dst) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.N) return;
+	for (int k = 0; k < 6; ++k) dst[(size_t)6 * i + k] = a.rng[(size_t)k * a.N + i];
+}
+__global__ void k_rng_import(const __grid_constant__ KArgs a, const uint32_t* src) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.N) return;
+	for (int k = 0; k < 6; ++k) a.rng[(size_t)k * a.N + i] = src[(size_t)6 * i + k];
+}
+
+cudaError_t launch_edge_inform_prep(const KArgs& a, cudaStream_t st) {
+	if (a.prm.use_edge) {
+		const int total = 2 * a.W + 2 * a.H + 4 * (a.W + a.H - 1);
+		k_edge_neigh_sweep<<<(total + 127) / 128, 128, 0, st>>>(a);
+	}
+	dim3 b(32, 8);
+	dim3 g((a.W + 31) / 32, (a.H + 7) / 8, 1);
+	k_edge_inform_pixel<<<g, b, 0, st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t launch_nearest_strong(const KArgs& a, cudaStream_t st) {
+	dim3 b(32, 8);
+	dim3 g((a.W + 31) / 32, (a.H + 7) / 8, 1);
+	k_nearest_strong<<<g, b, 0, st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t launch_neighbour_update(const KArgs& a, cudaStream_t st) {
+	k_neighbour_update<<<(a.N + 255) / 256, 256, 0, st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t launch_rng_export(const KArgs& a, uint32_t* dst, cudaStream_t st) {
+	k_rng_export<<<(a.N + 255) / 256, 256, 0, st>>>(a, dst);
+	return cudaGetLastError();
+}
+cudaError_t launch_rng_import(const KArgs& a, const uint32_t* src, cudaStream_t st) {
+	k_rng_import<<<(a.N + 255) / 256, 256, 0, st>>>(a, src);
+	return cudaGetLastError();
+}
+
+}  // namespace dvp

@@ -1,0 +1,629 @@
+// dvp_kernels_strong.cu — kernels K1, K6, K7/K8, K12, K13/K14, K15, K16 of the PatchMatch sequence
+// (reference APD.cu:1258-1309, 2010-2737, 3127-3328, 3892-4139), rewritten for sm_100a.
+#include "dvp_strong.cuh"
+#include "dvp_launch.h"
+#include <cfloat>
+
+namespace dvp {
+
+__constant__ int c_dir[8][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, 1}, {-1, 1}, {1, -1}};
+
+// ------------------------------------------------------------------------------------------------------
+// per-view constants.  Same expressions as the preamble of ComputeHomography (APD.cu:681-707) and the
+// R_c product of GenerateRandomNormal_YZL (APD.cu:540-542) so that rounding/contraction is unchanged.
+__global__ void k_setup_views(const dvp_camera* cams, ViewConst* views, int S) {
+	const int v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= S) return;
+	const dvp_camera ref_camera = cams[0];
+	const dvp_camera src_camera = cams[v + 1];
+	ViewConst vc;
+	float ref_C[3], src_C[3];
+	ref_C[0] = -(ref_camera.R[0] * ref_camera.t[0] + ref_camera.R[3] * ref_camera.t[1] + ref_camera.R[6] * ref_camera.t[2]);
+	ref_C[1] = -(ref_camera.R[1] * ref_camera.t[0] + ref_camera.R[4] * ref_camera.t[1] + ref_camera.R[7] * ref_camera.t[2]);
+	ref_C[2] = -(ref_camera.R[2] * ref_camera.t[0] + ref_camera.R[5] * ref_camera.t[1] + ref_camera.R[8] * ref_camera.t[2]);
+	src_C[0] = -(src_camera.R[0] * src_camera.t[0] + src_camera.R[3] * src_camera.t[1] + src_camera.R[6] * src_camera.t[2]);
+	src_C[1] = -(src_camera.R[1] * src_camera.t[0] + src_camera.R[4] * src_camera.t[1] + src_camera.R[7] * src_camera.t[2]);
+	src_C[2] = -(src_camera.R[2] * src_camera.t[0] + src_camera.R[5] * src_camera.t[1] + src_camera.R[8] * src_camera.t[2]);
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j)
+			vc.R_rel[i * 3 + j] = src_camera.R[i * 3 + 0] * ref_camera.R[j * 3 + 0] + src_camera.R[i * 3 + 1] * ref_camera.R[j * 3 + 1] +
+			                      src_camera.R[i * 3 + 2] * ref_camera.R[j * 3 + 2];
+	float C_rel[3];
+	C_rel[0] = (ref_C[0] - src_C[0]);
+	C_rel[1] = (ref_C[1] - src_C[1]);
+	C_rel[2] = (ref_C[2] - src_C[2]);
+	for (int i = 0; i < 3; ++i)
+		vc.t_rel[i] = src_camera.R[i * 3 + 0] * C_rel[0] + src_camera.R[i * 3 + 1] * C_rel[1] + src_camera.R[i * 3 + 2] * C_rel[2];
+	for (int i = 0; i < 9; ++i) { vc.sK[i] = src_camera.K[i]; vc.sR[i] = src_camera.R[i]; }
+	for (int i = 0; i < 3; ++i) { vc.st[i] = src_camera.t[i]; vc.sc[i] = src_camera.c[i]; }
+	// R_c = ref.R * transpose(src.R), accumulated from zero like matMul3x3 (APD.cu:3-12)
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j) {
+			float acc = 0;
+			for (int k = 0; k < 3; ++k) acc += ref_camera.R[i * 3 + k] * src_camera.R[j * 3 + k];
+			vc.R_c[i * 3 + j] = acc;
+		}
+	vc.pad = 0.f;
+	views[v] = vc;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K1: curand_init(seed, subsequence = y, offset = x) for every pixel (APD.cu:1258-1271).  The reference
+// pays a full skip-ahead per pixel; the state at (x, y) is the state at (x-1, y) advanced by one draw, so
+// each thread jumps to the start of a 32-pixel run once and then steps.
+__global__ void __launch_bounds__(128) k_init_rng(const __grid_constant__ KArgs a, unsigned long long seed) {
+	const int seg_per_row = (a.W + 31) / 32;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= seg_per_row * a.H) return;
+	const int y = t / seg_per_row;
+	const int x0 = (t - y * seg_per_row) * 32;
+	Rng r;
+	curand_init(seed, (unsigned long long)y, (unsigned long long)x0, &r.st);
+	const int x1 = min(x0 + 32, a.W);
+	for (int x = x0; x < x1; ++x) {
+		r.store(a.rng, a.N, y * a.W + x);
+		(void)curand(&r.st);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K6 RandomInitialization (APD.cu:1273-1309) with ComputeMultiViewInitialCost[andSelectedViews]
+// (APD.cu:1115-1194).
+__global__ void __launch_bounds__(256) k_random_init(const __grid_constant__ KArgs a) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int T = blockDim.x * blockDim.y;
+	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= a.W || y >= a.H) return;
+	const int center = y * a.W + x;
+	RefPatch rp;
+	rp.prepare(a, x, y, a.prm.use_radius ? a.radius[center] : a.prm.strong_radius, wt, T);
+
+	if (a.prm.state == DVP_FIRST_INIT) {
+		float4 pl = a.planes[center];
+		if (pl.w > a.prm.depth_max || pl.w < a.prm.depth_min) {
+			Rng rng; rng.load(a.rng, a.N, center);
+			const float depth = rng.uniform() * (a.prm.depth_max - a.prm.depth_min) + a.prm.depth_min;
+			pl = random_normal(a, x, y, rng, depth, a.selected[center]);
+			pl.w = get_distance2origin(a.ref, x, y, depth, pl);
+			a.planes[center] = pl;
+			rng.store(a.rng, a.N, center);
+		}  // else: left as (world normal, depth) — bug B20, reproduced
+		// cost over all views; keep the top_k cheapest valid views
+		float cv[kMaxImages];     // sorted copy (local memory; K6 runs once per pass)
+		float cv_copy[kMaxImages];
+		int cost_count = 0, num_valid = 0;
+		for (int v = 0; v < a.S; ++v) {
+			const float c = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+			cv[v] = c; cv_copy[v] = c; cost_count++;
+			if (c < kCostMax) num_valid++;
+		}
+		for (int i = 1; i < cost_count; i++) {  // insertion sort, ascending (sort_small, APD.cu:114-123)
+			const float tmp = cv[i];
+			int j;
+			for (j = i; j >= 1 && tmp < cv[j - 1]; j--) cv[j] = cv[j - 1];
+			cv[j] = tmp;
+		}
+		uint32_t sel = 0;
+		const int top_k = min(num_valid, a.prm.top_k);
+		float out_cost = kCostMax;
+		if (top_k > 0) {
+			float cost = 0.0f;
+			for (int i = 0; i < top_k; ++i) cost += cv[i];
+			const float thr = cv[top_k - 1];
+			for (int i = 0; i < a.S; ++i)
+				if (cv_copy[i] <= thr) sel |= (1u << i);
+			out_cost = cost / top_k;
+		}
+		a.selected[center] = sel;
+		a.costs[center] = out_cost;
+	} else {
+		float4 pl = a.planes[center];
+		pl = normal_to_refcam(a.ref, pl);
+		const float depth = pl.w;
+		pl.w = get_distance2origin(a.ref, x, y, depth, pl);
+		a.planes[center] = pl;
+		uint32_t sel = a.selected[center];
+		int cost_count = 0;
+		float cost = 0.0f;
+		for (int v = 0; v < a.S; ++v) {
+			if (is_set(sel, v)) {
+				const float c = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+				if (c < kCostMax) { cost_count++; cost += c; }
+				else unset_bit_ref(&sel, v);  // B1
+			}
+		}
+		a.selected[center] = sel;
+		a.costs[center] = (cost_count == 0) ? kCostMax : cost / cost_count;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K7/K8: red-black propagation sweep for non-WEAK pixels (edge-adaptive branch, params.use_edge).
+// shared memory per thread: 36 float2 (w, w r) + 9*S floats (8 direction cost vectors + 1 spare) + 8 ints.
+__global__ void __launch_bounds__(kSweepThreads, 3) k_strong_sweep(const __grid_constant__ KArgs a, int iter, int red, int yy_limit) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int T = blockDim.x * blockDim.y;
+	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
+	float* cost_arr = reinterpret_cast<float*>(smem_raw + (size_t)kHoistSamples * T * sizeof(float2)) + tid;
+	int* pos_arr = reinterpret_cast<int*>(smem_raw + (size_t)kHoistSamples * T * sizeof(float2) + (size_t)9 * a.S * T * sizeof(float)) + tid;
+	const int S = a.S, W = a.W, H = a.H;
+
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int yy = blockIdx.y * blockDim.y + threadIdx.y;
+	const int y = 2 * yy + ((x & 1) ^ red);  // black: even x -> even row; red: the other colour (APD.cu:3129-3136)
+	if (x >= W || y >= H || yy >= yy_limit) return;
+	const int center = y * W + x;
+	if (a.weak[center] == DVP_WEAK) return;
+
+	RefPatch rp;
+	rp.prepare(a, x, y, a.prm.use_radius ? a.radius[center] : a.prm.strong_radius, wt, T);
+
+	// `float cost_array[8][32] = {2.0f}` : element [0][0] is 2, everything else 0 (bug B2, reproduced)
+	for (int s = 0; s < 8; ++s)
+		for (int v = 0; v < S; ++v) cost_arr[(s * S + v) * T] = 0.0f;
+	cost_arr[0] = 2.0f;
+	uint32_t flag = 0;
+
+	const bool on_edge = a.edge[center] != 0;
+	const short2* edge_neigh = a.edge_neigh + (size_t)center * DVP_EDGE_NEIGH_NUM;
+	const float max_edge_dist = DVP_MAX(H, W) / 30.0f;
+	const int min_step_len = 2;
+	const float good_threshold = 0.8f * expf((iter) * (iter) / (-90.0f));
+	const float bad_threshold = 1.2f;
+
+#pragma unroll 1
+	for (int d = 0; d < 8; ++d) {
+		const int dx = c_dir[d][0], dy = c_dir[d][1];
+		const int sx = 5 * dx, sy = 5 * dy;
+		int fx = 0, fy = 0;
+		if (d > 4) { if (d % 2) fx = dx; else fy = dy; }  // colour fix on directions 5,6,7 only (B6: 4 is racy)
+		// ---- edge-adaptive ladder (APD.cu:2053-2087) ----
+		{
+			const short2 edge_pt = edge_neigh[d];
+			const int ex = edge_pt.x - x, ey = edge_pt.y - y;
+			float dist = (float)sqrt((double)(ex * ex) + (double)(ey * ey));
+			if (d >= 4) dist = (float)((double)dist / sqrt(2.0));
+			if (on_edge) {
+				dist = 11 * min_step_len;
+			} else if (edge_pt.y == -1 || dist >= max_edge_dist) {  // `!edge_pt.x == -1` is always false (B5)
+				dist = max_edge_dist;
+				if (d >= 4) dist = (float)((double)dist / sqrt(2.0));
+			}
+			const int step_num = DVP_MIN(DVP_MAX(11, (int)(1.0f * dist / min_step_len)), 22);
+			int step_len = DVP_MAX((int)(1.0f * dist / step_num), min_step_len);
+			if (d < 4 && step_len % 2 == 1) step_len -= 1;
+			int min_pos = -1;
+			float min_cost = FLT_MAX;
+			for (int step = 0; step < step_num; ++step) {
+				const int tx = x + sx + step * step_len * dx + fx, ty = y + sy + step * step_len * dy + fy;
+				if (!(tx >= 0 && ty >= 0 && tx < W && ty < H)) continue;
+				const int tc = tx + ty * W;
+				const float c = a.costs[tc];
+				if (min_cost > c) { min_pos = tc; min_cost = c; }
+			}
+			if (min_cost < FLT_MAX) {
+				flag |= 1u << d;
+				pos_arr[d * T] = min_pos;
+				const float4 pl = a.planes[min_pos];
+				for (int v = 0; v < S; ++v)
+					cost_arr[(d * S + v) * T] = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+			}
+		}
+		// ---- fixed 11 x 2 px ladder for non-edge pixels; keep the better of the two (APD.cu:2090-2140) ----
+		if (!on_edge) {
+			const bool has_before = (flag >> d) & 1;
+			int min_pos = -1;
+			float min_cost = FLT_MAX;
+			for (int step = 0; step < 11; ++step) {
+				const int tx = x + sx + step * min_step_len * dx + fx, ty = y + sy + step * min_step_len * dy + fy;
+				if (!(tx >= 0 && ty >= 0 && tx < W && ty < H)) continue;
+				const int tc = tx + ty * W;
+				const float c = a.costs[tc];
+				if (min_cost > c) { min_pos = tc; min_cost = c; }
+			}
+			if (min_cost < FLT_MAX) {
+				flag |= 1u << d;
+				const float4 pl = a.planes[min_pos];
+				int good0 = 0, good1 = 0, bad0 = 0, bad1 = 0;
+				for (int v = 0; v < S; ++v) {
+					const float c1 = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+					cost_arr[(8 * S + v) * T] = c1;
+					const float c0 = cost_arr[(d * S + v) * T];
+					if (c0 < good_threshold) good0++;
+					if (c0 > bad_threshold) bad0++;
+					if (c1 < good_threshold) good1++;
+					if (c1 > bad_threshold) bad1++;
+				}
+				if (!has_before || good1 > good0 || (good1 == good0 && bad1 < bad0)) {
+					pos_arr[d * T] = min_pos;
+					for (int v = 0; v < S; ++v) cost_arr[(d * S + v) * T] = cost_arr[(8 * S + v) * T];
+				}
+			}
+		}
+	}
+
+	// ---- multi-hypothesis joint view selection (APD.cu:2462-2530) ----
+	Rng rng; rng.load(a.rng, a.N, center);
+	ViewWeights vw; vw.clear();
+	{
+		// priors from the 4-neighbours, guarded by flag[0], flag[2], flag[4], flag[6] (B16, reproduced;
+		// `selected` has one padded row on each side so the border reads are defined)
+		const int npos[4] = {center - W, center + W, center - 1, center + 1};
+		uint32_t nsel[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) nsel[i] = ((flag >> (2 * i)) & 1) ? a.selected[npos[i]] : 0u;
+		const float cost_threshold = 0.8 * expf((iter) * (iter) / (-90.0f));
+		float* probs = cost_arr + (size_t)8 * S * T;  // spare slot
+		for (int i = 0; i < S; i++) {
+			float prior = 0.0f;
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				if ((flag >> (2 * k)) & 1) prior += is_set(nsel[k], i) ? 0.9f : 0.1f;
+			float count = 0;
+			int count_false = 0;
+			float tmpw = 0;
+			for (int j = 0; j < 8; j++) {
+				const float c = cost_arr[(j * S + i) * T];
+				if (c < cost_threshold) {
+					tmpw += expf(c * c / (-0.18f));
+					count++;
+				}
+				if (c > 1.2f) count_false++;
+			}
+			float prob = 0.0f;
+			if (count > 2 && count_false < 3) prob = tmpw / count;
+			else if (count_false < 3) prob = expf(cost_threshold * cost_threshold / (-0.32f));
+			prob = prob * prior;
+			probs[i * T] = prob;
+		}
+		// TransformPDFToCDF (APD.cu:356-370); all-zero probabilities give NaN here (B18, reproduced)
+		float prob_sum = 0.0f;
+		for (int i = 0; i < S; ++i) prob_sum += probs[i * T];
+		const float inv_prob_sum = 1.0f / prob_sum;
+		float cum_prob = 0.0f;
+		for (int i = 0; i < S; ++i) {
+			const float prob = probs[i * T] * inv_prob_sum;
+			cum_prob += prob;
+			probs[i * T] = cum_prob;
+		}
+		for (int sample = 0; sample < 15; ++sample) {
+			const float rand_prob = rng.uniform() - FLT_EPSILON;
+			for (int image_id = 0; image_id < S; ++image_id) {
+				if (probs[image_id * T] > rand_prob) { vw.inc(image_id); break; }
+			}
+		}
+	}
+	vw.store(a.view_weight + (size_t)center * DVP_MAX_IMAGES);
+
+	uint32_t temp_selected = 0;
+	float weight_norm = 0;
+	for (int i = 0; i < S; ++i) {
+		const int wv = vw.get(i);
+		if (wv > 0) { temp_selected |= 1u << i; weight_norm += wv; }
+	}
+
+	// ---- aggregated candidate costs and the current plane (APD.cu:2532-2567) ----
+	int min_cost_idx = 0;
+	float min_final = 0.f;
+	for (int i = 0; i < 8; ++i) {
+		float fc = 0.0f;
+		for (int j = 0; j < S; ++j) {
+			const int wv = vw.get(j);
+			if (wv > 0) fc += wv * cost_arr[(i * S + j) * T];
+		}
+		fc /= weight_norm;
+		if (i == 0 || fc <= min_final) { min_final = fc; min_cost_idx = i; }  // FindMinCostIndex: '<=' keeps the last
+	}
+
+	float4 plane_now = a.planes[center];
+	float cost_now = 0.0f;
+	for (int v = 0; v < S; ++v) {
+		const int wv = vw.get(v);
+		if (wv > 0) {  // zero-weight views contribute exactly 0 in the reference
+			const float c = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, plane_now, rp, wt, T);
+			cost_now += wv * c;
+		}
+	}
+	cost_now /= weight_norm;
+	const float cost_stored = cost_now;  // costs[center] = cost_now (APD.cu:2554)
+	float depth_now = depth_from_plane(a.ref, plane_now, x, y);
+	uint32_t sel_now = a.selected[center];
+
+	if ((flag >> min_cost_idx) & 1) {
+		const float4 cand = a.planes[pos_arr[min_cost_idx * T]];
+		const float depth_before = depth_from_plane(a.ref, cand, x, y);
+		if (depth_before >= a.prm.depth_min && depth_before <= a.prm.depth_max && min_final < cost_now) {
+			depth_now = depth_before;
+			plane_now = cand;
+			cost_now = min_final;
+			sel_now = temp_selected;
+			a.selected[center] = temp_selected;
+		}
+	}
+
+	refine_strong(a, x, y, &plane_now, &depth_now, &cost_now, rng, vw, weight_norm, sel_now, rp, wt, T);
+	rng.store(a.rng, a.N, center);
+
+	if (a.prm.state == DVP_REFINE_INIT) {
+		if (cost_now < cost_stored - 0.1) {
+			a.costs[center] = cost_now;
+			a.planes[center] = plane_now;
+		} else {
+			a.costs[center] = cost_stored;
+		}
+	} else {
+		a.costs[center] = cost_now;
+		a.planes[center] = plane_now;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K12 GetDepthandNormal (APD.cu:3167-3182): plane offset -> depth, camera normal -> world normal.
+__global__ void __launch_bounds__(256) k_depth_normal(const __grid_constant__ KArgs a) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= a.W || y >= a.H) return;
+	const int center = y * a.W + x;
+	float4 pl = a.planes[center];
+	pl.w = depth_from_plane(a.ref, pl, x, y);
+	a.planes[center] = normal_to_world(a.ref, pl);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K13/K14 CheckerboardFilterStrong (APD.cu:3184-3294): median of the own depth and up to 20 STRONG
+// neighbours at fixed opposite-colour offsets.
+__global__ void __launch_bounds__(256) k_filter(const __grid_constant__ KArgs a, int red, int yy_limit) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int yy = blockIdx.y * blockDim.y + threadIdx.y;
+	const int y = 2 * yy + ((x & 1) ^ red);
+	const int W = a.W, H = a.H;
+	if (x >= W || y >= H || yy >= yy_limit) return;
+	const int center = y * W + x;
+	if (a.weak[center] == DVP_WEAK) return;
+	if (a.costs[center] < 0.001f) return;
+	float f[21];
+	int n = 0;
+	f[n++] = a.planes[center].w;
+	// (dx, dy, guard) in the reference's order
+	auto take = [&](bool ok, int dx, int dy) {
+		if (ok) {
+			const int q = center + dy * W + dx;
+			if (a.weak[q] == DVP_STRONG) f[n++] = a.planes[q].w;
+		}
+	};
+	take(y > 0, 0, -1); take(y > 2, 0, -3); take(y > 4, 0, -5);
+	take(y < H - 1, 0, 1); take(y < H - 3, 0, 3); take(y < H - 5, 0, 5);
+	take(x > 0, -1, 0); take(x > 2, -3, 0); take(x > 4, -5, 0);
+	take(x < W - 1, 1, 0); take(x < W - 3, 3, 0); take(x < W - 5, 5, 0);
+	take(y > 0 && x < W - 2, 2, -1); take(y < H - 1 && x < W - 2, 2, 1);
+	take(y > 0 && x > 1, -2, -1); take(y < H - 1 && x > 1, -2, 1);
+	take(x > 0 && y > 2, -1, -2); take(x < W - 1 && y > 2, 1, -2);
+	take(x > 0 && y < H - 2, -1, 2); take(x < W - 1 && y < H - 2, 1, 2);
+	for (int i = 1; i < n; i++) {  // insertion sort (sort_small)
+		const float tmp = f[i];
+		int j;
+		for (j = i; j >= 1 && tmp < f[j - 1]; j--) f[j] = f[j - 1];
+		f[j] = tmp;
+	}
+	const int m = n / 2;
+	a.planes[center].w = (n % 2 == 0) ? (f[m - 1] + f[m]) / 2 : f[m];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Shared front end of K15/K16: plane at rest -> reference camera, weighted cost of the current depth,
+// mean baseline of the selected views (APD.cu:3918-3960, 4067-4108).
+struct ProfileCtx {
+	float4 plane;        // normal in ref-camera frame, w = depth
+	float depth;
+	float weight_normal;
+	float base_line;
+	float cost_now;
+	int valid;
+};
+
+__device__ __forceinline__ float profile_cost_sum(const KArgs& a, int x, int y, const float4 pl, uint32_t sel, const ViewWeights& vw,
+                                                  const RefPatch& rp, const float2* wt, int T, bool k16_form) {
+	// K15: temp = ncc (+ geom_factor*geom); p_cost += temp * w          (APD.cu:3976-3986)
+	// K16: temp_cost += ncc * w; temp_cost += geom_factor * geom * w     (APD.cu:4121-4129)
+	float acc = 0.0f;
+	for (int v = 0; v < a.S; ++v) {
+		if (!is_set(sel, v)) continue;
+		const int wv = vw.get(v);
+		if (k16_form) {
+			acc += (ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T) * wv);
+			if (a.prm.geom_consistency) acc += (a.prm.geom_factor * geom_cost(a, a.views[v], a.tex_depth[v + 1], x, y, pl) * wv);
+		} else {
+			float temp_cost = 0.0f;
+			temp_cost += ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+			if (a.prm.geom_consistency) temp_cost += a.prm.geom_factor * geom_cost(a, a.views[v], a.tex_depth[v + 1], x, y, pl);
+			acc += (temp_cost * wv);
+		}
+	}
+	return acc;
+}
+
+__device__ __forceinline__ void profile_front(const KArgs& a, int x, int y, int center, uint32_t sel, const ViewWeights& vw,
+                                              const RefPatch& rp, const float2* wt, int T, ProfileCtx& pc) {
+	pc.cost_now = 0.0f; pc.base_line = 0; pc.valid = 0; pc.weight_normal = 0.0f;
+	for (int v = 0; v < a.S; ++v) {
+		if (!is_set(sel, v)) continue;
+		float4 t = pc.plane;
+		t.w = get_distance2origin(a.ref, x, y, pc.depth, t);
+		float temp_cost = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, t, rp, wt, T);
+		if (a.prm.geom_consistency) temp_cost += a.prm.geom_factor * geom_cost(a, a.views[v], a.tex_depth[v + 1], x, y, t);
+		const int wv = vw.get(v);
+		pc.cost_now += (temp_cost * wv);
+		pc.weight_normal += wv;
+		const dvp_camera& sc = a.cams[v + 1];
+		float c_dist[3];
+		c_dist[0] = a.ref.c[0] - sc.c[0];
+		c_dist[1] = a.ref.c[1] - sc.c[1];
+		c_dist[2] = a.ref.c[2] - sc.c[2];
+		const double temp_val = c_dist[0] * c_dist[0] + c_dist[1] * c_dist[1] + c_dist[2] * c_dist[2];
+		pc.base_line += sqrtf(temp_val);
+		pc.valid++;
+	}
+}
+
+// K15 DepthToWeak (APD.cu:3892-4051): 61-step disparity cost profile -> STRONG / WEAK / UNKNOWN.
+__global__ void __launch_bounds__(256) k_depth_to_weak(const __grid_constant__ KArgs a) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int T = blockDim.x * blockDim.y;
+	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= a.W || y >= a.H) return;
+	const int min_margin = 6;
+	const int center = x + y * a.W;
+	if (a.prm.use_radius && a.radius[center] == 0) a.radius[center] = a.prm.strong_radius;
+	if (x < min_margin || y < min_margin || x >= a.W - min_margin || y >= a.H - min_margin) { a.weak[center] = DVP_UNKNOWN; return; }
+	ProfileCtx pc;
+	pc.plane = normal_to_refcam(a.ref, a.planes[center]);
+	pc.depth = pc.plane.w;
+	if (pc.depth == 0) { a.weak[center] = DVP_UNKNOWN; return; }
+	const uint32_t sel = a.selected[center];
+	ViewWeights vw; vw.load(a.view_weight + (size_t)center * DVP_MAX_IMAGES);
+	RefPatch rp;
+	rp.prepare(a, x, y, a.prm.use_radius ? a.radius[center] : a.prm.strong_radius, wt, T);
+	profile_front(a, x, y, center, sel, vw, rp, wt, T, pc);
+	if (pc.valid == 0) { a.weak[center] = DVP_UNKNOWN; return; }
+	pc.cost_now /= pc.weight_normal;
+	pc.base_line /= pc.valid;
+
+	const float disp = a.ref.K[0] * pc.base_line / pc.depth;
+	const int radius = 30;
+	const int p_costs_size = 2 * radius + 1;
+	float p_costs[p_costs_size];  // 244 B of local memory per thread, touched ~240 times per ~8000 texture samples
+	for (int idx = 0; idx < p_costs_size; ++idx) {
+		const int p_disp = idx - radius;
+		const float p_depth = a.ref.K[0] * pc.base_line / (disp + p_disp);
+		if (p_depth < a.prm.depth_min || p_depth > a.prm.depth_max) { p_costs[idx] = 2.0f; continue; }
+		float4 t = pc.plane;
+		t.w = get_distance2origin(a.ref, x, y, p_depth, t);
+		float p_cost = profile_cost_sum(a, x, y, t, sel, vw, rp, wt, T, false);
+		p_cost /= pc.weight_normal;
+		p_costs[idx] = DVP_MIN(2.0f, p_cost);
+	}
+	// local minima of the profile (APD.cu:3999-4016)
+	uint64_t is_peak = 0;
+	int peak_count = 0, min_peak = 0;
+	float min_cost = 2.0f;
+	for (int i = 2; i < p_costs_size - 2; ++i) {
+		if (p_costs[i - 1] > p_costs[i] && p_costs[i + 1] > p_costs[i]) {
+			is_peak |= 1ull << i;
+			peak_count++;
+			if (p_costs[i] < min_cost) { min_peak = i; min_cost = p_costs[i]; }
+		}
+	}
+	if (abs(min_peak - radius) > a.prm.weak_peak_radius || p_costs[min_peak] > 0.5f) { a.weak[center] = DVP_WEAK; return; }
+	if (peak_count == 1) { a.weak[center] = (p_costs[min_peak] <= 0.15f) ? DVP_STRONG : DVP_WEAK; return; }
+	float var = 0.0f;
+	for (int i = 2; i < p_costs_size - 2; ++i) {
+		if (((is_peak >> i) & 1) && i != min_peak) {
+			const float dist = p_costs[i] - min_cost;
+			var += dist * dist;
+		}
+	}
+	var = sqrtf(var);
+	var /= (peak_count - 1);
+	a.weak[center] = (var > 0.2f) ? DVP_STRONG : DVP_WEAK;
+}
+
+// K16 LocalRefine (APD.cu:4053-4139): 11-step disparity scan, keep the best depth if it improves by > 0.1.
+__global__ void __launch_bounds__(256) k_local_refine(const __grid_constant__ KArgs a) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int T = blockDim.x * blockDim.y;
+	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= a.W || y >= a.H) return;
+	const int center = x + y * a.W;
+	ProfileCtx pc;
+	pc.plane = normal_to_refcam(a.ref, a.planes[center]);
+	pc.depth = pc.plane.w;
+	if (pc.depth == 0) return;
+	const uint32_t sel = a.selected[center];
+	if (sel == 0) return;  // valid_neighbour == 0
+	ViewWeights vw; vw.load(a.view_weight + (size_t)center * DVP_MAX_IMAGES);
+	RefPatch rp;
+	rp.prepare(a, x, y, a.prm.use_radius ? a.radius[center] : a.prm.strong_radius, wt, T);
+	profile_front(a, x, y, center, sel, vw, rp, wt, T, pc);
+	if (pc.weight_normal == 0 || pc.valid == 0) return;
+	pc.cost_now /= pc.weight_normal;
+	pc.base_line /= pc.valid;
+	const float disp = a.ref.K[0] * pc.base_line / pc.depth;
+	const int radius = 5;
+	float min_cost = 2.0f;
+	float best_depth = pc.depth;
+	for (int p_disp = -radius; p_disp <= radius; ++p_disp) {
+		const float p_depth = a.ref.K[0] * pc.base_line / (disp + p_disp);
+		if (p_depth < a.prm.depth_min || p_depth > a.prm.depth_max) continue;
+		float4 t = pc.plane;
+		t.w = get_distance2origin(a.ref, x, y, p_depth, t);
+		float temp_cost = profile_cost_sum(a, x, y, t, sel, vw, rp, wt, T, true);
+		temp_cost /= pc.weight_normal;
+		if (temp_cost < min_cost) { min_cost = temp_cost; best_depth = p_depth; }
+	}
+	if (pc.cost_now - min_cost > 0.1) a.planes[center].w = best_depth;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// launchers
+static inline dim3 full_grid(const KArgs& a, dim3 b) { return dim3((a.W + b.x - 1) / b.x, (a.H + b.y - 1) / b.y, 1); }
+static inline int ref_half_rows(int H) { return (((H / 2) + 15) / 16) * 16; }  // rows-of-pairs covered by the reference's half grid
+
+cudaError_t launch_setup_views(const dvp_camera* cams, ViewConst* views, int S, cudaStream_t st) {
+	k_setup_views<<<1, 32, 0, st>>>(cams, views, S);
+	return cudaGetLastError();
+}
+cudaError_t launch_init_rng(const KArgs& a, unsigned long long seed, cudaStream_t st) {
+	const int n = ((a.W + 31) / 32) * a.H;
+	k_init_rng<<<(n + 127) / 128, 128, 0, st>>>(a, seed);
+	return cudaGetLastError();
+}
+cudaError_t launch_random_init(const KArgs& a, cudaStream_t st) {
+	dim3 b(32, 8);
+	k_random_init<<<full_grid(a, b), b, patch_smem_bytes(256), st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, cudaStream_t st) {
+	dim3 b(32, kSweepThreads / 32);
+	const int yy_limit = ref_half_rows(a.H);
+	dim3 g((a.W + 31) / 32, (yy_limit + b.y - 1) / b.y, 1);
+	k_strong_sweep<<<g, b, sweep_smem_bytes(kSweepThreads, a.S), st>>>(a, iter, red, yy_limit);
+	return cudaGetLastError();
+}
+cudaError_t launch_depth_normal(const KArgs& a, cudaStream_t st) {
+	dim3 b(32, 8);
+	k_depth_normal<<<full_grid(a, b), b, 0, st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t launch_filter(const KArgs& a, int red, cudaStream_t st) {
+	dim3 b(32, 8);
+	const int yy_limit = ref_half_rows(a.H);
+	dim3 g((a.W + 31) / 32, (yy_limit + b.y - 1) / b.y, 1);
+	k_filter<<<g, b, 0, st>>>(a, red, yy_limit);
+	return cudaGetLastError();
+}
+cudaError_t launch_depth_to_weak(const KArgs& a, cudaStream_t st) {
+	dim3 b(32, 8);
+	k_depth_to_weak<<<full_grid(a, b), b, patch_smem_bytes(256), st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t launch_local_refine(const KArgs& a, cudaStream_t st) {
+	dim3 b(32, 8);
+	k_local_refine<<<full_grid(a, b), b, patch_smem_bytes(256), st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t configure_strong_kernels(int S) {
+	cudaError_t e;
+	if ((e = cudaFuncSetAttribute(k_random_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
+	if ((e = cudaFuncSetAttribute(k_depth_to_weak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
+	if ((e = cudaFuncSetAttribute(k_local_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
+	if ((e = cudaFuncSetAttribute(k_strong_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kSweepThreads, S)))) return e;
+	return cudaSuccess;
+}
+
+}  // namespace dvp

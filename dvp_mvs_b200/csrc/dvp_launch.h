@@ -1,0 +1,36 @@
+// dvp_launch.h — host-callable launchers of every stage kernel (one per reference kernel, see dvp_stage).
+#pragma once
+#include "dvp_common.cuh"
+
+namespace dvp {
+
+constexpr int kSweepThreads = 128;  // threads per block of the propagation sweep (3 blocks / SM at S = 4)
+
+// shared memory: 36 (w, w*r) pairs per thread
+inline size_t patch_smem_bytes(int threads) { return (size_t)kHoistSamples * threads * sizeof(float2); }
+// + 9 cost vectors of S floats + 8 candidate positions per thread
+inline size_t sweep_smem_bytes(int threads, int S) { return patch_smem_bytes(threads) + (size_t)(9 * S + 8) * threads * 4; }
+
+cudaError_t configure_strong_kernels(int S);
+cudaError_t configure_weak_kernels(int S);
+
+cudaError_t launch_setup_views(const dvp_camera* cams, ViewConst* views, int S, cudaStream_t st);
+cudaError_t launch_init_rng(const KArgs& a, unsigned long long seed, cudaStream_t st);          // K1
+cudaError_t launch_edge_inform(const KArgs& a, cudaStream_t st);                                 // K2
+cudaError_t launch_nearest_strong(const KArgs& a, cudaStream_t st);                              // K3
+cudaError_t launch_gen_neighbours(const KArgs& a, cudaStream_t st);                              // K4
+cudaError_t launch_neighbour_update(const KArgs& a, cudaStream_t st);                            // K5
+cudaError_t launch_random_init(const KArgs& a, cudaStream_t st);                                 // K6
+cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, cudaStream_t st);             // K7 / K8
+cudaError_t launch_ransac_fit(const KArgs& a, cudaStream_t st);                                  // K9
+cudaError_t launch_weak_sweep(const KArgs& a, int iter, int red, cudaStream_t st);               // K10 / K11
+cudaError_t launch_depth_normal(const KArgs& a, cudaStream_t st);                                // K12
+cudaError_t launch_filter(const KArgs& a, int red, cudaStream_t st);                             // K13 / K14
+cudaError_t launch_depth_to_weak(const KArgs& a, cudaStream_t st);                               // K15
+cudaError_t launch_local_refine(const KArgs& a, cudaStream_t st);                                // K16
+
+// canonical RNG exchange format <-> SoA planes
+cudaError_t launch_rng_export(const KArgs& a, uint32_t* dst_aos, cudaStream_t st);
+cudaError_t launch_rng_import(const KArgs& a, const uint32_t* src_aos, cudaStream_t st);
+
+}  // namespace dvp

@@ -1,0 +1,204 @@
+/*
+ * dvp_mvs.h — flat C ABI of the B200-native PatchMatch-MVS engine (libdvp_mvs.so).
+ *
+ * This is the drop-in boundary for ONE path of ZhenlongYuan/DVP-MVS: APD::RunPatchMatch()
+ * and the 16 CUDA kernels it launches (reference APD.cu:4406-4532).  The reference has no
+ * FFI/plugin layer; its boundary is the C++ class `APD` (reference APD.h:94-199) as driven by
+ * ProcessProblem (reference main.cpp:267-419).  Every entry point below names the reference
+ * interface it replaces.  `include/dvp_apd_adapter.hpp` is the header-only `APD` class a
+ * maintainer compiles main.cpp against.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch/OpenCV types cross this boundary.
+ *  - all image-shaped arrays are row-major, index y*W + x, W/H = reference-view size.
+ *  - every function returns 0 on success or a negative dvp_status; CUDA errors are returned as
+ *    DVP_ERR_CUDA with the cudaError_t retrievable through dvp_last_cuda_error().  Nothing in the
+ *    library calls exit() (the reference's CUDA_SAFE_CALL does, APD.cpp:943-951; the adapter
+ *    restores that behaviour for main.cpp).
+ *  - a context is bound to one device and owns one stream; contexts on different devices may be
+ *    driven from different host threads concurrently (the 8-GPU view farm relies on this).
+ */
+#ifndef DVP_MVS_H
+#define DVP_MVS_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVP_MAX_IMAGES 32      /* reference main.h:39  MAX_IMAGES      */
+#define DVP_NEIGHBOUR_NUM 12   /* reference main.h:40  NEIGHBOUR_NUM   */
+#define DVP_NUM_IMAGES 4       /* reference main.h:41  NUM_IMAGES      */
+#define DVP_EDGE_NEIGH_NUM 8   /* reference main.h:43  EDGE_NEIGH_NUM  */
+#define DVP_LAB_BOUNDARY_NUM 8 /* reference main.h:44  LAB_BOUNDARY_NUM*/
+
+typedef enum dvp_status {
+	DVP_OK = 0,
+	DVP_ERR_ARG = -1,      /* null pointer / bad size / bad id                         */
+	DVP_ERR_CUDA = -2,     /* a CUDA runtime call failed; see dvp_last_cuda_error()    */
+	DVP_ERR_STATE = -3,    /* call order violated (e.g. run before upload)             */
+	DVP_ERR_UNSUPPORTED = -4
+} dvp_status;
+
+/* reference main.h:74-78 RunState */
+enum { DVP_FIRST_INIT = 0, DVP_REFINE_INIT = 1, DVP_REFINE_ITER = 2 };
+/* reference main.h:80-84 PixelState */
+enum { DVP_WEAK = 0, DVP_STRONG = 1, DVP_UNKNOWN = 2 };
+
+/* reference main.h:58-67 `struct Camera` — identical byte layout (112 B). */
+typedef struct dvp_camera {
+	float K[9];
+	float R[9];
+	float t[3];
+	float c[3];
+	int32_t height;
+	int32_t width;
+	float depth_min;
+	float depth_max;
+} dvp_camera;
+
+/* reference main.h:86-112 `struct PatchMatchParams`, one field per reference field, same order.
+ * bools are widened to int32 so the struct has one layout in C, C++ and ctypes. */
+typedef struct dvp_params {
+	int32_t max_iterations;    /* 3     */
+	int32_t num_images;        /* 1 + S */
+	float sigma_spatial;       /* 5.0   */
+	float sigma_color;         /* 3.0   */
+	int32_t top_k;             /* 4     */
+	float depth_min;
+	float depth_max;
+	int32_t geom_consistency;
+	int32_t strong_radius;     /* 5 */
+	int32_t strong_increment;  /* 2 */
+	int32_t weak_radius;       /* 5 */
+	int32_t weak_increment;    /* 5 */
+	int32_t use_APD;
+	int32_t use_edge;
+	int32_t use_limit;
+	int32_t use_label;
+	int32_t use_detail;
+	int32_t use_radius;
+	int32_t weak_peak_radius;  /* 2 */
+	int32_t rotate_time;       /* 4 */
+	float ransac_threshold;    /* 0.005 */
+	float geom_factor;         /* 0.2   */
+	int32_t state;             /* DVP_FIRST_INIT / DVP_REFINE_INIT / DVP_REFINE_ITER */
+} dvp_params;
+
+/* Host-side inputs of one RunPatchMatch call == what InuputInitialization + SupportInitialization
+ * leave in the APD object (reference APD.cpp:1045-1495, 1615-1668) and CudaSpaceInitialization
+ * uploads (APD.cpp:1497-1613).  Optional pointers may be NULL. */
+typedef struct dvp_inputs {
+	const float* images;          /* [(1+S)][H][W] f32 grey levels; image 0 = reference view           */
+	const float* depths;          /* [(1+S)][H][W] f32 or NULL; required iff params.geom_consistency   */
+	const dvp_camera* cameras;    /* [1+S]                                                             */
+	const float* planes;          /* [H][W][4] (world nx,ny,nz, depth) — plane_hypotheses_host         */
+	const uint32_t* selected_views; /* [H][W] bit i = source i+1, or NULL = all zero (FIRST_INIT)      */
+	const uint8_t* weak_info;     /* [H][W] DVP_WEAK/STRONG/UNKNOWN or NULL = all STRONG (use_APD=0)   */
+	const uint8_t* edge;          /* [H][W] 0/255, or NULL = no edges                                  */
+	const int32_t* label;         /* [H][W] region label (0 boundary, -1 small, >0 id) or NULL = zeros */
+	const int32_t* radius;        /* [H][W] NCC patch radius or NULL = strong_radius everywhere        */
+	uint64_t seed;                /* cuRAND XORWOW seed (the reference uses clock64(), APD.cu:1270)    */
+} dvp_inputs;
+
+/* Device buffers addressable through dvp_get_buffer / dvp_set_buffer (parity stepping).
+ * Element layout is the reference's except DVP_BUF_RAND, exchanged as 6 x u32
+ * per pixel {d, v0, v1, v2, v3, v4} (the live part of curandStateXORWOW). */
+typedef enum dvp_buffer {
+	DVP_BUF_PLANES = 0,        /* float4  [N]        plane_hypotheses_cuda          */
+	DVP_BUF_COSTS = 1,         /* float   [N]        costs_cuda (never leaves the device in the reference) */
+	DVP_BUF_SELECTED = 2,      /* uint32  [N]        selected_views_cuda            */
+	DVP_BUF_WEAK = 3,          /* uint8   [N]        weak_info_cuda                 */
+	DVP_BUF_RADIUS = 4,        /* int32   [N]        radius_cuda                    */
+	DVP_BUF_VIEW_WEIGHT = 5,   /* uint8   [N][32]    view_weight_cuda               */
+	DVP_BUF_RAND = 6,          /* uint32  [N][6]     rand_states_cuda (canonical)   */
+	DVP_BUF_FIT_PLANES = 7,    /* float4  [N]        fit_plane_hypotheses_cuda      */
+	DVP_BUF_EDGE_NEIGH = 8,    /* short2  [N][8]     edge_neigh_cuda                */
+	DVP_BUF_CANDIDATE = 9,     /* short2  [N][4][8]  candidate_cuda                 */
+	DVP_BUF_NEAREST_STRONG = 10, /* short2 [N]       weak_nearest_strong            */
+	DVP_BUF_WEAK_RELIABLE = 11,  /* uint8  [N]       weak_reliable_cuda             */
+	DVP_BUF_NEIGHBOURS_MAP = 12, /* int32  [N]       neighbours_map_cuda            */
+	DVP_BUF_NEIGHBOURS = 13,   /* short2  [weak_count][12]  neighbours_cuda         */
+	DVP_BUF_LABEL_BOUNDARY = 14, /* short2 [weak_count][8]  label_boundary_cuda     */
+	DVP_BUF_COMPLEX = 15,      /* float   [weak_count]      complex_cuda            */
+	DVP_BUF_COUNT = 16
+} dvp_buffer;
+
+/* One id per kernel launched by the reference RunPatchMatch, in launch order (APD.cu:4430-4505). */
+typedef enum dvp_stage {
+	DVP_K1_INIT_RANDOM_STATES = 0,   /* APD.cu:1258 */
+	DVP_K2_GEN_EDGE_INFORM = 1,      /* APD.cu:3731 */
+	DVP_K3_FIND_NEAREST_STRONG = 2,  /* APD.cu:4159 */
+	DVP_K4_GEN_NEIGHBOURS = 3,       /* APD.cu:3330 */
+	DVP_K5_NEIGHBOUR_UPDATE = 4,     /* APD.cu:3713 */
+	DVP_K6_RANDOM_INITIALIZATION = 5,/* APD.cu:1273 */
+	DVP_K7_BLACK_STRONG = 6,         /* APD.cu:3127 (iter) */
+	DVP_K8_RED_STRONG = 7,           /* APD.cu:3147 (iter) */
+	DVP_K9_RANSAC_FIT_PLANE = 8,     /* APD.cu:4195 */
+	DVP_K10_BLACK_WEAK = 9,          /* APD.cu:3091 (iter) */
+	DVP_K11_RED_WEAK = 10,           /* APD.cu:3109 (iter) */
+	DVP_K12_DEPTH_NORMAL = 11,       /* APD.cu:3167 */
+	DVP_K13_BLACK_FILTER = 12,       /* APD.cu:3296 */
+	DVP_K14_RED_FILTER = 13,         /* APD.cu:3313 */
+	DVP_K15_DEPTH_TO_WEAK = 14,      /* APD.cu:3892 */
+	DVP_K16_LOCAL_REFINE = 15,       /* APD.cu:4053 */
+	DVP_STAGE_COUNT = 16
+} dvp_stage;
+
+typedef struct dvp_ctx dvp_ctx;
+
+/* Library identity: "dvp_mvs_b200 <version> sm_100a" (the oracle harness answers "reference"). */
+const char* dvp_version(void);
+
+/* Fill *p with the reference defaults (main.h:86-112). */
+void dvp_default_params(dvp_params* p);
+
+/* Replaces: APD::APD(problem) + the cudaMalloc half of CudaSpaceInitialization (APD.cpp:984, 1497-1613).
+ * Allocates every device buffer for a W x H reference view with S source views on `device`.
+ * Returns NULL on failure. */
+dvp_ctx* dvp_create(int device, int width, int height, int num_src, const dvp_params* params);
+
+/* Replaces: ~APD (APD.cpp:989-1043). */
+void dvp_destroy(dvp_ctx* ctx);
+
+/* Replaces: the H2D half of CudaSpaceInitialization + SetDataPassHelperInCuda (APD.cpp:1497-1613,
+ * 1670-1704).  `params` may change between uploads on the same context (multi-pass reuse).
+ * Host pointers may be pageable or pinned; copies are issued on the context stream. */
+int dvp_upload(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params);
+
+/* Replaces: APD::RunPatchMatch kernel sequence (APD.cu:4430-4505), all stages, one stream, no host
+ * synchronisation between stages.  Asynchronous unless `sync` != 0. */
+int dvp_run(dvp_ctx* ctx, int sync);
+
+/* One stage of the sequence (parity stepping; the reference has no equivalent — it is what lets
+ * tests compare kernel by kernel from identical device state). Synchronous. */
+int dvp_run_stage(dvp_ctx* ctx, int stage, int iter);
+
+/* Replaces: the D2H block at the end of RunPatchMatch (APD.cu:4525-4530) + GetPlaneHypothesis /
+ * GetPixelStates / GetSelectedViews / GetRadiusMap (APD.cpp:1706-1732).  Any pointer may be NULL. */
+int dvp_download(dvp_ctx* ctx, float* planes, uint8_t* weak_info, uint32_t* selected_views, int32_t* radius);
+
+/* Raw buffer access by id (sizes in bytes must match exactly; query with dvp_buffer_bytes). */
+size_t dvp_buffer_bytes(dvp_ctx* ctx, int buffer);
+int dvp_get_buffer(dvp_ctx* ctx, int buffer, void* dst, size_t bytes);
+int dvp_set_buffer(dvp_ctx* ctx, int buffer, const void* src, size_t bytes);
+
+/* Device time (CUDA events on the context stream) of the last dvp_run: total and per stage
+ * (stages launched several times are summed). `per_stage` has DVP_STAGE_COUNT entries or is NULL.
+ * Also reports how many kernels that run launched. */
+int dvp_last_run_times(dvp_ctx* ctx, float* total_ms, float* per_stage_ms, int* launches);
+
+/* Device pointers of the resident maps, for callers that keep data on the GPU between passes
+ * (bench.py's HBM-resident leg; "next" row N2).  `images`/`depths`/`planes` follow dvp_inputs layouts. */
+int dvp_upload_device(dvp_ctx* ctx, const dvp_inputs* device_in, const dvp_params* params);
+
+int dvp_weak_count(dvp_ctx* ctx);
+int dvp_last_cuda_error(dvp_ctx* ctx);
+void* dvp_stream(dvp_ctx* ctx); /* cudaStream_t */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVP_MVS_H */

@@ -1,0 +1,525 @@
+// ref_harness.cu — TEST INFRASTRUCTURE ONLY (oracle/_ref/libapd_ref.so).
+//
+// Wraps the reference's own CUDA implementation of the hot path — /root/reference/APD.cu, compiled
+// UNMODIFIED from where it lies (it is #included below, never copied into this repository) against the
+// stub OpenCV/Boost headers in oracle/stubs — behind the same flat C ABI as the product library
+// (include/dvp_mvs.h) with the prefix `ref_` instead of `dvp_`.  It is the ground truth that
+//   * tests/ compare the product kernels with, stage by stage, on the GPU box, and that
+//   * oracle/cpu (the CPU restatement) is pinned against through tests/golden fixtures, and
+//   * bench.py --impl reference times ("reference APD.cu recompiled for sm_100a on one B200").
+// Only tests/, __graft_entry__.smoke() and bench.py may load the resulting .so; the product library
+// never links or dlopens it.
+//
+// What is ours here: device-memory set-up equivalent to APD::CudaSpaceInitialization /
+// SetDataPassHelperInCuda (reference APD.cpp:1497-1613, 1670-1704 — those live in APD.cpp, which needs a
+// real OpenCV and cannot be built in this image), per-stage launching, buffer get/set, timing.
+// What is the reference's: every __global__/__device__ function and APD::RunPatchMatch itself.
+//
+// Deliberate differences from the reference's allocation, all to make its undefined behaviour
+// repeatable without touching its code:
+//   B16: selected_views is allocated with one zeroed row of padding before and after, so the
+//        out-of-bounds 4-neighbour reads at the image border return 0 instead of foreign memory.
+//   B11: candidate is allocated for max(S,4) views plus one pixel of slack.
+//   B19: neighbours_map is always allocated and zero-filled.
+//   all buffers are zero-filled at creation (the reference leaves them uninitialised).
+
+// standard + CUDA headers first, so the `private` override below only reaches the reference's own headers
+#include <cuda_runtime.h>
+#include <curand_kernel.h>
+#include <vector>
+#include <string>
+#include <iostream>
+#include <fstream>
+#include <sstream>
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <chrono>
+#include <iomanip>
+#include <unordered_set>
+#include <cstdarg>
+#include <random>
+#include <unordered_map>
+#include <cstdio>
+#include <opencv2/opencv.hpp>
+#include <boost/filesystem.hpp>
+
+#define private public
+#include <APD.cu>   // resolved through -I/root/reference : the unmodified reference translation unit
+#undef private
+
+#include "../include/dvp_mvs.h"
+#include <cstdio>
+#include <sstream>
+
+// ---- symbols APD.cu expects from APD.cpp (which cannot be compiled here) -------------------------------
+void CudaSafeCall(const cudaError_t error, const std::string& file, const int line) {
+	if (error != cudaSuccess) {
+		fprintf(stderr, "[ref] CUDA error %s at %s:%d\n", cudaGetErrorString(error), file.c_str(), line);
+		exit(EXIT_FAILURE);  // same policy as the reference (APD.cpp:943-951)
+	}
+}
+void CudaCheckError(const char* file, const int line) { CudaSafeCall(cudaGetLastError(), file, line); }
+bool WriteBinMat(const path&, const cv::Mat&) { return true; }
+APD::APD(const Problem& p) : plane_hypotheses_host(nullptr) {
+	params_host = p.params;
+	problem = p;
+}
+APD::~APD() {}
+
+namespace {
+
+struct RefCtx {
+	int device = 0, W = 0, H = 0, S = 0, N = 0;
+	int weak_count = 0;
+	bool uploaded = false;
+	dvp_params dparams;
+	Problem problem;
+	APD* apd = nullptr;
+	// device allocations we own
+	cudaArray* img_arr[MAX_IMAGES] = {nullptr};
+	cudaArray* dep_arr[MAX_IMAGES] = {nullptr};
+	cudaTextureObjects tex_img_host, tex_dep_host;
+	bool have_depth_tex = false;
+	unsigned int* selected_alloc = nullptr;  // padded allocation (B16)
+	std::vector<float4> planes_host;
+	float stage_ms[DVP_STAGE_COUNT] = {0};
+	float total_ms = 0.f;
+	int launches = 0;
+	int last_err = 0;
+};
+
+PatchMatchParams to_ref_params(const dvp_params& d) {
+	PatchMatchParams p;
+	p.max_iterations = d.max_iterations; p.num_images = d.num_images;
+	p.sigma_spatial = d.sigma_spatial; p.sigma_color = d.sigma_color; p.top_k = d.top_k;
+	p.depth_min = d.depth_min; p.depth_max = d.depth_max; p.geom_consistency = d.geom_consistency != 0;
+	p.strong_radius = d.strong_radius; p.strong_increment = d.strong_increment;
+	p.weak_radius = d.weak_radius; p.weak_increment = d.weak_increment;
+	p.use_APD = d.use_APD != 0; p.use_edge = d.use_edge != 0; p.use_limit = d.use_limit != 0;
+	p.use_label = d.use_label != 0; p.use_detail = d.use_detail != 0; p.use_radius = d.use_radius != 0;
+	p.weak_peak_radius = d.weak_peak_radius; p.rotate_time = d.rotate_time;
+	p.ransac_threshold = d.ransac_threshold; p.geom_factor = d.geom_factor; p.state = (RunState)d.state;
+	return p;
+}
+
+#define RCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { c->last_err = (int)e_; \
+	fprintf(stderr, "[ref] %s failed: %s\n", #call, cudaGetErrorString(e_)); return DVP_ERR_CUDA; } } while (0)
+
+template <typename T> cudaError_t zalloc(T** p, size_t count) {
+	if (count == 0) count = 1;
+	cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+	if (e != cudaSuccess) return e;
+	return cudaMemset(*p, 0, count * sizeof(T));
+}
+
+int make_texture(RefCtx* c, cudaArray** arr, cudaTextureObject_t* tex, const float* host) {
+	// same texture configuration as the reference (APD.cpp:1502-1516): float array, linear filter,
+	// element read mode, unnormalised coordinates, address mode "wrap" requested (clamp in effect).
+	cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
+	if (!*arr) RCK(cudaMallocArray(arr, &desc, c->W, c->H));
+	RCK(cudaMemcpy2DToArray(*arr, 0, 0, host, c->W * sizeof(float), c->W * sizeof(float), c->H, cudaMemcpyHostToDevice));
+	if (!*tex) {
+		cudaResourceDesc res; memset(&res, 0, sizeof(res));
+		res.resType = cudaResourceTypeArray; res.res.array.array = *arr;
+		cudaTextureDesc td; memset(&td, 0, sizeof(td));
+		td.addressMode[0] = cudaAddressModeWrap; td.addressMode[1] = cudaAddressModeWrap;
+		td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 0;
+		RCK(cudaCreateTextureObject(tex, &res, &td, NULL));
+	}
+	return DVP_OK;
+}
+
+__global__ void rand_to_canonical(const curandState* st, unsigned int* out, int n) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	out[6 * i + 0] = st[i].d;
+	for (int k = 0; k < 5; ++k) out[6 * i + 1 + k] = st[i].v[k];
+}
+__global__ void rand_from_canonical(curandState* st, const unsigned int* in, int n) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	st[i].d = in[6 * i + 0];
+	for (int k = 0; k < 5; ++k) st[i].v[k] = in[6 * i + 1 + k];
+	st[i].boxmuller_flag = 0; st[i].boxmuller_flag_double = 0;
+	st[i].boxmuller_extra = 0.f; st[i].boxmuller_extra_double = 0.0;
+}
+__global__ void tex_probe_kernel(cudaTextureObject_t tex, const float* xy, float* out, int n) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	out[i] = tex2D<float>(tex, xy[2 * i], xy[2 * i + 1]);
+}
+
+struct BufDesc { void* ptr; size_t bytes; };
+
+BufDesc buf_desc(RefCtx* c, int id) {
+	APD* a = c->apd; size_t N = (size_t)c->N; size_t wc = (size_t)(c->weak_count > 0 ? c->weak_count : 0);
+	switch (id) {
+	case DVP_BUF_PLANES: return {a->plane_hypotheses_cuda, N * 16};
+	case DVP_BUF_COSTS: return {a->costs_cuda, N * 4};
+	case DVP_BUF_SELECTED: return {a->selected_views_cuda, N * 4};
+	case DVP_BUF_WEAK: return {a->weak_info_cuda, N};
+	case DVP_BUF_RADIUS: return {a->radius_cuda, N * 4};
+	case DVP_BUF_VIEW_WEIGHT: return {a->view_weight_cuda, N * MAX_IMAGES};
+	case DVP_BUF_RAND: return {a->rand_states_cuda, N * 24};
+	case DVP_BUF_FIT_PLANES: return {a->fit_plane_hypotheses_cuda, N * 16};
+	case DVP_BUF_EDGE_NEIGH: return {a->edge_neigh_cuda, N * EDGE_NEIGH_NUM * 4};
+	case DVP_BUF_CANDIDATE: return {a->candidate_cuda, N * LAB_BOUNDARY_NUM * NUM_IMAGES * 4};
+	case DVP_BUF_NEAREST_STRONG: return {a->weak_nearest_strong, N * 4};
+	case DVP_BUF_WEAK_RELIABLE: return {a->weak_reliable_cuda, N};
+	case DVP_BUF_NEIGHBOURS_MAP: return {a->neigbours_map_cuda, N * 4};
+	case DVP_BUF_NEIGHBOURS: return {a->neighbours_cuda, wc * NEIGHBOUR_NUM * 4};
+	case DVP_BUF_LABEL_BOUNDARY: return {a->label_boundary_cuda, wc * LAB_BOUNDARY_NUM * 4};
+	case DVP_BUF_COMPLEX: return {a->complex_cuda, wc * 4};
+	default: return {nullptr, 0};
+	}
+}
+
+void grids(RefCtx* c, dim3& gf, dim3& bf, dim3& gh, dim3& bh) {
+	// launch shapes of the reference (APD.cu:4409-4428)
+	gf = dim3((c->W + 15) / 16, (c->H + 15) / 16, 1); bf = dim3(16, 16, 1);
+	gh = dim3((c->W + 31) / 32, ((c->H / 2) + 15) / 16, 1); bh = dim3(32, 16, 1);
+}
+
+int launch_stage(RefCtx* c, int stage, int iter) {
+	dim3 gf, bf, gh, bh; grids(c, gf, bf, gh, bh);
+	DataPassHelper* h = c->apd->helper_cuda;
+	switch (stage) {
+	case DVP_K1_INIT_RANDOM_STATES: InitRandomStates<<<gf, bf>>>(h); break;
+	case DVP_K2_GEN_EDGE_INFORM: GenEdgeInform<<<gf, bf>>>(h); break;
+	case DVP_K3_FIND_NEAREST_STRONG: FindNearestStrongPoint<<<gf, bf>>>(h); break;
+	case DVP_K4_GEN_NEIGHBOURS: GenNeighbours<<<gf, bf>>>(h); break;
+	case DVP_K5_NEIGHBOUR_UPDATE: NeigbourUpdate<<<gf, bf>>>(h); break;
+	case DVP_K6_RANDOM_INITIALIZATION: RandomInitialization<<<gf, bf>>>(h); break;
+	case DVP_K7_BLACK_STRONG: BlackPixelUpdateStrong<<<gh, bh>>>(iter, h); break;
+	case DVP_K8_RED_STRONG: RedPixelUpdateStrong<<<gh, bh>>>(iter, h); break;
+	case DVP_K9_RANSAC_FIT_PLANE: RANSACToGetFitPlane<<<gf, bf>>>(h); break;
+	case DVP_K10_BLACK_WEAK: BlackPixelUpdateWeak<<<gh, bh>>>(iter, h); break;
+	case DVP_K11_RED_WEAK: RedPixelUpdateWeak<<<gh, bh>>>(iter, h); break;
+	case DVP_K12_DEPTH_NORMAL: GetDepthandNormal<<<gf, bf>>>(h); break;
+	case DVP_K13_BLACK_FILTER: BlackPixelFilterStrong<<<gh, bh>>>(h); break;
+	case DVP_K14_RED_FILTER: RedPixelFilterStrong<<<gh, bh>>>(h); break;
+	case DVP_K15_DEPTH_TO_WEAK: DepthToWeak<<<gf, bf>>>(h); break;
+	case DVP_K16_LOCAL_REFINE: LocalRefine<<<gf, bf>>>(h); break;
+	default: return DVP_ERR_ARG;
+	}
+	RCK(cudaGetLastError());
+	return DVP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ref_version(void) { return "reference APD.cu (unmodified) sm_100a"; }
+
+void ref_default_params(dvp_params* d) {
+	PatchMatchParams p;  // the reference's own default member initialisers (main.h:86-112)
+	d->max_iterations = p.max_iterations; d->num_images = p.num_images; d->sigma_spatial = p.sigma_spatial;
+	d->sigma_color = p.sigma_color; d->top_k = p.top_k; d->depth_min = p.depth_min; d->depth_max = p.depth_max;
+	d->geom_consistency = p.geom_consistency; d->strong_radius = p.strong_radius; d->strong_increment = p.strong_increment;
+	d->weak_radius = p.weak_radius; d->weak_increment = p.weak_increment; d->use_APD = p.use_APD; d->use_edge = p.use_edge;
+	d->use_limit = p.use_limit; d->use_label = p.use_label; d->use_detail = p.use_detail; d->use_radius = p.use_radius;
+	d->weak_peak_radius = p.weak_peak_radius; d->rotate_time = p.rotate_time; d->ransac_threshold = p.ransac_threshold;
+	d->geom_factor = p.geom_factor; d->state = FIRST_INIT;
+}
+
+dvp_ctx* ref_create(int device, int width, int height, int num_src, const dvp_params* params) {
+	if (!params || width <= 0 || height <= 0 || num_src < 1 || num_src + 1 > MAX_IMAGES) return nullptr;
+	if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+	RefCtx* c = new RefCtx();
+	c->device = device; c->W = width; c->H = height; c->S = num_src; c->N = width * height;
+	c->dparams = *params;
+	memset(&c->tex_img_host, 0, sizeof(c->tex_img_host));
+	memset(&c->tex_dep_host, 0, sizeof(c->tex_dep_host));
+	c->problem.index = 0; c->problem.ref_image_id = 0; c->problem.iteration = 0;
+	c->problem.params = to_ref_params(*params);
+	c->problem.show_medium_result = false;
+	c->apd = new APD(c->problem);
+	APD* a = c->apd;
+	a->width = width; a->height = height; a->num_images = num_src + 1;
+	a->weak_count = 0;
+	a->texture_objects_cuda = nullptr; a->texture_depths_cuda = nullptr;
+	a->neighbours_cuda = nullptr; a->label_boundary_cuda = nullptr; a->complex_cuda = nullptr;
+	size_t N = (size_t)c->N;
+	bool ok = true;
+	ok &= zalloc(&a->texture_objects_cuda, 1) == cudaSuccess;
+	ok &= zalloc(&a->texture_depths_cuda, 1) == cudaSuccess;
+	ok &= zalloc(&a->cameras_cuda, (size_t)num_src + 1) == cudaSuccess;
+	ok &= zalloc(&a->costs_cuda, N) == cudaSuccess;
+	ok &= zalloc(&a->rand_states_cuda, N) == cudaSuccess;
+	ok &= zalloc(&c->selected_alloc, N + 2 * (size_t)width + 2) == cudaSuccess;
+	a->selected_views_cuda = c->selected_alloc + width + 1;
+	ok &= zalloc(&a->view_weight_cuda, N * MAX_IMAGES) == cudaSuccess;
+	ok &= zalloc(&a->plane_hypotheses_cuda, N) == cudaSuccess;
+	ok &= zalloc(&a->fit_plane_hypotheses_cuda, N) == cudaSuccess;
+	int cand_views = num_src > NUM_IMAGES ? num_src : NUM_IMAGES;
+	ok &= zalloc(&a->candidate_cuda, (N + 1) * LAB_BOUNDARY_NUM * cand_views) == cudaSuccess;
+	ok &= zalloc(&a->edge_cuda, N) == cudaSuccess;
+	ok &= zalloc(&a->edge_neigh_cuda, N * EDGE_NEIGH_NUM) == cudaSuccess;
+	ok &= zalloc(&a->label_cuda, N) == cudaSuccess;
+	ok &= zalloc(&a->radius_cuda, N) == cudaSuccess;
+	ok &= zalloc(&a->weak_info_cuda, N) == cudaSuccess;
+	ok &= zalloc(&a->weak_reliable_cuda, N) == cudaSuccess;
+	ok &= zalloc(&a->weak_nearest_strong, N) == cudaSuccess;
+	ok &= zalloc(&a->neigbours_map_cuda, N) == cudaSuccess;
+	ok &= zalloc(&a->params_cuda, 1) == cudaSuccess;
+	ok &= zalloc(&a->helper_cuda, 1) == cudaSuccess;
+	if (!ok) { fprintf(stderr, "[ref] allocation failed\n"); return nullptr; }
+	a->weak_info_host.create(height, width, CV_8UC1);
+	a->selected_views_host.create(height, width, CV_32SC1);
+	a->radius_host.create(height, width, CV_32SC1);
+	c->planes_host.resize(N);
+	a->plane_hypotheses_host = c->planes_host.data();
+	return reinterpret_cast<dvp_ctx*>(c);
+}
+
+void ref_destroy(dvp_ctx* ctx) {
+	RefCtx* c = reinterpret_cast<RefCtx*>(ctx);
+	if (!c) return;
+	cudaSetDevice(c->device);
+	APD* a = c->apd;
+	for (int i = 0; i < MAX_IMAGES; ++i) {
+		if (c->tex_img_host.images[i]) cudaDestroyTextureObject(c->tex_img_host.images[i]);
+		if (c->tex_dep_host.images[i]) cudaDestroyTextureObject(c->tex_dep_host.images[i]);
+		if (c->img_arr[i]) cudaFreeArray(c->img_arr[i]);
+		if (c->dep_arr[i]) cudaFreeArray(c->dep_arr[i]);
+	}
+	cudaFree(a->texture_objects_cuda); cudaFree(a->texture_depths_cuda); cudaFree(a->cameras_cuda);
+	cudaFree(a->costs_cuda); cudaFree(a->rand_states_cuda); cudaFree(c->selected_alloc);
+	cudaFree(a->view_weight_cuda); cudaFree(a->plane_hypotheses_cuda); cudaFree(a->fit_plane_hypotheses_cuda);
+	cudaFree(a->candidate_cuda); cudaFree(a->edge_cuda); cudaFree(a->edge_neigh_cuda); cudaFree(a->label_cuda);
+	cudaFree(a->radius_cuda); cudaFree(a->weak_info_cuda); cudaFree(a->weak_reliable_cuda);
+	cudaFree(a->weak_nearest_strong); cudaFree(a->neigbours_map_cuda); cudaFree(a->params_cuda);
+	cudaFree(a->helper_cuda); cudaFree(a->neighbours_cuda); cudaFree(a->label_boundary_cuda); cudaFree(a->complex_cuda);
+	a->plane_hypotheses_host = nullptr;
+	delete a;
+	delete c;
+}
+
+int ref_upload(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params) {
+	RefCtx* c = reinterpret_cast<RefCtx*>(ctx);
+	if (!c || !in || !in->images || !in->cameras || !in->planes) return DVP_ERR_ARG;
+	RCK(cudaSetDevice(c->device));
+	APD* a = c->apd;
+	if (params) c->dparams = *params;
+	if (c->dparams.num_images != c->S + 1) return DVP_ERR_ARG;
+	if (c->dparams.geom_consistency && !in->depths) return DVP_ERR_ARG;
+	const size_t N = (size_t)c->N;
+	a->params_host = to_ref_params(c->dparams);
+	a->problem.params = a->params_host;
+	a->problem.show_medium_result = false;
+	// images / depths
+	for (int i = 0; i <= c->S; ++i) {
+		int r = make_texture(c, &c->img_arr[i], &c->tex_img_host.images[i], in->images + (size_t)i * N);
+		if (r) return r;
+		if (in->depths) {
+			r = make_texture(c, &c->dep_arr[i], &c->tex_dep_host.images[i], in->depths + (size_t)i * N);
+			if (r) return r;
+		}
+	}
+	RCK(cudaMemcpy(a->texture_objects_cuda, &c->tex_img_host, sizeof(cudaTextureObjects), cudaMemcpyHostToDevice));
+	RCK(cudaMemcpy(a->texture_depths_cuda, &c->tex_dep_host, sizeof(cudaTextureObjects), cudaMemcpyHostToDevice));
+	static_assert(sizeof(dvp_camera) == sizeof(Camera), "camera layout");
+	RCK(cudaMemcpy(a->cameras_cuda, in->cameras, sizeof(Camera) * (c->S + 1), cudaMemcpyHostToDevice));
+	// planes
+	memcpy(c->planes_host.data(), in->planes, N * sizeof(float4));
+	RCK(cudaMemcpy(a->plane_hypotheses_cuda, in->planes, N * sizeof(float4), cudaMemcpyHostToDevice));
+	RCK(cudaMemset(a->fit_plane_hypotheses_cuda, 0, N * sizeof(float4)));
+	// selected views
+	if (in->selected_views) {
+		memcpy(a->selected_views_host.ptr<unsigned int>(0), in->selected_views, N * 4);
+		RCK(cudaMemcpy(a->selected_views_cuda, in->selected_views, N * 4, cudaMemcpyHostToDevice));
+	} else {
+		memset(a->selected_views_host.ptr<unsigned int>(0), 0, N * 4);
+		RCK(cudaMemset(a->selected_views_cuda, 0, N * 4));
+	}
+	// weak info + neighbours map (APD.cpp:1169-1204)
+	std::vector<int> nmap(N, 0);
+	uchar* wh = a->weak_info_host.ptr<uchar>(0);
+	int weak_count = 0;
+	if (c->dparams.use_APD && in->weak_info) {
+		memcpy(wh, in->weak_info, N);
+		for (size_t i = 0; i < N; ++i) if (wh[i] == WEAK) nmap[i] = weak_count++;
+	} else {
+		memset(wh, STRONG, N);
+	}
+	c->weak_count = weak_count; a->weak_count = weak_count;
+	RCK(cudaMemcpy(a->weak_info_cuda, wh, N, cudaMemcpyHostToDevice));
+	RCK(cudaMemcpy(a->neigbours_map_cuda, nmap.data(), N * 4, cudaMemcpyHostToDevice));
+	cudaFree(a->neighbours_cuda); cudaFree(a->label_boundary_cuda); cudaFree(a->complex_cuda);
+	a->neighbours_cuda = nullptr; a->label_boundary_cuda = nullptr; a->complex_cuda = nullptr;
+	RCK(zalloc(&a->neighbours_cuda, (size_t)weak_count * NEIGHBOUR_NUM));
+	RCK(zalloc(&a->label_boundary_cuda, (size_t)weak_count * LAB_BOUNDARY_NUM));
+	RCK(zalloc(&a->complex_cuda, (size_t)weak_count));
+	// priors
+	if (in->edge) RCK(cudaMemcpy(a->edge_cuda, in->edge, N, cudaMemcpyHostToDevice)); else RCK(cudaMemset(a->edge_cuda, 0, N));
+	if (in->label) RCK(cudaMemcpy(a->label_cuda, in->label, N * 4, cudaMemcpyHostToDevice)); else RCK(cudaMemset(a->label_cuda, 0, N * 4));
+	{
+		int* rh = a->radius_host.ptr<int>(0);
+		if (in->radius) memcpy(rh, in->radius, N * 4);
+		else for (size_t i = 0; i < N; ++i) rh[i] = c->dparams.strong_radius;
+		// SupportInitialization resets UNKNOWN pixels to strong_radius (APD.cpp:1663-1666)
+		for (size_t i = 0; i < N; ++i) if (wh[i] == UNKNOWN) rh[i] = c->dparams.strong_radius;
+		RCK(cudaMemcpy(a->radius_cuda, rh, N * 4, cudaMemcpyHostToDevice));
+	}
+	RCK(cudaMemcpy(a->params_cuda, &a->params_host, sizeof(PatchMatchParams), cudaMemcpyHostToDevice));
+	unsigned long long seed = in->seed;
+	RCK(cudaMemcpyToSymbol(dvp_oracle_seed, &seed, sizeof(seed)));
+	// the pointer bundle (reference APD.cpp:1670-1704)
+	DataPassHelper& hh = a->helper_host;
+	memset(&hh, 0, sizeof(hh));
+	hh.width = c->W; hh.height = c->H; hh.ref_index = 0;
+	hh.texture_objects_cuda = a->texture_objects_cuda; hh.texture_depths_cuda = a->texture_depths_cuda;
+	hh.cameras_cuda = a->cameras_cuda; hh.plane_hypotheses_cuda = a->plane_hypotheses_cuda;
+	hh.rand_states_cuda = a->rand_states_cuda; hh.selected_views_cuda = a->selected_views_cuda;
+	hh.neighbours_cuda = a->neighbours_cuda; hh.neighbours_map_cuda = a->neigbours_map_cuda;
+	hh.weak_info_cuda = a->weak_info_cuda; hh.costs_cuda = a->costs_cuda; hh.params = a->params_cuda;
+	hh.debug_point = make_int2(DEBUG_POINT_X, DEBUG_POINT_Y); hh.show_ncc_info = false;
+	hh.fit_plane_hypotheses_cuda = a->fit_plane_hypotheses_cuda; hh.label_cuda = a->label_cuda;
+	hh.label_boundary_cuda = a->label_boundary_cuda; hh.candidate_cuda = a->candidate_cuda;
+	hh.weak_reliable_cuda = a->weak_reliable_cuda; hh.view_weight_cuda = a->view_weight_cuda;
+	hh.weak_nearest_strong = a->weak_nearest_strong; hh.edge_cuda = a->edge_cuda; hh.edge_neigh_cuda = a->edge_neigh_cuda;
+	hh.complex_cuda = a->complex_cuda; hh.radius_cuda = a->radius_cuda;
+	RCK(cudaMemcpy(a->helper_cuda, &hh, sizeof(DataPassHelper), cudaMemcpyHostToDevice));
+	RCK(cudaDeviceSynchronize());
+	c->uploaded = true;
+	return DVP_OK;
+}
+
+int ref_run_stage(dvp_ctx* ctx, int stage, int iter) {
+	RefCtx* c = reinterpret_cast<RefCtx*>(ctx);
+	if (!c) return DVP_ERR_ARG;
+	if (!c->uploaded) return DVP_ERR_STATE;
+	RCK(cudaSetDevice(c->device));
+	int r = launch_stage(c, stage, iter);
+	if (r) return r;
+	RCK(cudaDeviceSynchronize());
+	return DVP_OK;
+}
+
+// The reference's kernel sequence (APD.cu:4430-4505) with a cudaDeviceSynchronize after every launch,
+// exactly as RunPatchMatch does, but timed per launch with CUDA events and without the host prints
+// and D2H copies.  mode 1 calls the reference's own APD::RunPatchMatch() instead (prints silenced).
+int ref_run(dvp_ctx* ctx, int mode) {
+	RefCtx* c = reinterpret_cast<RefCtx*>(ctx);
+	if (!c) return DVP_ERR_ARG;
+	if (!c->uploaded) return DVP_ERR_STATE;
+	RCK(cudaSetDevice(c->device));
+	cudaEvent_t e0, e1; RCK(cudaEventCreate(&e0)); RCK(cudaEventCreate(&e1));
+	for (int i = 0; i < DVP_STAGE_COUNT; ++i) c->stage_ms[i] = 0.f;
+	c->launches = 0;
+	if (mode == 1) {
+		std::stringstream sink; std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+		RCK(cudaEventRecord(e0));
+		c->apd->RunPatchMatch();
+		RCK(cudaEventRecord(e1)); RCK(cudaEventSynchronize(e1));
+		std::cout.rdbuf(old);
+		RCK(cudaEventElapsedTime(&c->total_ms, e0, e1));
+		c->launches = 11 + 5 * c->dparams.max_iterations;
+	} else {
+		float total = 0.f;
+		auto timed = [&](int stage, int iter) -> int {
+			RCK(cudaEventRecord(e0));
+			int r = launch_stage(c, stage, iter); if (r) return r;
+			RCK(cudaEventRecord(e1)); RCK(cudaDeviceSynchronize());
+			float ms = 0.f; RCK(cudaEventElapsedTime(&ms, e0, e1));
+			c->stage_ms[stage] += ms; total += ms; c->launches++;
+			return DVP_OK;
+		};
+		int r;
+		for (int s = DVP_K1_INIT_RANDOM_STATES; s <= DVP_K6_RANDOM_INITIALIZATION; ++s) if ((r = timed(s, 0))) return r;
+		for (int it = 0; it < c->dparams.max_iterations; ++it)
+			for (int s = DVP_K7_BLACK_STRONG; s <= DVP_K11_RED_WEAK; ++s) if ((r = timed(s, it))) return r;
+		for (int s = DVP_K12_DEPTH_NORMAL; s <= DVP_K16_LOCAL_REFINE; ++s) if ((r = timed(s, 0))) return r;
+		c->total_ms = total;
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	return DVP_OK;
+}
+
+int ref_last_run_times(dvp_ctx* ctx, float* total_ms, float* per_stage_ms, int* launches) {
+	RefCtx* c = reinterpret_cast<RefCtx*>(ctx);
+	if (!c) return DVP_ERR_ARG;
+	if (total_ms) *total_ms = c->total_ms;
+	if (per_stage_ms) for (int i = 0; i < DVP_STAGE_COUNT; ++i) per_stage_ms[i] = c->stage_ms[i];
+	if (launches) *launches = c->launches;
+	return DVP_OK;
+}
+
+size_t ref_buffer_bytes(dvp_ctx* ctx, int buffer) {
+	RefCtx* c = reinterpret_cast<RefCtx*>(ctx);
+	if (!c) return 0;
+	return buf_desc(c, buffer).bytes;
+}
+
+int ref_get_buffer(dvp_ctx* ctx, int buffer, void* dst, size_t bytes) {
+	RefCtx* c = reinterpret_cast<RefCtx*>(ctx);
+	if (!c || !dst) return DVP_ERR_ARG;
+	RCK(cudaSetDevice(c->device));
+	BufDesc b = buf_desc(c, buffer);
+	if (!b.ptr && b.bytes) return DVP_ERR_ARG;
+	if (bytes != b.bytes) return DVP_ERR_ARG;
+	if (bytes == 0) return DVP_OK;
+	if (buffer == DVP_BUF_RAND) {
+		unsigned int* tmp = nullptr; RCK(cudaMalloc((void**)&tmp, bytes));
+		rand_to_canonical<<<(c->N + 255) / 256, 256>>>(c->apd->rand_states_cuda, tmp, c->N);
+		RCK(cudaMemcpy(dst, tmp, bytes, cudaMemcpyDeviceToHost));
+		cudaFree(tmp);
+		return DVP_OK;
+	}
+	RCK(cudaMemcpy(dst, b.ptr, bytes, cudaMemcpyDeviceToHost));
+	return DVP_OK;
+}
+
+int ref_set_buffer(dvp_ctx* ctx, int buffer, const void* src, size_t bytes) {
+	RefCtx* c = reinterpret_cast<RefCtx*>(ctx);
+	if (!c || !src) return DVP_ERR_ARG;
+	RCK(cudaSetDevice(c->device));
+	BufDesc b = buf_desc(c, buffer);
+	if (bytes != b.bytes) return DVP_ERR_ARG;
+	if (bytes == 0) return DVP_OK;
+	if (buffer == DVP_BUF_RAND) {
+		unsigned int* tmp = nullptr; RCK(cudaMalloc((void**)&tmp, bytes));
+		RCK(cudaMemcpy(tmp, src, bytes, cudaMemcpyHostToDevice));
+		rand_from_canonical<<<(c->N + 255) / 256, 256>>>(c->apd->rand_states_cuda, tmp, c->N);
+		RCK(cudaDeviceSynchronize());
+		cudaFree(tmp);
+		return DVP_OK;
+	}
+	RCK(cudaMemcpy(b.ptr, src, bytes, cudaMemcpyHostToDevice));
+	return DVP_OK;
+}
+
+int ref_download(dvp_ctx* ctx, float* planes, uint8_t* weak_info, uint32_t* selected_views, int32_t* radius) {
+	RefCtx* c = reinterpret_cast<RefCtx*>(ctx);
+	if (!c) return DVP_ERR_ARG;
+	RCK(cudaSetDevice(c->device));
+	size_t N = (size_t)c->N; APD* a = c->apd;
+	if (planes) RCK(cudaMemcpy(planes, a->plane_hypotheses_cuda, N * 16, cudaMemcpyDeviceToHost));
+	if (weak_info) RCK(cudaMemcpy(weak_info, a->weak_info_cuda, N, cudaMemcpyDeviceToHost));
+	if (selected_views) RCK(cudaMemcpy(selected_views, a->selected_views_cuda, N * 4, cudaMemcpyDeviceToHost));
+	if (radius) RCK(cudaMemcpy(radius, a->radius_cuda, N * 4, cudaMemcpyDeviceToHost));
+	return DVP_OK;
+}
+
+int ref_weak_count(dvp_ctx* ctx) { RefCtx* c = reinterpret_cast<RefCtx*>(ctx); return c ? c->weak_count : -1; }
+int ref_last_cuda_error(dvp_ctx* ctx) { RefCtx* c = reinterpret_cast<RefCtx*>(ctx); return c ? c->last_err : 0; }
+void* ref_stream(dvp_ctx*) { return nullptr; }
+
+// Samples image `img` of the context through the reference's texture configuration at n (x, y) pairs.
+// Used to pin the CPU restatement's emulation of the hardware bilinear filter.
+int ref_tex_probe(dvp_ctx* ctx, int img, const float* xy, float* out, int n) {
+	RefCtx* c = reinterpret_cast<RefCtx*>(ctx);
+	if (!c || !xy || !out || img < 0 || img > c->S || !c->tex_img_host.images[img]) return DVP_ERR_ARG;
+	RCK(cudaSetDevice(c->device));
+	float *dxy = nullptr, *dout = nullptr;
+	RCK(cudaMalloc((void**)&dxy, (size_t)n * 8)); RCK(cudaMalloc((void**)&dout, (size_t)n * 4));
+	RCK(cudaMemcpy(dxy, xy, (size_t)n * 8, cudaMemcpyHostToDevice));
+	tex_probe_kernel<<<(n + 255) / 256, 256>>>(c->tex_img_host.images[img], dxy, dout, n);
+	RCK(cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
+	cudaFree(dxy); cudaFree(dout);
+	return DVP_OK;
+}
+
+}  // extern "C"

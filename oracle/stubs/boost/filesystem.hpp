@@ -1,0 +1,20 @@
+// Minimal stand-in for Boost.Filesystem (not installed in this image).
+// TEST INFRASTRUCTURE ONLY (oracle/_ref): provides the names main.h / APD.h mention.
+#ifndef DVP_ORACLE_BOOST_FS_STUB_HPP
+#define DVP_ORACLE_BOOST_FS_STUB_HPP
+#include <string>
+#include <fstream>
+namespace boost { namespace filesystem {
+class path {
+	std::string s_;
+public:
+	path() {}
+	path(const char* s) : s_(s) {}
+	path(const std::string& s) : s_(s) {}
+	const std::string& string() const { return s_; }
+	path operator/(const path& o) const { return path(s_ + "/" + o.s_); }
+};
+typedef std::ifstream ifstream;
+typedef std::ofstream ofstream;
+} }
+#endif

@@ -1,0 +1,67 @@
+// Minimal stand-in for the OpenCV C++ headers (OpenCV is not installed in this image).
+// TEST INFRASTRUCTURE ONLY: lets the reference's unmodified APD.cu / APD.h / main.h compile
+// (oracle/_ref). Provides only the names those three files mention: uchar, MIN/MAX (same
+// definitions as opencv2/core/cvdef.h), cv::Mat{rows,cols,ptr<T>()}, cv::Mat_, cv::Vec3f,
+// cv::Point, cv::Size2i. Nothing here is used by the product library.
+#ifndef DVP_ORACLE_OPENCV_STUB_HPP
+#define DVP_ORACLE_OPENCV_STUB_HPP
+#include <cstdint>
+#include <cstddef>
+#include <cstring>
+#include <cfloat>
+#include <cassert>
+#include <cmath>
+#include <vector>
+#include <string>
+
+typedef unsigned char uchar;
+#ifndef MIN
+#define MIN(a, b) ((a) > (b) ? (b) : (a))
+#endif
+#ifndef MAX
+#define MAX(a, b) ((a) < (b) ? (b) : (a))
+#endif
+#define CV_8U 0
+#define CV_32S 4
+#define CV_32F 5
+#define CV_8UC1 0
+#define CV_32SC1 4
+#define CV_32FC1 5
+#define CV_32FC3 21
+
+namespace cv {
+struct Point {
+	int x, y;
+	Point() : x(0), y(0) {}
+	Point(int _x, int _y) : x(_x), y(_y) {}
+};
+struct Size2i {
+	int width, height;
+	Size2i() : width(0), height(0) {}
+	Size2i(int w, int h) : width(w), height(h) {}
+};
+typedef Size2i Size;
+struct Vec3f {
+	float val[3];
+	float& operator[](int i) { return val[i]; }
+	const float& operator[](int i) const { return val[i]; }
+};
+// A non-owning-or-owning dense matrix: just enough for `rows`, `cols`, `ptr<T>(r)`.
+class Mat {
+public:
+	int rows, cols;
+	size_t elem_size;
+	std::vector<unsigned char> storage;
+	Mat() : rows(0), cols(0), elem_size(1) {}
+	Mat(int r, int c, int type) { create(r, c, type); }
+	void create(int r, int c, int type) {
+		rows = r; cols = c;
+		elem_size = (type == CV_8U) ? 1 : (type == CV_32FC3 ? 12 : 4);
+		storage.assign((size_t)r * c * elem_size, 0);
+	}
+	template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(storage.data() + (size_t)r * cols * elem_size); }
+	template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(storage.data() + (size_t)r * cols * elem_size); }
+};
+template <typename T> class Mat_ : public Mat {};
+}  // namespace cv
+#endif
