@@ -8,8 +8,8 @@ Only what the hot path needs lives here:
   farm.py      per-view sharding across the GPUs of one box (NCCL-free)
 """
 from ._lib import (Engine, Params, Inputs, DvpError, default_params, FIRST_INIT, REFINE_INIT, REFINE_ITER,
-                   WEAK, STRONG, UNKNOWN, STAGES, PRODUCT_LIB, REFERENCE_LIB)
+                   WEAK, STRONG, UNKNOWN, STAGES, PRODUCT_LIB)
 from . import synth
 
 __all__ = ["Engine", "Params", "Inputs", "DvpError", "default_params", "FIRST_INIT", "REFINE_INIT", "REFINE_ITER",
-           "WEAK", "STRONG", "UNKNOWN", "STAGES", "PRODUCT_LIB", "REFERENCE_LIB", "synth"]
+           "WEAK", "STRONG", "UNKNOWN", "STAGES", "PRODUCT_LIB", "synth"]

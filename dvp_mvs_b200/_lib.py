@@ -1,10 +1,11 @@
 """ctypes binding of the flat C ABI in include/dvp_mvs.h.
 
-`Engine` drives any shared library that exports that ABI under a prefix:
-  * prefix "dvp_"  -> dvp_mvs_b200/libdvp_mvs.so, the product (hand-written sm_100a CUDA);
-  * prefix "ref_"  -> oracle/_ref/libapd_ref.so, the reference's own APD.cu compiled unmodified
-                      (TEST INFRASTRUCTURE; only tests/, bench.py --impl reference and smoke() load it).
-There is no CPU fallback: if the CUDA library is missing, importing the product engine raises.
+`Engine` drives a shared library that exports that ABI under a prefix.  By default that is the product,
+dvp_mvs_b200/libdvp_mvs.so (prefix "dvp_", hand-written sm_100a CUDA).  There is no CPU fallback: if the
+CUDA library is missing, constructing an Engine raises.  The test-only checkers under oracle/ export the
+same ABI under other prefixes ("ref_", "cpu_") and are opened through oracle/ref_oracle.py and
+oracle/cpu_oracle.py — from tests/, bench.py and smoke() only — by passing `lib_path`/`prefix` explicitly;
+nothing in this package refers to them.
 """
 from __future__ import annotations
 
@@ -16,7 +17,6 @@ from .synth import CAMERA_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PRODUCT_LIB = os.path.join(_HERE, "libdvp_mvs.so")
-REFERENCE_LIB = os.path.join(os.path.dirname(_HERE), "oracle", "_ref", "libapd_ref.so")
 
 FIRST_INIT, REFINE_INIT, REFINE_ITER = 0, 1, 2
 WEAK, STRONG, UNKNOWN = 0, 1, 2
@@ -130,11 +130,10 @@ class Engine:
     """One PatchMatch context (one reference view on one GPU)."""
 
     def __init__(self, width: int, height: int, num_src: int, params: Params, device: int = 0,
-                 impl: str = "product", lib_path: str | None = None):
-        self.prefix = "dvp_" if impl == "product" else "ref_"
-        self.impl = impl
-        path = lib_path or (PRODUCT_LIB if impl == "product" else REFERENCE_LIB)
-        self.lib = load_library(path, self.prefix)
+                 lib_path: str | None = None, prefix: str = "dvp_"):
+        self.prefix = prefix
+        self.impl = {"dvp_": "product", "ref_": "reference", "cpu_": "cpu"}.get(prefix, prefix)
+        self.lib = load_library(lib_path or PRODUCT_LIB, self.prefix)
         self.W, self.H, self.S, self.N = width, height, num_src, width * height
         self.params = params.copy()
         self.params.num_images = num_src + 1

@@ -1,0 +1,77 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/dvp_mvs.h declares; argument validation that needs no GPU behaves as documented."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from util import ROOT
+from dvp_mvs_b200 import _lib, default_params, Params
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "dvp_mvs.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(dvp_[a-z_]+)\s*\(", hdr)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for name in ["dvp_create", "dvp_destroy", "dvp_upload", "dvp_upload_device", "dvp_run", "dvp_run_stage",
+                 "dvp_download", "dvp_get_buffer", "dvp_set_buffer", "dvp_buffer_bytes", "dvp_last_run_times",
+                 "dvp_default_params", "dvp_version", "dvp_weak_count", "dvp_last_cuda_error", "dvp_stream"]:
+        assert name in syms
+
+
+def test_product_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.PRODUCT_LIB), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = C.CDLL(_lib.PRODUCT_LIB)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_version_and_defaults_match_reference_main_h():
+    lib = _lib.load_library(_lib.PRODUCT_LIB, "dvp_")
+    assert b"sm_100a" in lib.dvp_version()
+    p = default_params(lib)
+    q = default_params()  # python-side copy of main.h:86-112
+    for f, _ in Params._fields_:
+        assert getattr(p, f) == pytest.approx(getattr(q, f)), f
+    assert (p.max_iterations, p.top_k, p.strong_radius, p.weak_peak_radius, p.rotate_time) == (3, 4, 5, 2, 4)
+    assert p.ransac_threshold == pytest.approx(0.005) and p.geom_factor == pytest.approx(0.2)
+
+
+def test_struct_layouts():
+    from dvp_mvs_b200.synth import CAMERA_DTYPE
+    assert CAMERA_DTYPE.itemsize == 112          # reference `struct Camera`, main.h:58-67
+    assert C.sizeof(Params) == 23 * 4
+    assert C.sizeof(_lib.Inputs) == 9 * 8 + 8
+
+
+def test_null_arguments_are_rejected_without_a_gpu():
+    lib = _lib.load_library(_lib.PRODUCT_LIB, "dvp_")
+    assert lib.dvp_run(None, 1) == -1                 # DVP_ERR_ARG
+    assert lib.dvp_run_stage(None, 0, 0) == -1
+    assert lib.dvp_buffer_bytes(None, 0) == 0
+    assert lib.dvp_weak_count(None) == -1
+    p = default_params()
+    assert not lib.dvp_create(0, 0, 10, 2, C.byref(p))       # bad size
+    assert not lib.dvp_create(0, 10, 10, 40, C.byref(p))     # more than MAX_IMAGES views
+    assert not lib.dvp_create(0, 10, 10, 2, None)
+
+
+def test_no_cpu_fallback_when_library_is_missing(tmp_path):
+    with pytest.raises(_lib.DvpError):
+        _lib.load_library(str(tmp_path / "libdvp_mvs.so"), "dvp_")
+
+
+def test_product_package_never_references_the_oracle():
+    pkg = os.path.join(ROOT, "dvp_mvs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "libapd_" not in src, f                                   # never names an oracle library
+                assert not re.search(r"^\s*(import|from)\s+(cpu_oracle|ref_oracle)", src, flags=re.M), f
+                assert "dlopen" not in src and "/oracle/_ref" not in src, f

@@ -1,0 +1,64 @@
+"""Host-side logic that needs no GPU: synthetic scenes, stage sequence, comparison helpers."""
+import numpy as np
+
+from util import c1_params
+from dvp_mvs_b200 import synth, STAGES
+from dvp_mvs_b200.parity import sequence, compare, STAGE_OUTPUTS
+
+
+def test_scene_is_deterministic_and_well_formed():
+    a = synth.make_scene(96, 64, 2)
+    b = synth.make_scene(96, 64, 2)
+    assert (a.images == b.images).all() and (a.planes_init == b.planes_init).all() and (a.edge == b.edge).all()
+    assert a.images.shape == (3, 64, 96) and a.images.dtype == np.float32
+    assert a.images.min() >= 0 and a.images.max() <= 255 and (a.images == np.rint(a.images)).all()
+    assert a.cameras.shape == (3,) and a.cameras["width"][0] == 96 and a.cameras["height"][0] == 64
+    for cam in a.cameras:                      # t = -R c and R orthonormal
+        R = cam["R"].reshape(3, 3).astype(np.float64)
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-5)
+        assert np.allclose(cam["t"], -R @ cam["c"], atol=1e-5)
+    assert a.depths[0].min() > 1.0 and a.depths[0].max() < 9.0
+    assert set(np.unique(a.edge)) <= {0, 255} and 0 < (a.edge > 0).mean() < 0.1
+    assert (a.label[a.edge > 0] == 0).all() and (a.label[a.edge == 0] > 0).all()
+    assert 0.05 < (a.planes_init[..., 3] == 0).mean() < 0.15   # 10 % invalid depths force random initialisation
+
+
+def test_source_views_are_consistent_with_the_geometry():
+    """Warp the reference image into a source view with the true depth: photo-consistent where visible."""
+    sc = synth.make_scene(160, 120, 2, quantize=False)
+    K = sc.cameras["K"][0].reshape(3, 3).astype(np.float64)
+    R0 = sc.cameras["R"][0].reshape(3, 3).astype(np.float64); c0 = sc.cameras["c"][0].astype(np.float64)
+    R1 = sc.cameras["R"][1].reshape(3, 3).astype(np.float64); t1 = sc.cameras["t"][1].astype(np.float64)
+    ys, xs = np.mgrid[8:112, 8:152]
+    d = sc.depths[0][ys, xs].astype(np.float64)
+    Xc = np.stack([(xs - K[0, 2]) / K[0, 0] * d, (ys - K[1, 2]) / K[1, 1] * d, d], -1)
+    Xw = Xc @ R0 + c0
+    Xs = Xw @ R1.T + t1
+    u = K[0, 0] * Xs[..., 0] / Xs[..., 2] + K[0, 2]; v = K[1, 1] * Xs[..., 1] / Xs[..., 2] + K[1, 2]
+    ok = (u > 1) & (u < 158) & (v > 1) & (v < 118)
+    ui = np.clip(np.rint(u).astype(int), 0, 159); vi = np.clip(np.rint(v).astype(int), 0, 119)
+    visible = ok & (np.abs(sc.depths[1][vi, ui] - Xs[..., 2]) < 0.02 * Xs[..., 2])
+    diff = np.abs(sc.images[1][vi, ui] - sc.images[0][ys, xs])[visible]
+    assert visible.mean() > 0.4 and np.median(diff) < 12.0
+
+
+def test_stage_sequence_matches_run_patch_match():
+    seq = sequence(3)   # reference APD.cu:4430-4505: 6 + 5*iters + 5 launches
+    assert len(seq) == 6 + 5 * 3 + 5
+    assert [s for s, _ in seq[:6]] == STAGES[:6]
+    assert seq[6] == ("K7_BLACK_STRONG", 0) and seq[10] == ("K11_RED_WEAK", 0) and seq[16] == ("K7_BLACK_STRONG", 2)
+    assert [s for s, _ in seq[-5:]] == STAGES[11:]
+    assert set(STAGE_OUTPUTS) == set(STAGES)
+
+
+def test_compare_counts_pixels_not_components():
+    a = np.zeros((4, 5, 3), np.float32); b = a.copy(); b[1, 2] = 1.0; b[3, 4, 0] = np.nan; a[3, 4, 0] = np.nan
+    r = compare("planes", a, b)
+    assert r["mismatched"] == 1 and r["pixels"] == 20 and r["first_bad"] == [1, 2]
+    m = np.zeros((4, 5), bool); m[0, 0] = True
+    assert compare("planes", a, b, mask=m)["mismatched"] == 0
+
+
+def test_params_mirror():
+    p = c1_params(0.9, 14.4, 2)
+    assert p.num_images == 3 and p.state == 0 and p.use_APD == 0 and p.max_iterations == 1

@@ -9,7 +9,7 @@ p = default_params(); p.max_iterations = 1; p.num_images = S + 1
 p.depth_min, p.depth_max = sc.depth_min, sc.depth_max
 p.use_APD = 0; p.state = FIRST_INIT
 kw = dict(images=sc.images, cameras=sc.cameras, planes=sc.planes_init, edge=sc.edge, label=sc.label, seed=synth.SEED_RNG)
-ref = Engine(W, H, S, p, impl="reference"); prod = Engine(W, H, S, p, impl="product")
+ref = Engine(W, H, S, p, lib_path=ref_oracle.REFERENCE_LIB, prefix="ref_"); prod = Engine(W, H, S, p, )
 ref.upload(**kw); prod.upload(**kw)
 for st in ["K1_INIT_RANDOM_STATES", "K2_GEN_EDGE_INFORM"]:
     ref.run_stage(st); prod.run_stage(st)

@@ -17,7 +17,7 @@ p.use_APD = 1; p.state = FIRST_INIT; p.weak_peak_radius = 6
 yy, xx = np.mgrid[0:H, 0:W]
 weak = np.where(((xx + yy) % 128) < 2, STRONG, WEAK).astype(np.uint8)
 kw = dict(images=sc.images, cameras=sc.cameras, planes=sc.planes_init, edge=sc.edge, label=sc.label, weak_info=weak, seed=synth.SEED_RNG)
-ref = Engine(W, H, S, p, impl="reference"); prod = Engine(W, H, S, p, impl="product")
+ref = ref_oracle.engine(W, H, S, p); prod = Engine(W, H, S, p)
 ref.upload(**kw); prod.upload(**kw)
 ref.run_stage("K1_INIT_RANDOM_STATES"); ref.run_stage("K2_GEN_EDGE_INFORM"); ref.run_stage("K6_RANDOM_INITIALIZATION")
 outs = ("planes", "costs", "selected", "view_weight", "rand")

@@ -12,7 +12,7 @@ p = default_params(); p.max_iterations = 1; p.num_images = S + 1
 p.depth_min, p.depth_max = sc.depth_min, sc.depth_max
 p.use_APD = 0; p.state = FIRST_INIT; p.weak_peak_radius = 6
 kw = dict(images=sc.images, cameras=sc.cameras, planes=sc.planes_init, edge=sc.edge, label=sc.label, seed=synth.SEED_RNG)
-ref = Engine(W, H, S, p, impl="reference"); prod = Engine(W, H, S, p, impl="product")
+ref = Engine(W, H, S, p, lib_path=ref_oracle.REFERENCE_LIB, prefix="ref_"); prod = Engine(W, H, S, p, )
 ref.upload(**kw); prod.upload(**kw)
 
 def state(e): return {n: e.get(n) for n in STATE_BUFS}

@@ -5,6 +5,8 @@ import json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dvp_mvs_b200 import Engine, default_params, synth, FIRST_INIT
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import ref_oracle
 from dvp_mvs_b200.parity import step_compare, compare, sequence, STATE_BUFS
 
 
@@ -16,7 +18,7 @@ def main():
     p.use_APD = 0; p.state = FIRST_INIT; p.geom_consistency = 0; p.weak_peak_radius = 6
     out = dict(config=dict(W=W, H=H, S=S, iters=iters))
     kw = dict(images=sc.images, cameras=sc.cameras, planes=sc.planes_init, edge=sc.edge, label=sc.label, seed=synth.SEED_RNG)
-    ref = Engine(W, H, S, p, impl="reference"); prod = Engine(W, H, S, p, impl="product")
+    ref = ref_oracle.engine(W, H, S, p); prod = Engine(W, H, S, p)
     print(ref.version(), "|", prod.version())
     ref.upload(**kw); prod.upload(**kw)
     t = time.time()
