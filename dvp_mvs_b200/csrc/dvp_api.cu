@@ -238,6 +238,8 @@ int upload_common(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params, 
 				for (size_t i = 0; i < N; ++i) if (wh[i] == DVP_UNKNOWN && ctx->h_i32[i] != ctx->prm.strong_radius) { ctx->h_i32[i] = ctx->prm.strong_radius; any = true; }
 				if (any) { CK(cudaMemcpyAsync(ctx->radius, ctx->h_i32.data(), N * 4, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
 			}
+		} else if (!in->radius && !have_weak) {
+			CK(launch_fill_i32(ctx->radius, ctx->prm.strong_radius, ctx->N, st));  // no host pass needed
 		} else {
 			ctx->h_i32.resize(N);
 			if (in->radius) memcpy(ctx->h_i32.data(), in->radius, N * 4);

@@ -136,6 +136,15 @@ __global__ void k_rng_import(const __grid_constant__ KArgs a, const uint32_t* sr
 	for (int k = 0; k < 6; ++k) a.rng[(size_t)k * a.N + i] = src[(size_t)6 * i + k];
 }
 
+__global__ void k_fill_i32(int32_t* dst, int32_t v, int n) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) dst[i] = v;
+}
+cudaError_t launch_fill_i32(int32_t* dst, int32_t v, int n, cudaStream_t st) {
+	k_fill_i32<<<(n + 255) / 256, 256, 0, st>>>(dst, v, n);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_edge_inform_prep(const KArgs& a, cudaStream_t st) {
 	if (a.prm.use_edge) {
 		const int total = 2 * a.W + 2 * a.H + 4 * (a.W + a.H - 1);

@@ -447,10 +447,22 @@ __device__ __forceinline__ float profile_cost_sum(const KArgs& a, int x, int y, 
 __device__ __forceinline__ void profile_front(const KArgs& a, int x, int y, int center, uint32_t sel, const ViewWeights& vw,
                                               const RefPatch& rp, const float2* wt, int T, ProfileCtx& pc) {
 	pc.cost_now = 0.0f; pc.base_line = 0; pc.valid = 0; pc.weight_normal = 0.0f;
+	// GetDistance2Origin(origin_depth) as the reference's LocalRefine compiles it (APD.cu:4083-4084): the
+	// product depth*n.z is loop-invariant over the views and gets hoisted, so it is rounded on its own and
+	// ADDED to fma(X0, n.x, X1*n.y) instead of being fused (SASS of the reference build, LocalRefine+0x0720).
+	// DepthToWeak never uses the cost computed here, so only K16 observes the difference.
+	float w_front;
+	{
+		const float rcp_k0 = rcp_approx(a.ref.K[0]), rcp_k4 = rcp_approx(a.ref.K[4]);
+		const float x0 = __fmul_rn(__fmul_rn(pc.depth, __fadd_rn((float)x, -a.ref.K[2])), rcp_k0);
+		const float x1 = __fmul_rn(__fmul_rn(pc.depth, __fadd_rn((float)y, -a.ref.K[5])), rcp_k4);
+		const float dz = __fmul_rn(pc.depth, pc.plane.z);
+		w_front = -__fadd_rn(dz, __fmaf_rn(x0, pc.plane.x, __fmul_rn(x1, pc.plane.y)));
+	}
 	for (int v = 0; v < a.S; ++v) {
 		if (!is_set(sel, v)) continue;
 		float4 t = pc.plane;
-		t.w = get_distance2origin(a.ref, x, y, pc.depth, t);
+		t.w = w_front;
 		float temp_cost = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, t, rp, wt, T);
 		if (a.prm.geom_consistency) temp_cost += a.prm.geom_factor * geom_cost(a, a.views[v], a.tex_depth[v + 1], x, y, t);
 		const int wv = vw.get(v);

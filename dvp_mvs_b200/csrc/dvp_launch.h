@@ -29,6 +29,8 @@ cudaError_t launch_filter(const KArgs& a, int red, cudaStream_t st);            
 cudaError_t launch_depth_to_weak(const KArgs& a, cudaStream_t st);                               // K15
 cudaError_t launch_local_refine(const KArgs& a, cudaStream_t st);                                // K16
 
+cudaError_t launch_fill_i32(int32_t* dst, int32_t v, int n, cudaStream_t st);
+
 // canonical RNG exchange format <-> SoA planes
 cudaError_t launch_rng_export(const KArgs& a, uint32_t* dst_aos, cudaStream_t st);
 cudaError_t launch_rng_import(const KArgs& a, const uint32_t* src_aos, cudaStream_t st);
