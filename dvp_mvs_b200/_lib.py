@@ -164,9 +164,10 @@ class Engine:
     def upload(self, images, cameras, planes, depths=None, selected_views=None, weak_info=None, edge=None,
                label=None, radius=None, seed=0x5EED, params: Params | None = None):
         S, H, W = self.S, self.H, self.W
+        new_params = self.params
         if params is not None:
-            self.params = params.copy()
-            self.params.num_images = S + 1
+            new_params = params.copy()
+            new_params.num_images = S + 1
         keep = dict(
             images=_carr(images, np.float32, (S + 1, H, W)),
             depths=_carr(depths, np.float32, (S + 1, H, W)),
@@ -180,8 +181,9 @@ class Engine:
         )
         inp = Inputs(*[_ptr(keep[k]) for k in ("images", "depths", "cameras", "planes", "selected_views",
                                                   "weak_info", "edge", "label", "radius")], int(seed))
+        self._check(self._f("upload")(self.ctx, C.byref(inp), C.byref(new_params)), "upload")
         self._keep = keep
-        self._check(self._f("upload")(self.ctx, C.byref(inp), C.byref(self.params)), "upload")
+        self.params = new_params
 
     def upload_raw(self, inp: Inputs, device: bool = False):
         fn = self._f("upload_device") if device else self._f("upload")

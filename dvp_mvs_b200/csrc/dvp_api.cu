@@ -166,10 +166,14 @@ cudaError_t launch_stage(dvp_ctx* c, const KArgs& a, int stage, int iter) {
 int upload_common(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params, bool from_device) {
 	if (!ctx || !in || !in->images || !in->cameras || !in->planes) return DVP_ERR_ARG;
 	CK(cudaSetDevice(ctx->device));
+	{   // validate first: a rejected upload must leave the context as it was
+		const dvp_params& q = params ? *params : ctx->prm;
+		if (q.num_images != ctx->S + 1) return DVP_ERR_ARG;
+		if (q.geom_consistency && !in->depths) return DVP_ERR_ARG;
+		if (q.max_iterations < 0 || q.max_iterations > 64) return DVP_ERR_ARG;
+		if (!q.use_edge) return DVP_ERR_UNSUPPORTED;  // the ACMH-style branch (APD.cu:2142-2460) is never enabled by main.cpp
+	}
 	if (params) ctx->prm = *params;
-	if (ctx->prm.num_images != ctx->S + 1) return DVP_ERR_ARG;
-	if (ctx->prm.geom_consistency && !in->depths) return DVP_ERR_ARG;
-	if (!ctx->prm.use_edge) return DVP_ERR_UNSUPPORTED;  // the ACMH-style branch (APD.cu:2142-2460) is never enabled by main.cpp
 	const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
 	const size_t N = (size_t)ctx->N;
 	cudaStream_t st = ctx->stream;

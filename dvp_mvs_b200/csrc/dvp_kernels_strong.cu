@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) k_init_rng(const __grid_constant__ KArgs 
 // ------------------------------------------------------------------------------------------------------
 // K6 RandomInitialization (APD.cu:1273-1309) with ComputeMultiViewInitialCost[andSelectedViews]
 // (APD.cu:1115-1194).
-__global__ void __launch_bounds__(256) k_random_init(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(256, 3) k_random_init(const __grid_constant__ KArgs a) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int T = blockDim.x * blockDim.y;
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) k_random_init(const __grid_constant__ KAr
 		float cv_copy[kMaxImages];
 		int cost_count = 0, num_valid = 0;
 		for (int v = 0; v < a.S; ++v) {
-			const float c = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+			const float c = ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
 			cv[v] = c; cv_copy[v] = c; cost_count++;
 			if (c < kCostMax) num_valid++;
 		}
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_random_init(const __grid_constant__ KAr
 		float cost = 0.0f;
 		for (int v = 0; v < a.S; ++v) {
 			if (is_set(sel, v)) {
-				const float c = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+				const float c = ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
 				if (c < kCostMax) { cost_count++; cost += c; }
 				else unset_bit_ref(&sel, v);  // B1
 			}
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_strong_sweep(const __grid_
 				pos_arr[d * T] = min_pos;
 				const float4 pl = a.planes[min_pos];
 				for (int v = 0; v < S; ++v)
-					cost_arr[(d * S + v) * T] = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+					cost_arr[(d * S + v) * T] = ncc_cost<kSweepRB>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
 			}
 		}
 		// ---- fixed 11 x 2 px ladder for non-edge pixels; keep the better of the two (APD.cu:2090-2140) ----
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_strong_sweep(const __grid_
 				const float4 pl = a.planes[min_pos];
 				int good0 = 0, good1 = 0, bad0 = 0, bad1 = 0;
 				for (int v = 0; v < S; ++v) {
-					const float c1 = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+					const float c1 = ncc_cost<kSweepRB>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
 					cost_arr[(8 * S + v) * T] = c1;
 					const float c0 = cost_arr[(d * S + v) * T];
 					if (c0 < good_threshold) good0++;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_strong_sweep(const __grid_
 	for (int v = 0; v < S; ++v) {
 		const int wv = vw.get(v);
 		if (wv > 0) {  // zero-weight views contribute exactly 0 in the reference
-			const float c = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, plane_now, rp, wt, T);
+			const float c = ncc_cost<kSweepRB>(a, a.views[v], a.tex_img[v + 1], x, y, plane_now, rp, wt, T);
 			cost_now += wv * c;
 		}
 	}
@@ -432,11 +432,11 @@ __device__ __forceinline__ float profile_cost_sum(const KArgs& a, int x, int y, 
 		if (!is_set(sel, v)) continue;
 		const int wv = vw.get(v);
 		if (k16_form) {
-			acc += (ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T) * wv);
+			acc += (ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T) * wv);
 			if (a.prm.geom_consistency) acc += (a.prm.geom_factor * geom_cost(a, a.views[v], a.tex_depth[v + 1], x, y, pl) * wv);
 		} else {
 			float temp_cost = 0.0f;
-			temp_cost += ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+			temp_cost += ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
 			if (a.prm.geom_consistency) temp_cost += a.prm.geom_factor * geom_cost(a, a.views[v], a.tex_depth[v + 1], x, y, pl);
 			acc += (temp_cost * wv);
 		}
@@ -463,7 +463,7 @@ __device__ __forceinline__ void profile_front(const KArgs& a, int x, int y, int 
 		if (!is_set(sel, v)) continue;
 		float4 t = pc.plane;
 		t.w = w_front;
-		float temp_cost = ncc_cost(a, a.views[v], a.tex_img[v + 1], x, y, t, rp, wt, T);
+		float temp_cost = ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, t, rp, wt, T);
 		if (a.prm.geom_consistency) temp_cost += a.prm.geom_factor * geom_cost(a, a.views[v], a.tex_depth[v + 1], x, y, t);
 		const int wv = vw.get(v);
 		pc.cost_now += (temp_cost * wv);
@@ -480,7 +480,7 @@ __device__ __forceinline__ void profile_front(const KArgs& a, int x, int y, int 
 }
 
 // K15 DepthToWeak (APD.cu:3892-4051): 61-step disparity cost profile -> STRONG / WEAK / UNKNOWN.
-__global__ void __launch_bounds__(256) k_depth_to_weak(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(256, 3) k_depth_to_weak(const __grid_constant__ KArgs a) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int T = blockDim.x * blockDim.y;
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(256) k_depth_to_weak(const __grid_constant__ K
 }
 
 // K16 LocalRefine (APD.cu:4053-4139): 11-step disparity scan, keep the best depth if it improves by > 0.1.
-__global__ void __launch_bounds__(256) k_local_refine(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(256, 3) k_local_refine(const __grid_constant__ KArgs a) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int T = blockDim.x * blockDim.y;
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;

@@ -137,6 +137,10 @@ __device__ __forceinline__ float ncc_finish(const RefPatch& rp, float s_s, float
 }
 
 // One bilateral NCC of pixel (px,py) against source view `v` (0-based) under plane hypothesis `pl`.
+// RB = patch rows whose 6 texture fetches are issued back to back before any is consumed (RB*6 fetches in
+// flight per thread).  The propagation sweep is shared-memory-limited to 12 warps/SM, has registers to
+// spare and is latency-bound on TEX (ncu: long-scoreboard stalls), so it uses RB = 6; the 24-warp kernels use 2.
+template <int RB>
 __device__ __forceinline__ float ncc_cost(const KArgs& a, const ViewConst& vc, cudaTextureObject_t src, int px, int py,
                                           const float4 pl, const RefPatch& rp, const float2* wt, int stride) {
 	float H[9];
@@ -153,35 +157,40 @@ __device__ __forceinline__ float ncc_cost(const KArgs& a, const ViewConst& vc, c
 
 	float s_s = 0.f, s_ss = 0.f, s_rs = 0.f;
 	if (rp.hoisted) {
-		int i = -rp.radius;
+		static_assert(kHoistAxis % RB == 0, "row batch must divide the patch height");
 #pragma unroll 1
-		for (int ii = 0; ii < kHoistAxis; ++ii, i += rp.inc) {
-			const float xf = (float)(px + i);
-			const float hx = __fmul_rn(H[0], xf), hy = __fmul_rn(H[3], xf), hz = __fmul_rn(H[6], xf);
-			float r_s = 0.f, r_ss = 0.f, r_rs = 0.f;
-			int j = -rp.radius;
-			float sv[kHoistAxis];
+		for (int ii = 0; ii < kHoistAxis; ii += RB) {
+			float sv[RB * kHoistAxis];
 #pragma unroll
-			for (int jj = 0; jj < kHoistAxis; ++jj) {
-				const float yf = (float)(py + j + jj * rp.inc);
-				const float z = __fadd_rn(H[8], __fmaf_rn(H[7], yf, hz));
-				const float x = __fadd_rn(H[2], __fmaf_rn(H[1], yf, hx));
-				const float y = __fadd_rn(H[5], __fmaf_rn(H[4], yf, hy));
-				const float rz = rcp_approx(z);
-				sv[jj] = tex2D<float>(src, __fmaf_rn(x, rz, 0.5f), __fmaf_rn(y, rz, 0.5f));
+			for (int r = 0; r < RB; ++r) {
+				const float xf = (float)(px - rp.radius + (ii + r) * rp.inc);
+				const float hx = __fmul_rn(H[0], xf), hy = __fmul_rn(H[3], xf), hz = __fmul_rn(H[6], xf);
+#pragma unroll
+				for (int jj = 0; jj < kHoistAxis; ++jj) {
+					const float yf = (float)(py - rp.radius + jj * rp.inc);
+					const float z = __fadd_rn(H[8], __fmaf_rn(H[7], yf, hz));
+					const float x = __fadd_rn(H[2], __fmaf_rn(H[1], yf, hx));
+					const float y = __fadd_rn(H[5], __fmaf_rn(H[4], yf, hy));
+					const float rz = rcp_approx(z);
+					sv[r * kHoistAxis + jj] = tex2D<float>(src, __fmaf_rn(x, rz, 0.5f), __fmaf_rn(y, rz, 0.5f));
+				}
 			}
 #pragma unroll
-			for (int jj = 0; jj < kHoistAxis; ++jj) {
-				const float2 w_t = wt[(ii * kHoistAxis + jj) * stride];
-				const float s = sv[jj];
-				const float u = __fmul_rn(s, w_t.x);
-				r_rs = __fmaf_rn(s, w_t.y, r_rs);
-				r_ss = __fmaf_rn(s, u, r_ss);
-				r_s = __fadd_rn(u, r_s);
+			for (int r = 0; r < RB; ++r) {
+				float r_s = 0.f, r_ss = 0.f, r_rs = 0.f;
+#pragma unroll
+				for (int jj = 0; jj < kHoistAxis; ++jj) {
+					const float2 w_t = wt[((ii + r) * kHoistAxis + jj) * stride];
+					const float s = sv[r * kHoistAxis + jj];
+					const float u = __fmul_rn(s, w_t.x);
+					r_rs = __fmaf_rn(s, w_t.y, r_rs);
+					r_ss = __fmaf_rn(s, u, r_ss);
+					r_s = __fadd_rn(u, r_s);
+				}
+				s_s = __fadd_rn(r_s, s_s);
+				s_ss = __fadd_rn(r_ss, s_ss);
+				s_rs = __fadd_rn(r_rs, s_rs);
 			}
-			s_s = __fadd_rn(r_s, s_s);
-			s_ss = __fadd_rn(r_ss, s_ss);
-			s_rs = __fadd_rn(r_rs, s_rs);
 		}
 	} else {
 		// general radius (not a multiple of 5): recompute the reference side per call, like the reference
@@ -214,6 +223,9 @@ __device__ __forceinline__ float ncc_cost(const KArgs& a, const ViewConst& vc, c
 	return ncc_finish(rp, s_s, s_ss, s_rs);
 }
 
+// (An out-of-line, __noinline__ variant of ncc_cost was tried to shrink the code: it halves throughput,
+// because the source texture handle stops being warp-uniform inside the callee and every fetch turns into the
+// divergent-handle loop; the call sites stay inlined.)
 // Forward-backward reprojection error against the neighbour depth map, clamped at 3 px.
 // reference ComputeGeomConsistencyCost, APD.cu:1218-1256 (same expression shapes).
 __device__ __forceinline__ float geom_cost(const KArgs& a, const ViewConst& vc, cudaTextureObject_t depth_tex, int px, int py, const float4 pl) {
