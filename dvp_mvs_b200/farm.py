@@ -1,0 +1,90 @@
+"""Per-view sharding of a scene across the GPUs of one box.
+
+One reference view = one GPU job.  Within a pass every view is independent given the previous pass's maps, so
+views are dealt to ranks and processed with NO data-path collective; the only communication is the exchange of
+per-view results at the end of a pass (depth maps feed the next pass's geometric consistency), done with
+torch.distributed (NCCL on GPUs, gloo in the CPU tests).  The reference processes views sequentially in one
+process and exchanges maps through files (main.cpp:486-507, APD.cpp:1150-1158); a parallel pass is therefore
+Jacobi-ordered (all views see pass k-1 maps), which is stated wherever end-to-end results are compared.
+
+One process per GPU, launched with torchrun; rank r owns device LOCAL_RANK.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Dict, List, Sequence
+
+import numpy as np
+
+
+def partition(num_views: int, world: int, rank: int, costs: Sequence[float] | None = None) -> List[int]:
+    """Views owned by `rank`.  Equal-cost views: round-robin.  With per-view cost estimates (e.g. pixel count
+    times number of source views, or the WEAK-pixel count of the previous pass): longest-processing-time-first
+    greedy, deterministic (ties broken by view id) so that every rank computes the same assignment."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    if costs is None:
+        return list(range(rank, num_views, world))
+    if len(costs) != num_views:
+        raise ValueError("costs must have one entry per view")
+    order = sorted(range(num_views), key=lambda v: (-float(costs[v]), v))
+    load = [0.0] * world
+    owner: Dict[int, int] = {}
+    for v in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        owner[v] = r
+        load[r] += float(costs[v])
+    return sorted(v for v, r in owner.items() if r == rank)
+
+
+def run_pass(num_views: int, process_view: Callable[[int], Dict[str, np.ndarray]], costs: Sequence[float] | None = None,
+             gather: bool = True) -> Dict[int, Dict[str, np.ndarray]]:
+    """Process this rank's share of the views with `process_view(view_id) -> {name: array}` and (optionally)
+    all-gather the results so every rank holds every view's maps for the next pass.
+    Works without torch.distributed being initialised (single process)."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    mine = partition(num_views, world, rank, costs)
+    local = {v: process_view(v) for v in mine}
+    if world == 1 or not gather:
+        return local
+    import torch
+    backend = dist.get_backend()
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if backend == "nccl" else torch.device("cpu")
+    # every view has the same set of maps; the owner broadcasts each of them (no reduction, no staging through files)
+    out: Dict[int, Dict[str, np.ndarray]] = {}
+    for v in range(num_views):
+        owner = next(r for r in range(world) if v in partition(num_views, world, r, costs))
+        meta = [None]
+        if rank == owner:
+            meta = [{k: (a.shape, str(a.dtype)) for k, a in local[v].items()}]
+        dist.broadcast_object_list(meta, src=owner)
+        maps = {}
+        for k, (shape, dtype) in meta[0].items():
+            if rank == owner:
+                t = torch.from_numpy(np.ascontiguousarray(local[v][k]).view(np.uint8).reshape(-1)).to(device)
+            else:
+                t = torch.empty(int(np.prod(shape)) * np.dtype(dtype).itemsize, dtype=torch.uint8, device=device)
+            dist.broadcast(t, src=owner)
+            maps[k] = t.cpu().numpy().view(dtype).reshape(shape)
+        out[v] = maps
+    return out
+
+
+def make_gpu_view_processor(scenes, params, iters_hint: int | None = None):
+    """process_view for synthetic scenes: one Engine per rank, reused across its views."""
+    from . import Engine
+    cache = {}
+
+    def process(v: int):
+        sc = scenes[v]
+        key = (sc.width, sc.height, sc.num_src)
+        if key not in cache:
+            cache[key] = Engine(sc.width, sc.height, sc.num_src, params, device=int(os.environ.get("LOCAL_RANK", "0")))
+        e = cache[key]
+        e.upload(images=sc.images, cameras=sc.cameras, planes=sc.planes_init, edge=sc.edge, label=sc.label, seed=1000 + v, params=params)
+        e.run()
+        planes, weak, sel, rad = e.download()
+        return dict(depth=np.ascontiguousarray(planes[..., 3]), normal=np.ascontiguousarray(planes[..., :3]), weak=weak, selected=sel, radius=rad)
+    return process

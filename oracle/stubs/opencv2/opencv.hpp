@@ -59,6 +59,8 @@ public:
 		elem_size = (type == CV_8U) ? 1 : (type == CV_32FC3 ? 12 : 4);
 		storage.assign((size_t)r * c * elem_size, 0);
 	}
+	bool empty() const { return rows == 0 || cols == 0; }
+	template <typename T> T& at(int r, int c) { return ptr<T>(r)[c]; }
 	template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(storage.data() + (size_t)r * cols * elem_size); }
 	template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(storage.data() + (size_t)r * cols * elem_size); }
 };
