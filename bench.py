@@ -106,18 +106,26 @@ def make_workload(args, seed):
     p.depth_min, p.depth_max = sc.depth_min, sc.depth_max
     p.state = {"first_init": FIRST_INIT, "refine_init": REFINE_INIT, "refine_iter": REFINE_ITER}[args.state]
     p.geom_consistency = int(bool(args.geom))
-    p.use_APD = 0            # all pixels STRONG (the WEAK path is listed as not yet built in DESIGN.md)
     p.weak_peak_radius = 6 if not args.geom else 4
+    weak = None
     if args.state == "first_init":
+        p.use_APD = 0        # round 0 of the reference's schedule: every pixel STRONG (main.cpp:458-477)
         planes = sc.planes_init; selected = None
     else:
+        # rounds >= 1 (main.cpp:463-477): use_APD, use_detail, rotate_time 2, ransac threshold 0.00875.  Pixel
+        # states as DepthToWeak leaves them on this scene: the textureless wall WEAK, a 6 px border UNKNOWN.
+        p.use_APD = 1; p.use_detail = 1; p.rotate_time = 2; p.ransac_threshold = 0.00875
+        weak = np.full((H, W), 1, np.uint8)
+        weak[sc.plane_id == 3] = 0
+        weak[:6, :] = 2; weak[-6:, :] = 2; weak[:, :6] = 2; weak[:, -6:] = 2
         rng = np.random.default_rng(20250104 + seed)   # "previous pass" output: truth with 2 % depth noise
         planes = sc.planes_true.copy()
         planes[..., 3] *= (1.0 + rng.normal(0.0, 0.02, planes.shape[:2])).astype(np.float32)
         selected = np.full((H, W), (1 << S) - 1, np.uint32)
     inputs = dict(images=sc.images, depths=sc.depths if args.geom else None, cameras=sc.cameras, planes=np.ascontiguousarray(planes),
-                  selected_views=selected, edge=sc.edge, label=sc.label, seed=synth.SEED_RNG)
-    name = f"eth3d_shaped_{W}x{H}_S{S}_it{args.iters}_{args.state}_geom{int(bool(args.geom))}_allstrong"
+                  selected_views=selected, weak_info=weak, edge=sc.edge, label=sc.label, seed=synth.SEED_RNG)
+    wfrac = 0.0 if weak is None else float((weak == 0).mean())
+    name = f"eth3d_shaped_{W}x{H}_S{S}_it{args.iters}_{args.state}_geom{int(bool(args.geom))}_weak{int(round(100 * wfrac))}pct"
     return sc, p, inputs, name
 
 
@@ -129,11 +137,13 @@ def cpu_baseline(args, cores):
     w, h = (int(v) for v in args.cpu_sample.split("x"))
     a2 = argparse.Namespace(**vars(args)); a2.width, a2.height = w, h
     sc, p, inputs, _ = make_workload(a2, seed=0)
+    p.use_APD = 0; inputs["weak_info"] = None   # the CPU restatement covers the STRONG path only (oracle/cpu/apd_cpu.cpp)
     e = cpu_oracle.engine(w, h, args.src, p)
     e.upload(**inputs)
     t0 = time.perf_counter(); e.run(); dt = time.perf_counter() - t0
     return {"value": w * h / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
-            "sample": f"one full RunPatchMatch pass of the same configuration on a {w}x{h} view ({dt:.1f} s, OpenMP over pixels)"}
+            "sample": f"one full RunPatchMatch pass of the same configuration with every pixel STRONG on a {w}x{h} view "
+                      f"({dt:.1f} s, OpenMP over pixels)"}
 
 
 def main():
@@ -202,14 +212,14 @@ def main():
     def ptr(t):
         return None if t is None else C.c_void_p(t.data_ptr())
     d_in = Inputs(ptr(dev["images"]), ptr(dev.get("depths")), ptr(dev["cameras"]), ptr(dev["planes"]), ptr(dev.get("selected_views")),
-                  None, ptr(dev["edge"]), ptr(dev["label"]), None, int(inputs["seed"]))
+                  ptr(dev.get("weak_info")), ptr(dev["edge"]), ptr(dev["label"]), None, int(inputs["seed"]))
     # pinned host copies for the end-to-end leg
     pin = {k: (torch.from_numpy(np.ascontiguousarray(v).view(np.uint8) if k == "cameras" else np.ascontiguousarray(v)).pin_memory()
                if isinstance(v, np.ndarray) else None) for k, v in inputs.items() if k != "seed"}
     def hptr(t):
         return None if t is None else C.c_void_p(t.data_ptr())
     h_in = Inputs(hptr(pin["images"]), hptr(pin.get("depths")), hptr(pin["cameras"]), hptr(pin["planes"]), hptr(pin.get("selected_views")),
-                  None, hptr(pin["edge"]), hptr(pin["label"]), None, int(inputs["seed"]))
+                  hptr(pin.get("weak_info")), hptr(pin["edge"]), hptr(pin["label"]), None, int(inputs["seed"]))
     h2d = sum(t.numel() * t.element_size() for t in pin.values() if t is not None) + N * 4  # + radius map built by the host side
     out_planes = torch.empty((H, W, 4), dtype=torch.float32).pin_memory(); out_weak = torch.empty((H, W), dtype=torch.uint8).pin_memory()
     out_sel = torch.empty((H, W), dtype=torch.int32).pin_memory(); out_rad = torch.empty((H, W), dtype=torch.int32).pin_memory()

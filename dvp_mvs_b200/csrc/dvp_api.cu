@@ -60,9 +60,16 @@ struct dvp_ctx {
 	short2* neighbours = nullptr;
 	short2* label_boundary = nullptr;
 	float* complex_ = nullptr;
+	int* weak_list = nullptr;   // pixel index of every WEAK pixel, in neighbours_map order
+	int* scan_blocks = nullptr; // per-1024-pixel WEAK counts / offsets
+	int* scan_total = nullptr;  // [3]: all WEAK, black WEAK, red WEAK
+	int* colour_list[2] = {nullptr, nullptr};  // WEAK pixels of one checkerboard colour (dense warps in the weak sweep)
+	int colour_count[2] = {0, 0};
+	int* scan_blocks_c[2] = {nullptr, nullptr};
 	// host staging
 	std::vector<int32_t> h_i32;
 	std::vector<uint8_t> h_u8;
+	std::vector<int32_t> h_list;
 	// timing
 	static const int kMaxLaunch = 16 + 5 * 64;
 	cudaEvent_t ev[2 * (16 + 5 * 64) + 2] = {nullptr};
@@ -146,14 +153,14 @@ cudaError_t launch_stage(dvp_ctx* c, const KArgs& a, int stage, int iter) {
 	case DVP_K1_INIT_RANDOM_STATES: return launch_init_rng(a, c->seed, st);
 	case DVP_K2_GEN_EDGE_INFORM: return launch_edge_inform(a, st);
 	case DVP_K3_FIND_NEAREST_STRONG: return launch_nearest_strong(a, st);
-	case DVP_K4_GEN_NEIGHBOURS: return launch_gen_neighbours(a, st);
+	case DVP_K4_GEN_NEIGHBOURS: return launch_gen_neighbours(a, c->weak_list, st);
 	case DVP_K5_NEIGHBOUR_UPDATE: return launch_neighbour_update(a, st);
 	case DVP_K6_RANDOM_INITIALIZATION: return launch_random_init(a, st);
 	case DVP_K7_BLACK_STRONG: return launch_strong_sweep(a, iter, 0, st);
 	case DVP_K8_RED_STRONG: return launch_strong_sweep(a, iter, 1, st);
 	case DVP_K9_RANSAC_FIT_PLANE: return launch_ransac_fit(a, st);
-	case DVP_K10_BLACK_WEAK: return launch_weak_sweep(a, iter, 0, st);
-	case DVP_K11_RED_WEAK: return launch_weak_sweep(a, iter, 1, st);
+	case DVP_K10_BLACK_WEAK: return launch_weak_sweep(a, c->colour_list[0], c->colour_count[0], iter, 0, st);
+	case DVP_K11_RED_WEAK: return launch_weak_sweep(a, c->colour_list[1], c->colour_count[1], iter, 1, st);
 	case DVP_K12_DEPTH_NORMAL: return launch_depth_normal(a, st);
 	case DVP_K13_BLACK_FILTER: return launch_filter(a, 0, st);
 	case DVP_K14_RED_FILTER: return launch_filter(a, 1, st);
@@ -200,59 +207,52 @@ int upload_common(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params, 
 	if (in->edge) CK(cudaMemcpyAsync(ctx->edge, in->edge, N, kind, st)); else CK(cudaMemsetAsync(ctx->edge, 0, N, st));
 	if (in->label) CK(cudaMemcpyAsync(ctx->label, in->label, N * 4, kind, st)); else CK(cudaMemsetAsync(ctx->label, 0, N * 4, st));
 
-	// pixel states, neighbours map, radius (APD.cpp:1169-1204, 1647-1667).  These need a host pass over the
-	// state map (the reference does the same on the host); device-resident callers provide host copies too.
+	// pixel states, neighbours map, WEAK list, radius (APD.cpp:1169-1204, 1647-1667) — all on the device: the
+	// reference's host loop over the state map becomes a prefix sum; only the WEAK count (4 bytes) comes back,
+	// because three buffers are sized by it.
 	int weak_count = 0;
 	const bool have_weak = ctx->prm.use_APD && in->weak_info;
-	if (from_device && (have_weak || in->radius)) {
-		// device-resident state maps: bring the (small, 1 B/px) state map to the host for the prefix count
-		ctx->h_u8.resize(N);
-		if (have_weak) CK(cudaMemcpyAsync(ctx->h_u8.data(), in->weak_info, N, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-	}
-	const uint8_t* wh = have_weak ? (from_device ? ctx->h_u8.data() : in->weak_info) : nullptr;
 	if (have_weak) {
-		ctx->h_i32.assign(N, 0);
-		for (size_t i = 0; i < N; ++i) if (wh[i] == DVP_WEAK) ctx->h_i32[i] = weak_count++;
 		CK(cudaMemcpyAsync(ctx->weak, in->weak_info, N, kind, st));
-		CK(cudaMemcpyAsync(ctx->neighbours_map, ctx->h_i32.data(), N * 4, cudaMemcpyHostToDevice, st));
-		CK(cudaStreamSynchronize(st));  // h_i32 is reused below
+		const int yy_limit = (((ctx->H / 2) + 15) / 16) * 16;
+		int counts[3] = {0, 0, 0};
+		CK(launch_weak_count(ctx->weak, ctx->N, ctx->W, -1, yy_limit, ctx->scan_blocks, ctx->scan_total, st));
+		for (int k = 0; k < 2; ++k) CK(launch_weak_count(ctx->weak, ctx->N, ctx->W, k, yy_limit, ctx->scan_blocks_c[k], ctx->scan_total + 1 + k, st));
+		CK(cudaMemcpyAsync(counts, ctx->scan_total, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		weak_count = counts[0]; ctx->colour_count[0] = counts[1]; ctx->colour_count[1] = counts[2];
 	} else {
 		CK(cudaMemsetAsync(ctx->weak, DVP_STRONG, N, st));
 		CK(cudaMemsetAsync(ctx->neighbours_map, 0, N * 4, st));
+		ctx->colour_count[0] = ctx->colour_count[1] = 0;
 	}
 	ctx->weak_count = weak_count;
 	if (weak_count > ctx->weak_capacity) {
-		cudaFree(ctx->neighbours); cudaFree(ctx->label_boundary); cudaFree(ctx->complex_);
-		ctx->neighbours = nullptr; ctx->label_boundary = nullptr; ctx->complex_ = nullptr;
+		cudaFree(ctx->neighbours); cudaFree(ctx->label_boundary); cudaFree(ctx->complex_); cudaFree(ctx->weak_list);
+		cudaFree(ctx->colour_list[0]); cudaFree(ctx->colour_list[1]);
+		ctx->neighbours = nullptr; ctx->label_boundary = nullptr; ctx->complex_ = nullptr; ctx->weak_list = nullptr;
+		ctx->colour_list[0] = ctx->colour_list[1] = nullptr;
+		CK(zalloc(&ctx->weak_list, (size_t)weak_count));
+		CK(zalloc(&ctx->colour_list[0], (size_t)weak_count));
+		CK(zalloc(&ctx->colour_list[1], (size_t)weak_count));
 		CK(zalloc(&ctx->neighbours, (size_t)weak_count * DVP_NEIGHBOUR_NUM));
 		CK(zalloc(&ctx->label_boundary, (size_t)weak_count * DVP_LAB_BOUNDARY_NUM));
 		CK(zalloc(&ctx->complex_, (size_t)weak_count));
 		ctx->weak_capacity = weak_count;
 	}
-	{
-		// radius map; UNKNOWN pixels are reset to strong_radius (APD.cpp:1663-1666)
-		if (from_device && in->radius) {
-			CK(cudaMemcpyAsync(ctx->radius, in->radius, N * 4, kind, st));
-			if (have_weak) {
-				ctx->h_i32.resize(N);
-				CK(cudaMemcpyAsync(ctx->h_i32.data(), in->radius, N * 4, cudaMemcpyDeviceToHost, st));
-				CK(cudaStreamSynchronize(st));
-				bool any = false;
-				for (size_t i = 0; i < N; ++i) if (wh[i] == DVP_UNKNOWN && ctx->h_i32[i] != ctx->prm.strong_radius) { ctx->h_i32[i] = ctx->prm.strong_radius; any = true; }
-				if (any) { CK(cudaMemcpyAsync(ctx->radius, ctx->h_i32.data(), N * 4, cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
-			}
-		} else if (!in->radius && !have_weak) {
-			CK(launch_fill_i32(ctx->radius, ctx->prm.strong_radius, ctx->N, st));  // no host pass needed
-		} else {
-			ctx->h_i32.resize(N);
-			if (in->radius) memcpy(ctx->h_i32.data(), in->radius, N * 4);
-			else for (size_t i = 0; i < N; ++i) ctx->h_i32[i] = ctx->prm.strong_radius;
-			if (have_weak) for (size_t i = 0; i < N; ++i) if (wh[i] == DVP_UNKNOWN) ctx->h_i32[i] = ctx->prm.strong_radius;
-			CK(cudaMemcpyAsync(ctx->radius, ctx->h_i32.data(), N * 4, cudaMemcpyHostToDevice, st));
-			CK(cudaStreamSynchronize(st));
-		}
+	if (have_weak) {
+		const int yy_limit = (((ctx->H / 2) + 15) / 16) * 16;
+		CK(launch_weak_index(ctx->weak, ctx->N, ctx->W, -1, yy_limit, ctx->scan_blocks, ctx->neighbours_map, weak_count > 0 ? ctx->weak_list : nullptr, st));
+		if (weak_count > 0)
+			for (int k = 0; k < 2; ++k)
+				CK(launch_weak_index(ctx->weak, ctx->N, ctx->W, k, yy_limit, ctx->scan_blocks_c[k], nullptr, ctx->colour_list[k], st));
+		if (weak_count > 0)
+			CK(cudaMemsetAsync(ctx->neighbours, 0xFF, (size_t)weak_count * DVP_NEIGHBOUR_NUM * sizeof(short2), st));  // (-1,-1): no anchor yet
 	}
+	// radius map; UNKNOWN pixels are reset to strong_radius (APD.cpp:1663-1666)
+	if (in->radius) CK(cudaMemcpyAsync(ctx->radius, in->radius, N * 4, kind, st));
+	else CK(launch_fill_i32(ctx->radius, ctx->prm.strong_radius, ctx->N, st));
+	if (have_weak && in->radius) CK(launch_reset_unknown_radius(ctx->weak, ctx->radius, ctx->prm.strong_radius, ctx->N, st));
 	CK(configure_strong_kernels(ctx->S));
 	CK(configure_weak_kernels(ctx->S));
 	CK(cudaStreamSynchronize(st));
@@ -309,6 +309,9 @@ dvp_ctx* dvp_create(int device, int width, int height, int num_src, const dvp_pa
 	ok = ok && zalloc(&c->neighbours, 1) == cudaSuccess;
 	ok = ok && zalloc(&c->label_boundary, 1) == cudaSuccess;
 	ok = ok && zalloc(&c->complex_, 1) == cudaSuccess;
+	ok = ok && zalloc(&c->scan_blocks, (N + kWeakScanBlock - 1) / kWeakScanBlock + 1) == cudaSuccess;
+	ok = ok && zalloc(&c->scan_total, 4) == cudaSuccess;
+	for (int k = 0; k < 2; ++k) ok = ok && zalloc(&c->scan_blocks_c[k], (N + kWeakScanBlock - 1) / kWeakScanBlock + 1) == cudaSuccess;
 	for (size_t i = 0; ok && i < sizeof(c->ev) / sizeof(c->ev[0]); ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
 	if (!ok) {
 		fprintf(stderr, "[dvp] dvp_create: allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -333,7 +336,7 @@ void dvp_destroy(dvp_ctx* c) {
 	cudaFree(c->planes); cudaFree(c->fit_planes); cudaFree(c->costs); cudaFree(c->selected_alloc); cudaFree(c->weak);
 	cudaFree(c->radius); cudaFree(c->view_weight); cudaFree(c->rng); cudaFree(c->edge); cudaFree(c->edge_neigh);
 	cudaFree(c->label); cudaFree(c->candidate); cudaFree(c->nearest_strong); cudaFree(c->weak_reliable);
-	cudaFree(c->neighbours_map); cudaFree(c->neighbours); cudaFree(c->label_boundary); cudaFree(c->complex_);
+	cudaFree(c->neighbours_map); cudaFree(c->neighbours); cudaFree(c->label_boundary); cudaFree(c->complex_); cudaFree(c->weak_list); cudaFree(c->scan_blocks); cudaFree(c->scan_total); for (int k = 0; k < 2; ++k) { cudaFree(c->scan_blocks_c[k]); cudaFree(c->colour_list[k]); }
 	for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;

@@ -145,6 +145,92 @@ cudaError_t launch_fill_i32(int32_t* dst, int32_t v, int n, cudaStream_t st) {
 	return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// WEAK-pixel indexing on the device: neighbours_map[p] = rank of p among the WEAK pixels in raster order
+// (what InuputInitialization builds on the host, APD.cpp:1182-1193) and its inverse, the compact WEAK list.
+constexpr int kScanBlock = 1024;
+// colour < 0: every WEAK pixel; colour 0/1: WEAK pixels with (x + y) % 2 == colour that the reference's half grid reaches
+__device__ __forceinline__ bool weak_pred(const uint8_t* weak, int p, int n, int W, int colour, int yy_limit) {
+	if (p >= n || weak[p] != DVP_WEAK) return false;
+	if (colour < 0) return true;
+	const int y = p / W, x = p - y * W;
+	return ((x + y) & 1) == colour && (y >> 1) < yy_limit;
+}
+__global__ void __launch_bounds__(256) k_weak_count_blocks(const uint8_t* weak, int n, int W, int colour, int yy_limit, int* block_sums) {
+	__shared__ int s[8];
+	const int base = blockIdx.x * kScanBlock;
+	int c = 0;
+	for (int i = threadIdx.x; i < kScanBlock; i += 256) { if (weak_pred(weak, base + i, n, W, colour, yy_limit)) ++c; }
+	for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+	if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s[w]; block_sums[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) k_weak_scan_blocks(int* block_sums, int nblocks, int* total) {
+	// exclusive scan of the per-block counts by one CTA (nblocks <= ~1e6 / 1024 chunks handled serially per thread)
+	__shared__ int s[1024];
+	const int per = (nblocks + 1023) / 1024;
+	const int lo = threadIdx.x * per, hi = min(lo + per, nblocks);
+	int sum = 0;
+	for (int i = lo; i < hi; ++i) sum += block_sums[i];
+	s[threadIdx.x] = sum;
+	__syncthreads();
+	for (int o = 1; o < 1024; o <<= 1) {
+		const int v = (threadIdx.x >= o) ? s[threadIdx.x - o] : 0;
+		__syncthreads();
+		s[threadIdx.x] += v;
+		__syncthreads();
+	}
+	int run = s[threadIdx.x] - sum;
+	for (int i = lo; i < hi; ++i) { const int c = block_sums[i]; block_sums[i] = run; run += c; }
+	if (threadIdx.x == 1023) *total = s[1023];
+}
+__global__ void __launch_bounds__(256) k_weak_index(const uint8_t* weak, int n, int W, int colour, int yy_limit, const int* block_offsets, int* nmap, int* weak_list) {
+	// one CTA per 1024-pixel chunk; thread t owns 4 consecutive pixels so that raster order is preserved
+	__shared__ int s[256];
+	const int base = blockIdx.x * kScanBlock + threadIdx.x * 4;
+	int f[4], c = 0;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) { f[k] = weak_pred(weak, base + k, n, W, colour, yy_limit) ? 1 : 0; c += f[k]; }
+	s[threadIdx.x] = c;
+	__syncthreads();
+	for (int o = 1; o < 256; o <<= 1) {
+		const int v = (threadIdx.x >= o) ? s[threadIdx.x - o] : 0;
+		__syncthreads();
+		s[threadIdx.x] += v;
+		__syncthreads();
+	}
+	int run = block_offsets[blockIdx.x] + s[threadIdx.x] - c;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const int p = base + k;
+		if (p < n) {
+			if (nmap) nmap[p] = f[k] ? run : 0;
+			if (f[k]) { if (weak_list) weak_list[run] = p; ++run; }
+		}
+	}
+}
+__global__ void k_reset_unknown_radius(const uint8_t* weak, int32_t* radius, int32_t strong_radius, int n) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && weak[i] == DVP_UNKNOWN) radius[i] = strong_radius;   // APD.cpp:1663-1666
+}
+cudaError_t launch_weak_count(const uint8_t* weak, int n, int W, int colour, int yy_limit, int* block_sums, int* total, cudaStream_t st) {
+	const int nb = (n + kScanBlock - 1) / kScanBlock;
+	k_weak_count_blocks<<<nb, 256, 0, st>>>(weak, n, W, colour, yy_limit, block_sums);
+	k_weak_scan_blocks<<<1, 1024, 0, st>>>(block_sums, nb, total);
+	return cudaGetLastError();
+}
+cudaError_t launch_weak_index(const uint8_t* weak, int n, int W, int colour, int yy_limit, const int* block_offsets, int* nmap, int* weak_list, cudaStream_t st) {
+	const int nb = (n + kScanBlock - 1) / kScanBlock;
+	k_weak_index<<<nb, 256, 0, st>>>(weak, n, W, colour, yy_limit, block_offsets, nmap, weak_list);
+	return cudaGetLastError();
+}
+cudaError_t launch_reset_unknown_radius(const uint8_t* weak, int32_t* radius, int32_t strong_radius, int n, cudaStream_t st) {
+	k_reset_unknown_radius<<<(n + 255) / 256, 256, 0, st>>>(weak, radius, strong_radius, n);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_edge_inform_prep(const KArgs& a, cudaStream_t st) {
 	if (a.prm.use_edge) {
 		const int total = 2 * a.W + 2 * a.H + 4 * (a.W + a.H - 1);

@@ -1,7 +1,7 @@
 // dvp_kernels_weak.cu — the adaptive-patch-deformation (WEAK pixel) path: K2 part (a) candidate offsets,
 // K4 GenNeighbours, K9 RANSACToGetFitPlane, K10/K11 weak propagation
 // (reference APD.cu:3746-3794, 3330-3711, 4195-4404, 2739-3125, 835-1021, 1897-2008).
-#include "dvp_strong.cuh"
+#include "dvp_weak.cuh"
 #include "dvp_launch.h"
 #include <cfloat>
 
@@ -9,32 +9,672 @@ namespace dvp {
 
 cudaError_t launch_edge_inform_prep(const KArgs& a, cudaStream_t st);  // dvp_kernels_prep.cu
 
-// ------------------------------------------------------------------------------------------------------
-// K9 RANSACToGetFitPlane (APD.cu:4195-4404).  Non-WEAK pixels: fit plane := current plane.
-__global__ void __launch_bounds__(256) k_ransac_fit_nonweak(const __grid_constant__ KArgs a) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= a.N) return;
-	if (a.weak[i] != DVP_WEAK) a.fit_planes[i] = a.planes[i];
+__constant__ int c_dirw[8][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, 1}, {-1, 1}, {1, -1}};
+// 30-degree sector of every offset of the 11x11 window, filled once on the device with the same double
+// atan2 the reference evaluates 120 times per pixel per view (calculateAngle / getRegion, APD.cu:797-821)
+__device__ int8_t g_sector[11][11];
+
+__global__ void k_fill_sector_table() {
+	const int i = (int)threadIdx.x - 5, j = (int)threadIdx.y - 5;
+	double angle = atan2((double)j, (double)i) * (180.0 / 3.14159265358979323846);
+	if (angle < 0) angle += 360.0;
+	int region = -1;
+	for (int r = 0; r < 12; ++r)
+		if (angle >= 30.0 * r && angle < 30.0 * (r + 1)) region = r;
+	g_sector[threadIdx.x][threadIdx.y] = (int8_t)region;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// K2 part (a) (APD.cu:3746-3794): per source view, the best (largest colour weight) pixel that sees the view
+// in each of 12 sectors of the 11x11 window; the 8 best sectors' offsets -> candidate[pixel][view][8].
+// Sectors without any visible pixel hold uninitialised stack data in the reference; here they
+// rank last and yield the offset (0,0), which the deformable NCC replaces by its default ring offset.
+__global__ void __launch_bounds__(256) k_candidate(const __grid_constant__ KArgs a) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	const int W = a.W, H = a.H;
+	if (x >= W || y >= H) return;
+	const int center = x + y * W;
+	float rcp_s, rcp_c; RefPatch::sigma_rcps(a.prm, rcp_s, rcp_c);
+	const float ref_center_pix = RefPatch::ref_pixel(a, x, y);
+	const int radius = a.prm.weak_radius;
+	for (int v = 0; v < a.S; ++v) {
+		float best_w[12]; int8_t bi[12], bj[12]; bool has[12];
+#pragma unroll
+		for (int r = 0; r < 12; ++r) { best_w[r] = 0.f; bi[r] = 0; bj[r] = 0; has[r] = false; }
+		for (int i = -radius; i <= radius; i++)
+			for (int j = -radius; j <= radius; j++) {
+				if (i == 0 && j == 0) continue;
+				const int rx = x + i, ry = y + j;
+				if (!(rx >= 0 && rx < W && ry >= 0 && ry < H)) continue;
+				if (is_set(a.selected[rx + ry * W], v) != 1) continue;
+				const float w = weight_colour(RefPatch::ref_pixel(a, rx, ry), ref_center_pix, rcp_c);
+				const int r = (abs(i) <= 5 && abs(j) <= 5) ? g_sector[i + 5][j + 5] : -1;
+				if (r < 0) continue;
+				// bubble sort descending, stable: the first pixel in scan order wins ties
+				if (!has[r] || w > best_w[r]) { has[r] = true; best_w[r] = w; bi[r] = (int8_t)i; bj[r] = (int8_t)j; }
+			}
+		// stable descending sort of the 12 sector winners; empty sectors last
+		int order[12];
+#pragma unroll
+		for (int r = 0; r < 12; ++r) order[r] = r;
+		for (int p = 0; p < 11; ++p)
+			for (int q = 0; q < 11 - p; ++q) {
+				const int r0 = order[q], r1 = order[q + 1];
+				const bool swap = has[r1] && (!has[r0] || best_w[r0] < best_w[r1]);
+				if (swap) { order[q] = r1; order[q + 1] = r0; }
+			}
+		short2* cand = a.candidate + ((size_t)center * DVP_NUM_IMAGES + v) * DVP_LAB_BOUNDARY_NUM;
+		for (int k = 0; k < DVP_LAB_BOUNDARY_NUM; ++k) {
+			const int r = order[k];
+			cand[k] = has[r] ? make_short2(bi[r], bj[r]) : make_short2(0, 0);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K4 GenNeighbours (APD.cu:3330-3711), one thread per WEAK pixel.
+constexpr int kMaxPts = 160;
+
+__device__ __forceinline__ void normalize2(float2* v) {
+	const float n2 = v->x * v->x + v->y * v->y;
+	const float inv = rsqrtf(n2);
+	v->x *= inv; v->y *= inv;
+}
+
+__global__ void __launch_bounds__(64) k_gen_neighbours(const __grid_constant__ KArgs a, const int* weak_list) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= a.weak_count) return;
+	const int center = weak_list[t];
+	const int W = a.W, H = a.H;
+	if (a.weak[center] != DVP_WEAK) return;   // demoted by K2 since the list was built
+	const int px = center % W, py = center / W;
+	const int min_margin = 6;
+	const float depth_diff = a.prm.depth_max - a.prm.depth_min;
+	const int nm = a.neighbours_map[center];
+	short2* neighbours = a.neighbours + (size_t)nm * DVP_NEIGHBOUR_NUM;
+	Rng rng; rng.load(a.rng, a.N, center);
+	for (int i = 0; i < DVP_NEIGHBOUR_NUM; ++i) neighbours[i] = make_short2(-1, -1);
+	neighbours[0] = make_short2((short)px, (short)py);
+	short2 strong_points[kMaxPts];
+	bool dir_valid[kMaxPts];
+	for (int i = 0; i < kMaxPts; ++i) { strong_points[i] = make_short2(-1, -1); dir_valid[i] = false; }
+	int origin_direction_index = -1;
+	int strong_point_size = 0;
+
+	const int rotate_time = a.prm.rotate_time;
+	const float angle = 45.0f / rotate_time;
+	const float cos_angle = cos(angle * 3.14159265358979323846 / 180.f);
+	const float sin_angle = sin(angle * 3.14159265358979323846 / 180.f);
+	const float threshhold = cos((angle / 2.0f) * 3.14159265358979323846 / 180.0f);
+	const int shift_range = DVP_MAX((int)(tan((angle / 2.0f) * 3.14159265358979323846 / 180.0f) * 20), 1);
+	const float ransac_threshold = a.prm.ransac_threshold;
+
+	bool edge_limit = false;
+	if (a.prm.use_limit) {
+		edge_limit = true;
+		if (a.prm.use_edge) {
+			const float complex_val = a.complex_[nm];
+			const float rand_prob = rng.uniform() - FLT_EPSILON;
+			if (rand_prob < complex_val) edge_limit = false;
+		}
+	}
+
+	for (int ox = -1; ox <= 1; ++ox) {
+		for (int oy = -1; oy <= 1; ++oy) {
+			if (ox == 0 && oy == 0) continue;
+			float2 origin_direction = make_float2(ox, oy);
+			normalize2(&origin_direction);
+			origin_direction_index++;
+			for (int rotate_iter = 0; rotate_iter < rotate_time; ++rotate_iter) {
+				const int dir_index = origin_direction_index * 4 + rotate_iter;
+				for (int radius = 2; radius <= 4096; radius = DVP_MIN(radius * 2, radius + 25)) {
+					const float2 test_pt = make_float2(px + origin_direction.x * radius, py + origin_direction.y * radius);
+					if (test_pt.x < 0 || test_pt.y < 0 || test_pt.x >= W || test_pt.y >= H) break;
+					for (int radius_iter = 0; radius_iter < 4; ++radius_iter) {
+						// (cond ? 1 : -1) * curand() % range : unsigned arithmetic, two draws per shift, left operand first
+						const unsigned int c0 = rng.next(); const unsigned int c1 = rng.next();
+						const int rand_x_shift = (int)(((unsigned int)(c0 % 2 == 0 ? 1 : -1) * c1) % (unsigned int)shift_range);
+						const unsigned int c2 = rng.next(); const unsigned int c3 = rng.next();
+						const int rand_y_shift = (int)(((unsigned int)(c2 % 2 == 0 ? 1 : -1) * c3) % (unsigned int)shift_range);
+						float2 direction = make_float2(origin_direction.x * 20 + rand_x_shift, origin_direction.y * 20 + rand_y_shift);
+						normalize2(&direction);
+						short2 np = make_short2(px + direction.x * radius, py + direction.y * radius);
+						if (np.x < min_margin || np.y < min_margin || np.x >= W - min_margin || np.y >= H - min_margin) continue;
+						int npc = np.x + np.y * W;
+						if (a.weak[npc] != DVP_STRONG) {
+							np = a.nearest_strong[npc];
+							if (np.x == -1 || np.y == -1) continue;
+							npc = np.x + np.y * W;
+						}
+						bool has_same_pt = false;
+						for (int k = 0; k < dir_index; k++)
+							if (strong_points[k].x == np.x && strong_points[k].y == np.y) { has_same_pt = true; break; }
+						if (has_same_pt) continue;
+						float2 test_direction = make_float2(np.x - px, np.y - py);
+						normalize2(&test_direction);
+						const float cosv = test_direction.x * origin_direction.x + test_direction.y * origin_direction.y;
+						if (cosv > threshhold && (!edge_limit || !bresenham_crosses_edge(a, px, py, np.x, np.y))) {
+							strong_points[dir_index] = np;
+							dir_valid[dir_index] = true;
+							strong_point_size++;
+							break;
+						}
+					}
+					if (dir_valid[dir_index]) break;
+				}
+				float2 rotated;
+				rotated.x = origin_direction.x * cos_angle - origin_direction.y * sin_angle;
+				rotated.y = origin_direction.x * sin_angle + origin_direction.y * cos_angle;
+				normalize2(&rotated);
+				origin_direction = rotated;
+			}
+		}
+	}
+
+	int extend_index = 31;
+	const int my_label = a.label[center];
+	if (a.prm.use_label && my_label > 0) {
+		// {1, 0.5} etc. are narrowed to int in the reference's `const int dir[16][2]` (APD.cu:3462): 0.5 -> 0
+		const int dir[16][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1, 1}, {-1, 1}, {1, -1},
+		                        {1, 0}, {0, 1}, {0, 1}, {-1, 0}, {-1, 0}, {0, -1}, {0, -1}, {1, 0}};
+		const short2* lab_bound = a.label_boundary + (size_t)nm * DVP_LAB_BOUNDARY_NUM;
+		float bound_dist[16] = {0};
+		int dir_step[16] = {0};
+		for (int i = 0; i < 8; ++i) {
+			const short2 bp = lab_bound[i];
+			float dist = 0.0f;
+			if (bp.x != -1 && bp.y != -1) {
+				const int ddx = px - bp.x, ddy = py - bp.y;
+				dist = (float)sqrt((double)(ddx * ddx) + (double)(ddy * ddy));
+				if (i >= 4) dist = (float)((double)dist / sqrt(2.0));
+			}
+			bound_dist[i] = dist;
+			if (i % 2 == 1) {
+				const float opposite_dist = bound_dist[i - 1];
+				const int step = DVP_MIN(1, DVP_MAX(4 * rotate_time - 1, (int)(4 * rotate_time * dist / (dist + opposite_dist))));  // B13: always 1
+				dir_step[i - 1] = 4 * rotate_time - step;
+				dir_step[i] = step;
+			}
+		}
+		dir_step[8] = (dir_step[3] + dir_step[5]) / 2;   bound_dist[8] = (bound_dist[3] + bound_dist[5]) / 2;
+		dir_step[9] = (dir_step[1] + dir_step[5]) / 2;   bound_dist[9] = (bound_dist[1] + bound_dist[5]) / 2;
+		dir_step[10] = (dir_step[1] + dir_step[6]) / 2;  bound_dist[10] = (bound_dist[1] + bound_dist[6]) / 2;
+		dir_step[11] = (dir_step[2] + dir_step[6]) / 2;  bound_dist[11] = (bound_dist[2] + bound_dist[6]) / 2;
+		dir_step[12] = (dir_step[2] + dir_step[4]) / 2;  bound_dist[12] = (bound_dist[2] + bound_dist[4]) / 2;
+		dir_step[13] = (dir_step[4] + dir_step[0]) / 2;  bound_dist[13] = (bound_dist[4] + bound_dist[0]) / 2;
+		dir_step[14] = (dir_step[7] + dir_step[0]) / 2;  bound_dist[14] = (bound_dist[7] + bound_dist[0]) / 2;
+		dir_step[15] = (dir_step[7] + dir_step[3]) / 2;  bound_dist[15] = (bound_dist[7] + bound_dist[3]) / 2;
+		for (int i = 0; i < 16; ++i) {
+			const float dist = bound_dist[i];
+			const int gap_num = dir_step[i] + 1;
+			const int step_len = DVP_MAX(1, (int)floor(1.0 * dist / gap_num));
+			for (int step = 1; step <= dir_step[i]; ++step) {
+				short2 np = make_short2(px + step * step_len * dir[i][0], py + step * step_len * dir[i][1]);
+				if (np.x < min_margin || np.y < min_margin || np.x >= W - min_margin || np.y >= H - min_margin) continue;
+				int npc = np.x + np.y * W;
+				if (a.weak[npc] != DVP_STRONG) {
+					np = a.nearest_strong[npc];
+					if (np.x == -1 || np.y == -1) continue;
+					npc = np.x + np.y * W;
+				}
+				bool has_same_pt = false;
+				for (int k = 0; k <= extend_index; k++)
+					if (strong_points[k].x == np.x && strong_points[k].y == np.y) { has_same_pt = true; break; }
+				if (has_same_pt) continue;
+				if (extend_index + 1 >= kMaxPts) continue;  // cannot happen with rotate_time <= 4 (31 + 128 slots)
+				extend_index++;
+				strong_points[extend_index] = np;
+				dir_valid[extend_index] = true;
+				strong_point_size++;
+			}
+		}
+	}
+
+	uint8_t* weak_reliable = a.weak_reliable + center;
+	if (strong_point_size <= 3) { *weak_reliable = 0; rng.store(a.rng, a.N, center); return; }
+
+	float4 best_plane = make_float4(0, 0, 0, 0);
+	bool has_valid_plane = false;
+	short2 valid_pts[kMaxPts];
+	float3 valid_3d[kMaxPts];
+	int valid_count = 0;
+	float X[3];
+	get_3d_point(a.ref, px, py, a.planes[center].w, X);
+	const float center_z = X[2];
+	for (int i = 0; i < kMaxPts; ++i) {
+		valid_pts[i] = make_short2(-1, -1);
+		if (dir_valid[i]) {
+			const short2 sp = strong_points[i];
+			const int spc = sp.x + sp.y * W;
+			valid_pts[valid_count] = sp;
+			get_3d_point(a.ref, sp.x, sp.y, a.planes[spc].w, X);
+			valid_3d[valid_count] = make_float3(X[0], X[1], X[2]);
+			valid_count++;
+		}
+	}
+	auto anchor_normal = [&](int idx) -> float3 {   // strong_points_valid_normals[idx], recomputed on demand
+		const short2 sp = valid_pts[idx];
+		const float4 n4 = normal_to_refcam(a.ref, a.planes[sp.x + sp.y * W]);
+		return make_float3(n4.x, n4.y, n4.z);
+	};
+	{
+		int iteration = 300, max_iter = 200;
+		float min_cost = FLT_MAX;
+		int max_count = 3;
+		// edge_test[160][160] of the reference, 2 bits per pair (0 unknown, 1 crosses an edge, 2 clear): 6.4 KB instead of 25.6 KB
+		uint32_t edge_test[kMaxPts * kMaxPts / 16];
+		for (int i = 0; i < kMaxPts * kMaxPts / 16; ++i) edge_test[i] = 0;
+		auto et_get = [&](int r, int c) -> int { const int b = r * kMaxPts + c; return (edge_test[b >> 4] >> ((b & 15) * 2)) & 3; };
+		auto et_set = [&](int r, int c, int val) { const int b = r * kMaxPts + c; edge_test[b >> 4] = (edge_test[b >> 4] & ~(3u << ((b & 15) * 2))) | ((uint32_t)val << ((b & 15) * 2)); };
+		auto crossing = [&](int i0, int i1) -> int {
+			int e = et_get(i0, i1);
+			if (e == 0) {
+				e = bresenham_crosses_edge(a, valid_pts[i0].x, valid_pts[i0].y, valid_pts[i1].x, valid_pts[i1].y) ? 1 : 2;
+				et_set(i0, i1, e); et_set(i1, i0, e);
+			}
+			return e;
+		};
+		bool has_strong_plane = false;
+		while (iteration > 0 && max_iter > 0) {
+			max_iter--;
+			const int a_index = rng.next() % valid_count;
+			const int b_index = rng.next() % valid_count;
+			const int c_index = rng.next() % valid_count;
+			if (a_index == b_index || b_index == c_index || a_index == c_index) continue;
+			if (!point_in_triangle(valid_pts[a_index], valid_pts[b_index], valid_pts[c_index], px, py)) continue;
+			if (edge_limit) {
+				const int e_ab = crossing(a_index, b_index);
+				const int e_bc = crossing(b_index, c_index);
+				const int e_ca = crossing(c_index, a_index);
+				if (e_ab == 1 || e_bc == 1 || e_ca == 1) continue;
+			}
+			const float3 AN = anchor_normal(a_index);   // B8: the reference compares normal A with itself
+			const float nn = AN.x * AN.x + AN.y * AN.y + AN.z * AN.z;
+			if (nn < 0.9f || nn < 0.9f || nn < 0.9f) continue;
+			const float3 A = valid_3d[a_index], B = valid_3d[b_index], C = valid_3d[c_index];
+			const float3 A_C = make_float3(A.x - C.x, A.y - C.y, A.z - C.z);
+			const float3 B_C = make_float3(B.x - C.x, B.y - C.y, B.z - C.z);
+			float4 cross_vec;
+			cross_vec.x = A_C.y * B_C.z - B_C.y * A_C.z;
+			cross_vec.y = -(A_C.x * B_C.z - B_C.x * A_C.z);
+			cross_vec.z = A_C.x * B_C.y - B_C.x * A_C.y;
+			if ((cross_vec.x == 0 && cross_vec.y == 0 && cross_vec.z == 0) || isnan(cross_vec.x) || isnan(cross_vec.y) || isnan(cross_vec.z)) continue;
+			iteration--;
+			normalize3(&cross_vec);
+			cross_vec.w = -(cross_vec.x * A.x + cross_vec.y * A.y + cross_vec.z * A.z);
+			bool is_strong_plane = true;
+			const float dn = fabs(AN.x * cross_vec.x + AN.y * cross_vec.y + AN.z * cross_vec.z);
+			if (a.prm.use_label && my_label > 0 && dn < 0.9f && dn < 0.9f && dn < 0.9f) is_strong_plane = false;
+			if (has_strong_plane && !is_strong_plane) continue;
+			int temp_count = 0;
+			float strong_dist = 0.0f;
+			for (int si = 0; si < valid_count; ++si) {
+				const float3 tp = valid_3d[si];
+				const short2 tpos = valid_pts[si];
+				const float factor_x = (tpos.x - a.ref.K[2]) / a.ref.K[0];
+				const float factor_y = (tpos.y - a.ref.K[5]) / a.ref.K[4];
+				const float fit_depth = -cross_vec.w / (cross_vec.x * factor_x + cross_vec.y * factor_y + cross_vec.z);
+				const float distance = fabs(fit_depth - tp.z);
+				if (distance / depth_diff < ransac_threshold) { temp_count++; strong_dist += distance; }
+			}
+			if (temp_count < 6) continue;
+			if (temp_count > max_count || (!has_strong_plane && is_strong_plane)) {
+				if (!has_strong_plane && is_strong_plane) has_strong_plane = true;
+				const float factor_x = (px - a.ref.K[2]) / a.ref.K[0];
+				const float factor_y = (py - a.ref.K[5]) / a.ref.K[4];
+				const float fit_depth = -cross_vec.w / (cross_vec.x * factor_x + cross_vec.y * factor_y + cross_vec.z);
+				const float center_distance = fabs(fit_depth - center_z);
+				best_plane = cross_vec;
+				max_count = temp_count;
+				min_cost = center_distance;
+				has_valid_plane = true;
+			} else if (temp_count == max_count) {
+				const float factor_x = (px - a.ref.K[2]) / a.ref.K[0];
+				const float factor_y = (py - a.ref.K[5]) / a.ref.K[4];
+				const float fit_depth = -cross_vec.w / (cross_vec.x * factor_x + cross_vec.y * factor_y + cross_vec.z);
+				const float center_distance = fabs(fit_depth - center_z);
+				if (center_distance < min_cost) { best_plane = cross_vec; max_count = temp_count; min_cost = center_distance; }
+			}
+		}
+	}
+	rng.store(a.rng, a.N, center);
+	if (!has_valid_plane) { *weak_reliable = 0; return; }
+
+	float weight[kMaxPts];
+	for (int i = 0; i < valid_count; ++i) {
+		const float3 tp = valid_3d[i];
+		const short2 tpos = valid_pts[i];
+		const float factor_x = (tpos.x - a.ref.K[2]) / a.ref.K[0];
+		const float factor_y = (tpos.y - a.ref.K[5]) / a.ref.K[4];
+		const float fit_depth = -best_plane.w / (best_plane.x * factor_x + best_plane.y * factor_y + best_plane.z);
+		const float distance = fabs(fit_depth - tp.z);
+		if (distance / depth_diff >= ransac_threshold) { valid_pts[i] = make_short2(-1, -1); weight[i] = FLT_MAX; continue; }
+		weight[i] = distance;
+	}
+	for (int i = 1; i < valid_count; i++) {   // sort_small_weighted, APD.cu:125-138
+		const short2 tmp = valid_pts[i];
+		const float tmp_w = weight[i];
+		int j;
+		for (j = i; j >= 1 && tmp_w < weight[j - 1]; j--) { valid_pts[j] = valid_pts[j - 1]; weight[j] = weight[j - 1]; }
+		valid_pts[j] = tmp; weight[j] = tmp_w;
+	}
+	for (int i = 1; i < DVP_NEIGHBOUR_NUM; ++i) neighbours[i] = valid_pts[i - 1];
+	*weak_reliable = 1;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K9 RANSACToGetFitPlane (APD.cu:4195-4404).
+__global__ void __launch_bounds__(256) k_ransac_fit(const __grid_constant__ KArgs a) {
+	const int center = blockIdx.x * blockDim.x + threadIdx.x;
+	if (center >= a.N) return;
+	const int W = a.W;
+	if (a.weak[center] != DVP_WEAK) { a.fit_planes[center] = a.planes[center]; return; }
+	const int px = center % W, py = center / W;
+	Rng rng; rng.load(a.rng, a.N, center);
+	const int nm = a.neighbours_map[center];
+	bool edge_limit = false;
+	if (a.prm.use_limit) {
+		edge_limit = true;
+		if (a.prm.use_edge) {
+			const float complex_val = a.complex_[nm];
+			const float rand_prob = rng.uniform() - FLT_EPSILON;
+			if (rand_prob < complex_val) edge_limit = false;
+		}
+	}
+	constexpr int M = DVP_NEIGHBOUR_NUM - 1;
+	short2 strong_points[M];
+	float3 pts3d[M], normals[M];
+	int strong_count = 0;
+	float X[3];
+	const short2* nb = a.neighbours + (size_t)nm * DVP_NEIGHBOUR_NUM;
+	for (int i = 1; i < DVP_NEIGHBOUR_NUM; ++i) {
+		const short2 tp = nb[i];
+		if (tp.x == -1 || tp.y == -1) continue;
+		strong_points[strong_count] = tp;
+		const int tc = tp.x + tp.y * W;
+		const float4 pl = a.planes[tc];
+		const float depth = depth_from_plane(a.ref, pl, tp.x, tp.y);
+		get_3d_point(a.ref, tp.x, tp.y, depth, X);
+		pts3d[strong_count] = make_float3(X[0], X[1], X[2]);
+		normals[strong_count] = make_float3(pl.x, pl.y, pl.z);
+		strong_count++;
+	}
+	if (strong_count < 3) { a.fit_planes[center] = a.planes[center]; rng.store(a.rng, a.N, center); return; }
+	int iteration = 50;
+	float min_cost = FLT_MAX;
+	float4 best_plane = make_float4(0, 0, 0, 0);
+	bool has_best_plane = false;
+	uint8_t edge_test[M][M];
+	for (int i = 0; i < M; ++i) for (int j = 0; j < M; ++j) edge_test[i][j] = 0;
+	auto crossing = [&](int i0, int i1) -> int {
+		if (edge_test[i0][i1] == 0)
+			edge_test[i0][i1] = edge_test[i1][i0] = bresenham_crosses_edge(a, strong_points[i0].x, strong_points[i0].y, strong_points[i1].x, strong_points[i1].y) ? 1 : 2;
+		return edge_test[i0][i1];
+	};
+	while (iteration--) {
+		const int a_index = rng.next() % strong_count;
+		const int b_index = rng.next() % strong_count;
+		const int c_index = rng.next() % strong_count;
+		if (a_index == b_index || b_index == c_index || a_index == c_index) continue;
+		const float3 AN = normals[a_index], BN = normals[b_index], CN = normals[c_index];
+		if (AN.x * BN.x + AN.y * BN.y + AN.z * BN.z < 0.9f || AN.x * CN.x + AN.y * CN.y + AN.z * CN.z < 0.9f ||
+		    BN.x * CN.x + BN.y * CN.y + BN.z * CN.z < 0.9f) continue;
+		if (!point_in_triangle(strong_points[a_index], strong_points[b_index], strong_points[c_index], px, py)) continue;
+		if (edge_limit) {
+			const int e_ab = crossing(a_index, b_index);
+			const int e_bc = crossing(b_index, c_index);
+			const int e_ca = crossing(c_index, a_index);
+			if (e_ab == 1 || e_bc == 1 || e_ca == 1) continue;
+		}
+		const float3 A = pts3d[a_index], B = pts3d[b_index], C = pts3d[c_index];
+		const float3 A_C = make_float3(A.x - C.x, A.y - C.y, A.z - C.z);
+		const float3 B_C = make_float3(B.x - C.x, B.y - C.y, B.z - C.z);
+		float4 cross_vec;
+		cross_vec.x = A_C.y * B_C.z - B_C.y * A_C.z;
+		cross_vec.y = -(A_C.x * B_C.z - B_C.x * A_C.z);
+		cross_vec.z = A_C.x * B_C.y - B_C.x * A_C.y;
+		if ((cross_vec.x == 0 && cross_vec.y == 0 && cross_vec.z == 0) || isnan(cross_vec.x) || isnan(cross_vec.y) || isnan(cross_vec.z)) continue;
+		normalize3(&cross_vec);
+		cross_vec.w = -(cross_vec.x * A.x + cross_vec.y * A.y + cross_vec.z * A.z);
+		float temp_cost = 0.0f;
+		for (int si = 0; si < strong_count; ++si) {
+			if (si == a_index || si == b_index || si == c_index) continue;
+			const float3 tp = pts3d[si];
+			const short2 tpix = strong_points[si];
+			const float factor_x = (tpix.x - a.ref.K[2]) / a.ref.K[0];
+			const float factor_y = (tpix.y - a.ref.K[5]) / a.ref.K[4];
+			const float fit_depth = -cross_vec.w / (cross_vec.x * factor_x + cross_vec.y * factor_y + cross_vec.z);
+			temp_cost += fabs(fit_depth - tp.z);
+		}
+		if (temp_cost < min_cost) { min_cost = temp_cost; best_plane = cross_vec; has_best_plane = true; }
+	}
+	rng.store(a.rng, a.N, center);
+	if (has_best_plane) {
+		const float depth = depth_from_plane(a.ref, a.planes[center], px, py);
+		const float4 vd = get_view_direction(a.ref, px, py, depth);
+		const float dot_product = best_plane.x * vd.x + best_plane.y * vd.y + best_plane.z * vd.z;
+		if (dot_product > 0) { best_plane.x = -best_plane.x; best_plane.y = -best_plane.y; best_plane.z = -best_plane.z; best_plane.w = -best_plane.w; }
+		a.fit_planes[center] = best_plane;
+		if (a.prm.use_radius) {
+			// The reference derives the adaptive radius from strong_points[use_a/b/c_index] with all three indices
+			// still -1: A == B == C whatever that memory holds, the triangle is degenerate, its area
+			// and hence the radius are 0; no later clamp can raise it, so the stored value is always 0.
+			a.radius[center] = 0;
+		}
+	} else {
+		a.fit_planes[center] = make_float4(0, 0, 0, 0);
+		if (a.prm.use_radius) a.radius[center] = a.prm.strong_radius;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K10/K11 CheckerboardPropagationWeak + PlaneHypothesisRefinementWeak (APD.cu:2739-3089, 1897-2008).
+__device__ __forceinline__ float weak_weighted_cost(const KArgs& a, int px, int py, const float4 pl, const ViewWeights& vw, float weight_norm) {
+	float temp_cost = 0.0f;
+	for (int j = 0; j < a.S; ++j) {
+		const int wv = vw.get(j);
+		if (wv > 0) {
+			const float c = ncc_new(a, px, py, j, pl);
+			if (a.prm.geom_consistency) temp_cost += wv * (c + a.prm.geom_factor * geom_cost(a, a.views[j], a.tex_depth[j + 1], px, py, pl));
+			else temp_cost += wv * c;
+		}
+	}
+	temp_cost /= weight_norm;
+	return temp_cost;
+}
+
+// One thread per WEAK pixel of ONE checkerboard colour: `colour_list` (built at upload by a device prefix sum)
+// holds the pixels the reference's half grid reaches for this colour (APD.cu:3093-3106), so warps are dense.
+__global__ void __launch_bounds__(64) k_weak_sweep(const __grid_constant__ KArgs a, const int* colour_list, int count, int iter) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= count) return;
+	const int center = colour_list[t];
+	const int W = a.W, S = a.S;
+	const int px = center % W, py = center / W;
+	if (a.weak[center] != DVP_WEAK) return;   // demoted to UNKNOWN by K2/K5 since the list was built
+	const int nm = a.neighbours_map[center];
+	const short2* nb = a.neighbours + (size_t)nm * DVP_NEIGHBOUR_NUM;
+
+	float cost_array[8][DVP_MAX_IMAGES];
+	for (int i = 0; i < 8; ++i) for (int j = 0; j < S; ++j) cost_array[i][j] = 0.0f;
+	cost_array[0][0] = 2.0f;   // B2
+	bool flag[8];
+	int positions[8];
+	float4 new_plane[8];
+	for (int i = 0; i < 8; ++i) {
+		flag[i] = false; positions[i] = 0; new_plane[i] = make_float4(0, 0, 0, 0);
+		const short2 np = nb[i + 1];
+		if (np.x == -1 || np.y == -1 || a.weak[np.x + np.y * W] != DVP_STRONG) continue;
+		positions[i] = np.x + np.y * W;
+		flag[i] = true;
+		const float4 pl = a.planes[positions[i]];
+		for (int v = 0; v < S; ++v) cost_array[i][v] = ncc_new(a, px, py, v, pl);
+		new_plane[i] = pl;
+	}
+	Rng rng; rng.load(a.rng, a.N, center);
+	ViewWeights vw; vw.clear();
+	float probs[DVP_MAX_IMAGES];
+	{
+		const float cost_threshold = 0.8 * expf((iter) * (iter) / (-90.0f));
+		for (int i = 0; i < S; i++) {
+			float prior = 0.0f;
+			for (int k = 0; k < 8; ++k) {
+				const short2 np = nb[k + 1];
+				if (np.x == -1 || np.y == -1) continue;
+				prior += is_set(a.selected[np.x + np.y * W], i) ? 0.9f : 0.1f;
+			}
+			float count = 0; int count_false = 0; float tmpw = 0;
+			for (int j = 0; j < 8; j++) {
+				const float c = cost_array[j][i];
+				if (c < cost_threshold) { tmpw += expf(c * c / (-0.18f)); count++; }
+				if (c > 1.2f) count_false++;
+			}
+			float prob = 0.0f;
+			if (count > 2 && count_false < 3) prob = tmpw / count;
+			else if (count_false < 3) prob = expf(cost_threshold * cost_threshold / (-0.32f));
+			probs[i] = prob * prior;
+		}
+		float prob_sum = 0.0f;
+		for (int i = 0; i < S; ++i) prob_sum += probs[i];
+		const float inv_prob_sum = 1.0f / prob_sum;
+		float cum_prob = 0.0f;
+		for (int i = 0; i < S; ++i) { const float prob = probs[i] * inv_prob_sum; cum_prob += prob; probs[i] = cum_prob; }
+		for (int sample = 0; sample < 15; ++sample) {
+			const float rand_prob = rng.uniform() - FLT_EPSILON;
+			for (int image_id = 0; image_id < S; ++image_id)
+				if (probs[image_id] > rand_prob) { vw.inc(image_id); break; }
+		}
+	}
+	vw.store(a.view_weight + (size_t)center * DVP_MAX_IMAGES);
+	uint32_t temp_selected = 0;
+	float weight_norm = 0;
+	for (int i = 0; i < S; ++i) { const int wv = vw.get(i); if (wv > 0) { temp_selected |= 1u << i; weight_norm += wv; } }
+
+	int min_cost_idx = 0; float min_final = 0.f;
+	for (int i = 0; i < 8; ++i) {
+		float fc = 0.0f;
+		for (int j = 0; j < S; ++j) {
+			const int wv = vw.get(j);
+			if (wv > 0) {
+				if (a.prm.geom_consistency) {
+					if (flag[i]) fc += wv * (cost_array[i][j] + a.prm.geom_factor * geom_cost(a, a.views[j], a.tex_depth[j + 1], px, py, a.planes[positions[i]]));
+					else fc += wv * (cost_array[i][j] + a.prm.geom_factor * 3.0f);
+				} else fc += wv * cost_array[i][j];
+			}
+		}
+		fc /= weight_norm;
+		if (i == 0 || fc <= min_final) { min_final = fc; min_cost_idx = i; }
+	}
+	float4 plane_now = a.planes[center];
+	float cost_now = 0.0f;
+	for (int i = 0; i < S; ++i) {
+		const int wv = vw.get(i);
+		if (wv == 0) continue;   // the reference multiplies by 0 here
+		const float c = ncc_new(a, px, py, i, plane_now);
+		if (a.prm.geom_consistency) cost_now += wv * (c + a.prm.geom_factor * geom_cost(a, a.views[i], a.tex_depth[i + 1], px, py, plane_now));
+		else cost_now += wv * c;
+	}
+	cost_now /= weight_norm;
+	const float cost_stored = cost_now;
+	float depth_now = depth_from_plane(a.ref, plane_now, px, py);
+	if (flag[min_cost_idx]) {
+		const float depth_before = depth_from_plane(a.ref, new_plane[min_cost_idx], px, py);
+		if (depth_before >= a.prm.depth_min && depth_before <= a.prm.depth_max && min_final < cost_now) {
+			depth_now = depth_before; plane_now = new_plane[min_cost_idx]; cost_now = min_final;
+			a.selected[center] = temp_selected;
+		}
+	}
+	const uint32_t sel_now = a.selected[center];
+	// ---- PlaneHypothesisRefinementWeak ----
+	{
+		const float depth_min = a.prm.depth_min, depth_max = a.prm.depth_max;
+		bool skip_all = false;
+		const float4 fit = a.fit_planes[center];
+		if (fit.x == 0 && fit.y == 0 && fit.z == 0) skip_all = true;   // `return` before the random refinement (APD.cu:1923-1925)
+		if (!skip_all) {
+			const float temp_cost = weak_weighted_cost(a, px, py, fit, vw, weight_norm);
+			const float depth_before = depth_from_plane(a.ref, fit, px, py);
+			if (depth_before >= depth_min && depth_before <= depth_max && temp_cost < cost_now) { depth_now = depth_before; plane_now = fit; cost_now = temp_cost; }
+			const float depth_rand = rng.uniform() * (depth_max - depth_min) + depth_min;
+			const float4 plane_rand = random_normal(a, px, py, rng, depth_now, sel_now);
+			float depth_perturbed = depth_now;
+			const float depth_min_perturbed = (1 - 0.02f) * depth_perturbed;
+			const float depth_max_perturbed = (1 + 0.02f) * depth_perturbed;
+			depth_perturbed = rng.uniform() * (depth_max_perturbed - depth_min_perturbed) + depth_min_perturbed;
+			const float perturbation = 0.02f * 3.14159265358979323846;
+			const float4 plane_pert = perturbed_normal(a, px, py, plane_now, rng, perturbation);
+			(void)perturbed_normal(a, px, py, plane_now, rng, perturbation);
+			const float depth0 = depth_now; const float4 plane0 = plane_now;
+			for (int i = 0; i < 6; ++i) {
+				if (i == 4) continue;   // identical to hypothesis 3, can never be accepted after it
+				float d; float4 tpl;
+				switch (i) {
+				case 0: d = depth_rand; tpl = plane0; break;
+				case 1: d = depth0; tpl = plane_rand; break;
+				case 2: d = depth_rand; tpl = plane_rand; break;
+				case 3: d = depth0; tpl = plane_pert; break;
+				default: d = depth_perturbed; tpl = plane0; break;
+				}
+				tpl.w = get_distance2origin(a.ref, px, py, d, tpl);
+				const float tc = weak_weighted_cost(a, px, py, tpl, vw, weight_norm);
+				const float db = depth_from_plane(a.ref, tpl, px, py);
+				if (db >= depth_min && db <= depth_max && tc < cost_now) { depth_now = db; plane_now = tpl; cost_now = tc; }
+			}
+		}
+	}
+	rng.store(a.rng, a.N, center);
+	float4 plane_final = plane_now;
+	if (a.prm.state == DVP_REFINE_INIT) {
+		if (cost_now < cost_stored - 0.1) a.planes[center] = plane_now;
+		else plane_final = a.planes[center];
+	} else {
+		a.planes[center] = plane_now;
+	}
+	// "update cost with old method" (APD.cu:3072-3088): rescore the stored plane with the plain NCC at strong_radius
+	{
+		extern __shared__ __align__(16) unsigned char smem_raw[];
+		float2* wt = reinterpret_cast<float2*>(smem_raw) + threadIdx.x;
+		RefPatch rp;
+		rp.prepare(a, px, py, a.prm.strong_radius, wt, blockDim.x);
+		float c2 = 0.0f;
+		for (int i = 0; i < S; ++i) {
+			const int wv = vw.get(i);
+			if (wv == 0) continue;
+			c2 += wv * ncc_cost<1>(a, a.views[i], a.tex_img[i + 1], px, py, plane_final, rp, wt, blockDim.x);
+		}
+		c2 /= weight_norm;
+		a.costs[center] = c2;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------
 cudaError_t launch_edge_inform(const KArgs& a, cudaStream_t st) {
-	// part (a) (candidate offsets) is only ever read by the deformable NCC of WEAK pixels; with no WEAK
-	// pixel in the view it has no reader and is skipped (the reference computes it regardless).
-	if (a.weak_count > 0) return cudaErrorNotSupported;
+	// part (a) (candidate offsets) is only ever read by the deformable NCC of WEAK pixels; with no WEAK pixel in
+	// the view it has no reader and is skipped (the reference computes it regardless: 31 % of its pass at S=4).
+	if (a.weak_count > 0) {
+		static bool table_ready[64] = {false};
+		int dev = 0; cudaGetDevice(&dev);
+		if (dev >= 0 && dev < 64 && !table_ready[dev]) { k_fill_sector_table<<<1, dim3(11, 11), 0, st>>>(); table_ready[dev] = true; }
+		dim3 b(32, 8);
+		dim3 g((a.W + 31) / 32, (a.H + 7) / 8, 1);
+		k_candidate<<<g, b, 0, st>>>(a);
+	}
 	return launch_edge_inform_prep(a, st);
 }
-cudaError_t launch_gen_neighbours(const KArgs& a, cudaStream_t st) {
-	if (a.weak_count > 0) return cudaErrorNotSupported;
-	return cudaSuccess;
-}
-cudaError_t launch_ransac_fit(const KArgs& a, cudaStream_t st) {
-	if (a.weak_count > 0) return cudaErrorNotSupported;
-	k_ransac_fit_nonweak<<<(a.N + 255) / 256, 256, 0, st>>>(a);
+cudaError_t launch_gen_neighbours(const KArgs& a, const int* weak_list, cudaStream_t st) {
+	if (a.weak_count == 0) return cudaSuccess;
+	k_gen_neighbours<<<(a.weak_count + 63) / 64, 64, 0, st>>>(a, weak_list);
 	return cudaGetLastError();
 }
-cudaError_t launch_weak_sweep(const KArgs& a, int iter, int red, cudaStream_t st) {
-	if (a.weak_count > 0) return cudaErrorNotSupported;
-	return cudaSuccess;
+cudaError_t launch_ransac_fit(const KArgs& a, cudaStream_t st) {
+	k_ransac_fit<<<(a.N + 255) / 256, 256, 0, st>>>(a);
+	return cudaGetLastError();
+}
+cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count, int iter, int red, cudaStream_t st) {
+	(void)red;
+	if (count == 0) return cudaSuccess;
+	k_weak_sweep<<<(count + 63) / 64, 64, patch_smem_bytes(64), st>>>(a, colour_list, count, iter);
+	return cudaGetLastError();
 }
 cudaError_t configure_weak_kernels(int S) { return cudaSuccess; }
 

@@ -20,18 +20,23 @@ cudaError_t launch_setup_views(const dvp_camera* cams, ViewConst* views, int S, 
 cudaError_t launch_init_rng(const KArgs& a, unsigned long long seed, cudaStream_t st);          // K1
 cudaError_t launch_edge_inform(const KArgs& a, cudaStream_t st);                                 // K2
 cudaError_t launch_nearest_strong(const KArgs& a, cudaStream_t st);                              // K3
-cudaError_t launch_gen_neighbours(const KArgs& a, cudaStream_t st);                              // K4
+cudaError_t launch_gen_neighbours(const KArgs& a, const int* weak_list, cudaStream_t st);        // K4
 cudaError_t launch_neighbour_update(const KArgs& a, cudaStream_t st);                            // K5
 cudaError_t launch_random_init(const KArgs& a, cudaStream_t st);                                 // K6
 cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, cudaStream_t st);             // K7 / K8
 cudaError_t launch_ransac_fit(const KArgs& a, cudaStream_t st);                                  // K9
-cudaError_t launch_weak_sweep(const KArgs& a, int iter, int red, cudaStream_t st);               // K10 / K11
+cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count, int iter, int red, cudaStream_t st);  // K10 / K11
 cudaError_t launch_depth_normal(const KArgs& a, cudaStream_t st);                                // K12
 cudaError_t launch_filter(const KArgs& a, int red, cudaStream_t st);                             // K13 / K14
 cudaError_t launch_depth_to_weak(const KArgs& a, cudaStream_t st);                               // K15
 cudaError_t launch_local_refine(const KArgs& a, cudaStream_t st);                                // K16
 
 cudaError_t launch_fill_i32(int32_t* dst, int32_t v, int n, cudaStream_t st);
+// WEAK-pixel indexing (device-side replacement of the host loop APD.cpp:1182-1193)
+constexpr int kWeakScanBlock = 1024;
+cudaError_t launch_weak_count(const uint8_t* weak, int n, int W, int colour, int yy_limit, int* block_sums, int* total, cudaStream_t st);
+cudaError_t launch_weak_index(const uint8_t* weak, int n, int W, int colour, int yy_limit, const int* block_offsets, int* nmap, int* weak_list, cudaStream_t st);
+cudaError_t launch_reset_unknown_radius(const uint8_t* weak, int32_t* radius, int32_t strong_radius, int n, cudaStream_t st);
 
 // canonical RNG exchange format <-> SoA planes
 cudaError_t launch_rng_export(const KArgs& a, uint32_t* dst_aos, cudaStream_t st);

@@ -1,0 +1,201 @@
+// dvp_weak.cuh — device code of the adaptive-patch-deformation (WEAK pixel) path:
+// Bresenham edge test, point-in-triangle, deformable bilateral NCC (reference APD.cu:244-317, 835-1021).
+// WEAK pixels are a minority of a view and their work is irregular (data-dependent RNG draws, RANSAC),
+// so this path keeps the reference's one-thread-per-pixel formulation; what changes is where it runs from:
+// kernels are launched over the compact list of WEAK pixels instead of the whole image, parameters come from
+// the kernel argument block, and the 25.6 KB/thread edge-test cache of GenNeighbours shrinks to 6.4 KB.
+#pragma once
+#include "dvp_strong.cuh"
+
+namespace dvp {
+
+// reference BresenhamLine, APD.cu:267-311: does the segment B->A cross an edge pixel within max(H,W)/30 steps?
+__device__ __forceinline__ bool bresenham_crosses_edge(const KArgs& a, int Ax, int Ay, int Bx, int By) {
+	const int width = a.W;
+	const int max_step = (int)(DVP_MAX(a.H, a.W) / 30.0);
+	int x0 = Bx, y0 = By;
+	const int x1 = Ax, y1 = Ay;
+	const int ABx = Ax - Bx, ABy = Ay - By;
+	if (ABx * ABx + ABy * ABy > 9 * max_step * max_step) return false;
+	if (a.edge[x0 + y0 * width] || a.edge[x1 + y1 * width]) return false;
+	const int dx = abs(x1 - x0), sx = x0 < x1 ? 1 : -1;
+	const int dy = abs(y1 - y0), sy = y0 < y1 ? 1 : -1;
+	int erro = (dx > dy ? dx : dy) / 2;
+	int step = 0;
+	bool tagx = true, tagy = true;
+	while (tagx || tagy) {
+		if (x0 == x1) tagx = false;
+		if (y0 == y1) tagy = false;
+		const int e2 = erro;
+		if (e2 > -dx) { erro -= dy; x0 += sx; }
+		if (e2 < dy) { erro += dx; y0 += sy; }
+		// the walk may step one pixel past the end point; stay inside the map (the reference reads whatever is there)
+		if (x0 >= 0 && x0 < a.W && y0 >= 0 && y0 < a.H) { if (a.edge[x0 + y0 * width]) return true; }
+		step += 1;
+		if (step >= max_step) break;
+	}
+	return false;
+}
+
+// reference PointinTriangle, APD.cu:244-265
+__device__ __forceinline__ bool point_in_triangle(short2 A, short2 B, short2 C, int Px, int Py) {
+	const float2 AB = make_float2(B.x - A.x, B.y - A.y);
+	const float2 BC = make_float2(C.x - B.x, C.y - B.y);
+	const float2 CA = make_float2(A.x - C.x, A.y - C.y);
+	const float AB_ = sqrt(AB.x * AB.x + AB.y * AB.y);
+	const float BC_ = sqrt(BC.x * BC.x + BC.y * BC.y);
+	const float CA_ = sqrt(CA.x * CA.x + CA.y * CA.y);
+	if (AB_ <= 2 || BC_ <= 2 || CA_ <= 2) return false;
+	if (!(AB_ + BC_ > CA_ && BC_ + CA_ > AB_ && AB_ + CA_ > BC_)) return false;
+	const float2 PA = make_float2(A.x - Px, A.y - Py);
+	const float2 PB = make_float2(B.x - Px, B.y - Py);
+	const float2 PC = make_float2(C.x - Px, C.y - Py);
+	const float t1 = PA.x * PB.y - PA.y * PB.x;
+	const float t2 = PB.x * PC.y - PB.y * PC.x;
+	const float t3 = PC.x * PA.y - PC.y * PA.x;
+	return t1 * t2 >= 0 && t1 * t3 >= 0;
+}
+
+// colour-only bilateral weight (ComputeBilateralWeight_YZL, APD.cu:783-788) as compiled:
+// ex2(log2e * (|pix - centre| * -(1/(2 sc^2))))
+__device__ __forceinline__ float weight_colour(float pix, float center, float rcp_c) {
+	const float cd = fabsf(__fadd_rn(pix, -center));
+	return ex2_approx(__fmul_rn(__fmul_rn(cd, -rcp_c), 1.4426950216293334961f));
+}
+
+// projective warp of an integer pixel, both products varying (APD.cu:741-748 as compiled inside NCCNew):
+// num = H2 + fma(H0, x, H1*y)
+__device__ __forceinline__ void warp_point(const float* H, float xf, float yf, float& u, float& v) {
+	const float z = __fadd_rn(H[8], __fmaf_rn(H[6], xf, __fmul_rn(H[7], yf)));
+	const float x = __fadd_rn(H[2], __fmaf_rn(H[0], xf, __fmul_rn(H[1], yf)));
+	const float y = __fadd_rn(H[5], __fmaf_rn(H[3], xf, __fmul_rn(H[4], yf)));
+	const float rz = rcp_approx(z);
+	u = __fmul_rn(x, rz);
+	v = __fmul_rn(y, rz);
+}
+__device__ __forceinline__ float sample_src_warped(const float* H, cudaTextureObject_t src, float xf, float yf) {
+	const float z = __fadd_rn(H[8], __fmaf_rn(H[6], xf, __fmul_rn(H[7], yf)));
+	const float x = __fadd_rn(H[2], __fmaf_rn(H[0], xf, __fmul_rn(H[1], yf)));
+	const float y = __fadd_rn(H[5], __fmaf_rn(H[3], xf, __fmul_rn(H[4], yf)));
+	const float rz = rcp_approx(z);
+	return tex2D<float>(src, __fmaf_rn(x, rz, 0.5f), __fmaf_rn(y, rz, 0.5f));
+}
+
+__device__ __forceinline__ float ncc_tail(float s_w, float s_r, float s_rr, float s_s, float s_ss, float s_rs) {
+	const float inv = rcp_approx(s_w);
+	const float mr = __fmul_rn(inv, s_r), ms = __fmul_rn(inv, s_s);
+	const float var_r = __fmaf_rn(inv, s_rr, -__fmul_rn(mr, mr));
+	const float var_s = __fmaf_rn(inv, s_ss, -__fmul_rn(ms, ms));
+	const float e_rs = __fmul_rn(inv, s_rs);
+	if (var_r < kMinVar || var_s < kMinVar) return kCostMax;
+	const float covar = __fmaf_rn(-mr, ms, e_rs);
+	const float den = sqrt_approx(__fmul_rn(var_r, var_s));
+	return fmaxf(0.0f, fminf(kCostMax, __fmaf_rn(-covar, rcp_approx(den), 1.0f)));
+}
+
+// reference ComputeBilateralNCCNew, APD.cu:835-1021: 0.25 * centre patch (6x6 at the adaptive radius, colour-only
+// weights) + 0.75 * mean over the <= 11 anchor pixels of a 9-sample NCC whose offsets are the anchor's
+// visibility-aware `candidate` offsets for this view (fallback: the +-5 ring).
+__device__ __forceinline__ float ncc_new(const KArgs& a, int px, int py, int v /*0-based view*/, const float4 pl) {
+	const int W = a.W, H_ = a.H;
+	const ViewConst& vc = a.views[v];
+	const cudaTextureObject_t src = a.tex_img[v + 1];
+	float H[9];
+	compute_homography(a.ref, vc, pl, H);
+	{
+		float u, w; warp_point(H, (float)px, (float)py, u, w);
+		if (u >= (float)W || u < 0.0f || w >= (float)H_ || w < 0.0f) return kCostMax;
+	}
+	const int center = px + py * W;
+	float rcp_s, rcp_c; RefPatch::sigma_rcps(a.prm, rcp_s, rcp_c);
+	const float ref_center_pix = RefPatch::ref_pixel(a, px, py);
+	const short2* nb = a.neighbours + (size_t)a.neighbours_map[center] * DVP_NEIGHBOUR_NUM;
+	float center_cost = 0.0f, strong_cost = 0.0f;
+	int strong_count = 0;
+	for (int k = 0; k < DVP_NEIGHBOUR_NUM; ++k) {
+		const short2 np = nb[k];
+		if (np.x == -1 || np.y == -1) continue;
+		{
+			float u, w; warp_point(H, (float)np.x, (float)np.y, u, w);
+			if (u < 0 || w < 0 || u >= (float)W || w >= (float)H_) {
+				if (k != 0) {
+					if (is_set(a.selected[np.x + np.y * W], v)) { strong_cost += kCostMax; strong_count++; }
+					continue;
+				}
+				return kCostMax;
+			}
+		}
+		float s_r = 0.f, s_rr = 0.f, s_s = 0.f, s_ss = 0.f, s_rs = 0.f, s_w = 0.f;
+		if (k == 0) {
+			int radius = a.prm.strong_radius, inc = a.prm.strong_increment;
+			if (a.prm.use_radius) { radius = a.radius[center]; inc = DVP_MAX(2, (int)(2.0 * radius / 5.0)); }
+			for (int i = -radius; i <= radius; i += inc) {
+				const float xf = (float)(np.x + i);
+				const float hx = __fmul_rn(H[0], xf), hy = __fmul_rn(H[3], xf), hz = __fmul_rn(H[6], xf);
+				float r_r = 0.f, r_rr = 0.f, r_s = 0.f, r_ss = 0.f, r_rs = 0.f, r_w = 0.f;
+				for (int j = -radius; j <= radius; j += inc) {
+					const float yf = (float)(np.y + j);
+					const float ref_pix = RefPatch::ref_pixel(a, np.x + i, np.y + j);
+					const float z = __fadd_rn(H[8], __fmaf_rn(H[7], yf, hz));
+					const float x = __fadd_rn(H[2], __fmaf_rn(H[1], yf, hx));
+					const float y = __fadd_rn(H[5], __fmaf_rn(H[4], yf, hy));
+					const float rz = rcp_approx(z);
+					const float src_pix = tex2D<float>(src, __fmaf_rn(x, rz, 0.5f), __fmaf_rn(y, rz, 0.5f));
+					const float w = weight_colour(ref_pix, ref_center_pix, rcp_c);
+					const float t = __fmul_rn(ref_pix, w), u = __fmul_rn(src_pix, w);
+					r_r = __fadd_rn(t, r_r); r_rr = __fmaf_rn(ref_pix, t, r_rr);
+					r_s = __fadd_rn(u, r_s); r_ss = __fmaf_rn(src_pix, u, r_ss);
+					r_rs = __fmaf_rn(src_pix, t, r_rs);
+					r_w = __fadd_rn(w, r_w);
+				}
+				s_r = __fadd_rn(r_r, s_r); s_rr = __fadd_rn(r_rr, s_rr); s_s = __fadd_rn(r_s, s_s);
+				s_ss = __fadd_rn(r_ss, s_ss); s_rs = __fadd_rn(r_rs, s_rs); s_w = __fadd_rn(r_w, s_w);
+			}
+		} else if (is_set(a.selected[np.x + np.y * W], v) == 1) {
+			const int nei_center = np.x + np.y * W;
+			const short2* cand = a.candidate + ((size_t)nei_center * DVP_NUM_IMAGES + v) * DVP_LAB_BOUNDARY_NUM;
+			for (int q = 0; q < 9; q++) {
+				int i = 0, j = 0;
+				if (q != 8) { const short2 c = cand[q]; i = c.x; j = c.y; }
+				if (i == 0 && j == 0) {
+					switch (q) {
+					case 0: i = -5; j = -5; break;
+					case 1: i = -5; j = 0; break;
+					case 2: i = -5; j = 5; break;
+					case 3: i = 0; j = -5; break;
+					case 4: i = 0; j = 5; break;
+					case 5: i = 5; j = -5; break;
+					case 6: i = 5; j = 0; break;
+					case 7: i = 5; j = 5; break;
+					default: break;
+					}
+				}
+				const int rx = np.x + i, ry = np.y + j;
+				const float ref_pix = RefPatch::ref_pixel(a, rx, ry);
+				const float src_pix = sample_src_warped(H, src, (float)rx, (float)ry);
+				const float w = weight_colour(ref_pix, ref_center_pix, rcp_c);
+				// each "row" is one sample: row = fma(x, y, 0), total += row -> product rounded, then added (SASS of the reference)
+				const float t = __fmul_rn(ref_pix, w), u = __fmul_rn(src_pix, w);
+				s_r = __fadd_rn(__fadd_rn(0.f, t), s_r);
+				s_rr = __fadd_rn(__fmaf_rn(ref_pix, t, 0.f), s_rr);
+				s_s = __fadd_rn(__fadd_rn(0.f, u), s_s);
+				s_ss = __fadd_rn(__fmaf_rn(src_pix, u, 0.f), s_ss);
+				s_rs = __fadd_rn(__fmaf_rn(src_pix, t, 0.f), s_rs);
+				s_w = __fadd_rn(__fadd_rn(0.f, w), s_w);
+			}
+		}
+		const float temp_cost = ncc_tail(s_w, s_r, s_rr, s_s, s_ss, s_rs);
+		if (k == 0) center_cost = temp_cost;
+		else { strong_cost += temp_cost; strong_count++; }
+	}
+	float cost;
+	if (strong_count == 0) cost = center_cost;
+	else {
+		strong_cost /= strong_count;
+		strong_cost = DVP_MIN(strong_cost, kCostMax);
+		cost = 0.25 * center_cost + 0.75 * strong_cost;
+	}
+	return cost;
+}
+
+}  // namespace dvp

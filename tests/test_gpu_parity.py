@@ -104,6 +104,55 @@ def test_sparse_mask_sweep_is_bit_exact_vs_reference():
     assert n_changed > 4000   # the sweep really did something
 
 
+def _second_pass_inputs(W, H, S, geom):
+    """Pass 1 (FIRST_INIT, all STRONG) on the reference -> inputs of a rounds>=1 pass with WEAK pixels."""
+    from dvp_mvs_b200 import REFINE_INIT, REFINE_ITER
+    sc = synth.make_scene(W, H, S)
+    p = c1_params(sc.depth_min, sc.depth_max, S, iters=2)
+    ref = ref_oracle.engine(W, H, S, p)
+    ref.upload(images=sc.images, cameras=sc.cameras, planes=sc.planes_init, edge=sc.edge, label=sc.label, seed=synth.SEED_RNG)
+    ref.run(mode=0)
+    planes, weak, sel, rad = ref.download()
+    q = c1_params(sc.depth_min, sc.depth_max, S, iters=1, use_apd=1)
+    q.state = REFINE_ITER if geom else REFINE_INIT
+    q.use_detail = 1; q.ransac_threshold = 0.00875; q.rotate_time = 2; q.geom_consistency = geom   # main.cpp:463-503, round 1
+    kw = dict(images=sc.images, depths=sc.depths if geom else None, cameras=sc.cameras, planes=planes, selected_views=sel,
+              weak_info=weak, edge=sc.edge, label=sc.label, radius=rad, seed=synth.SEED_RNG + 1)
+    return q, kw, weak
+
+
+@needs_ref
+@pytest.mark.parametrize("geom", [0, 1])
+def test_weak_path_stagewise_vs_reference(geom):
+    """Adaptive patch deformation: K2 (complex, label boundaries), K3, K4 GenNeighbours (anchors, RNG), K5, K9 RANSAC
+    fit + radius, K10/K11 weak sweep — stepping from the reference's state.  Integer outputs and RNG states must be
+    bit-exact; the weak sweep's float outputs within 1e-4 relative on all but a handful of pixels."""
+    W, H, S = 320, 240, 2 + 2 * geom
+    q, kw, weak = _second_pass_inputs(W, H, S, geom)
+    assert (weak == WEAK).sum() > 2000
+    ref = ref_oracle.engine(W, H, S, q); prod = Engine(W, H, S, q)
+    ref.upload(**kw); prod.upload(**kw)
+    assert ref.weak_count() == prod.weak_count() == int((weak == WEAK).sum())
+    assert (ref.get("neighbours_map") == prod.get("neighbours_map")).all()
+    res = step_compare(ref, prod, 1)
+    by = {(r["stage"], r.get("buffer")): r for r in res}
+    assert not [r for r in res if r.get("error")], [r for r in res if r.get("error")][:2]
+    for key in [("K2_GEN_EDGE_INFORM", "edge_neigh"), ("K2_GEN_EDGE_INFORM", "weak"), ("K2_GEN_EDGE_INFORM", "complex"),
+                ("K2_GEN_EDGE_INFORM", "label_boundary"), ("K3_FIND_NEAREST_STRONG", "nearest_strong"),
+                ("K4_GEN_NEIGHBOURS", "neighbours"), ("K4_GEN_NEIGHBOURS", "weak_reliable"), ("K4_GEN_NEIGHBOURS", "rand"),
+                ("K5_NEIGHBOUR_UPDATE", "weak"), ("K6_RANDOM_INITIALIZATION", "costs"), ("K6_RANDOM_INITIALIZATION", "selected"),
+                ("K9_RANSAC_FIT_PLANE", "fit_planes"), ("K9_RANSAC_FIT_PLANE", "radius"), ("K9_RANSAC_FIT_PLANE", "rand"),
+                ("K10_BLACK_WEAK", "view_weight"), ("K10_BLACK_WEAK", "radius"), ("K11_RED_WEAK", "view_weight"),
+                ("K15_DEPTH_TO_WEAK", "weak"), ("K16_LOCAL_REFINE", "planes")]:
+        assert by[key]["not_bit_exact"] == 0, (key, by[key])
+    for st in ("K10_BLACK_WEAK", "K11_RED_WEAK"):
+        # without the geometric term the weak sweep is bit-exact; with it a 1-ulp difference in the forward-backward
+        # reprojection cost flips an accept decision on a few pixels in 100 000 (measured: <= 6 of 307 200)
+        limit = 0 if geom == 0 else 8
+        for n in ("planes", "costs", "selected", "rand"):
+            assert by[(st, n)]["mismatched"] <= limit, (st, n, by[(st, n)])
+
+
 def test_product_matches_committed_golden_vectors():
     """Same stepping protocol against tests/golden/c1_64x48.npz (reference kernels, generated on B200)."""
     g = load_golden("c1_64x48.npz")
