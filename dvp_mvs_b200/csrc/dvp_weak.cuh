@@ -153,34 +153,33 @@ __device__ __forceinline__ float ncc_new(const KArgs& a, int px, int py, int v /
 			}
 		} else if (is_set(a.selected[np.x + np.y * W], v) == 1) {
 			const int nei_center = np.x + np.y * W;
-			const short2* cand = a.candidate + ((size_t)nei_center * DVP_NUM_IMAGES + v) * DVP_LAB_BOUNDARY_NUM;
+			// the anchor's 8 visibility-aware offsets for this view: one 32-byte record, two 16-byte loads
+			const uint4* cand4 = reinterpret_cast<const uint4*>(a.candidate + ((size_t)nei_center * DVP_NUM_IMAGES + v) * DVP_LAB_BOUNDARY_NUM);
+			const uint4 c_lo = __ldg(cand4), c_hi = __ldg(cand4 + 1);
+			const uint32_t cw[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
+			const int def_i[9] = {-5, -5, -5, 0, 0, 5, 5, 5, 0}, def_j[9] = {-5, 0, 5, -5, 5, -5, 0, 5, 0};
+			// all nine reference reads and texture fetches are issued before the first is consumed; the sums are
+			// then folded strictly in sample order (the reference's rounding sequence)
+			float ref_pix[9], src_pix[9];
+#pragma unroll
 			for (int q = 0; q < 9; q++) {
 				int i = 0, j = 0;
-				if (q != 8) { const short2 c = cand[q]; i = c.x; j = c.y; }
-				if (i == 0 && j == 0) {
-					switch (q) {
-					case 0: i = -5; j = -5; break;
-					case 1: i = -5; j = 0; break;
-					case 2: i = -5; j = 5; break;
-					case 3: i = 0; j = -5; break;
-					case 4: i = 0; j = 5; break;
-					case 5: i = 5; j = -5; break;
-					case 6: i = 5; j = 0; break;
-					case 7: i = 5; j = 5; break;
-					default: break;
-					}
-				}
+				if (q != 8) { i = (int)(short)(cw[q] & 0xffffu); j = (int)(short)(cw[q] >> 16); }
+				if (i == 0 && j == 0) { i = def_i[q]; j = def_j[q]; }
 				const int rx = np.x + i, ry = np.y + j;
-				const float ref_pix = RefPatch::ref_pixel(a, rx, ry);
-				const float src_pix = sample_src_warped(H, src, (float)rx, (float)ry);
-				const float w = weight_colour(ref_pix, ref_center_pix, rcp_c);
+				ref_pix[q] = RefPatch::ref_pixel(a, rx, ry);
+				src_pix[q] = sample_src_warped(H, src, (float)rx, (float)ry);
+			}
+#pragma unroll
+			for (int q = 0; q < 9; q++) {
+				const float w = weight_colour(ref_pix[q], ref_center_pix, rcp_c);
 				// each "row" is one sample: row = fma(x, y, 0), total += row -> product rounded, then added (SASS of the reference)
-				const float t = __fmul_rn(ref_pix, w), u = __fmul_rn(src_pix, w);
+				const float t = __fmul_rn(ref_pix[q], w), u = __fmul_rn(src_pix[q], w);
 				s_r = __fadd_rn(__fadd_rn(0.f, t), s_r);
-				s_rr = __fadd_rn(__fmaf_rn(ref_pix, t, 0.f), s_rr);
+				s_rr = __fadd_rn(__fmaf_rn(ref_pix[q], t, 0.f), s_rr);
 				s_s = __fadd_rn(__fadd_rn(0.f, u), s_s);
-				s_ss = __fadd_rn(__fmaf_rn(src_pix, u, 0.f), s_ss);
-				s_rs = __fadd_rn(__fmaf_rn(src_pix, t, 0.f), s_rs);
+				s_ss = __fadd_rn(__fmaf_rn(src_pix[q], u, 0.f), s_ss);
+				s_rs = __fadd_rn(__fmaf_rn(src_pix[q], t, 0.f), s_rs);
 				s_w = __fadd_rn(__fadd_rn(0.f, w), s_w);
 			}
 		}
