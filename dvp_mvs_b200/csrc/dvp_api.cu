@@ -61,6 +61,8 @@ struct dvp_ctx {
 	short2* label_boundary = nullptr;
 	float* complex_ = nullptr;
 	int* weak_list = nullptr;   // pixel index of every WEAK pixel, in neighbours_map order
+	short* next_right = nullptr; // K3 pointer maps: next STRONG pixel in the row / column
+	short* next_down = nullptr;
 	int* scan_blocks = nullptr; // per-1024-pixel WEAK counts / offsets
 	int* scan_total = nullptr;  // [3]: all WEAK, black WEAK, red WEAK
 	int* colour_list[2] = {nullptr, nullptr};  // WEAK pixels of one checkerboard colour (dense warps in the weak sweep)
@@ -152,7 +154,7 @@ cudaError_t launch_stage(dvp_ctx* c, const KArgs& a, int stage, int iter) {
 	switch (stage) {
 	case DVP_K1_INIT_RANDOM_STATES: return launch_init_rng(a, c->seed, st);
 	case DVP_K2_GEN_EDGE_INFORM: return launch_edge_inform(a, st);
-	case DVP_K3_FIND_NEAREST_STRONG: return launch_nearest_strong(a, st);
+	case DVP_K3_FIND_NEAREST_STRONG: return launch_nearest_strong(a, c->next_right, c->next_down, st);
 	case DVP_K4_GEN_NEIGHBOURS: return launch_gen_neighbours(a, c->weak_list, st);
 	case DVP_K5_NEIGHBOUR_UPDATE: return launch_neighbour_update(a, st);
 	case DVP_K6_RANDOM_INITIALIZATION: return launch_random_init(a, st);
@@ -311,6 +313,8 @@ dvp_ctx* dvp_create(int device, int width, int height, int num_src, const dvp_pa
 	ok = ok && zalloc(&c->complex_, 1) == cudaSuccess;
 	ok = ok && zalloc(&c->scan_blocks, (N + kWeakScanBlock - 1) / kWeakScanBlock + 1) == cudaSuccess;
 	ok = ok && zalloc(&c->scan_total, 4) == cudaSuccess;
+	ok = ok && zalloc(&c->next_right, N) == cudaSuccess;
+	ok = ok && zalloc(&c->next_down, N) == cudaSuccess;
 	for (int k = 0; k < 2; ++k) ok = ok && zalloc(&c->scan_blocks_c[k], (N + kWeakScanBlock - 1) / kWeakScanBlock + 1) == cudaSuccess;
 	for (size_t i = 0; ok && i < sizeof(c->ev) / sizeof(c->ev[0]); ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
 	if (!ok) {
@@ -336,7 +340,7 @@ void dvp_destroy(dvp_ctx* c) {
 	cudaFree(c->planes); cudaFree(c->fit_planes); cudaFree(c->costs); cudaFree(c->selected_alloc); cudaFree(c->weak);
 	cudaFree(c->radius); cudaFree(c->view_weight); cudaFree(c->rng); cudaFree(c->edge); cudaFree(c->edge_neigh);
 	cudaFree(c->label); cudaFree(c->candidate); cudaFree(c->nearest_strong); cudaFree(c->weak_reliable);
-	cudaFree(c->neighbours_map); cudaFree(c->neighbours); cudaFree(c->label_boundary); cudaFree(c->complex_); cudaFree(c->weak_list); cudaFree(c->scan_blocks); cudaFree(c->scan_total); for (int k = 0; k < 2; ++k) { cudaFree(c->scan_blocks_c[k]); cudaFree(c->colour_list[k]); }
+	cudaFree(c->neighbours_map); cudaFree(c->neighbours); cudaFree(c->label_boundary); cudaFree(c->complex_); cudaFree(c->weak_list); cudaFree(c->scan_blocks); cudaFree(c->scan_total); cudaFree(c->next_right); cudaFree(c->next_down); for (int k = 0; k < 2; ++k) { cudaFree(c->scan_blocks_c[k]); cudaFree(c->colour_list[k]); }
 	for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;

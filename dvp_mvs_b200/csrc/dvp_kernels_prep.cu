@@ -91,7 +91,33 @@ __global__ void __launch_bounds__(256) k_edge_inform_pixel(const __grid_constant
 // ------------------------------------------------------------------------------------------------------
 // K3 FindNearestStrongPoint (APD.cu:4159-4193): first STRONG pixel on growing square rings, radius <= 100,
 // scan order x-major then y inside each ring (the tie order is part of the result).
-__global__ void __launch_bounds__(256) k_nearest_strong(const __grid_constant__ KArgs a) {
+// The reference reads every pixel of every ring (up to 40 401 reads per WEAK pixel).  Here two pointer maps are
+// built by line sweeps — next STRONG pixel at or to the right in the row, at or below in the column — and each
+// ring is answered with four look-ups that reproduce the reference's scan order exactly:
+//   left column (all dy ascending), then the top/bottom rows interleaved by ascending dx (top first), then the
+//   right column.
+constexpr short kNone = 32767;
+__global__ void __launch_bounds__(128) k_next_strong_sweeps(const __grid_constant__ KArgs a, short* next_right, short* next_down) {
+	const int W = a.W, H = a.H;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < W) {            // column t, bottom to top (coalesced across threads)
+		short last = kNone;
+		for (int y = H - 1; y >= 0; --y) {
+			const int q = y * W + t;
+			if (a.weak[q] == DVP_STRONG) last = (short)y;
+			next_down[q] = last;
+		}
+	} else if (t < W + H) { // row t - W, right to left
+		const int y = t - W;
+		short last = kNone;
+		for (int x = W - 1; x >= 0; --x) {
+			const int q = y * W + x;
+			if (a.weak[q] == DVP_STRONG) last = (short)x;
+			next_right[q] = last;
+		}
+	}
+}
+__global__ void __launch_bounds__(256) k_nearest_strong(const __grid_constant__ KArgs a, const short* next_right, const short* next_down) {
 	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
 	const int W = a.W, H = a.H;
 	if (x >= W || y >= H) return;
@@ -99,17 +125,32 @@ __global__ void __launch_bounds__(256) k_nearest_strong(const __grid_constant__ 
 	short2 out = make_short2(-1, -1);
 	if (a.weak[center] == DVP_WEAK) {
 		const int max_radius = 100;
-		bool found = false;
-		for (int r = 0; r <= max_radius && !found; ++r) {
-			for (int dx = -r; dx <= r && !found; ++dx) {
-				const int nx = x + dx;
-				if (nx < 0 || nx >= W) continue;
-				const bool full_col = (dx == -r || dx == r);
-				// on the two outer columns every y of the ring qualifies, otherwise only y = -r and y = +r
-				for (int dy = -r; dy <= r; dy += (full_col ? 1 : (r > 0 ? 2 * r : 1))) {
-					const int ny = y + dy;
-					if (ny < 0 || ny >= H) continue;
-					if (a.weak[nx + ny * W] == DVP_STRONG) { out = make_short2((short)nx, (short)ny); found = true; break; }
+		for (int r = 0; r <= max_radius; ++r) {
+			const int y_lo = max(y - r, 0), y_hi = min(y + r, H - 1);
+			// dx = -r : whole column, dy ascending
+			if (x - r >= 0) {
+				const int yn = next_down[y_lo * W + (x - r)];
+				if (yn <= y_hi) { out = make_short2((short)(x - r), (short)yn); break; }
+			}
+			if (r > 0) {
+				// -r < dx < r : dy = -r, then dy = +r, for ascending dx
+				const int x_lo = max(x - r + 1, 0), x_hi = min(x + r - 1, W - 1);
+				if (x_lo <= x_hi) {
+					int xt = kNone, xb = kNone;
+					if (y - r >= 0) xt = next_right[(y - r) * W + x_lo];
+					if (y + r < H) xb = next_right[(y + r) * W + x_lo];
+					if (xt > x_hi) xt = kNone;
+					if (xb > x_hi) xb = kNone;
+					if (xt != kNone || xb != kNone) {
+						if (xt <= xb) out = make_short2((short)xt, (short)(y - r));   // same dx: the top row comes first
+						else out = make_short2((short)xb, (short)(y + r));
+						break;
+					}
+				}
+				// dx = +r : whole column
+				if (x + r < W) {
+					const int yn = next_down[y_lo * W + (x + r)];
+					if (yn <= y_hi) { out = make_short2((short)(x + r), (short)yn); break; }
 				}
 			}
 		}
@@ -241,10 +282,11 @@ cudaError_t launch_edge_inform_prep(const KArgs& a, cudaStream_t st) {
 	k_edge_inform_pixel<<<g, b, 0, st>>>(a);
 	return cudaGetLastError();
 }
-cudaError_t launch_nearest_strong(const KArgs& a, cudaStream_t st) {
+cudaError_t launch_nearest_strong(const KArgs& a, short* next_right, short* next_down, cudaStream_t st) {
 	dim3 b(32, 8);
 	dim3 g((a.W + 31) / 32, (a.H + 7) / 8, 1);
-	k_nearest_strong<<<g, b, 0, st>>>(a);
+	if (a.weak_count > 0) k_next_strong_sweeps<<<(a.W + a.H + 127) / 128, 128, 0, st>>>(a, next_right, next_down);
+	k_nearest_strong<<<g, b, 0, st>>>(a, next_right, next_down);   // non-WEAK pixels only store (-1,-1)
 	return cudaGetLastError();
 }
 cudaError_t launch_neighbour_update(const KArgs& a, cudaStream_t st) {

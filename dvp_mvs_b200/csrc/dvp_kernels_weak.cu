@@ -30,13 +30,30 @@ __global__ void k_fill_sector_table() {
 // Sectors without any visible pixel hold uninitialised stack data in the reference; here they
 // rank last and yield the offset (0,0), which the deformable NCC replaces by its default ring offset.
 __global__ void __launch_bounds__(256) k_candidate(const __grid_constant__ KArgs a) {
-	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	// 32x8 pixel tile + 5 px halo of the reference image and of the selected-view masks, staged once in shared
+	// memory and reused by the 120 window reads of every pixel for every view (weak_radius is 5 in every schedule
+	// of the reference; other radii fall back to global reads)
+	constexpr int R = 5, TW = 32 + 2 * R, TH = 8 + 2 * R;
+	__shared__ float s_img[TH][TW];
+	__shared__ uint32_t s_sel[TH][TW];
 	const int W = a.W, H = a.H;
+	const int x0 = blockIdx.x * 32 - R, y0 = blockIdx.y * 8 - R;
+	for (int i = threadIdx.y * 32 + threadIdx.x; i < TW * TH; i += 256) {
+		const int ty = i / TW, tx = i - ty * TW;
+		const int gx = x0 + tx, gy = y0 + ty;
+		const bool in = gx >= 0 && gx < W && gy >= 0 && gy < H;
+		s_img[ty][tx] = in ? a.ref_img[(size_t)gy * W + gx] : 0.f;
+		s_sel[ty][tx] = in ? a.selected[gx + gy * W] : 0u;   // out-of-image pixels are skipped by the reference: no view set
+	}
+	__syncthreads();
+	const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
 	if (x >= W || y >= H) return;
 	const int center = x + y * W;
 	float rcp_s, rcp_c; RefPatch::sigma_rcps(a.prm, rcp_s, rcp_c);
-	const float ref_center_pix = RefPatch::ref_pixel(a, x, y);
 	const int radius = a.prm.weak_radius;
+	const bool tiled = (radius == R);
+	const int lx = threadIdx.x + R, ly = threadIdx.y + R;
+	const float ref_center_pix = s_img[ly][lx];
 	for (int v = 0; v < a.S; ++v) {
 		float best_w[12]; int8_t bi[12], bj[12]; bool has[12];
 #pragma unroll
@@ -46,8 +63,10 @@ __global__ void __launch_bounds__(256) k_candidate(const __grid_constant__ KArgs
 				if (i == 0 && j == 0) continue;
 				const int rx = x + i, ry = y + j;
 				if (!(rx >= 0 && rx < W && ry >= 0 && ry < H)) continue;
-				if (is_set(a.selected[rx + ry * W], v) != 1) continue;
-				const float w = weight_colour(RefPatch::ref_pixel(a, rx, ry), ref_center_pix, rcp_c);
+				const uint32_t selv = tiled ? s_sel[ly + j][lx + i] : a.selected[rx + ry * W];
+				if (is_set(selv, v) != 1) continue;
+				const float pix = tiled ? s_img[ly + j][lx + i] : RefPatch::ref_pixel(a, rx, ry);
+				const float w = weight_colour(pix, ref_center_pix, rcp_c);
 				const int r = (abs(i) <= 5 && abs(j) <= 5) ? g_sector[i + 5][j + 5] : -1;
 				if (r < 0) continue;
 				// bubble sort descending, stable: the first pixel in scan order wins ties
