@@ -65,26 +65,68 @@ __global__ void __launch_bounds__(256) k_edge_inform_pixel(const __grid_constant
 		}
 	}
 	if (a.prm.use_label && state == DVP_WEAK) {
-		const int center_label = a.label[center];
-		if (center_label > 0) {
-			short2* lab_bound = a.label_boundary + (size_t)a.neighbours_map[center] * DVP_LAB_BOUNDARY_NUM;
-			for (int i = 0; i < DVP_LAB_BOUNDARY_NUM; i++) {
-				const int dx = c_dir8[i][0], dy = c_dir8[i][1];
-				int nx = x + dx, ny = y + dy;
-				int last_x = -1, last_y = -1;
-				while (true) {
-					if (nx < 0 || nx >= W || ny < 0 || ny >= H) break;
-					const int next_label = a.label[nx + ny * W];
-					if (next_label == center_label) { last_x = nx; last_y = ny; }
-					else if (next_label == -1) break;
-					nx += dx; ny += dy;
-				}
-				lab_bound[i] = make_short2((short)last_x, (short)last_y);
-			}
-		}
-		if (a.prm.state == DVP_REFINE_INIT && a.prm.use_detail && center_label == 0) {
+		// the label-boundary rays of part (d) are produced by k_label_boundary_sweep (launched before this kernel)
+		if (a.prm.state == DVP_REFINE_INIT && a.prm.use_detail && a.label[center] == 0) {
 			if (state != DVP_STRONG) a.weak[center] = DVP_UNKNOWN;
 		}
+	}
+}
+
+// K2 part (d) (APD.cu:3855-3885): for every WEAK pixel with a positive label, the LAST pixel carrying the same
+// label along each of 8 rays before the ray leaves the image or meets a label of -1.  The reference walks every
+// ray from every WEAK pixel (rays are unbounded: thousands of reads per pixel inside a large region).  Walking
+// each image line ONCE from its far end, "last same-label pixel ahead of p" is the first position at which that
+// label was met since the last -1 barrier; a 12-entry (label, position) table per line holds it.  If a segment
+// ever carries more than 12 distinct labels, pixels whose label is not in the table fall back to the reference's
+// forward walk, so the result is exact in every case.
+__global__ void __launch_bounds__(128) k_label_boundary_sweep(const __grid_constant__ KArgs a) {
+	const int W = a.W, H = a.H;
+	const int n_diag = W + H - 1;
+	const int counts[8] = {W, W, H, H, n_diag, n_diag, n_diag, n_diag};
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	int d = 0;
+	while (d < 8 && t >= counts[d]) { t -= counts[d]; ++d; }
+	if (d >= 8) return;
+	const int dx = c_dir8[d][0], dy = c_dir8[d][1];
+	int x, y;
+	if (dx == 0) { x = t; y = (dy > 0) ? H - 1 : 0; }
+	else if (dy == 0) { y = t; x = (dx > 0) ? W - 1 : 0; }
+	else {
+		const int ex = (dx > 0) ? W - 1 : 0, ey = (dy > 0) ? H - 1 : 0;
+		if (t < W) { x = t; y = ey; }
+		else { const int k = t - W; x = ex; y = (ey == 0) ? k + 1 : k; }
+	}
+	constexpr int CAP = 12;
+	int lab[CAP]; short2 pos[CAP];
+	int n = 0;
+	bool overflow = false;
+	const bool demote_edges = a.prm.use_edge && a.prm.state == DVP_REFINE_INIT && a.prm.use_detail;
+	while (x >= 0 && x < W && y >= 0 && y < H) {
+		const int q = y * W + x;
+		const int L = a.label[q];
+		int hit = -1;
+		for (int k = 0; k < n; ++k) if (lab[k] == L) { hit = k; break; }
+		// same condition as the reference thread: still WEAK after its own edge demotion (APD.cu:3847-3855)
+		if (L > 0 && a.weak[q] == DVP_WEAK && !(demote_edges && a.edge[q])) {
+			short2 out = make_short2(-1, -1);
+			if (hit >= 0) out = pos[hit];
+			else if (overflow) {   // exact fallback: the reference's forward walk
+				int nx = x + dx, ny = y + dy;
+				while (nx >= 0 && nx < W && ny >= 0 && ny < H) {
+					const int nl = a.label[nx + ny * W];
+					if (nl == L) out = make_short2((short)nx, (short)ny);
+					else if (nl == -1) break;
+					nx += dx; ny += dy;
+				}
+			}
+			a.label_boundary[(size_t)a.neighbours_map[q] * DVP_LAB_BOUNDARY_NUM + d] = out;
+		}
+		if (L == -1) { n = 0; overflow = false; }
+		else if (hit < 0) {
+			if (n < CAP) { lab[n] = L; pos[n] = make_short2((short)x, (short)y); ++n; }
+			else overflow = true;
+		}
+		x -= dx; y -= dy;
 	}
 }
 
@@ -276,6 +318,10 @@ cudaError_t launch_edge_inform_prep(const KArgs& a, cudaStream_t st) {
 	if (a.prm.use_edge) {
 		const int total = 2 * a.W + 2 * a.H + 4 * (a.W + a.H - 1);
 		k_edge_neigh_sweep<<<(total + 127) / 128, 128, 0, st>>>(a);
+	}
+	if (a.prm.use_label && a.weak_count > 0) {
+		const int total = 2 * a.W + 2 * a.H + 4 * (a.W + a.H - 1);
+		k_label_boundary_sweep<<<(total + 127) / 128, 128, 0, st>>>(a);   // reads the pixel states before the demotions below
 	}
 	dim3 b(32, 8);
 	dim3 g((a.W + 31) / 32, (a.H + 7) / 8, 1);

@@ -444,6 +444,7 @@ __device__ __forceinline__ float profile_cost_sum(const KArgs& a, int x, int y, 
 	return acc;
 }
 
+template <bool WITH_COST>   // DepthToWeak never uses the cost of the current depth (APD.cu:3957 is dead there): K15 skips those NCCs
 __device__ __forceinline__ void profile_front(const KArgs& a, int x, int y, int center, uint32_t sel, const ViewWeights& vw,
                                               const RefPatch& rp, const float2* wt, int T, ProfileCtx& pc) {
 	pc.cost_now = 0.0f; pc.base_line = 0; pc.valid = 0; pc.weight_normal = 0.0f;
@@ -461,12 +462,14 @@ __device__ __forceinline__ void profile_front(const KArgs& a, int x, int y, int 
 	}
 	for (int v = 0; v < a.S; ++v) {
 		if (!is_set(sel, v)) continue;
-		float4 t = pc.plane;
-		t.w = w_front;
-		float temp_cost = ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, t, rp, wt, T);
-		if (a.prm.geom_consistency) temp_cost += a.prm.geom_factor * geom_cost(a, a.views[v], a.tex_depth[v + 1], x, y, t);
 		const int wv = vw.get(v);
-		pc.cost_now += (temp_cost * wv);
+		if (WITH_COST) {
+			float4 t = pc.plane;
+			t.w = w_front;
+			float temp_cost = ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, t, rp, wt, T);
+			if (a.prm.geom_consistency) temp_cost += a.prm.geom_factor * geom_cost(a, a.views[v], a.tex_depth[v + 1], x, y, t);
+			pc.cost_now += (temp_cost * wv);
+		}
 		pc.weight_normal += wv;
 		const dvp_camera& sc = a.cams[v + 1];
 		float c_dist[3];
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(256, 3) k_depth_to_weak(const __grid_constant_
 	ViewWeights vw; vw.load(a.view_weight + (size_t)center * DVP_MAX_IMAGES);
 	RefPatch rp;
 	rp.prepare(a, x, y, a.prm.use_radius ? a.radius[center] : a.prm.strong_radius, wt, T);
-	profile_front(a, x, y, center, sel, vw, rp, wt, T, pc);
+	profile_front<false>(a, x, y, center, sel, vw, rp, wt, T, pc);
 	if (pc.valid == 0) { a.weak[center] = DVP_UNKNOWN; return; }
 	pc.cost_now /= pc.weight_normal;
 	pc.base_line /= pc.valid;
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(256, 3) k_local_refine(const __grid_constant__
 	ViewWeights vw; vw.load(a.view_weight + (size_t)center * DVP_MAX_IMAGES);
 	RefPatch rp;
 	rp.prepare(a, x, y, a.prm.use_radius ? a.radius[center] : a.prm.strong_radius, wt, T);
-	profile_front(a, x, y, center, sel, vw, rp, wt, T, pc);
+	profile_front<true>(a, x, y, center, sel, vw, rp, wt, T, pc);
 	if (pc.weight_normal == 0 || pc.valid == 0) return;
 	pc.cost_now /= pc.weight_normal;
 	pc.base_line /= pc.valid;

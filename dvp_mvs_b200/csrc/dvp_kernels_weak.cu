@@ -13,6 +13,9 @@ __constant__ int c_dirw[8][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}, {-1, -1}, {1,
 // 30-degree sector of every offset of the 11x11 window, filled once on the device with the same double
 // atan2 the reference evaluates 120 times per pixel per view (calculateAngle / getRegion, APD.cu:797-821)
 __device__ int8_t g_sector[11][11];
+// the same table, sector-major: the offsets of each sector in the reference's scan order (i outer, j inner)
+__device__ int g_sector_cnt[12];
+__device__ char2 g_sector_off[12][24];
 
 __global__ void k_fill_sector_table() {
 	const int i = (int)threadIdx.x - 5, j = (int)threadIdx.y - 5;
@@ -22,6 +25,16 @@ __global__ void k_fill_sector_table() {
 	for (int r = 0; r < 12; ++r)
 		if (angle >= 30.0 * r && angle < 30.0 * (r + 1)) region = r;
 	g_sector[threadIdx.x][threadIdx.y] = (int8_t)region;
+	__syncthreads();
+	if (threadIdx.x == 0 && threadIdx.y == 0) {
+		for (int r = 0; r < 12; ++r) g_sector_cnt[r] = 0;
+		for (int ii = -5; ii <= 5; ++ii)
+			for (int jj = -5; jj <= 5; ++jj) {
+				if (ii == 0 && jj == 0) continue;
+				const int r = g_sector[ii + 5][jj + 5];
+				if (r >= 0 && g_sector_cnt[r] < 24) g_sector_off[r][g_sector_cnt[r]++] = make_char2((signed char)ii, (signed char)jj);
+			}
+	}
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -55,38 +68,66 @@ __global__ void __launch_bounds__(256) k_candidate(const __grid_constant__ KArgs
 	const int lx = threadIdx.x + R, ly = threadIdx.y + R;
 	const float ref_center_pix = s_img[ly][lx];
 	for (int v = 0; v < a.S; ++v) {
-		float best_w[12]; int8_t bi[12], bj[12]; bool has[12];
+		// sector by sector (static register indexing): the winner of a sector is its largest weight, first in scan
+		// order on ties — what the reference's stable descending bubble sort leaves in regions[r][0]
+		float best_w[12]; int best_ij[12];   // (i, j) packed; -1 = empty sector
 #pragma unroll
-		for (int r = 0; r < 12; ++r) { best_w[r] = 0.f; bi[r] = 0; bj[r] = 0; has[r] = false; }
-		for (int i = -radius; i <= radius; i++)
-			for (int j = -radius; j <= radius; j++) {
-				if (i == 0 && j == 0) continue;
+		for (int r = 0; r < 12; ++r) {
+			float bw = 0.f; int bij = -1;
+			const int cnt = tiled ? g_sector_cnt[r] : 0;
+			for (int k = 0; k < cnt; ++k) {
+				const char2 o = g_sector_off[r][k];
+				const int i = o.x, j = o.y;
 				const int rx = x + i, ry = y + j;
 				if (!(rx >= 0 && rx < W && ry >= 0 && ry < H)) continue;
-				const uint32_t selv = tiled ? s_sel[ly + j][lx + i] : a.selected[rx + ry * W];
-				if (is_set(selv, v) != 1) continue;
-				const float pix = tiled ? s_img[ly + j][lx + i] : RefPatch::ref_pixel(a, rx, ry);
-				const float w = weight_colour(pix, ref_center_pix, rcp_c);
-				const int r = (abs(i) <= 5 && abs(j) <= 5) ? g_sector[i + 5][j + 5] : -1;
-				if (r < 0) continue;
-				// bubble sort descending, stable: the first pixel in scan order wins ties
-				if (!has[r] || w > best_w[r]) { has[r] = true; best_w[r] = w; bi[r] = (int8_t)i; bj[r] = (int8_t)j; }
+				if (is_set(s_sel[ly + j][lx + i], v) != 1) continue;
+				const float w = weight_colour(s_img[ly + j][lx + i], ref_center_pix, rcp_c);
+				if (bij < 0 || w > bw) { bw = w; bij = ((i + 5) << 4) | (j + 5); }
 			}
-		// stable descending sort of the 12 sector winners; empty sectors last
-		int order[12];
+			best_w[r] = bw; best_ij[r] = bij;
+		}
+		if (!tiled) {   // weak_radius != 5: generic window, global reads (never the case in the reference's schedules)
+			for (int i = -radius; i <= radius; i++)
+				for (int j = -radius; j <= radius; j++) {
+					if (i == 0 && j == 0) continue;
+					const int rx = x + i, ry = y + j;
+					if (!(rx >= 0 && rx < W && ry >= 0 && ry < H)) continue;
+					if (is_set(a.selected[rx + ry * W], v) != 1) continue;
+					double angle = atan2((double)j, (double)i) * (180.0 / 3.14159265358979323846);
+					if (angle < 0) angle += 360.0;
+					const int r = (int)(angle / 30.0);
+					if (r < 0 || r > 11) continue;
+					const float w = weight_colour(RefPatch::ref_pixel(a, rx, ry), ref_center_pix, rcp_c);
 #pragma unroll
-		for (int r = 0; r < 12; ++r) order[r] = r;
+					for (int rr = 0; rr < 12; ++rr)
+						if (rr == r && (best_ij[rr] < 0 || w > best_w[rr])) { best_w[rr] = w; best_ij[rr] = ((i + 64) << 8) | (j + 64) | (1 << 20); }
+				}
+		}
+		// stable descending sort of the 12 sector winners (bubbleSort, APD.cu:823-833); empty sectors last
+#pragma unroll
 		for (int p = 0; p < 11; ++p)
+#pragma unroll
 			for (int q = 0; q < 11 - p; ++q) {
-				const int r0 = order[q], r1 = order[q + 1];
-				const bool swap = has[r1] && (!has[r0] || best_w[r0] < best_w[r1]);
-				if (swap) { order[q] = r1; order[q + 1] = r0; }
+				const bool swap = best_ij[q + 1] >= 0 && (best_ij[q] < 0 || best_w[q] < best_w[q + 1]);
+				if (swap) {
+					const float tw = best_w[q]; best_w[q] = best_w[q + 1]; best_w[q + 1] = tw;
+					const int ti = best_ij[q]; best_ij[q] = best_ij[q + 1]; best_ij[q + 1] = ti;
+				}
 			}
 		short2* cand = a.candidate + ((size_t)center * DVP_NUM_IMAGES + v) * DVP_LAB_BOUNDARY_NUM;
+		short2 outc[DVP_LAB_BOUNDARY_NUM];
+#pragma unroll
 		for (int k = 0; k < DVP_LAB_BOUNDARY_NUM; ++k) {
-			const int r = order[k];
-			cand[k] = has[r] ? make_short2(bi[r], bj[r]) : make_short2(0, 0);
+			const int b = best_ij[k];
+			if (b < 0) outc[k] = make_short2(0, 0);
+			else if (b & (1 << 20)) outc[k] = make_short2((short)(((b >> 8) & 0xff) - 64), (short)((b & 0xff) - 64));
+			else outc[k] = make_short2((short)((b >> 4) - 5), (short)((b & 15) - 5));
 		}
+		// one 32-byte record per (pixel, view): two 16-byte stores
+		uint4* c4 = reinterpret_cast<uint4*>(cand);
+		const uint32_t* o32 = reinterpret_cast<const uint32_t*>(outc);
+		c4[0] = make_uint4(o32[0], o32[1], o32[2], o32[3]);
+		c4[1] = make_uint4(o32[4], o32[5], o32[6], o32[7]);
 	}
 }
 
@@ -281,10 +322,12 @@ __global__ void __launch_bounds__(64) k_gen_neighbours(const __grid_constant__ K
 		float min_cost = FLT_MAX;
 		int max_count = 3;
 		// edge_test[160][160] of the reference, 2 bits per pair (0 unknown, 1 crosses an edge, 2 clear): 6.4 KB instead of 25.6 KB
+		// (indexed with the actual number of anchors, so a typical pixel touches ~2 KB of it)
 		uint32_t edge_test[kMaxPts * kMaxPts / 16];
-		for (int i = 0; i < kMaxPts * kMaxPts / 16; ++i) edge_test[i] = 0;
-		auto et_get = [&](int r, int c) -> int { const int b = r * kMaxPts + c; return (edge_test[b >> 4] >> ((b & 15) * 2)) & 3; };
-		auto et_set = [&](int r, int c, int val) { const int b = r * kMaxPts + c; edge_test[b >> 4] = (edge_test[b >> 4] & ~(3u << ((b & 15) * 2))) | ((uint32_t)val << ((b & 15) * 2)); };
+		const int et_words = (valid_count * valid_count + 15) / 16;
+		for (int i = 0; i < et_words; ++i) edge_test[i] = 0;
+		auto et_get = [&](int r, int c) -> int { const int b = r * valid_count + c; return (edge_test[b >> 4] >> ((b & 15) * 2)) & 3; };
+		auto et_set = [&](int r, int c, int val) { const int b = r * valid_count + c; edge_test[b >> 4] = (edge_test[b >> 4] & ~(3u << ((b & 15) * 2))) | ((uint32_t)val << ((b & 15) * 2)); };
 		auto crossing = [&](int i0, int i1) -> int {
 			int e = et_get(i0, i1);
 			if (e == 0) {

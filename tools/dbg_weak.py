@@ -33,6 +33,17 @@ res = step_compare(ref2, prod, 1, log=print)
 bad = [r for r in res if r.get("error") or r["mismatched"]]
 print("stages with mismatches:", sorted(set((r["stage"], r.get("buffer")) for r in bad)))
 
+# K2 candidate offsets: the reference leaves empty sectors uninitialised (B17), so compare per (pixel, view) record
+ref2.upload(**kw); prod.upload(**kw)
+ref2.run_stage("K1_INIT_RANDOM_STATES"); prod.run_stage("K1_INIT_RANDOM_STATES")
+ref2.run_stage("K2_GEN_EDGE_INFORM"); prod.run_stage("K2_GEN_EDGE_INFORM")
+ca, cb = ref2.get("candidate"), prod.get("candidate")
+rec_eq = (ca == cb).reshape(H, W, 4, -1).all(-1)[:, :, :S]
+# records where the whole 11x11 window sees the view: all 12 sectors are populated, nothing is undefined
+seen = np.stack([((sel >> v) & 1).astype(bool) for v in range(S)], -1)
+from scipy.ndimage import minimum_filter
+full = np.stack([minimum_filter(seen[..., v].astype(np.uint8), size=11, mode="constant", cval=0) > 0 for v in range(S)], -1)
+print("candidate records equal: all %.4f | fully visible windows %.6f (%d records)" % (rec_eq.mean(), rec_eq[full].mean(), full.sum()))
 # how much did the weak path actually do?
 ref2.upload(**kw); prod.upload(**kw)
 ref2.run(mode=0); prod.run()
