@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) k_init_rng(const __grid_constant__ KArgs 
 // (APD.cu:1115-1194).
 __global__ void __launch_bounds__(256, 3) k_random_init(const __grid_constant__ KArgs a) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int T = blockDim.x * blockDim.y;
+	constexpr int T = 256;   // compile-time stride: shared-memory offsets become immediates
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
 	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
 	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, 3) k_random_init(const __grid_constant__ 
 // shared memory per thread: 36 float2 (w, w r) + 9*S floats (8 direction cost vectors + 1 spare) + 8 ints.
 __global__ void __launch_bounds__(kSweepThreads, 3) k_strong_sweep(const __grid_constant__ KArgs a, int iter, int red, int yy_limit) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int T = blockDim.x * blockDim.y;
+	constexpr int T = kSweepThreads;   // compile-time stride: shared-memory offsets become immediates
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
 	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
 	float* cost_arr = reinterpret_cast<float*>(smem_raw + (size_t)kHoistSamples * T * sizeof(float2)) + tid;
@@ -485,7 +485,7 @@ __device__ __forceinline__ void profile_front(const KArgs& a, int x, int y, int 
 // K15 DepthToWeak (APD.cu:3892-4051): 61-step disparity cost profile -> STRONG / WEAK / UNKNOWN.
 __global__ void __launch_bounds__(256, 3) k_depth_to_weak(const __grid_constant__ KArgs a) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int T = blockDim.x * blockDim.y;
+	constexpr int T = 256;   // compile-time stride: shared-memory offsets become immediates
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
 	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
 	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(256, 3) k_depth_to_weak(const __grid_constant_
 // K16 LocalRefine (APD.cu:4053-4139): 11-step disparity scan, keep the best depth if it improves by > 0.1.
 __global__ void __launch_bounds__(256, 3) k_local_refine(const __grid_constant__ KArgs a) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int T = blockDim.x * blockDim.y;
+	constexpr int T = 256;   // compile-time stride: shared-memory offsets become immediates
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
 	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
 	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;

@@ -697,12 +697,12 @@ __global__ void __launch_bounds__(64) k_weak_sweep(const __grid_constant__ KArgs
 		extern __shared__ __align__(16) unsigned char smem_raw[];
 		float2* wt = reinterpret_cast<float2*>(smem_raw) + threadIdx.x;
 		RefPatch rp;
-		rp.prepare(a, px, py, a.prm.strong_radius, wt, blockDim.x);
+		rp.prepare(a, px, py, a.prm.strong_radius, wt, 64);
 		float c2 = 0.0f;
 		for (int i = 0; i < S; ++i) {
 			const int wv = vw.get(i);
 			if (wv == 0) continue;
-			c2 += wv * ncc_cost<1>(a, a.views[i], a.tex_img[i + 1], px, py, plane_final, rp, wt, blockDim.x);
+			c2 += wv * ncc_cost<1>(a, a.views[i], a.tex_img[i + 1], px, py, plane_final, rp, wt, 64);
 		}
 		c2 /= weight_norm;
 		a.costs[center] = c2;

@@ -5,7 +5,7 @@
 namespace dvp {
 
 constexpr int kSweepThreads = 128;  // threads per block of the propagation sweep (3 blocks / SM at S = 4)
-constexpr int kSweepRB = 2;         // patch rows of texture fetches in flight per thread in the sweep (all 36 samples)
+constexpr int kSweepRB = 3;         // patch rows of texture fetches in flight per thread in the sweep (all 36 samples)
 constexpr int kWideRB = 2;          // ... in the 256-thread, 24-warp/SM kernels (K6, K15, K16)
 
 // shared memory: 36 (w, w*r) pairs per thread

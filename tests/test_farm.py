@@ -59,8 +59,12 @@ def test_two_rank_gloo_pass_gathers_every_view(tmp_path):
         print("RANK_OK", rank, seen)
         dist.destroy_process_group()
     """))
+    import socket
+    with socket.socket() as sock:   # a free rendezvous port (a fixed one can still be in TIME_WAIT from an earlier run)
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29641", str(script)], capture_output=True, text=True, env=env, timeout=300)
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "RANK_OK 0 [0, 2, 4]" in r.stdout and "RANK_OK 1 [1, 3]" in r.stdout

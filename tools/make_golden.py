@@ -81,5 +81,28 @@ for it in range(2):
             gold[f"{k:02d}_{st}_{it}__{n}"] = a[weak == STRONG]   # only STRONG pixels can change
         k += 1
 np.savez_compressed(os.path.join(out_dir, "sparse_128x96.npz"), **gold)
+# ---- WEAK path: pass 2 (rounds >= 1 parameters) on the output of a reference pass 1 ------------------------------
+from dvp_mvs_b200 import REFINE_INIT
+W, H, S = 96, 72, 2
+sc = synth.make_scene(W, H, S)
+p1 = params_for(sc, S, 2, 0)
+ref = ref_oracle.engine(W, H, S, p1)
+ref.upload(images=sc.images, cameras=sc.cameras, planes=sc.planes_init, edge=sc.edge, label=sc.label, seed=synth.SEED_RNG)
+ref.run(mode=0)
+planes1, weak1, sel1, rad1 = ref.download()
+q = params_for(sc, S, 1, 1)
+q.state = REFINE_INIT; q.use_detail = 1; q.ransac_threshold = 0.00875; q.rotate_time = 2
+ref2 = ref_oracle.engine(W, H, S, q)
+ref2.upload(images=sc.images, cameras=sc.cameras, planes=planes1, selected_views=sel1, weak_info=weak1, edge=sc.edge, label=sc.label,
+            radius=rad1, seed=synth.SEED_RNG + 1)
+gold = dict(images=sc.images, cameras=sc.cameras.view(np.uint8), edge=sc.edge, label=sc.label, planes_in=planes1, weak_in=weak1,
+            selected_in=sel1, radius_in=rad1, depth_min=np.float32(sc.depth_min), depth_max=np.float32(sc.depth_max),
+            seed=np.uint64(synth.SEED_RNG + 1))
+for k, (stage, it) in enumerate(sequence(1)):
+    ref2.run_stage(stage, it)
+    for n in STAGE_OUTPUTS[stage] + (("candidate",) if stage == "K2_GEN_EDGE_INFORM" else ()):
+        gold[f"{k:02d}_{stage}__{n}"] = ref2.get(n)
+np.savez_compressed(os.path.join(out_dir, "weak_96x72.npz"), **gold)
+print("weak golden: weak pixels", int((weak1 == 0).sum()))
 for f in sorted(os.listdir(out_dir)):
     print(f, os.path.getsize(os.path.join(out_dir, f)))
