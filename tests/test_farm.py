@@ -56,7 +56,7 @@ def test_two_rank_gloo_pass_gathers_every_view(tmp_path):
             owner = v % 2
             assert (out[v]["depth"] == 10 * v + owner).all() and out[v]["weak"].dtype == np.uint8 and (out[v]["weak"] == v).all()
         assert seen == partition(5, 2, rank)
-        print("RANK_OK", rank, seen)
+        open(os.path.join({str(tmp_path)!r}, f"rank{{rank}}.txt"), "w").write(f"RANK_OK {{rank}} {{seen}}")
         dist.destroy_process_group()
     """))
     import socket
@@ -67,4 +67,5 @@ def test_two_rank_gloo_pass_gathers_every_view(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "RANK_OK 0 [0, 2, 4]" in r.stdout and "RANK_OK 1 [1, 3]" in r.stdout
+    assert (tmp_path / "rank0.txt").read_text() == "RANK_OK 0 [0, 2, 4]"   # one file per rank: stdout of two ranks interleaves
+    assert (tmp_path / "rank1.txt").read_text() == "RANK_OK 1 [1, 3]"
