@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from util import c1_params, load_golden, golden_inputs, close, per_pixel
+from dvp_mvs_b200 import synth
 import cpu_oracle
 from dvp_mvs_b200.parity import sequence, STAGE_OUTPUTS
 
