@@ -224,7 +224,11 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_strong_sweep(const __grid_
 				const float c = a.costs[tc];
 				if (min_cost > c) { min_pos = tc; min_cost = c; }
 			}
-			if (min_cost < FLT_MAX) {
+			// Same winner as the adaptive ladder (always the case within 24 px of an edge, where both ladders are
+			// 11 x 2 px): the plane is the one just scored, every c1 equals its c0, the tallies tie and nothing is
+			// replaced (APD.cu:2126) — so the S NCCs are not recomputed.
+			const bool same_winner = has_before && min_pos == pos_arr[d * T];
+			if (min_cost < FLT_MAX && !same_winner) {
 				flag |= 1u << d;
 				const float4 pl = a.planes[min_pos];
 				int good0 = 0, good1 = 0, bad0 = 0, bad1 = 0;
