@@ -14,6 +14,9 @@ Everything is a pure function of (W, H, S, seed).
 from __future__ import annotations
 
 import dataclasses
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 
 CAMERA_DTYPE = np.dtype(
@@ -92,14 +95,14 @@ def _bilinear_periodic(tex: np.ndarray, u: np.ndarray, v: np.ndarray) -> np.ndar
             + (1 - fu) * fv * tex[iv1, iu] + fu * fv * tex[iv1, iu1])
 
 
-def _render(K, R, c, W, H, planes, textures, texels_per_m, rows_per_chunk=256):
+def _render(K, R, c, W, H, planes, textures, texels_per_m, rows_per_chunk=64):
     """Ray-cast one view. Returns image, z-depth, plane id, camera-frame normal per pixel."""
     img = np.zeros((H, W), np.float32); dep = np.zeros((H, W), np.float32)
     pid = np.full((H, W), -1, np.int32)
     fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
     xs = (np.arange(W, dtype=np.float64) - cx) / fx
     Rt = R.T
-    for y0 in range(0, H, rows_per_chunk):
+    def chunk(y0):
         y1 = min(H, y0 + rows_per_chunk)
         ys = (np.arange(y0, y1, dtype=np.float64) - cy) / fy
         dx, dy = np.meshgrid(xs, ys)
@@ -127,6 +130,16 @@ def _render(K, R, c, W, H, planes, textures, texels_per_m, rows_per_chunk=256):
         img[y0:y1] = best_val.astype(np.float32)
         dep[y0:y1] = np.where(np.isfinite(best_t), best_t, 0.0).astype(np.float32)
         pid[y0:y1] = best_id
+
+    # row chunks are independent (each writes its own rows): rendered on a thread pool, numpy releases the GIL
+    starts = list(range(0, H, rows_per_chunk))
+    workers = min(len(starts), os.cpu_count() or 1)
+    if workers > 1:
+        with ThreadPoolExecutor(workers) as ex:
+            list(ex.map(chunk, starts))
+    else:
+        for y0 in starts:
+            chunk(y0)
     return img, dep, pid
 
 
