@@ -16,7 +16,8 @@ import numpy as np
 from .synth import CAMERA_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_LIB = os.path.join(_HERE, "libdvp_mvs.so")
+# DVP_MVS_LIB selects another build of the same CUDA library (tuning variants, see csrc/Makefile); never a CPU path
+PRODUCT_LIB = os.environ.get("DVP_MVS_LIB") or os.path.join(_HERE, "libdvp_mvs.so")
 
 FIRST_INIT, REFINE_INIT, REFINE_ITER = 0, 1, 2
 WEAK, STRONG, UNKNOWN = 0, 1, 2
@@ -64,7 +65,7 @@ STATUS = {0: "DVP_OK", -1: "DVP_ERR_ARG", -2: "DVP_ERR_CUDA", -3: "DVP_ERR_STATE
 
 ABI_SYMBOLS = ["version", "default_params", "create", "destroy", "upload", "run", "run_stage", "download",
                "buffer_bytes", "get_buffer", "set_buffer", "last_run_times", "weak_count", "last_cuda_error", "stream"]
-PRODUCT_ONLY_SYMBOLS = ["upload_device"]
+PRODUCT_ONLY_SYMBOLS = ["upload_device", "restore_visibility"]
 
 
 class DvpError(RuntimeError):
@@ -96,6 +97,7 @@ def load_library(path: str, prefix: str):
     f("stream").argtypes = [C.c_void_p]; f("stream").restype = C.c_void_p
     if prefix == "dvp_":
         f("upload_device").argtypes = [C.c_void_p, C.POINTER(Inputs), C.POINTER(Params)]; f("upload_device").restype = C.c_int
+        f("restore_visibility").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]; f("restore_visibility").restype = C.c_int
     return lib
 
 
@@ -201,6 +203,12 @@ class Engine:
         total = C.c_float(); per = (C.c_float * 16)(); n = C.c_int()
         self._check(self._f("last_run_times")(self.ctx, C.byref(total), per, C.byref(n)), "last_run_times")
         return float(total.value), [float(x) for x in per], int(n.value)
+
+    def restore_visibility(self, scale_size: int) -> float:
+        """Post-pass of ProcessProblem on the resident maps (main.cpp:297-363); returns the device time in ms."""
+        ms = C.c_float()
+        self._check(self._f("restore_visibility")(self.ctx, int(scale_size), C.byref(ms)), "restore_visibility")
+        return float(ms.value)
 
     def weak_count(self) -> int:
         return int(self._f("weak_count")(self.ctx))

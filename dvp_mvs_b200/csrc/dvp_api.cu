@@ -68,6 +68,8 @@ struct dvp_ctx {
 	int* colour_list[2] = {nullptr, nullptr};  // WEAK pixels of one checkerboard colour (dense warps in the weak sweep)
 	int colour_count[2] = {0, 0};
 	int* scan_blocks_c[2] = {nullptr, nullptr};
+	int* vis_parent = nullptr;  // union-find links / region sizes of dvp_restore_visibility (allocated on first use)
+	int* vis_count = nullptr;
 	// host staging
 	std::vector<int32_t> h_i32;
 	std::vector<uint8_t> h_u8;
@@ -255,6 +257,7 @@ int upload_common(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params, 
 	if (in->radius) CK(cudaMemcpyAsync(ctx->radius, in->radius, N * 4, kind, st));
 	else CK(launch_fill_i32(ctx->radius, ctx->prm.strong_radius, ctx->N, st));
 	if (have_weak && in->radius) CK(launch_reset_unknown_radius(ctx->weak, ctx->radius, ctx->prm.strong_radius, ctx->N, st));
+	CK(launch_fill_sd_table(st));
 	CK(configure_strong_kernels(ctx->S));
 	CK(configure_weak_kernels(ctx->S));
 	CK(cudaStreamSynchronize(st));
@@ -341,6 +344,7 @@ void dvp_destroy(dvp_ctx* c) {
 	cudaFree(c->radius); cudaFree(c->view_weight); cudaFree(c->rng); cudaFree(c->edge); cudaFree(c->edge_neigh);
 	cudaFree(c->label); cudaFree(c->candidate); cudaFree(c->nearest_strong); cudaFree(c->weak_reliable);
 	cudaFree(c->neighbours_map); cudaFree(c->neighbours); cudaFree(c->label_boundary); cudaFree(c->complex_); cudaFree(c->weak_list); cudaFree(c->scan_blocks); cudaFree(c->scan_total); cudaFree(c->next_right); cudaFree(c->next_down); for (int k = 0; k < 2; ++k) { cudaFree(c->scan_blocks_c[k]); cudaFree(c->colour_list[k]); }
+	cudaFree(c->vis_parent); cudaFree(c->vis_count);
 	for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -473,6 +477,24 @@ int dvp_set_buffer(dvp_ctx* ctx, int buffer, const void* src, size_t bytes) {
 	}
 	CK(cudaMemcpyAsync(b.ptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
+	return DVP_OK;
+}
+
+int dvp_restore_visibility(dvp_ctx* ctx, int scale_size, float* device_ms) {
+	if (!ctx || scale_size <= 0) return DVP_ERR_ARG;
+	if (!ctx->uploaded) return DVP_ERR_STATE;
+	CK(cudaSetDevice(ctx->device));
+	if (!ctx->vis_parent) CK(zalloc(&ctx->vis_parent, (size_t)ctx->N));
+	if (!ctx->vis_count) CK(zalloc(&ctx->vis_count, (size_t)ctx->N));
+	const KArgs a = make_args(ctx);
+	cudaStream_t st = ctx->stream;
+	const int e0 = 2 * dvp_ctx::kMaxLaunch, e1 = e0 + 1;   // the two spare events after the per-launch pairs
+	CK(cudaEventRecord(ctx->ev[e0], st));
+	CK(launch_invalidate_depth(a, st));
+	CK(launch_restore_visibility(a, scale_size, ctx->vis_parent, ctx->vis_count, st));
+	CK(cudaEventRecord(ctx->ev[e1], st));
+	CK(cudaStreamSynchronize(st));
+	if (device_ms) CK(cudaEventElapsedTime(device_ms, ctx->ev[e0], ctx->ev[e1]));
 	return DVP_OK;
 }
 

@@ -141,14 +141,17 @@ __global__ void __launch_bounds__(256, 3) k_random_init(const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------------------
 // K7/K8: red-black propagation sweep for non-WEAK pixels (edge-adaptive branch, params.use_edge).
-// shared memory per thread: 36 float2 (w, w r) + 9*S floats (8 direction cost vectors + 1 spare) + 8 ints.
-__global__ void __launch_bounds__(kSweepThreads, 3) k_strong_sweep(const __grid_constant__ KArgs a, int iter, int red, int yy_limit) {
+// shared memory per thread: 36 float2 (w, w r) + 9*S floats (8 direction cost vectors + 1 spare) + 8 u16 ladder offsets.
+__global__ void __launch_bounds__(kSweepThreads, kSweepMinBlocks) k_strong_sweep(const __grid_constant__ KArgs a, int iter, int red, int yy_limit) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	constexpr int T = kSweepThreads;   // compile-time stride: shared-memory offsets become immediates
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
-	float* cost_arr = reinterpret_cast<float*>(smem_raw + (size_t)kHoistSamples * T * sizeof(float2)) + tid;
-	int* pos_arr = reinterpret_cast<int*>(smem_raw + (size_t)kHoistSamples * T * sizeof(float2) + (size_t)9 * a.S * T * sizeof(float)) + tid;
+	float2* wt = kSweepRW ? reinterpret_cast<float2*>(reinterpret_cast<float*>(smem_raw) + tid)   // RW: a column of 36 floats (r)
+	                      : reinterpret_cast<float2*>(smem_raw) + tid;                              // else 36 (w, w r) pairs
+	constexpr size_t kTable = (size_t)kHoistSamples * T * (kSweepRW ? sizeof(float) : sizeof(float2));
+	float* cost_arr = reinterpret_cast<float*>(smem_raw + kTable) + tid;
+	// winning ladder offset per direction, in pixels along the direction (step * step_len <= 21 * max(H,W)/660 < 2^16)
+	uint16_t* pos_arr = reinterpret_cast<uint16_t*>(smem_raw + kTable + (size_t)9 * a.S * T * sizeof(float)) + tid;
 	const int S = a.S, W = a.W, H = a.H;
 
 	const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_strong_sweep(const __grid_
 	if (a.weak[center] == DVP_WEAK) return;
 
 	RefPatch rp;
-	rp.prepare(a, x, y, a.prm.use_radius ? a.radius[center] : a.prm.strong_radius, wt, T);
+	rp.prepare<kSweepRW>(a, x, y, a.prm.use_radius ? a.radius[center] : a.prm.strong_radius, wt, T);
 
 	// `float cost_array[8][32] = {2.0f}` : element [0][0] is 2, everything else 0 (bug B2, reproduced)
 	for (int s = 0; s < 8; ++s)
@@ -195,45 +198,45 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_strong_sweep(const __grid_
 			const int step_num = DVP_MIN(DVP_MAX(11, (int)(1.0f * dist / min_step_len)), 22);
 			int step_len = DVP_MAX((int)(1.0f * dist / step_num), min_step_len);
 			if (d < 4 && step_len % 2 == 1) step_len -= 1;
-			int min_pos = -1;
+			int min_pos = -1, min_k = 0;
 			float min_cost = FLT_MAX;
 			for (int step = 0; step < step_num; ++step) {
 				const int tx = x + sx + step * step_len * dx + fx, ty = y + sy + step * step_len * dy + fy;
 				if (!(tx >= 0 && ty >= 0 && tx < W && ty < H)) continue;
 				const int tc = tx + ty * W;
 				const float c = a.costs[tc];
-				if (min_cost > c) { min_pos = tc; min_cost = c; }
+				if (min_cost > c) { min_pos = tc; min_k = step * step_len; min_cost = c; }
 			}
 			if (min_cost < FLT_MAX) {
 				flag |= 1u << d;
-				pos_arr[d * T] = min_pos;
+				pos_arr[d * T] = (uint16_t)min_k;
 				const float4 pl = a.planes[min_pos];
 				for (int v = 0; v < S; ++v)
-					cost_arr[(d * S + v) * T] = ncc_cost<kSweepRB>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+					cost_arr[(d * S + v) * T] = ncc_cost<kSweepRB, kSweepRW>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
 			}
 		}
 		// ---- fixed 11 x 2 px ladder for non-edge pixels; keep the better of the two (APD.cu:2090-2140) ----
 		if (!on_edge) {
 			const bool has_before = (flag >> d) & 1;
-			int min_pos = -1;
+			int min_pos = -1, min_k = 0;
 			float min_cost = FLT_MAX;
 			for (int step = 0; step < 11; ++step) {
 				const int tx = x + sx + step * min_step_len * dx + fx, ty = y + sy + step * min_step_len * dy + fy;
 				if (!(tx >= 0 && ty >= 0 && tx < W && ty < H)) continue;
 				const int tc = tx + ty * W;
 				const float c = a.costs[tc];
-				if (min_cost > c) { min_pos = tc; min_cost = c; }
+				if (min_cost > c) { min_pos = tc; min_k = step * min_step_len; min_cost = c; }
 			}
 			// Same winner as the adaptive ladder (always the case within 24 px of an edge, where both ladders are
 			// 11 x 2 px): the plane is the one just scored, every c1 equals its c0, the tallies tie and nothing is
 			// replaced (APD.cu:2126) — so the S NCCs are not recomputed.
-			const bool same_winner = has_before && min_pos == pos_arr[d * T];
+			const bool same_winner = has_before && min_k == (int)pos_arr[d * T];
 			if (min_cost < FLT_MAX && !same_winner) {
 				flag |= 1u << d;
 				const float4 pl = a.planes[min_pos];
 				int good0 = 0, good1 = 0, bad0 = 0, bad1 = 0;
 				for (int v = 0; v < S; ++v) {
-					const float c1 = ncc_cost<kSweepRB>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+					const float c1 = ncc_cost<kSweepRB, kSweepRW>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
 					cost_arr[(8 * S + v) * T] = c1;
 					const float c0 = cost_arr[(d * S + v) * T];
 					if (c0 < good_threshold) good0++;
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_strong_sweep(const __grid_
 					if (c1 > bad_threshold) bad1++;
 				}
 				if (!has_before || good1 > good0 || (good1 == good0 && bad1 < bad0)) {
-					pos_arr[d * T] = min_pos;
+					pos_arr[d * T] = (uint16_t)min_k;
 					for (int v = 0; v < S; ++v) cost_arr[(d * S + v) * T] = cost_arr[(8 * S + v) * T];
 				}
 			}
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_strong_sweep(const __grid_
 	for (int v = 0; v < S; ++v) {
 		const int wv = vw.get(v);
 		if (wv > 0) {  // zero-weight views contribute exactly 0 in the reference
-			const float c = ncc_cost<kSweepRB>(a, a.views[v], a.tex_img[v + 1], x, y, plane_now, rp, wt, T);
+			const float c = ncc_cost<kSweepRB, kSweepRW>(a, a.views[v], a.tex_img[v + 1], x, y, plane_now, rp, wt, T);
 			cost_now += wv * c;
 		}
 	}
@@ -337,7 +340,14 @@ __global__ void __launch_bounds__(kSweepThreads, 3) k_strong_sweep(const __grid_
 	uint32_t sel_now = a.selected[center];
 
 	if ((flag >> min_cost_idx) & 1) {
-		const float4 cand = a.planes[pos_arr[min_cost_idx * T]];
+		int cx, cy;
+		{
+			const int dx = c_dir[min_cost_idx][0], dy = c_dir[min_cost_idx][1], k = pos_arr[min_cost_idx * T];
+			int fx = 0, fy = 0;
+			if (min_cost_idx > 4) { if (min_cost_idx % 2) fx = dx; else fy = dy; }
+			cx = x + 5 * dx + k * dx + fx; cy = y + 5 * dy + k * dy + fy;
+		}
+		const float4 cand = a.planes[cx + cy * W];
 		const float depth_before = depth_from_plane(a.ref, cand, x, y);
 		if (depth_before >= a.prm.depth_min && depth_before <= a.prm.depth_max && min_final < cost_now) {
 			depth_now = depth_before;
@@ -593,6 +603,24 @@ __global__ void __launch_bounds__(256, 3) k_local_refine(const __grid_constant__
 static inline dim3 full_grid(const KArgs& a, dim3 b) { return dim3((a.W + b.x - 1) / b.x, (a.H + b.y - 1) / b.y, 1); }
 static inline int ref_half_rows(int H) { return (((H / 2) + 15) / 16) * 16; }  // rows-of-pairs covered by the reference's half grid
 
+__global__ void k_fill_sd_table(float* out) {
+	const int k = threadIdx.x;
+	if (k < kHoistSamples) out[k] = RefPatch::spatial_dist(-5 + 2 * (k / kHoistAxis), -5 + 2 * (k % kHoistAxis));
+}
+cudaError_t launch_fill_sd_table(cudaStream_t st) {
+	static bool ready[64] = {false};
+	int dev = 0; cudaGetDevice(&dev);
+	if (dev >= 0 && dev < 64 && ready[dev]) return cudaSuccess;
+	float* tmp = nullptr;
+	cudaError_t e = cudaMalloc((void**)&tmp, kHoistSamples * sizeof(float));
+	if (e != cudaSuccess) return e;
+	k_fill_sd_table<<<1, 64, 0, st>>>(tmp);
+	e = cudaMemcpyToSymbolAsync(c_sd_r5, tmp, kHoistSamples * sizeof(float), 0, cudaMemcpyDeviceToDevice, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	cudaFree(tmp);
+	if (e == cudaSuccess && dev >= 0 && dev < 64) ready[dev] = true;
+	return e;
+}
 cudaError_t launch_setup_views(const dvp_camera* cams, ViewConst* views, int S, cudaStream_t st) {
 	k_setup_views<<<1, 32, 0, st>>>(cams, views, S);
 	return cudaGetLastError();

@@ -4,18 +4,31 @@
 
 namespace dvp {
 
-constexpr int kSweepThreads = 128;  // threads per block of the propagation sweep (3 blocks / SM at S = 4)
+#ifndef DVP_SWEEP_THREADS
+#define DVP_SWEEP_THREADS 128
+#endif
+#ifndef DVP_SWEEP_MIN_BLOCKS
+#define DVP_SWEEP_MIN_BLOCKS 3
+#endif
+constexpr int kSweepThreads = DVP_SWEEP_THREADS;  // threads per block of the propagation sweep
+constexpr int kSweepMinBlocks = DVP_SWEEP_MIN_BLOCKS;  // resident blocks per SM the register budget is cut for
+#ifndef DVP_SWEEP_RW
+#define DVP_SWEEP_RW 0
+#endif
+constexpr bool kSweepRW = DVP_SWEEP_RW != 0;  // sweep keeps only the reference samples in shared memory and re-evaluates the bilateral weight per use
 constexpr int kSweepRB = 3;         // patch rows of texture fetches in flight per thread in the sweep (all 36 samples)
 constexpr int kWideRB = 2;          // ... in the 256-thread, 24-warp/SM kernels (K6, K15, K16)
 
 // shared memory: 36 (w, w*r) pairs per thread
 inline size_t patch_smem_bytes(int threads) { return (size_t)kHoistSamples * threads * sizeof(float2); }
-// + 9 cost vectors of S floats + 8 candidate positions per thread
-inline size_t sweep_smem_bytes(int threads, int S) { return patch_smem_bytes(threads) + (size_t)(9 * S + 8) * threads * 4; }
+// + 9 cost vectors of S floats + 8 16-bit ladder offsets per thread
+inline size_t sweep_table_bytes(int threads) { return kSweepRW ? patch_smem_bytes(threads) / 2 : patch_smem_bytes(threads); }
+inline size_t sweep_smem_bytes(int threads, int S) { return sweep_table_bytes(threads) + (size_t)(9 * S + 4) * threads * 4; }
 
 cudaError_t configure_strong_kernels(int S);
 cudaError_t configure_weak_kernels(int S);
 
+cudaError_t launch_fill_sd_table(cudaStream_t st);
 cudaError_t launch_setup_views(const dvp_camera* cams, ViewConst* views, int S, cudaStream_t st);
 cudaError_t launch_init_rng(const KArgs& a, unsigned long long seed, cudaStream_t st);          // K1
 cudaError_t launch_edge_inform(const KArgs& a, cudaStream_t st);                                 // K2
@@ -37,6 +50,10 @@ constexpr int kWeakScanBlock = 1024;
 cudaError_t launch_weak_count(const uint8_t* weak, int n, int W, int colour, int yy_limit, int* block_sums, int* total, cudaStream_t st);
 cudaError_t launch_weak_index(const uint8_t* weak, int n, int W, int colour, int yy_limit, const int* block_offsets, int* nmap, int* weak_list, cudaStream_t st);
 cudaError_t launch_reset_unknown_radius(const uint8_t* weak, int32_t* radius, int32_t strong_radius, int n, cudaStream_t st);
+
+// post-pass on the resident maps (main.cpp:297-363): dvp_kernels_post.cu
+cudaError_t launch_invalidate_depth(const KArgs& a, cudaStream_t st);
+cudaError_t launch_restore_visibility(const KArgs& a, int scale_size, int* parent, int* count, cudaStream_t st);
 
 // canonical RNG exchange format <-> SoA planes
 cudaError_t launch_rng_export(const KArgs& a, uint32_t* dst_aos, cudaStream_t st);

@@ -27,6 +27,10 @@ namespace dvp {
 constexpr float kCostMax = 2.0f;
 constexpr float kMinVar = 1e-5f;
 
+// sqrt.approx(i*i + j*j) of the 36 offsets of the radius-5 / increment-2 patch, filled on the device with the
+// very instruction RefPatch::weight uses (launch_fill_sd_table); read by the "recompute w" form of the NCC.
+static __constant__ float c_sd_r5[kHoistSamples];
+
 // reference APD.cu:709-738 with R_relative / t_relative hoisted into ViewConst.
 __device__ __forceinline__ void compute_homography(const dvp_camera& ref, const ViewConst& vc, const float4 pl, float* H) {
 	H[0] = vc.R_rel[0] - vc.t_rel[0] * pl.x / pl.w;
@@ -70,6 +74,10 @@ struct RefPatch {
 	float var_ref;        // fma(inv_w, sum(w r r), -mean_ref^2)
 	bool degenerate;      // var_ref < kMinVar  -> every cost is kCostMax
 	bool hoisted;         // n == kHoistAxis: shared-memory table valid; otherwise the slow path recomputes weights
+	// "recompute w" form (RW): the table holds only the 36 reference samples r; w = weight(...) is re-evaluated
+	// per use (one ex2) from these.  Halves the table, which hands the freed shared memory to the L1/TEX cache.
+	float center, rcp_s, rcp_c;
+	bool sd_const;        // radius 5, increment 2: spatial distances come from c_sd_r5
 
 	__device__ __forceinline__ static float ref_pixel(const KArgs& a, int x, int y) {
 		// texture clamp addressing at texel centres == clamped integer read
@@ -78,27 +86,33 @@ struct RefPatch {
 		return __ldg(a.ref_img + (size_t)y * a.W + x);
 	}
 	// reference APD.cu:776-781 as compiled: ex2(log2e * fma(-sqrt(i*i + j*j), 1/(2 ss^2), -(|r - rc| * 1/(2 sc^2))))
-	__device__ __forceinline__ static float weight(int i, int j, float pix, float center, float rcp_s, float rcp_c) {
+	__device__ __forceinline__ static float spatial_dist(int i, int j) {
 		const float fi = (float)i, fj = (float)j;
-		const float d2 = __fmaf_rn(fj, fj, __fmul_rn(fi, fi));
-		const float sd = sqrt_approx(d2);
+		return sqrt_approx(__fmaf_rn(fj, fj, __fmul_rn(fi, fi)));
+	}
+	__device__ __forceinline__ static float weight_sd(float sd, float pix, float center, float rcp_s, float rcp_c) {
 		const float cd = __fmul_rn(fabsf(__fadd_rn(pix, -center)), rcp_c);
 		const float e = __fmaf_rn(-sd, rcp_s, -cd);
 		return ex2_approx(__fmul_rn(e, 1.4426950216293334961f));
+	}
+	__device__ __forceinline__ static float weight(int i, int j, float pix, float center, float rcp_s, float rcp_c) {
+		return weight_sd(spatial_dist(i, j), pix, center, rcp_s, rcp_c);
 	}
 	__device__ __forceinline__ static void sigma_rcps(const dvp_params& p, float& rcp_s, float& rcp_c) {
 		rcp_s = rcp_approx(__fmul_rn(p.sigma_spatial, __fadd_rn(p.sigma_spatial, p.sigma_spatial)));
 		rcp_c = rcp_approx(__fmul_rn(p.sigma_color, __fadd_rn(p.sigma_color, p.sigma_color)));
 	}
 
+	template <bool RW = false>
 	__device__ __forceinline__ void prepare(const KArgs& a, int px, int py, int rad, float2* wt, int stride) {
 		radius = rad;
 		inc = a.prm.strong_increment;
 		if (a.prm.use_radius) inc = DVP_MAX(2, (int)(2.0 * rad / 5.0));
 		n = (rad >= 0) ? (2 * rad) / inc + 1 : 0;
 		hoisted = (n == kHoistAxis);
-		float rcp_s, rcp_c; sigma_rcps(a.prm, rcp_s, rcp_c);
-		const float center = ref_pixel(a, px, py);
+		sigma_rcps(a.prm, rcp_s, rcp_c);
+		center = ref_pixel(a, px, py);
+		sd_const = (rad == 5 && inc == 2);
 		float s_w = 0.f, s_r = 0.f, s_rr = 0.f;
 		int k = 0;
 		for (int i = -rad; i <= rad; i += inc) {
@@ -110,7 +124,10 @@ struct RefPatch {
 				r_w = __fadd_rn(w, r_w);
 				r_r = __fadd_rn(t, r_r);
 				r_rr = __fmaf_rn(pix, t, r_rr);
-				if (hoisted) wt[k * stride] = make_float2(w, t);
+				if (hoisted) {
+					if (RW) reinterpret_cast<float*>(wt)[k * stride] = pix;
+					else wt[k * stride] = make_float2(w, t);
+				}
 				++k;
 			}
 			s_w = __fadd_rn(r_w, s_w);
@@ -140,7 +157,7 @@ __device__ __forceinline__ float ncc_finish(const RefPatch& rp, float s_s, float
 // RB = patch rows whose 6 texture fetches are issued back to back before any is consumed (RB*6 fetches in
 // flight per thread).  The propagation sweep is shared-memory-limited to 12 warps/SM, has registers to
 // spare and is latency-bound on TEX (ncu: long-scoreboard stalls), so it uses RB = 6; the 24-warp kernels use 2.
-template <int RB>
+template <int RB, bool RW = false>
 __device__ __forceinline__ float ncc_cost(const KArgs& a, const ViewConst& vc, cudaTextureObject_t src, int px, int py,
                                           const float4 pl, const RefPatch& rp, const float2* wt, int stride) {
 	float H[9];
@@ -180,7 +197,16 @@ __device__ __forceinline__ float ncc_cost(const KArgs& a, const ViewConst& vc, c
 				float r_s = 0.f, r_ss = 0.f, r_rs = 0.f;
 #pragma unroll
 				for (int jj = 0; jj < kHoistAxis; ++jj) {
-					const float2 w_t = wt[((ii + r) * kHoistAxis + jj) * stride];
+					float2 w_t;
+					if (RW) {
+						const int k = (ii + r) * kHoistAxis + jj;
+						const float pix = reinterpret_cast<const float*>(wt)[k * stride];
+						const float sd = rp.sd_const ? c_sd_r5[k] : RefPatch::spatial_dist(-rp.radius + (ii + r) * rp.inc, -rp.radius + jj * rp.inc);
+						w_t.x = RefPatch::weight_sd(sd, pix, rp.center, rp.rcp_s, rp.rcp_c);
+						w_t.y = __fmul_rn(pix, w_t.x);
+					} else {
+						w_t = wt[((ii + r) * kHoistAxis + jj) * stride];
+					}
 					const float s = sv[r * kHoistAxis + jj];
 					const float u = __fmul_rn(s, w_t.x);
 					r_rs = __fmaf_rn(s, w_t.y, r_rs);

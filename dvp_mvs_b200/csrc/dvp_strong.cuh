@@ -139,7 +139,7 @@ __device__ __forceinline__ float weighted_cost(const KArgs& a, int px, int py, c
 	for (int v = 0; v < a.S; ++v) {
 		const int wv = vw.get(v);
 		if (wv > 0) {
-			const float c = ncc_cost<kSweepRB>(a, a.views[v], a.tex_img[v + 1], px, py, pl, rp, wt, stride);
+			const float c = ncc_cost<kSweepRB, kSweepRW>(a, a.views[v], a.tex_img[v + 1], px, py, pl, rp, wt, stride);
 			acc += wv * c;
 		}
 	}

@@ -194,6 +194,15 @@ int dvp_last_run_times(dvp_ctx* ctx, float* total_ms, float* per_stage_ms, int* 
  * (bench.py's HBM-resident leg; "next" row N2).  `images`/`depths`/`planes` follow dvp_inputs layouts. */
 int dvp_upload_device(dvp_ctx* ctx, const dvp_inputs* device_in, const dvp_params* params);
 
+/* "Next" row N1 — replaces the host post-processing ProcessProblem runs on the downloaded maps right after
+ * RunPatchMatch (main.cpp:297-363; Connect / Label_Seek / Label_Update, APD.cpp:138-346), in place on the
+ * resident maps: (1) depths outside [depth_min, depth_max] become 0 and their state UNKNOWN
+ * (main.cpp:300-306); (2) for every source view, 4-connected regions of pixels that do not select the view and
+ * hold fewer than 20 * (8 / scale_size)^2 pixels get the view's bit set (main.cpp:323-363).
+ * `scale_size` is Problem::scale_size (8, 4, 2 or 1).  Follow with dvp_download. Synchronous.
+ * `device_ms` (may be NULL) receives the device time of the call. */
+int dvp_restore_visibility(dvp_ctx* ctx, int scale_size, float* device_ms);
+
 int dvp_weak_count(dvp_ctx* ctx);
 int dvp_last_cuda_error(dvp_ctx* ctx);
 void* dvp_stream(dvp_ctx* ctx); /* cudaStream_t */
