@@ -3,13 +3,13 @@
 Only what the hot path needs lives here:
   csrc/        hand-written sm_100a CUDA kernels + the flat C ABI (include/dvp_mvs.h) -> libdvp_mvs.so
   _lib.py      ctypes binding of that ABI (`Engine`)
-  apd.py       host-side mirror of the reference's `APD` class surface (same method names / call order)
+  (the C++ mirror of the reference's `APD` class is include/dvp_apd_adapter.hpp)
   synth.py     deterministic synthetic scenes (the reference ships no data)
   farm.py      per-view sharding across the GPUs of one box (NCCL-free)
 """
-from ._lib import (Engine, Params, Inputs, DvpError, default_params, FIRST_INIT, REFINE_INIT, REFINE_ITER,
+from ._lib import (Engine, Scene, Params, Inputs, DvpError, default_params, FIRST_INIT, REFINE_INIT, REFINE_ITER,
                    WEAK, STRONG, UNKNOWN, STAGES, PRODUCT_LIB)
 from . import synth
 
-__all__ = ["Engine", "Params", "Inputs", "DvpError", "default_params", "FIRST_INIT", "REFINE_INIT", "REFINE_ITER",
+__all__ = ["Engine", "Scene", "Params", "Inputs", "DvpError", "default_params", "FIRST_INIT", "REFINE_INIT", "REFINE_ITER",
            "WEAK", "STRONG", "UNKNOWN", "STAGES", "PRODUCT_LIB", "synth"]

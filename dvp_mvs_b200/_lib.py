@@ -65,7 +65,9 @@ STATUS = {0: "DVP_OK", -1: "DVP_ERR_ARG", -2: "DVP_ERR_CUDA", -3: "DVP_ERR_STATE
 
 ABI_SYMBOLS = ["version", "default_params", "create", "destroy", "upload", "run", "run_stage", "download",
                "buffer_bytes", "get_buffer", "set_buffer", "last_run_times", "weak_count", "last_cuda_error", "stream"]
-PRODUCT_ONLY_SYMBOLS = ["upload_device", "restore_visibility"]
+PRODUCT_ONLY_SYMBOLS = ["upload_device", "restore_visibility", "rescale_map", "scene_create", "scene_destroy", "scene_level_size",
+                        "scene_pass_params", "scene_set_max_iterations", "scene_set_view", "scene_set_level",
+                        "scene_set_initial_planes", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats"]
 
 
 class DvpError(RuntimeError):
@@ -98,6 +100,19 @@ def load_library(path: str, prefix: str):
     if prefix == "dvp_":
         f("upload_device").argtypes = [C.c_void_p, C.POINTER(Inputs), C.POINTER(Params)]; f("upload_device").restype = C.c_int
         f("restore_visibility").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]; f("restore_visibility").restype = C.c_int
+        f("rescale_map").argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]; f("rescale_map").restype = C.c_int
+        f("scene_create").argtypes = [C.c_int, C.c_int, C.c_int]; f("scene_create").restype = C.c_void_p
+        f("scene_destroy").argtypes = [C.c_void_p]; f("scene_destroy").restype = None
+        f("scene_level_size").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]; f("scene_level_size").restype = C.c_int
+        f("scene_pass_params").argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Params)]; f("scene_pass_params").restype = C.c_int
+        f("scene_set_max_iterations").argtypes = [C.c_void_p, C.c_int]; f("scene_set_max_iterations").restype = C.c_int
+        f("scene_set_view").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]; f("scene_set_view").restype = C.c_int
+        f("scene_set_level").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]; f("scene_set_level").restype = C.c_int
+        f("scene_set_initial_planes").argtypes = [C.c_void_p, C.c_int, C.c_void_p]; f("scene_set_initial_planes").restype = C.c_int
+        f("scene_run_pass").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64]; f("scene_run_pass").restype = C.c_int
+        f("scene_run").argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_float)]; f("scene_run").restype = C.c_int
+        f("scene_get_view").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)] + [C.c_void_p] * 4; f("scene_get_view").restype = C.c_int
+        f("scene_stats").argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]; f("scene_stats").restype = C.c_int
     return lib
 
 
@@ -250,3 +265,82 @@ class Engine:
     def restore(self, snap: dict):
         for n, a in snap.items():
             self.set(n, a)
+
+
+class Scene:
+    """In-memory multi-scale scene driver (include/dvp_mvs.h, row N2): the schedule of the reference's main()
+    (main.cpp:449-511) with every map resident on the GPU between passes."""
+
+    def __init__(self, num_views: int, num_levels: int, device: int = 0):
+        self.lib = load_library(PRODUCT_LIB, "dvp_")
+        self.num_views, self.num_levels = num_views, num_levels
+        self.h = self.lib.dvp_scene_create(device, num_views, num_levels)
+        if not self.h:
+            raise DvpError(f"dvp_scene_create failed (device {device}, {num_views} views, {num_levels} levels)")
+        self._sizes = {}
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise DvpError(f"dvp_scene_{what} -> {STATUS.get(rc, rc)}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dvp_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def level_size(self, full_w: int, full_h: int, level: int):
+        w, h = C.c_int(), C.c_int()
+        self._check(self.lib.dvp_scene_level_size(self.h, full_w, full_h, level, C.byref(w), C.byref(h)), "level_size")
+        return int(w.value), int(h.value)
+
+    def pass_params(self, level: int, pass_: int) -> Params:
+        p = Params()
+        self._check(self.lib.dvp_scene_pass_params(self.h, level, pass_, C.byref(p)), "pass_params")
+        return p
+
+    def set_max_iterations(self, n: int):
+        self._check(self.lib.dvp_scene_set_max_iterations(self.h, n), "set_max_iterations")
+
+    def set_view(self, view: int, camera, full_w: int, full_h: int, src_views):
+        cam = np.ascontiguousarray(camera, dtype=CAMERA_DTYPE).reshape(1)
+        src = (C.c_int * len(src_views))(*[int(s) for s in src_views])
+        self._check(self.lib.dvp_scene_set_view(self.h, view, _ptr(cam), full_w, full_h, len(src_views), src), "set_view")
+        self._sizes[view] = (full_w, full_h)
+
+    def set_level(self, view: int, level: int, image, edge=None, label=None):
+        w, h = self.level_size(*self._sizes[view], level)
+        img = _carr(image, np.float32, (h, w)); e = _carr(edge, np.uint8, (h, w)); l = _carr(label, np.int32, (h, w))
+        self._check(self.lib.dvp_scene_set_level(self.h, view, level, _ptr(img), _ptr(e), _ptr(l)), "set_level")
+
+    def set_initial_planes(self, view: int, planes):
+        w, h = self.level_size(*self._sizes[view], 0)
+        p = _carr(planes, np.float32, (h, w, 4))
+        self._check(self.lib.dvp_scene_set_initial_planes(self.h, view, _ptr(p)), "set_initial_planes")
+
+    def run_pass(self, level: int, pass_: int, seed: int):
+        self._check(self.lib.dvp_scene_run_pass(self.h, level, pass_, int(seed)), "run_pass")
+
+    def run(self, seed: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.dvp_scene_run(self.h, int(seed), C.byref(ms)), "run")
+        return float(ms.value)
+
+    def stats(self):
+        ms, n = C.c_double(), C.c_longlong()
+        self._check(self.lib.dvp_scene_stats(self.h, C.byref(ms), C.byref(n)), "stats")
+        return float(ms.value), int(n.value)
+
+    def get_view(self, view: int):
+        w, h = C.c_int(), C.c_int()
+        self._check(self.lib.dvp_scene_get_view(self.h, view, C.byref(w), C.byref(h), None, None, None, None), "get_view")
+        W, H = int(w.value), int(h.value)
+        planes = np.empty((H, W, 4), np.float32); weak = np.empty((H, W), np.uint8)
+        sel = np.empty((H, W), np.uint32); rad = np.empty((H, W), np.int32)
+        self._check(self.lib.dvp_scene_get_view(self.h, view, C.byref(w), C.byref(h), _ptr(planes), _ptr(weak), _ptr(sel), _ptr(rad)), "get_view")
+        return planes, weak, sel, rad

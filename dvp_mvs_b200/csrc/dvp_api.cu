@@ -174,13 +174,47 @@ cudaError_t launch_stage(dvp_ctx* c, const KArgs& a, int stage, int iter) {
 	}
 }
 
-int upload_common(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params, bool from_device) {
-	if (!ctx || !in || !in->images || !in->cameras || !in->planes) return DVP_ERR_ARG;
+// One upload, with every image / depth map addressed on its own (the scene driver keeps them in separate
+// per-view buffers) and the cameras possibly on the host while the maps are on the device.
+struct UploadSrc {
+	const float* images[DVP_MAX_IMAGES] = {nullptr};
+	const float* depths[DVP_MAX_IMAGES] = {nullptr};
+	bool have_depths = false;
+	const dvp_camera* cameras = nullptr;
+	bool cameras_on_device = false;
+	const float* planes = nullptr;
+	const uint32_t* selected_views = nullptr;
+	const uint8_t* weak_info = nullptr;
+	const uint8_t* edge = nullptr;
+	const int32_t* label = nullptr;
+	const int32_t* radius = nullptr;
+	uint64_t seed = 0;
+};
+
+int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bool from_device);
+
+int upload_common(dvp_ctx* ctx, const dvp_inputs* din, const dvp_params* params, bool from_device) {
+	if (!ctx || !din || !din->images || !din->cameras || !din->planes) return DVP_ERR_ARG;
+	UploadSrc u;
+	const size_t N = (size_t)ctx->N;
+	for (int i = 0; i <= ctx->S; ++i) {
+		u.images[i] = din->images + (size_t)i * N;
+		if (din->depths) u.depths[i] = din->depths + (size_t)i * N;
+	}
+	u.have_depths = din->depths != nullptr;
+	u.cameras = din->cameras; u.cameras_on_device = from_device;
+	u.planes = din->planes; u.selected_views = din->selected_views; u.weak_info = din->weak_info;
+	u.edge = din->edge; u.label = din->label; u.radius = din->radius; u.seed = din->seed;
+	return upload_parts(ctx, &u, params, from_device);
+}
+
+int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bool from_device) {
+	if (!ctx || !in || !in->images[0] || !in->cameras || !in->planes) return DVP_ERR_ARG;
 	CK(cudaSetDevice(ctx->device));
 	{   // validate first: a rejected upload must leave the context as it was
 		const dvp_params& q = params ? *params : ctx->prm;
 		if (q.num_images != ctx->S + 1) return DVP_ERR_ARG;
-		if (q.geom_consistency && !in->depths) return DVP_ERR_ARG;
+		if (q.geom_consistency && !in->have_depths) return DVP_ERR_ARG;
 		if (q.max_iterations < 0 || q.max_iterations > 64) return DVP_ERR_ARG;
 		if (!q.use_edge) return DVP_ERR_UNSUPPORTED;  // the ACMH-style branch (APD.cu:2142-2460) is never enabled by main.cpp
 	}
@@ -190,18 +224,19 @@ int upload_common(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params, 
 	cudaStream_t st = ctx->stream;
 	ctx->seed = in->seed;
 	for (int i = 0; i <= ctx->S; ++i) {
-		int r = make_texture(ctx, &ctx->img_arr[i], &ctx->img_tex[i], in->images + (size_t)i * N, kind);
+		if (!in->images[i] || (in->have_depths && !in->depths[i])) return DVP_ERR_ARG;
+		int r = make_texture(ctx, &ctx->img_arr[i], &ctx->img_tex[i], in->images[i], kind);
 		if (r) return r;
-		if (in->depths) {
-			r = make_texture(ctx, &ctx->dep_arr[i], &ctx->dep_tex[i], in->depths + (size_t)i * N, kind);
+		if (in->have_depths) {
+			r = make_texture(ctx, &ctx->dep_arr[i], &ctx->dep_tex[i], in->depths[i], kind);
 			if (r) return r;
 		}
 	}
-	CK(cudaMemcpyAsync(ctx->ref_img, in->images, N * 4, kind, st));
+	CK(cudaMemcpyAsync(ctx->ref_img, in->images[0], N * 4, kind, st));
 	CK(cudaMemcpyAsync(ctx->d_img_tex, ctx->img_tex, sizeof(ctx->img_tex), cudaMemcpyHostToDevice, st));
 	CK(cudaMemcpyAsync(ctx->d_dep_tex, ctx->dep_tex, sizeof(ctx->dep_tex), cudaMemcpyHostToDevice, st));
-	CK(cudaMemcpyAsync(ctx->cams, in->cameras, sizeof(dvp_camera) * (ctx->S + 1), kind, st));
-	if (from_device) CK(cudaMemcpyAsync(&ctx->ref_cam, in->cameras, sizeof(dvp_camera), cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(ctx->cams, in->cameras, sizeof(dvp_camera) * (ctx->S + 1), in->cameras_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+	if (in->cameras_on_device) CK(cudaMemcpyAsync(&ctx->ref_cam, in->cameras, sizeof(dvp_camera), cudaMemcpyDeviceToHost, st));
 	else ctx->ref_cam = in->cameras[0];
 	CK(launch_setup_views(ctx->cams, ctx->views, ctx->S, st));
 	CK(cudaMemcpyAsync(ctx->planes, in->planes, N * 16, kind, st));
@@ -428,10 +463,11 @@ int dvp_download(dvp_ctx* ctx, float* planes, uint8_t* weak_info, uint32_t* sele
 	CK(cudaSetDevice(ctx->device));
 	const size_t N = (size_t)ctx->N;
 	cudaStream_t st = ctx->stream;
-	if (planes) CK(cudaMemcpyAsync(planes, ctx->planes, N * 16, cudaMemcpyDeviceToHost, st));
-	if (weak_info) CK(cudaMemcpyAsync(weak_info, ctx->weak, N, cudaMemcpyDeviceToHost, st));
-	if (selected_views) CK(cudaMemcpyAsync(selected_views, ctx->selected, N * 4, cudaMemcpyDeviceToHost, st));
-	if (radius) CK(cudaMemcpyAsync(radius, ctx->radius, N * 4, cudaMemcpyDeviceToHost, st));
+	// cudaMemcpyDefault: destinations may be host (pageable / pinned) or device memory (in-memory pass chaining, row N2)
+	if (planes) CK(cudaMemcpyAsync(planes, ctx->planes, N * 16, cudaMemcpyDefault, st));
+	if (weak_info) CK(cudaMemcpyAsync(weak_info, ctx->weak, N, cudaMemcpyDefault, st));
+	if (selected_views) CK(cudaMemcpyAsync(selected_views, ctx->selected, N * 4, cudaMemcpyDefault, st));
+	if (radius) CK(cudaMemcpyAsync(radius, ctx->radius, N * 4, cudaMemcpyDefault, st));
 	CK(cudaStreamSynchronize(st));
 	return DVP_OK;
 }
@@ -503,3 +539,5 @@ int dvp_last_cuda_error(dvp_ctx* ctx) { return ctx ? ctx->last_err : 0; }
 void* dvp_stream(dvp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 }  // extern "C"
+
+#include "dvp_scene.inc"

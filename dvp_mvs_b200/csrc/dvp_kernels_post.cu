@@ -9,6 +9,7 @@
 // maps never leave HBM.  Region sizes, and therefore the result, do not depend on label numbering.
 #include "dvp_common.cuh"
 #include "dvp_launch.h"
+#include <cstring>
 
 namespace dvp {
 
@@ -75,6 +76,44 @@ __global__ void __launch_bounds__(256) k_invalidate_depth(int n, float depth_min
 	if (p >= n) return;
 	const float d = planes[p].w;
 	if (d < depth_min || d > depth_max) { planes[p].w = 0.0f; weak[p] = DVP_UNKNOWN; }
+}
+
+// RescaleMatToTargetSize (APD.cpp:1773-1796): nearest-neighbour resampling with the two scale factors swapped
+// (row index divided by scale_x, column index by scale_y — SURVEY B10, reproduced).  Host float arithmetic is
+// IEEE, so the divisions are __fdiv_rn here (the library is built with --use_fast_math).  Target pixels whose
+// source falls outside are left uninitialised by the reference; they are defined as zero here.
+template <typename T>
+__global__ void __launch_bounds__(256) k_rescale(const T* __restrict__ src, int sw, int sh, T* __restrict__ dst, int dw, int dh) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * blockDim.y + threadIdx.y;
+	if (c >= dw || r >= dh) return;
+	const float scale_x = __fdiv_rn((float)dw, (float)sw);
+	const float scale_y = __fdiv_rn((float)dh, (float)sh);
+	const int o_r = (int)__fdiv_rn((float)r, scale_x);
+	const int o_c = (int)__fdiv_rn((float)c, scale_y);
+	T v; memset(&v, 0, sizeof(T));
+	if (o_r >= 0 && o_c >= 0 && o_r < sh && o_c < sw) v = src[(size_t)o_r * sw + o_c];
+	dst[(size_t)r * dw + c] = v;
+}
+
+cudaError_t launch_rescale(const void* src, int sw, int sh, void* dst, int dw, int dh, int elem_bytes, cudaStream_t st) {
+	const dim3 b(32, 8), g((dw + 31) / 32, (dh + 7) / 8);
+	switch (elem_bytes) {
+	case 1: k_rescale<uint8_t><<<g, b, 0, st>>>((const uint8_t*)src, sw, sh, (uint8_t*)dst, dw, dh); break;
+	case 4: k_rescale<uint32_t><<<g, b, 0, st>>>((const uint32_t*)src, sw, sh, (uint32_t*)dst, dw, dh); break;
+	case 16: k_rescale<uint4><<<g, b, 0, st>>>((const uint4*)src, sw, sh, (uint4*)dst, dw, dh); break;
+	default: return cudaErrorInvalidValue;
+	}
+	return cudaGetLastError();
+}
+
+// depth map of a finished pass: the w component of the plane map (what ProcessProblem writes to depths.dmb)
+__global__ void __launch_bounds__(256) k_extract_depth(int n, const float4* __restrict__ planes, float* __restrict__ depth) {
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < n) depth[p] = planes[p].w;
+}
+cudaError_t launch_extract_depth(const float4* planes, float* depth, int n, cudaStream_t st) {
+	k_extract_depth<<<(n + 255) / 256, 256, 0, st>>>(n, planes, depth);
+	return cudaGetLastError();
 }
 
 cudaError_t launch_invalidate_depth(const KArgs& a, cudaStream_t st) {

@@ -53,6 +53,8 @@ cudaError_t launch_reset_unknown_radius(const uint8_t* weak, int32_t* radius, in
 
 // post-pass on the resident maps (main.cpp:297-363): dvp_kernels_post.cu
 cudaError_t launch_invalidate_depth(const KArgs& a, cudaStream_t st);
+cudaError_t launch_rescale(const void* src, int sw, int sh, void* dst, int dw, int dh, int elem_bytes, cudaStream_t st);
+cudaError_t launch_extract_depth(const float4* planes, float* depth, int n, cudaStream_t st);
 cudaError_t launch_restore_visibility(const KArgs& a, int scale_size, int* parent, int* count, cudaStream_t st);
 
 // canonical RNG exchange format <-> SoA planes

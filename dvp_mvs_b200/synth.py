@@ -154,6 +154,39 @@ def make_camera(K, R, c, W, H, dmin, dmax) -> np.ndarray:
     return cam
 
 
+def _first_init_planes(depth, K, R_ref, rng_init):
+    """FIRST_INIT input: noisy depth (10 % of pixels invalid = 0), normals by finite differences of that depth
+    map, flipped towards the camera and rotated to the world frame (as APD.cpp:1365-1422 does)."""
+    H, W = depth.shape
+    noisy = depth.astype(np.float64) * (1.0 + rng_init.normal(0.0, 0.05, (H, W)))
+    noisy[rng_init.uniform(size=(H, W)) < 0.10] = 0.0
+    xs = (np.arange(W) - K[0, 2]) / K[0, 0]; ys = (np.arange(H) - K[1, 2]) / K[1, 1]
+    X = np.stack([xs[None, :] * noisy, ys[:, None] * noisy, noisy], -1)
+    dPdx = np.zeros_like(X); dPdy = np.zeros_like(X)
+    dPdx[:, :-1] = X[:, 1:] - X[:, :-1]
+    dPdy[:-1, :] = X[1:, :] - X[:-1, :]
+    nrm = np.cross(dPdx, dPdy)
+    ln = np.linalg.norm(nrm, axis=-1, keepdims=True)
+    nrm = np.where(ln > 0, nrm / np.maximum(ln, 1e-30), np.array([0.0, 0.0, -1.0]))
+    flip = (nrm * X).sum(-1) > 0
+    nrm[flip] *= -1.0
+    nrm_world = nrm @ R_ref  # R^T n, row-vector form
+    nrm_world[0, :] = 0; nrm_world[-1, :] = 0; nrm_world[:, 0] = 0; nrm_world[:, -1] = 0  # border left unset by the reference loop
+    return np.concatenate([nrm_world, noisy[..., None]], -1).astype(np.float32)
+
+
+def _edge_label(pid):
+    """priors: edges = plane-id boundaries; labels = plane id + 1, 0 on boundaries"""
+    H, W = pid.shape
+    edge = np.zeros((H, W), np.uint8)
+    edge[:, :-1] |= (pid[:, :-1] != pid[:, 1:]).astype(np.uint8)
+    edge[:-1, :] |= (pid[:-1, :] != pid[1:, :]).astype(np.uint8)
+    edge *= 255
+    label = (pid + 1).astype(np.int32)
+    label[edge > 0] = 0
+    return edge, label
+
+
 def make_scene(width: int, height: int, num_src: int, seed: int = 0, quantize: bool = True) -> Scene:
     """Build the scene. `quantize` rounds grey levels to integers like an 8-bit image would be."""
     W, H, S = int(width), int(height), int(num_src)
@@ -200,31 +233,87 @@ def make_scene(width: int, height: int, num_src: int, seed: int = 0, quantize: b
         planes_true[m, 0:3] = pl["n"].astype(np.float32)
     planes_true[..., 3] = depths[0]
 
-    # FIRST_INIT input: noisy depth (10 % of pixels invalid = 0), normals by finite differences of that
-    # depth map, flipped towards the camera and rotated to the world frame (as APD.cpp:1365-1422 does)
-    noisy = depths[0].astype(np.float64) * (1.0 + rng_init.normal(0.0, 0.05, (H, W)))
-    noisy[rng_init.uniform(size=(H, W)) < 0.10] = 0.0
-    xs = (np.arange(W) - K[0, 2]) / K[0, 0]; ys = (np.arange(H) - K[1, 2]) / K[1, 1]
-    X = np.stack([xs[None, :] * noisy, ys[:, None] * noisy, noisy], -1)
-    dPdx = np.zeros_like(X); dPdy = np.zeros_like(X)
-    dPdx[:, :-1] = X[:, 1:] - X[:, :-1]
-    dPdy[:-1, :] = X[1:, :] - X[:-1, :]
-    nrm = np.cross(dPdx, dPdy)
-    ln = np.linalg.norm(nrm, axis=-1, keepdims=True)
-    nrm = np.where(ln > 0, nrm / np.maximum(ln, 1e-30), np.array([0.0, 0.0, -1.0]))
-    flip = (nrm * X).sum(-1) > 0
-    nrm[flip] *= -1.0
-    nrm_world = nrm @ R_ref  # R^T n, row-vector form
-    nrm_world[0, :] = 0; nrm_world[-1, :] = 0; nrm_world[:, 0] = 0; nrm_world[:, -1] = 0  # border left unset by the reference loop
-    planes_init = np.concatenate([nrm_world, noisy[..., None]], -1).astype(np.float32)
+    planes_init = _first_init_planes(depths[0], K, R_ref, rng_init)
 
-    # priors: edges = plane-id boundaries; labels = plane id + 1, 0 on boundaries
-    edge = np.zeros((H, W), np.uint8)
-    edge[:, :-1] |= (pid0[:, :-1] != pid0[:, 1:]).astype(np.uint8)
-    edge[:-1, :] |= (pid0[:-1, :] != pid0[1:, :]).astype(np.uint8)
-    edge *= 255
-    label = (pid0 + 1).astype(np.int32)
-    label[edge > 0] = 0
+    edge, label = _edge_label(pid0)
 
     return Scene(W, H, S, images, depths, cameras, planes_init, planes_true, pid0, edge, label,
                  0.6 * cam_dmin, 1.2 * cam_dmax)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# multi-view, multi-level scenes for the in-memory schedule (dvp_scene_*)
+def level_size(full_w: int, full_h: int, scale: int):
+    """round(cols * (1 / scale)) in float32, half away from zero (APD.cpp:1119-1123)."""
+    f = np.float32(1.0) / np.float32(scale)
+    return int(np.floor(np.float32(full_w) * f + np.float32(0.5))), int(np.floor(np.float32(full_h) * f + np.float32(0.5)))
+
+
+def level_camera(cam_full: np.ndarray, full_w: int, full_h: int, w: int, h: int, scale: int) -> np.ndarray:
+    """Intrinsics scaled by the achieved ratios, float32 (APD.cpp:1125-1140)."""
+    cam = np.array(cam_full, dtype=CAMERA_DTYPE, copy=True).reshape(())
+    if scale != 1:
+        sx = np.float32(w) / np.float32(full_w); sy = np.float32(h) / np.float32(full_h)
+        K = cam["K"].copy()
+        K[0] *= sx; K[2] *= sx; K[4] *= sy; K[5] *= sy
+        cam["K"] = K
+    cam["width"] = w; cam["height"] = h
+    return cam
+
+
+@dataclasses.dataclass
+class MultiView:
+    full_w: int
+    full_h: int
+    num_levels: int
+    cameras: np.ndarray        # [V] CAMERA_DTYPE, full resolution
+    src_views: list            # [V] list of source view indices
+    levels: list               # [level][view] dict(w, h, image, edge, label, depth, camera)
+    planes_init: list          # [V] [h0][w0][4] FIRST_INIT prior at level 0
+    depth_min: float
+    depth_max: float
+
+
+def make_multiview(full_w: int, full_h: int, num_views: int, num_levels: int, seed: int = 0, num_src: int | None = None) -> MultiView:
+    """The room of make_scene seen from `num_views` cameras; every view is rendered directly at each pyramid level
+    (scale 2^num_levels ... 2) with the level's intrinsics — standing in for the reference's cv::resize pyramid."""
+    V = int(num_views)
+    S = V - 1 if num_src is None else int(num_src)
+    rng_img = np.random.default_rng(SEED_IMAGE + seed)
+    rng_cam = np.random.default_rng(SEED_CAMERA + seed)
+    rng_init = np.random.default_rng(SEED_INIT + seed)
+    planes = _room()
+    fx = 0.55 * full_w
+    K = np.array([[fx, 0, full_w / 2.0], [0, fx, full_h / 2.0], [0, 0, 1.0]])
+    textures = [_make_texture(rng_img, 2048, 40.0 if i == 3 else 1.5) for i in range(len(planes))]
+    c_ref = np.array([0.10, -0.05, 0.20])
+    KRc = [(K, _rot_yx(np.deg2rad(3.0), np.deg2rad(-2.0)), c_ref)]
+    centre = np.array([0.0, 0.0, 5.0])
+    for i in range(V - 1):
+        ang = 2 * np.pi * (i + 0.25 * rng_cam.uniform()) / max(V - 1, 1)
+        rad = rng_cam.uniform(0.25, 0.6)
+        c = c_ref + np.array([rad * np.cos(ang), 0.6 * rad * np.sin(ang), rng_cam.uniform(-0.05, 0.05)])
+        to = centre - c
+        yaw = np.arctan2(to[0], to[2]) + np.deg2rad(rng_cam.uniform(-1, 1))
+        pitch = -np.arctan2(to[1], np.hypot(to[0], to[2])) + np.deg2rad(rng_cam.uniform(-1, 1))
+        KRc.append((K, _rot_yx(yaw, pitch), c))
+    cam_dmin, cam_dmax = 1.5, 12.0
+    cameras = np.zeros((V,), CAMERA_DTYPE)
+    for v, (Kv, Rv, cv_) in enumerate(KRc):
+        cameras[v] = make_camera(Kv, Rv, cv_, full_w, full_h, cam_dmin, cam_dmax)
+    src_views = [[(v + 1 + k) % V for k in range(S)] for v in range(V)]
+    levels, planes_init = [], []
+    for level in range(num_levels):
+        scale = 1 << (num_levels - level)
+        w, h = level_size(full_w, full_h, scale)
+        per_view = []
+        for v, (Kv, Rv, cv_) in enumerate(KRc):
+            cam = level_camera(cameras[v], full_w, full_h, w, h, scale)
+            Kl = cam["K"].astype(np.float64).reshape(3, 3)
+            img, dep, pid = _render(Kl, Rv, cv_, w, h, planes, textures, Kl[0, 0] / 8.0)
+            edge, label = _edge_label(pid)
+            per_view.append(dict(w=w, h=h, image=np.rint(img).astype(np.float32), edge=edge, label=label, depth=dep, camera=cam))
+            if level == 0:
+                planes_init.append(_first_init_planes(dep, Kl, Rv, rng_init))
+        levels.append(per_view)
+    return MultiView(full_w, full_h, num_levels, cameras, src_views, levels, planes_init, 0.6 * cam_dmin, 1.2 * cam_dmax)

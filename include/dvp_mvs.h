@@ -203,6 +203,40 @@ int dvp_upload_device(dvp_ctx* ctx, const dvp_inputs* device_in, const dvp_param
  * `device_ms` (may be NULL) receives the device time of the call. */
 int dvp_restore_visibility(dvp_ctx* ctx, int scale_size, float* device_ms);
 
+/* ---- "Next" row N2: the multi-scale schedule with every map resident in HBM between passes ------------------------
+ * Replaces the file round trips between the (view, pass) jobs of main() (main.cpp:449-511): ProcessProblem's writes
+ * (main.cpp:365-376), InuputInitialization's reads + host rescales (APD.cpp:1147-1180, 1427-1456) and
+ * SupportInitialization's (APD.cpp:1615-1668).  Pyramid level 0 is the coarsest (scale_size 2^num_levels ... 2; the
+ * reference never runs scale 1).  Per level the caller supplies what the reference computes with OpenCV or reads from
+ * other tools: the resized grey image, the edge map and the label map; and for level 0 the FIRST_INIT plane prior.
+ * All views of a scene must share one full-resolution size.  Views run in index order (the reference's order). */
+typedef struct dvp_scene dvp_scene;
+dvp_scene* dvp_scene_create(int device, int num_views, int num_levels);
+void dvp_scene_destroy(dvp_scene* scene);
+/* Level size as InuputInitialization computes it: round(full * (1 / scale)) (APD.cpp:1119-1123). */
+int dvp_scene_level_size(dvp_scene* scene, int full_w, int full_h, int level, int* w, int* h);
+/* PatchMatchParams of pass 0 (FIRST_INIT / REFINE_INIT) or 1..3 (REFINE_ITER) of round `level` (main.cpp:452-505);
+ * depth_min / depth_max / num_images are per view and left at their defaults. */
+int dvp_scene_pass_params(dvp_scene* scene, int level, int pass, dvp_params* out);
+/* PatchMatch iterations per pass: 3 in the reference (main.cpp:481, 502).  0 leaves only the race-free stages, which
+ * makes whole-schedule results reproducible bit for bit (used by the chain parity test). */
+int dvp_scene_set_max_iterations(dvp_scene* scene, int iterations);
+/* Full-resolution camera (cam.txt), size and source views (pair.txt) of one view. */
+int dvp_scene_set_view(dvp_scene* scene, int view, const dvp_camera* cam_full, int full_w, int full_h, int num_src, const int* src_views);
+/* Per-level data of one view, host or device pointers: image [h][w] f32 (required), edge u8 / label i32 (or NULL). */
+int dvp_scene_set_level(dvp_scene* scene, int view, int level, const float* image, const uint8_t* edge, const int32_t* label);
+/* FIRST_INIT prior of one view at level 0: [h0][w0][4] (world normal, depth), APD.cpp:1410-1420. */
+int dvp_scene_set_initial_planes(dvp_scene* scene, int view, const float* planes);
+/* One pass over every view (one inner loop of main.cpp:452-511); view v runs with seed + v. */
+int dvp_scene_run_pass(dvp_scene* scene, int level, int pass, uint64_t seed);
+/* The whole schedule: num_levels rounds x 4 passes x all views. `device_ms` (may be NULL): summed device time. */
+int dvp_scene_run(dvp_scene* scene, uint64_t seed, float* device_ms);
+/* Current maps of one view (size returned in *w, *h); destinations may be host or device memory, or NULL. */
+int dvp_scene_get_view(dvp_scene* scene, int view, int* w, int* h, float* planes, uint8_t* weak_info, uint32_t* selected_views, int32_t* radius);
+int dvp_scene_stats(dvp_scene* scene, double* device_ms, long long* passes);
+/* RescaleMatToTargetSize (APD.cpp:1773-1796, swapped scale factors reproduced) on device memory; elem_bytes 1, 4 or 16. */
+int dvp_rescale_map(int device, const void* src, int src_w, int src_h, void* dst, int dst_w, int dst_h, int elem_bytes);
+
 int dvp_weak_count(dvp_ctx* ctx);
 int dvp_last_cuda_error(dvp_ctx* ctx);
 void* dvp_stream(dvp_ctx* ctx); /* cudaStream_t */
