@@ -282,7 +282,15 @@ def main():
     bytes_per_launch = N * (218 + 4 * S) / 2.0                             # half the pixels (one colour) per launch
     achieved = bytes_per_launch / (sweep_ms * 1e-3) / 1e9
     ncc_per_px_iter = 22 * S                                               # 16 candidate + 1 current + 5 refinement (hyp. 4 folded) NCCs, all views
-    samples_per_launch = (N / 2.0) * ncc_per_px_iter * 36
+    weak_px = 0 if inputs.get("weak_info") is None else int((inputs["weak_info"] == 0).sum())   # WEAK pixels leave the sweep at once (K10/K11 own them)
+    samples_per_launch = ((N - weak_px) / 2.0) * ncc_per_px_iter * 36
+    traffic = None   # measured DRAM bytes per sweep launch, from the committed ncu capture of this very workload
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(workload, {}).get("k_strong_sweep")
+        if tr:
+            traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
+    except Exception:
+        pass
     out = {"metric": "patchmatch_mpix_per_s_per_view", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
@@ -292,10 +300,11 @@ def main():
                    "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall_ms / args.steps},
            "gpu_launches": int(launches * args.steps),
            "roofline": {"kernel": "k_strong_sweep (K7/K8)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "avg_launch_ms": sweep_ms,
+                        "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": bytes_per_launch, "peak_source": peak_src, "avg_launch_ms": sweep_ms,
                         "share_of_step": (per_stage[6] + per_stage[7]) / max(total_ms, 1e-9),
-                        "note": "TEX/FP32-bound kernel: ~%d bilinear source fetches per byte of compulsory traffic" % int(samples_per_launch / bytes_per_launch),
-                        "tex_gsamples_per_s": samples_per_launch / (sweep_ms * 1e-3) / 1e9},
+                        "note": "TEX-bound kernel: ~%d bilinear source fetches per byte of compulsory traffic; the binding roof is the texture unit "
+                                "(measured 1155 Gfetch/s coherent, profiles/r01_tex_coherence_ubench.txt), not HBM" % int(samples_per_launch / bytes_per_launch),
+                        "tex_gsamples_per_s": samples_per_launch / (sweep_ms * 1e-3) / 1e9, "tex_peak_gsamples_per_s": 1155.0},
            "per_stage_ms": [round(v, 3) for v in per_stage], "clocks": clocks}
     cb = cpu_baseline(args, cores)
     if cb:

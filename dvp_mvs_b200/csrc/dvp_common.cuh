@@ -91,6 +91,10 @@ struct Rng {
 		rng[N + idx] = st.v[0]; rng[2 * N + idx] = st.v[1]; rng[3 * N + idx] = st.v[2];
 		rng[4 * N + idx] = st.v[3]; rng[5 * N + idx] = st.v[4];
 	}
+	// the six live words, for callers that draw ahead speculatively and roll back (K4's direction search)
+	struct Snap { uint32_t d, v0, v1, v2, v3, v4; };
+	__device__ __forceinline__ Snap snap() const { return Snap{st.d, st.v[0], st.v[1], st.v[2], st.v[3], st.v[4]}; }
+	__device__ __forceinline__ void restore(const Snap& s) { st.d = s.d; st.v[0] = s.v0; st.v[1] = s.v1; st.v[2] = s.v2; st.v[3] = s.v3; st.v[4] = s.v4; }
 	__device__ __forceinline__ float uniform() { return curand_uniform(&st); }
 	__device__ __forceinline__ unsigned int next() { return curand(&st); }
 };

@@ -190,6 +190,14 @@ __global__ void __launch_bounds__(64) k_gen_neighbours(const __grid_constant__ K
 				for (int radius = 2; radius <= 4096; radius = DVP_MIN(radius * 2, radius + 25)) {
 					const float2 test_pt = make_float2(px + origin_direction.x * radius, py + origin_direction.y * radius);
 					if (test_pt.x < 0 || test_pt.y < 0 || test_pt.x >= W || test_pt.y >= H) break;
+					// The reference makes up to four tries per radius, each: 4 RNG draws -> a probe pixel -> its state and,
+					// if it is not STRONG, its nearest STRONG pixel (two dependent gathers) -> tests.  Tries only interact
+					// through the RNG and the early exit, so all four probes are drawn first, their eight gathers are
+					// issued together, and the tests then run in the reference's order; if try j succeeds, the RNG is
+					// rolled back to its state after try j (the draws the reference never made).  The cheap angle test
+					// goes before the duplicate scan (both merely skip the try, neither has side effects).
+					short2 probe[4]; int probe_idx[4]; Rng::Snap after[4];
+#pragma unroll
 					for (int radius_iter = 0; radius_iter < 4; ++radius_iter) {
 						// (cond ? 1 : -1) * curand() % range : unsigned arithmetic, two draws per shift, left operand first
 						const unsigned int c0 = rng.next(); const unsigned int c1 = rng.next();
@@ -198,26 +206,43 @@ __global__ void __launch_bounds__(64) k_gen_neighbours(const __grid_constant__ K
 						const int rand_y_shift = (int)(((unsigned int)(c2 % 2 == 0 ? 1 : -1) * c3) % (unsigned int)shift_range);
 						float2 direction = make_float2(origin_direction.x * 20 + rand_x_shift, origin_direction.y * 20 + rand_y_shift);
 						normalize2(&direction);
-						short2 np = make_short2(px + direction.x * radius, py + direction.y * radius);
-						if (np.x < min_margin || np.y < min_margin || np.x >= W - min_margin || np.y >= H - min_margin) continue;
-						int npc = np.x + np.y * W;
-						if (a.weak[npc] != DVP_STRONG) {
-							np = a.nearest_strong[npc];
-							if (np.x == -1 || np.y == -1) continue;
-							npc = np.x + np.y * W;
+						const short2 np = make_short2(px + direction.x * radius, py + direction.y * radius);
+						const bool outside = np.x < min_margin || np.y < min_margin || np.x >= W - min_margin || np.y >= H - min_margin;
+						probe[radius_iter] = np;
+						probe_idx[radius_iter] = outside ? -1 : np.x + np.y * W;
+						after[radius_iter] = rng.snap();
+					}
+					uint8_t probe_state[4]; short2 probe_ns[4];
+#pragma unroll
+					for (int radius_iter = 0; radius_iter < 4; ++radius_iter) {
+						probe_state[radius_iter] = DVP_STRONG; probe_ns[radius_iter] = make_short2(-1, -1);
+						if (probe_idx[radius_iter] >= 0) {
+							probe_state[radius_iter] = a.weak[probe_idx[radius_iter]];
+							probe_ns[radius_iter] = a.nearest_strong[probe_idx[radius_iter]];
 						}
+					}
+#pragma unroll
+					for (int radius_iter = 0; radius_iter < 4; ++radius_iter) {
+						if (dir_valid[dir_index]) continue;   // an earlier try of this batch succeeded: the reference has left the loop
+						if (probe_idx[radius_iter] < 0) continue;
+						short2 np = probe[radius_iter];
+						if (probe_state[radius_iter] != DVP_STRONG) {
+							np = probe_ns[radius_iter];
+							if (np.x == -1 || np.y == -1) continue;
+						}
+						float2 test_direction = make_float2(np.x - px, np.y - py);
+						normalize2(&test_direction);
+						const float cosv = test_direction.x * origin_direction.x + test_direction.y * origin_direction.y;
+						if (!(cosv > threshhold)) continue;
 						bool has_same_pt = false;
 						for (int k = 0; k < dir_index; k++)
 							if (strong_points[k].x == np.x && strong_points[k].y == np.y) { has_same_pt = true; break; }
 						if (has_same_pt) continue;
-						float2 test_direction = make_float2(np.x - px, np.y - py);
-						normalize2(&test_direction);
-						const float cosv = test_direction.x * origin_direction.x + test_direction.y * origin_direction.y;
-						if (cosv > threshhold && (!edge_limit || !bresenham_crosses_edge(a, px, py, np.x, np.y))) {
+						if (!edge_limit || !bresenham_crosses_edge(a, px, py, np.x, np.y)) {
 							strong_points[dir_index] = np;
 							dir_valid[dir_index] = true;
 							strong_point_size++;
-							break;
+							rng.restore(after[radius_iter]);
 						}
 					}
 					if (dir_valid[dir_index]) break;
@@ -470,7 +495,7 @@ __global__ void __launch_bounds__(256) k_ransac_fit(const __grid_constant__ KArg
 	for (int i = 0; i < M; ++i) for (int j = 0; j < M; ++j) edge_test[i][j] = 0;
 	auto crossing = [&](int i0, int i1) -> int {
 		if (edge_test[i0][i1] == 0)
-			edge_test[i0][i1] = edge_test[i1][i0] = bresenham_crosses_edge(a, strong_points[i0].x, strong_points[i0].y, strong_points[i1].x, strong_points[i1].y) ? 1 : 2;
+			edge_test[i0][i1] = edge_test[i1][i0] = bresenham_crosses_edge<4>(a, strong_points[i0].x, strong_points[i0].y, strong_points[i1].x, strong_points[i1].y) ? 1 : 2;
 		return edge_test[i0][i1];
 	};
 	while (iteration--) {

@@ -95,6 +95,16 @@ public:
 	float GetDepthMin() { return params_host.depth_min; }
 	float GetDepthMax() { return params_host.depth_max; }
 
+	// Not in the reference (row N1, optional): what ProcessProblem does to the maps on the host right after
+	// RunPatchMatch — depth range check + per-view visibility restoration (main.cpp:297-363) — run on the device
+	// on the maps that are still resident, then mirrored into the host members.  A maintainer who calls this can
+	// delete main.cpp:288-363 except the two lines that copy depth and normal out.
+	void RestoreVisibilityOnDevice() {
+		if (dvp_restore_visibility(ctx_, problem.scale_size, nullptr) != DVP_OK) die("dvp_restore_visibility");
+		if (dvp_download(ctx_, reinterpret_cast<float*>(plane_hypotheses_host), weak_info_host.ptr<uchar>(0),
+		                 selected_views_host.ptr<unsigned int>(0), nullptr) != DVP_OK) die("dvp_download");
+	}
+
 	// Not in the reference: costs never leave the device there. Fills a CV_32F map.
 	void GetCostMap(cv::Mat& out) {
 		out.create(height, width, CV_32FC1);

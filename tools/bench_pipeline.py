@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Whole multi-scale schedule (BASELINE config C2 shape: pyramid rounds x 4 passes x V views) on one GPU:
+the resident scene driver (dvp_scene_run, rows N1 + N2) next to the same schedule chained through host memory the way
+the reference chains it through files (download -> host rescale -> CPU connected components -> upload), both on our
+kernels.  Prints one JSON line.   usage: python tools/bench_pipeline.py [--full 3111x2073] [--views 5] [--levels 3]"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", default="3111x2073", help="full-resolution size; the finest level run is half of it (the reference never runs scale 1)")
+    ap.add_argument("--views", type=int, default=5)
+    ap.add_argument("--levels", type=int, default=3)
+    ap.add_argument("--host-chain", type=int, default=1)
+    a = ap.parse_args()
+    fw, fh = (int(v) for v in a.full.split("x"))
+    from dvp_mvs_b200 import synth, Scene, Engine
+    import torch
+    t0 = time.perf_counter()
+    mv = synth.make_multiview(fw, fh, a.views, a.levels, seed=0)
+    t_synth = time.perf_counter() - t0
+    V = a.views
+    # warm-up: load every kernel module and create the CUDA context outside the timed regions
+    wmv = synth.make_multiview(320, 240, 3, 1, seed=9)
+    wsc = Scene(3, 1)
+    for v in range(3):
+        wsc.set_view(v, wmv.cameras[v], 320, 240, wmv.src_views[v])
+        wsc.set_level(v, 0, wmv.levels[0][v]["image"], wmv.levels[0][v]["edge"], wmv.levels[0][v]["label"])
+        wsc.set_initial_planes(v, wmv.planes_init[v])
+    wsc.run(seed=1); wsc.close()
+    sc = Scene(V, a.levels)
+    for v in range(V):
+        sc.set_view(v, mv.cameras[v], fw, fh, mv.src_views[v])
+        for l in range(a.levels):
+            L = mv.levels[l][v]
+            sc.set_level(v, l, L["image"], L["edge"], L["label"])
+        sc.set_initial_planes(v, mv.planes_init[v])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev_ms = sc.run(seed=0x5EED)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    pix = sum(mv.levels[l][0]["w"] * mv.levels[l][0]["h"] for l in range(a.levels)) * 4 * V
+    errs = []
+    for v in range(V):
+        planes, weak, sel, rad = sc.get_view(v)
+        truth = mv.levels[-1][v]["depth"]; ok = planes[..., 3] > 0
+        errs.append(float(np.median(np.abs(planes[..., 3][ok] - truth[ok]) / truth[ok])))
+    out = {"workload": f"{V} views x {a.levels} levels x 4 passes, finest level {mv.levels[-1][0]['w']}x{mv.levels[-1][0]['h']}, S={V - 1}",
+           "passes": a.levels * 4 * V, "pixels_processed": pix,
+           "resident": {"device_ms": dev_ms, "wall_ms": wall * 1e3, "mpix_per_s_wall": pix / wall / 1e6},
+           "median_rel_depth_error_per_view": [round(e, 5) for e in errs], "synth_s": round(t_synth, 1)}
+    if a.host_chain:
+        import host_chain
+        hc = host_chain.HostChain(mv, lambda w, h, S, p: Engine(w, h, S, p))
+        t0 = time.perf_counter()
+        hc.run(seed=0x5EED)
+        wall_h = time.perf_counter() - t0
+        out["host_chained"] = {"wall_ms": wall_h * 1e3, "mpix_per_s_wall": pix / wall_h / 1e6,
+                               "note": "same kernels; maps round-trip through host memory, numpy RescaleMat, CPU Connect/Label_Update restatement"}
+        out["speedup_wall"] = wall_h / wall
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
