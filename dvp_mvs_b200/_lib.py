@@ -61,6 +61,7 @@ STAGES = ["K1_INIT_RANDOM_STATES", "K2_GEN_EDGE_INFORM", "K3_FIND_NEAREST_STRONG
           "K9_RANSAC_FIT_PLANE", "K10_BLACK_WEAK", "K11_RED_WEAK", "K12_DEPTH_NORMAL", "K13_BLACK_FILTER",
           "K14_RED_FILTER", "K15_DEPTH_TO_WEAK", "K16_LOCAL_REFINE"]
 STAGE = {n: i for i, n in enumerate(STAGES)}
+STAGE["K15_K16_FUSED"] = 16   # product only: K15 and K16 in one launch, as dvp_run issues them
 STATUS = {0: "DVP_OK", -1: "DVP_ERR_ARG", -2: "DVP_ERR_CUDA", -3: "DVP_ERR_STATE", -4: "DVP_ERR_UNSUPPORTED"}
 
 ABI_SYMBOLS = ["version", "default_params", "create", "destroy", "upload", "run", "run_stage", "download",

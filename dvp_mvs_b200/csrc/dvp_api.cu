@@ -151,6 +151,19 @@ BufDesc buf_desc(dvp_ctx* c, int id) {
 	}
 }
 
+// kernels one stage launches (K2 and K3 are several kernels; WEAK-only work is skipped when no pixel is WEAK)
+int stage_kernel_count(const dvp_ctx* c, int stage) {
+	const bool weak = c->weak_count > 0;
+	switch (stage) {
+	case DVP_K2_GEN_EDGE_INFORM: return (weak ? 1 : 0) + (c->prm.use_edge ? 1 : 0) + ((c->prm.use_label && weak) ? 1 : 0) + 1;
+	case DVP_K3_FIND_NEAREST_STRONG: return (weak ? 1 : 0) + 1;
+	case DVP_K4_GEN_NEIGHBOURS: return weak ? 1 : 0;
+	case DVP_K10_BLACK_WEAK: return c->colour_count[0] > 0 ? 1 : 0;
+	case DVP_K11_RED_WEAK: return c->colour_count[1] > 0 ? 1 : 0;
+	default: return 1;
+	}
+}
+
 cudaError_t launch_stage(dvp_ctx* c, const KArgs& a, int stage, int iter) {
 	cudaStream_t st = c->stream;
 	switch (stage) {
@@ -170,6 +183,7 @@ cudaError_t launch_stage(dvp_ctx* c, const KArgs& a, int stage, int iter) {
 	case DVP_K14_RED_FILTER: return launch_filter(a, 1, st);
 	case DVP_K15_DEPTH_TO_WEAK: return launch_depth_to_weak(a, st);
 	case DVP_K16_LOCAL_REFINE: return launch_local_refine(a, st);
+	case DVP_K15_K16_FUSED: return launch_depth_to_weak_refine(a, st);
 	default: return cudaErrorInvalidValue;
 	}
 }
@@ -391,7 +405,7 @@ int dvp_upload_device(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* para
 int dvp_run_stage(dvp_ctx* ctx, int stage, int iter) {
 	if (!ctx) return DVP_ERR_ARG;
 	if (!ctx->uploaded) return DVP_ERR_STATE;
-	if (stage < 0 || stage >= DVP_STAGE_COUNT) return DVP_ERR_ARG;
+	if (stage < 0 || stage > DVP_K15_K16_FUSED) return DVP_ERR_ARG;
 	CK(cudaSetDevice(ctx->device));
 	const KArgs a = make_args(ctx);
 	cudaError_t e = launch_stage(ctx, a, stage, iter);
@@ -424,7 +438,8 @@ int dvp_run(dvp_ctx* ctx, int sync) {
 	for (int s = DVP_K1_INIT_RANDOM_STATES; s <= DVP_K6_RANDOM_INITIALIZATION; ++s) if ((r = go(s, 0))) return r;
 	for (int it = 0; it < ctx->prm.max_iterations; ++it)
 		for (int s = DVP_K7_BLACK_STRONG; s <= DVP_K11_RED_WEAK; ++s) if ((r = go(s, it))) return r;
-	for (int s = DVP_K12_DEPTH_NORMAL; s <= DVP_K16_LOCAL_REFINE; ++s) if ((r = go(s, 0))) return r;
+	for (int s = DVP_K12_DEPTH_NORMAL; s <= DVP_K14_RED_FILTER; ++s) if ((r = go(s, 0))) return r;
+	if ((r = go(DVP_K15_K16_FUSED, 0))) return r;   // K15 + K16 in one launch (timed under K15)
 	ctx->n_timed = n;
 	ctx->timed_valid = true;
 	if (sync) CK(cudaStreamSynchronize(st));
@@ -441,7 +456,7 @@ int dvp_last_run_times(dvp_ctx* ctx, float* total_ms, float* per_stage_ms, int* 
 	for (int i = 0; i < ctx->n_timed; ++i) {
 		float ms = 0.f;
 		CK(cudaEventElapsedTime(&ms, ctx->ev[2 * i], ctx->ev[2 * i + 1]));
-		if (per_stage_ms) per_stage_ms[ctx->ev_stage[i]] += ms;
+		if (per_stage_ms) per_stage_ms[ctx->ev_stage[i] == DVP_K15_K16_FUSED ? DVP_K15_DEPTH_TO_WEAK : ctx->ev_stage[i]] += ms;
 		sum += ms;
 	}
 	if (total_ms) {
@@ -452,8 +467,9 @@ int dvp_last_run_times(dvp_ctx* ctx, float* total_ms, float* per_stage_ms, int* 
 	}
 	(void)sum;
 	if (launches) {
-		// kernels launched by one dvp_run: K2 is two kernels when use_edge, the rest one each
-		*launches = ctx->n_timed + (ctx->prm.use_edge ? 1 : 0);
+		int n = 0;
+		for (int i = 0; i < ctx->n_timed; ++i) n += stage_kernel_count(ctx, ctx->ev_stage[i]);
+		*launches = n;
 	}
 	return DVP_OK;
 }

@@ -561,14 +561,8 @@ __global__ void __launch_bounds__(256, 3) k_depth_to_weak(const __grid_constant_
 }
 
 // K16 LocalRefine (APD.cu:4053-4139): 11-step disparity scan, keep the best depth if it improves by > 0.1.
-__global__ void __launch_bounds__(256, 3) k_local_refine(const __grid_constant__ KArgs a) {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	constexpr int T = 256;   // compile-time stride: shared-memory offsets become immediates
-	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
-	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-	if (x >= a.W || y >= a.H) return;
-	const int center = x + y * a.W;
+__device__ __forceinline__ void local_refine_pixel(const KArgs& a, int x, int y, int center, float2* wt) {
+	constexpr int T = 256;
 	ProfileCtx pc;
 	pc.plane = normal_to_refcam(a.ref, a.planes[center]);
 	pc.depth = pc.plane.w;
@@ -596,6 +590,114 @@ __global__ void __launch_bounds__(256, 3) k_local_refine(const __grid_constant__
 		if (temp_cost < min_cost) { min_cost = temp_cost; best_depth = p_depth; }
 	}
 	if (pc.cost_now - min_cost > 0.1) a.planes[center].w = best_depth;
+}
+__global__ void __launch_bounds__(256, 3) k_local_refine(const __grid_constant__ KArgs a) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= a.W || y >= a.H) return;
+	local_refine_pixel(a, x, y, x + y * a.W, wt);
+}
+
+// K15 + K16 in one kernel (what dvp_run launches).  LocalRefine's 11 disparity hypotheses (-5..5) are the middle
+// of DepthToWeak's 61 (-30..30): same plane, same depth formula, same views, and DepthToWeak changes nothing that
+// LocalRefine reads — so the per-view NCC and reprojection costs of those 11 are computed once and folded twice, in
+// DepthToWeak's order (temp = ncc + f*geom; sum += temp*w, APD.cu:3976-3986) and in LocalRefine's
+// (sum += ncc*w; sum += f*geom*w, APD.cu:4121-4129).  12*S_sel of the 73*S_sel NCCs of the two kernels remain as
+// S_sel (the cost of the current depth, which only LocalRefine uses).  The 6-pixel margin DepthToWeak skips is
+// refined by the stand-alone LocalRefine code.  Bit-exact against K15 followed by K16 (tests/test_gpu_parity.py).
+__global__ void __launch_bounds__(256, 3) k_depth_to_weak_refine(const __grid_constant__ KArgs a) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	constexpr int T = 256;
+	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= a.W || y >= a.H) return;
+	const int min_margin = 6;
+	const int center = x + y * a.W;
+	if (a.prm.use_radius && a.radius[center] == 0) a.radius[center] = a.prm.strong_radius;
+	if (x < min_margin || y < min_margin || x >= a.W - min_margin || y >= a.H - min_margin) {
+		a.weak[center] = DVP_UNKNOWN;
+		local_refine_pixel(a, x, y, center, wt);
+		return;
+	}
+	ProfileCtx pc;
+	pc.plane = normal_to_refcam(a.ref, a.planes[center]);
+	pc.depth = pc.plane.w;
+	if (pc.depth == 0) { a.weak[center] = DVP_UNKNOWN; return; }   // LocalRefine returns here too
+	const uint32_t sel = a.selected[center];
+	ViewWeights vw; vw.load(a.view_weight + (size_t)center * DVP_MAX_IMAGES);
+	RefPatch rp;
+	rp.prepare(a, x, y, a.prm.use_radius ? a.radius[center] : a.prm.strong_radius, wt, T);
+	profile_front<true>(a, x, y, center, sel, vw, rp, wt, T, pc);
+	if (pc.valid == 0) { a.weak[center] = DVP_UNKNOWN; return; }   // no selected view: LocalRefine returns as well (sel == 0)
+	const bool refine = (pc.weight_normal != 0);
+	pc.cost_now /= pc.weight_normal;
+	pc.base_line /= pc.valid;
+
+	const float disp = a.ref.K[0] * pc.base_line / pc.depth;
+	const int radius = 30;
+	const int p_costs_size = 2 * radius + 1;
+	float p_costs[p_costs_size];
+	float refine_min = 2.0f, refine_depth = pc.depth;   // LocalRefine's running minimum over p_disp = -5..5, in its order
+	for (int idx = 0; idx < p_costs_size; ++idx) {
+		const int p_disp = idx - radius;
+		const float p_depth = a.ref.K[0] * pc.base_line / (disp + p_disp);
+		if (p_depth < a.prm.depth_min || p_depth > a.prm.depth_max) { p_costs[idx] = 2.0f; continue; }
+		float4 t = pc.plane;
+		t.w = get_distance2origin(a.ref, x, y, p_depth, t);
+		float p_cost;
+		if (refine && p_disp >= -5 && p_disp <= 5) {
+			float acc15 = 0.0f, acc16 = 0.0f;
+			for (int v = 0; v < a.S; ++v) {
+				if (!is_set(sel, v)) continue;
+				const float wvf = (float)vw.get(v);
+				const float ncc = ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, t, rp, wt, T);
+				float temp = __fadd_rn(0.0f, ncc);
+				acc16 = __fmaf_rn(ncc, wvf, acc16);
+				if (a.prm.geom_consistency) {
+					const float g = geom_cost(a, a.views[v], a.tex_depth[v + 1], x, y, t);
+					temp = __fmaf_rn(a.prm.geom_factor, g, temp);
+					acc16 = __fmaf_rn(__fmul_rn(a.prm.geom_factor, g), wvf, acc16);
+				}
+				acc15 = __fmaf_rn(temp, wvf, acc15);
+			}
+			p_cost = acc15;
+			float temp_cost = acc16;
+			temp_cost /= pc.weight_normal;
+			if (temp_cost < refine_min) { refine_min = temp_cost; refine_depth = p_depth; }
+		} else {
+			p_cost = profile_cost_sum(a, x, y, t, sel, vw, rp, wt, T, false);
+		}
+		p_cost /= pc.weight_normal;
+		p_costs[idx] = DVP_MIN(2.0f, p_cost);
+	}
+	// LocalRefine's decision; DepthToWeak reads neither planes nor costs after this point
+	if (refine && pc.cost_now - refine_min > 0.1) a.planes[center].w = refine_depth;
+	// local minima of the profile (APD.cu:3999-4016)
+	uint64_t is_peak = 0;
+	int peak_count = 0, min_peak = 0;
+	float min_cost = 2.0f;
+	for (int i = 2; i < p_costs_size - 2; ++i) {
+		if (p_costs[i - 1] > p_costs[i] && p_costs[i + 1] > p_costs[i]) {
+			is_peak |= 1ull << i;
+			peak_count++;
+			if (p_costs[i] < min_cost) { min_peak = i; min_cost = p_costs[i]; }
+		}
+	}
+	if (abs(min_peak - radius) > a.prm.weak_peak_radius || p_costs[min_peak] > 0.5f) { a.weak[center] = DVP_WEAK; return; }
+	if (peak_count == 1) { a.weak[center] = (p_costs[min_peak] <= 0.15f) ? DVP_STRONG : DVP_WEAK; return; }
+	float var = 0.0f;
+	for (int i = 2; i < p_costs_size - 2; ++i) {
+		if (((is_peak >> i) & 1) && i != min_peak) {
+			const float dist = p_costs[i] - min_cost;
+			var += dist * dist;
+		}
+	}
+	var = sqrtf(var);
+	var /= (peak_count - 1);
+	a.weak[center] = (var > 0.2f) ? DVP_STRONG : DVP_WEAK;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -659,6 +761,11 @@ cudaError_t launch_depth_to_weak(const KArgs& a, cudaStream_t st) {
 	k_depth_to_weak<<<full_grid(a, b), b, patch_smem_bytes(256), st>>>(a);
 	return cudaGetLastError();
 }
+cudaError_t launch_depth_to_weak_refine(const KArgs& a, cudaStream_t st) {
+	dim3 b(32, 8);
+	k_depth_to_weak_refine<<<full_grid(a, b), b, patch_smem_bytes(256), st>>>(a);
+	return cudaGetLastError();
+}
 cudaError_t launch_local_refine(const KArgs& a, cudaStream_t st) {
 	dim3 b(32, 8);
 	k_local_refine<<<full_grid(a, b), b, patch_smem_bytes(256), st>>>(a);
@@ -669,6 +776,7 @@ cudaError_t configure_strong_kernels(int S) {
 	if ((e = cudaFuncSetAttribute(k_random_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
 	if ((e = cudaFuncSetAttribute(k_depth_to_weak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
 	if ((e = cudaFuncSetAttribute(k_local_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
+	if ((e = cudaFuncSetAttribute(k_depth_to_weak_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
 	if ((e = cudaFuncSetAttribute(k_strong_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kSweepThreads, S)))) return e;
 	return cudaSuccess;
 }

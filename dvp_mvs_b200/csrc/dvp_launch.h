@@ -43,6 +43,7 @@ cudaError_t launch_depth_normal(const KArgs& a, cudaStream_t st);               
 cudaError_t launch_filter(const KArgs& a, int red, cudaStream_t st);                             // K13 / K14
 cudaError_t launch_depth_to_weak(const KArgs& a, cudaStream_t st);                               // K15
 cudaError_t launch_local_refine(const KArgs& a, cudaStream_t st);                                // K16
+cudaError_t launch_depth_to_weak_refine(const KArgs& a, cudaStream_t st);                        // K15 + K16 fused (dvp_run)
 
 cudaError_t launch_fill_i32(int32_t* dst, int32_t v, int n, cudaStream_t st);
 // WEAK-pixel indexing (device-side replacement of the host loop APD.cpp:1182-1193)

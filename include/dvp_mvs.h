@@ -144,7 +144,9 @@ typedef enum dvp_stage {
 	DVP_K14_RED_FILTER = 13,         /* APD.cu:3313 */
 	DVP_K15_DEPTH_TO_WEAK = 14,      /* APD.cu:3892 */
 	DVP_K16_LOCAL_REFINE = 15,       /* APD.cu:4053 */
-	DVP_STAGE_COUNT = 16
+	DVP_STAGE_COUNT = 16,
+	/* product only: K15 and K16 in one launch, as dvp_run issues them (accepted by dvp_run_stage for parity tests) */
+	DVP_K15_K16_FUSED = 16
 } dvp_stage;
 
 typedef struct dvp_ctx dvp_ctx;

@@ -153,6 +153,46 @@ def test_weak_path_stagewise_vs_reference(geom):
             assert by[(st, n)]["mismatched"] <= limit, (st, n, by[(st, n)])
 
 
+@pytest.mark.parametrize("geom", [0, 1])
+def test_fused_k15_k16_equals_the_two_kernels(geom):
+    """dvp_run issues DepthToWeak and LocalRefine as one kernel that shares the NCCs of the 11 common disparity
+    hypotheses; from identical state it must leave exactly what K15 followed by K16 leave."""
+    from dvp_mvs_b200 import REFINE_ITER, REFINE_INIT
+    W, H, S = 320, 240, 2 + 2 * geom
+    sc = synth.make_scene(W, H, S)
+    p = c1_params(sc.depth_min, sc.depth_max, S, iters=2)
+    e = Engine(W, H, S, p)
+    e.upload(images=sc.images, cameras=sc.cameras, planes=sc.planes_init, edge=sc.edge, label=sc.label, seed=synth.SEED_RNG)
+    e.run()
+    planes, weak, sel, rad = e.download()
+    q = c1_params(sc.depth_min, sc.depth_max, S, iters=1, use_apd=1)
+    q.state = REFINE_ITER if geom else REFINE_INIT
+    q.use_detail = 1; q.ransac_threshold = 0.00875; q.rotate_time = 2; q.geom_consistency = geom
+    planes[40:60, 50:90, 3] = 0.0          # depth 0: both kernels leave these pixels alone
+    sel[100:110, 100:140] = 0              # no selected view
+    rad[::9, ::7] = 0                      # radius 0 is reset to strong_radius by DepthToWeak before LocalRefine reads it
+    e.upload(images=sc.images, depths=sc.depths if geom else None, cameras=sc.cameras, planes=planes, selected_views=sel,
+             weak_info=weak, edge=sc.edge, label=sc.label, radius=rad, seed=synth.SEED_RNG + 1, params=q)
+    for st, it in sequence(1):
+        if st in ("K15_DEPTH_TO_WEAK", "K16_LOCAL_REFINE"):
+            continue
+        e.run_stage(st, it)
+    vw = e.get("view_weight"); vw[120:130, 30:60] = 0; e.set("view_weight", vw)   # selected views with zero weight: LocalRefine returns
+    names = ("planes", "costs", "selected", "weak", "radius", "view_weight")
+    s0 = e.snapshot(names)
+    e.run_stage("K15_DEPTH_TO_WEAK"); e.run_stage("K16_LOCAL_REFINE")
+    two = e.snapshot(names)
+    e.restore(s0)
+    e.run_stage("K15_K16_FUSED")
+    one = e.snapshot(names)
+    assert (two["planes"][..., 3] != s0["planes"][..., 3]).sum() > 100     # LocalRefine moved some depths
+    assert (two["weak"] != s0["weak"]).sum() > 100                         # DepthToWeak relabelled some pixels
+    for n in names:
+        a, b = two[n], one[n]
+        same = (a.view(np.uint32) == b.view(np.uint32)) if a.dtype == np.float32 else (a == b)
+        assert same.all(), (n, int((~same).sum()))
+
+
 def test_product_matches_committed_golden_vectors():
     """Same stepping protocol against tests/golden/c1_64x48.npz (reference kernels, generated on B200)."""
     g = load_golden("c1_64x48.npz")
@@ -234,7 +274,9 @@ def test_full_size_properties():
     e.upload(**kw); e.run()
     out, weak, sel_out, rad = e.download()
     total, per_stage, launches = e.last_run_times()
-    assert launches == 11 + 5 * 2 + 1 and total > 0
+    # kernels actually launched: K1, K2 (edge sweep + per-pixel pass; nothing WEAK), K3, K5, K6; K7, K8, K9 per iteration
+    # (no WEAK pixel: K4, K10, K11 launch nothing); K12, K13, K14 and the fused K15+K16
+    assert launches == 6 + 3 * 2 + 4 and total > 0
     assert set(np.unique(weak)) <= {WEAK, STRONG, UNKNOWN}
     border = np.ones((H, W), bool); border[6:-6, 6:-6] = False
     assert (weak[border] == UNKNOWN).all()                      # APD.cu:3907-3910
