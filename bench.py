@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--state", default="refine_iter", choices=["first_init", "refine_init", "refine_iter"])
     ap.add_argument("--geom", type=int, default=1)
-    ap.add_argument("--cpu-sample", default="512x384", help="WxH of the bounded CPU-baseline sample (0 = skip)")
+    ap.add_argument("--cpu-sample", default="640x480", help="WxH of the bounded CPU-baseline sample (0 = skip)")
     return ap.parse_args()
 
 

@@ -738,9 +738,9 @@ cudaError_t launch_random_init(const KArgs& a, cudaStream_t st) {
 	return cudaGetLastError();
 }
 cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, cudaStream_t st) {
-	dim3 b(32, kSweepThreads / 32);
+	dim3 b(kSweepBlockX, kSweepThreads / kSweepBlockX);
 	const int yy_limit = ref_half_rows(a.H);
-	dim3 g((a.W + 31) / 32, (yy_limit + b.y - 1) / b.y, 1);
+	dim3 g((a.W + b.x - 1) / b.x, (yy_limit + b.y - 1) / b.y, 1);
 	k_strong_sweep<<<g, b, sweep_smem_bytes(kSweepThreads, a.S), st>>>(a, iter, red, yy_limit);
 	return cudaGetLastError();
 }

@@ -10,13 +10,20 @@ namespace dvp {
 #ifndef DVP_SWEEP_MIN_BLOCKS
 #define DVP_SWEEP_MIN_BLOCKS 3
 #endif
+#ifndef DVP_SWEEP_BX
+#define DVP_SWEEP_BX 32
+#endif
+constexpr int kSweepBlockX = DVP_SWEEP_BX;        // block width in pixels; height = threads / width row pairs (2 image rows each)
 constexpr int kSweepThreads = DVP_SWEEP_THREADS;  // threads per block of the propagation sweep
 constexpr int kSweepMinBlocks = DVP_SWEEP_MIN_BLOCKS;  // resident blocks per SM the register budget is cut for
 #ifndef DVP_SWEEP_RW
 #define DVP_SWEEP_RW 0
 #endif
 constexpr bool kSweepRW = DVP_SWEEP_RW != 0;  // sweep keeps only the reference samples in shared memory and re-evaluates the bilateral weight per use
-constexpr int kSweepRB = 3;         // patch rows of texture fetches in flight per thread in the sweep (all 36 samples)
+#ifndef DVP_SWEEP_RB
+#define DVP_SWEEP_RB 3
+#endif
+constexpr int kSweepRB = DVP_SWEEP_RB;         // patch rows of texture fetches in flight per thread in the sweep (all 36 samples)
 constexpr int kWideRB = 2;          // ... in the 256-thread, 24-warp/SM kernels (K6, K15, K16)
 
 // shared memory: 36 (w, w*r) pairs per thread

@@ -104,6 +104,38 @@ def test_sparse_mask_sweep_is_bit_exact_vs_reference():
     assert n_changed > 4000   # the sweep really did something
 
 
+@needs_ref
+@pytest.mark.parametrize("S", [8, 16])
+def test_many_source_views_strong_path_vs_reference(S):
+    """BASELINE config C5's view counts (8 and 16 source views; photometric, every pixel STRONG — the reference's WEAK
+    path is undefined beyond 4 views): race-free stages bit-exact, then the sweep on a sparse STRONG mask."""
+    W, H = 200, 152
+    sc = synth.make_scene(W, H, S)
+    p = c1_params(sc.depth_min, sc.depth_max, S)
+    ref = ref_oracle.engine(W, H, S, p); prod = Engine(W, H, S, p)
+    kw = dict(images=sc.images, cameras=sc.cameras, planes=sc.planes_init, edge=sc.edge, label=sc.label, seed=synth.SEED_RNG)
+    ref.upload(**kw); prod.upload(**kw)
+    res = step_compare(ref, prod, 1, stages=RACE_FREE)
+    bad = [r for r in res if r.get("error") or r["not_bit_exact"]]
+    assert len(res) >= 14 and not bad, bad[:4]
+    # sparse STRONG mask: no two processed pixels interact, so the sweep is race-free and must match bit for bit
+    q = c1_params(sc.depth_min, sc.depth_max, S, iters=1, use_apd=1)
+    yy, xx = np.mgrid[0:H, 0:W]
+    weak = np.where(((xx + yy) % 64) < 2, STRONG, WEAK).astype(np.uint8)
+    ref.upload(weak_info=weak, params=q, **kw); prod.upload(weak_info=weak, params=q, **kw)
+    for st in ("K1_INIT_RANDOM_STATES", "K2_GEN_EDGE_INFORM", "K6_RANDOM_INITIALIZATION"):
+        ref.run_stage(st)
+    for st in ("K7_BLACK_STRONG", "K8_RED_STRONG"):
+        pre = {n: ref.get(n) for n in STATE_BUFS}
+        ref.run_stage(st, 0)
+        for n, a in pre.items():
+            prod.set(n, a)
+        prod.run_stage(st, 0)
+        for n in STAGE_OUTPUTS[st]:
+            r = compare(n, ref.get(n), prod.get(n))
+            assert r["not_bit_exact"] == 0, (S, st, r)
+
+
 def _second_pass_inputs(W, H, S, geom):
     """Pass 1 (FIRST_INIT, all STRONG) on the reference -> inputs of a rounds>=1 pass with WEAK pixels."""
     from dvp_mvs_b200 import REFINE_INIT, REFINE_ITER
