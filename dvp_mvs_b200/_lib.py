@@ -68,7 +68,8 @@ ABI_SYMBOLS = ["version", "default_params", "create", "destroy", "upload", "run"
                "buffer_bytes", "get_buffer", "set_buffer", "last_run_times", "weak_count", "last_cuda_error", "stream"]
 PRODUCT_ONLY_SYMBOLS = ["upload_device", "restore_visibility", "rescale_map", "scene_create", "scene_destroy", "scene_level_size",
                         "scene_pass_params", "scene_set_max_iterations", "scene_set_view", "scene_set_level",
-                        "scene_set_initial_planes", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats"]
+                        "scene_set_initial_planes", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats",
+                        "scene_run_view", "scene_depth_map", "scene_remote_depth"]
 
 
 class DvpError(RuntimeError):
@@ -112,6 +113,9 @@ def load_library(path: str, prefix: str):
         f("scene_set_initial_planes").argtypes = [C.c_void_p, C.c_int, C.c_void_p]; f("scene_set_initial_planes").restype = C.c_int
         f("scene_run_pass").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64]; f("scene_run_pass").restype = C.c_int
         f("scene_run").argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_float)]; f("scene_run").restype = C.c_int
+        f("scene_run_view").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64]; f("scene_run_view").restype = C.c_int
+        f("scene_depth_map").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int)]; f("scene_depth_map").restype = C.c_int
+        f("scene_remote_depth").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]; f("scene_remote_depth").restype = C.c_int
         f("scene_get_view").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)] + [C.c_void_p] * 4; f("scene_get_view").restype = C.c_int
         f("scene_stats").argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]; f("scene_stats").restype = C.c_int
     return lib
@@ -274,7 +278,7 @@ class Scene:
 
     def __init__(self, num_views: int, num_levels: int, device: int = 0):
         self.lib = load_library(PRODUCT_LIB, "dvp_")
-        self.num_views, self.num_levels = num_views, num_levels
+        self.num_views, self.num_levels, self.device = num_views, num_levels, device
         self.h = self.lib.dvp_scene_create(device, num_views, num_levels)
         if not self.h:
             raise DvpError(f"dvp_scene_create failed (device {device}, {num_views} views, {num_levels} levels)")
@@ -331,6 +335,28 @@ class Scene:
         ms = C.c_float()
         self._check(self.lib.dvp_scene_run(self.h, int(seed), C.byref(ms)), "run")
         return float(ms.value)
+
+    def run_view(self, view: int, level: int, pass_: int, seed: int):
+        self._check(self.lib.dvp_scene_run_view(self.h, view, level, pass_, int(seed)), "run_view")
+
+    def view_level_size(self, view: int, level: int):
+        return self.level_size(*self._sizes[view], level)
+
+    def depth_tensor(self, view: int, level: int, owned: bool):
+        """The view's depth map as a zero-copy torch CUDA tensor [h, w] f32: the buffer to broadcast from (owned) or to
+        receive into (owned elsewhere; sized for `level`)."""
+        import torch
+        ptr, w, h = C.c_void_p(), C.c_int(), C.c_int()
+        if owned:
+            self._check(self.lib.dvp_scene_depth_map(self.h, view, C.byref(ptr), C.byref(w), C.byref(h)), "depth_map")
+            W, H = int(w.value), int(h.value)
+        else:
+            W, H = self.view_level_size(view, level)
+            self._check(self.lib.dvp_scene_remote_depth(self.h, view, W, H, C.byref(ptr)), "remote_depth")
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (H, W), "typestr": "<f4", "data": (int(ptr.value), False), "version": 2}
+        return torch.as_tensor(_Buf(), device=torch.device("cuda", self.device))
 
     def stats(self):
         ms, n = C.c_double(), C.c_longlong()

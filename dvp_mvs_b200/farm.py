@@ -72,6 +72,32 @@ def run_pass(num_views: int, process_view: Callable[[int], Dict[str, np.ndarray]
     return out
 
 
+def run_scene_schedule(scene, num_views: int, num_levels: int, seed: int, costs: Sequence[float] | None = None) -> Dict[int, int]:
+    """The multi-scale schedule (main.cpp:449-511) with the views of every pass dealt to the ranks.
+
+    `scene` holds every view's pyramid on this rank's GPU (dvp_mvs_b200.Scene, or anything with `run_view(view, level,
+    pass, seed)` and `depth_tensor(view, level, owned) -> torch tensor`).  Each rank runs its own views of a pass in
+    index order; the one exchange step per pass is a broadcast of every view's depth map from its owner straight between
+    the scenes' device buffers (NCCL; gloo in the CPU tests) — depth is all a view needs from its sources.  Within a
+    pass a rank sees its own views' fresh depths and the other ranks' previous-pass depths (block Gauss-Seidel); with
+    one rank this is exactly the reference's sequential order.  Returns {view: owner rank}."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    owner = {v: r for r in range(world) for v in partition(num_views, world, r, costs)}
+    mine = [v for v in range(num_views) if owner[v] == rank]
+    it = 0
+    for level in range(num_levels):
+        for pass_ in range(4):
+            for v in mine:
+                scene.run_view(v, level, pass_, seed + 1000 * it + v)   # same seeds as dvp_scene_run
+            if world > 1:
+                for v in range(num_views):
+                    dist.broadcast(scene.depth_tensor(v, level, owner[v] == rank), src=owner[v])
+            it += 1
+    return owner
+
+
 def make_gpu_view_processor(scenes, params, iters_hint: int | None = None):
     """process_view for synthetic scenes: one Engine per rank, reused across its views."""
     from . import Engine

@@ -231,6 +231,14 @@ int dvp_scene_set_level(dvp_scene* scene, int view, int level, const float* imag
 int dvp_scene_set_initial_planes(dvp_scene* scene, int view, const float* planes);
 /* One pass over every view (one inner loop of main.cpp:452-511); view v runs with seed + v. */
 int dvp_scene_run_pass(dvp_scene* scene, int level, int pass, uint64_t seed);
+/* One (view, pass) job — one ProcessProblem — for callers that deal views to several GPUs. */
+int dvp_scene_run_view(dvp_scene* scene, int view, int level, int pass, uint64_t seed);
+/* The exchange step of a farmed pass: a view's depth map is all another rank needs from it (geometric consistency reads
+ * the source views' depths, APD.cpp:1147-1166).  dvp_scene_depth_map returns the device buffer of a view this rank
+ * owns (to broadcast from); dvp_scene_remote_depth sizes and returns the buffer of a view owned elsewhere (to
+ * receive into) and marks it usable as a source. */
+int dvp_scene_depth_map(dvp_scene* scene, int view, float** device_ptr, int* w, int* h);
+int dvp_scene_remote_depth(dvp_scene* scene, int view, int w, int h, float** device_ptr);
 /* The whole schedule: num_levels rounds x 4 passes x all views. `device_ms` (may be NULL): summed device time. */
 int dvp_scene_run(dvp_scene* scene, uint64_t seed, float* device_ms);
 /* Current maps of one view (size returned in *w, *h); destinations may be host or device memory, or NULL. */

@@ -69,3 +69,80 @@ def test_two_rank_gloo_pass_gathers_every_view(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert (tmp_path / "rank0.txt").read_text() == "RANK_OK 0 [0, 2, 4]"   # one file per rank: stdout of two ranks interleaves
     assert (tmp_path / "rank1.txt").read_text() == "RANK_OK 1 [1, 3]"
+
+
+FAKE_SCENE = '''
+import numpy as np, torch
+class FakeScene:
+    """Stands in for dvp_mvs_b200.Scene on the CPU: a view's new depth is a function of the pass, the seed and the depth
+    maps of its sources as this rank currently holds them - enough to expose any ordering or exchange mistake."""
+    def __init__(self, num_views, sizes):
+        self.V, self.sizes = num_views, sizes
+        self.depth = {v: torch.full((sizes[0][1], sizes[0][0]), float(v + 1)) for v in range(num_views)}
+        self.log = []
+    def src(self, v):
+        return [(v + 1) % self.V, (v + 2) % self.V]
+    def run_view(self, v, level, pass_, seed):
+        w, h = self.sizes[level]
+        s = sum(float(self.depth[u].double().mean()) for u in self.src(v)) if pass_ > 0 else 0.0   # pass 0: no geometric term
+        self.depth[v] = torch.full((h, w), float((seed % 9973) * 1e-3 + 0.5 * s + level), dtype=torch.float32)
+        self.log.append((v, level, pass_, seed))
+    def depth_tensor(self, v, level, owned):
+        w, h = self.sizes[level]
+        if not owned and tuple(self.depth[v].shape) != (h, w):
+            self.depth[v] = torch.zeros((h, w), dtype=torch.float32)
+        return self.depth[v]
+'''
+
+
+def test_scene_schedule_single_process_order_and_seeds():
+    ns = {}
+    exec(FAKE_SCENE, ns)
+    from dvp_mvs_b200.farm import run_scene_schedule
+    sc = ns["FakeScene"](3, [(8, 6), (16, 12)])
+    owner = run_scene_schedule(sc, 3, 2, seed=100)
+    assert owner == {0: 0, 1: 0, 2: 0}
+    # 2 levels x 4 passes x 3 views, views in index order inside a pass, seed + 1000 * pass index + view (as dvp_scene_run)
+    assert sc.log == [(v, it // 4, it % 4, 100 + 1000 * it + v) for it in range(8) for v in range(3)]
+    assert tuple(sc.depth[0].shape) == (12, 16)
+
+
+def test_scene_schedule_two_ranks_exchange_depth_maps(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text("import os, sys, json\nsys.path.insert(0, %r)\n" % ROOT + FAKE_SCENE + textwrap.dedent(f"""
+        import torch.distributed as dist
+        from dvp_mvs_b200.farm import run_scene_schedule, partition
+        dist.init_process_group("gloo")
+        rank = dist.get_rank()
+        V, sizes = 5, [(8, 6), (16, 12)]
+        sc = FakeScene(V, sizes)
+        owner = run_scene_schedule(sc, V, 2, seed=7)
+        assert owner == {{0: 0, 1: 1, 2: 0, 3: 1, 4: 0}}, owner
+        assert [e[0] for e in sc.log[:2]] == partition(V, 2, rank)[:2]
+        # reference semantics: both ranks simulated in one process (own views fresh, remote views from the previous pass)
+        sims = [FakeScene(V, sizes) for _ in range(2)]
+        it = 0
+        for level in range(2):
+            for p in range(4):
+                for r in range(2):
+                    for v in partition(V, 2, r):
+                        sims[r].run_view(v, level, p, 7 + 1000 * it + v)
+                for v in range(V):
+                    for r in range(2):
+                        sims[r].depth[v] = sims[owner[v]].depth[v].clone()
+                it += 1
+        for v in range(V):
+            assert torch.equal(sc.depth[v], sims[rank].depth[v]), v
+        open(os.path.join({str(tmp_path)!r}, f"rank{{rank}}.json"), "w").write(json.dumps([float(sc.depth[v][0, 0]) for v in range(V)]))
+        dist.destroy_process_group()
+    """))
+    import socket, json
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    a = json.loads((tmp_path / "rank0.json").read_text()); b = json.loads((tmp_path / "rank1.json").read_text())
+    assert a == b and len(set(a)) == 5          # every rank ends with every view's depth map, and they are the same maps

@@ -175,3 +175,21 @@ def test_scene_error_behaviour():
         sc.run_pass(1, 0, 1)                       # level out of range
     with pytest.raises(DvpError):
         Scene(1, 1)                                # a scene needs a source view
+
+
+@pytest.mark.gpu
+def test_scene_farm_with_one_rank_is_the_sequential_schedule():
+    """dvp_mvs_b200.farm.run_scene_schedule drives the scene view by view (what each rank of a multi-GPU run does);
+    with a single rank it must reproduce dvp_scene_run exactly (0 iterations: deterministic stages only)."""
+    from dvp_mvs_b200.farm import run_scene_schedule
+    mv = synth.make_multiview(320, 240, 3, 2, seed=6)
+    a = _fill_scene(mv); a.set_max_iterations(0); a.run(seed=31)
+    b = _fill_scene(mv); b.set_max_iterations(0)
+    owner = run_scene_schedule(b, 3, 2, seed=31)
+    assert owner == {0: 0, 1: 0, 2: 0}
+    for v in range(3):
+        pa, wa, sa, ra = a.get_view(v); pb, wb, sb, rb = b.get_view(v)
+        assert (pa.view(np.uint32) == pb.view(np.uint32)).all() and (wa == wb).all() and (sa == sb).all() and (ra == rb).all()
+        t = b.depth_tensor(v, 1, True)
+        # zero-copy view of the resident depth map (bit patterns: a few depths are NaN, bug B18)
+        assert tuple(t.shape) == (120, 160) and (t.cpu().numpy().view(np.uint32) == np.ascontiguousarray(pb[..., 3]).view(np.uint32)).all()

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Multi-GPU run of the whole multi-scale schedule: views dealt to the ranks, one NCCL broadcast of each
+view's depth map per pass, straight between the scenes' device buffers.
+  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/farm_scene_demo.py [--full 1280x960] [--views 6]
+Rank 0 prints one JSON line: wall time, agreement of the exchanged depth maps across ranks, depth error per view."""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", default="1280x960"); ap.add_argument("--views", type=int, default=6); ap.add_argument("--levels", type=int, default=2)
+    ap.add_argument("--src", type=int, default=4)
+    a = ap.parse_args()
+    fw, fh = (int(v) for v in a.full.split("x"))
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from dvp_mvs_b200 import synth, Scene
+    from dvp_mvs_b200.farm import run_scene_schedule
+    # warm-up: CUDA context, kernel modules and NCCL communicator outside the timed region
+    wmv = synth.make_multiview(320, 240, 3, 1, seed=9)
+    wsc = Scene(3, 1, device=local)
+    for v in range(3):
+        wsc.set_view(v, wmv.cameras[v], 320, 240, wmv.src_views[v])
+        wsc.set_level(v, 0, wmv.levels[0][v]["image"], wmv.levels[0][v]["edge"], wmv.levels[0][v]["label"])
+        wsc.set_initial_planes(v, wmv.planes_init[v])
+    run_scene_schedule(wsc, 3, 1, seed=1); wsc.close()
+    mv = synth.make_multiview(fw, fh, a.views, a.levels, seed=0, num_src=a.src)
+    V = a.views
+    sc = Scene(V, a.levels, device=local)
+    for v in range(V):
+        sc.set_view(v, mv.cameras[v], fw, fh, mv.src_views[v])
+        for l in range(a.levels):
+            L = mv.levels[l][v]
+            sc.set_level(v, l, L["image"], L["edge"], L["label"])
+        sc.set_initial_planes(v, mv.planes_init[v])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    owner = run_scene_schedule(sc, V, a.levels, seed=0x5EED)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    # every rank must hold the same depth map for every view after the last exchange
+    # checksum of the bit patterns (a few depths are NaN — reference bug B18 — so values cannot be compared with ==)
+    sums = torch.stack([sc.depth_tensor(v, a.levels - 1, owner[v] == rank).view(torch.int32).to(torch.int64).sum() for v in range(V)])
+    lo, hi = sums.clone(), sums.clone()
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    errs = {}
+    for v in range(V):
+        d = sc.depth_tensor(v, a.levels - 1, owner[v] == rank).cpu().numpy()
+        truth = mv.levels[-1][v]["depth"]; ok = d > 0
+        errs[v] = float(np.median(np.abs(d[ok] - truth[ok]) / truth[ok]))
+    if rank == 0:
+        print(json.dumps({"world": world, "views": V, "levels": a.levels, "finest": [mv.levels[-1][0]["w"], mv.levels[-1][0]["h"]],
+                          "wall_s": round(wall, 3), "depth_maps_identical_across_ranks": bool(torch.equal(lo, hi)),
+                          "owner": owner, "median_rel_depth_error": {k: round(e, 5) for k, e in errs.items()}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
