@@ -3,6 +3,7 @@
 #include "dvp_strong.cuh"
 #include "dvp_launch.h"
 #include <cfloat>
+#include <mutex>
 
 namespace dvp {
 
@@ -710,9 +711,11 @@ __global__ void k_fill_sd_table(float* out) {
 	if (k < kHoistSamples) out[k] = RefPatch::spatial_dist(-5 + 2 * (k / kHoistAxis), -5 + 2 * (k % kHoistAxis));
 }
 cudaError_t launch_fill_sd_table(cudaStream_t st) {
-	static bool ready[64] = {false};
+	static std::mutex mu;
+	static bool ready[256] = {false};
 	int dev = 0; cudaGetDevice(&dev);
-	if (dev >= 0 && dev < 64 && ready[dev]) return cudaSuccess;
+	std::lock_guard<std::mutex> lock(mu);
+	if (dev >= 0 && dev < 256 && ready[dev]) return cudaSuccess;
 	float* tmp = nullptr;
 	cudaError_t e = cudaMalloc((void**)&tmp, kHoistSamples * sizeof(float));
 	if (e != cudaSuccess) return e;
@@ -720,7 +723,7 @@ cudaError_t launch_fill_sd_table(cudaStream_t st) {
 	e = cudaMemcpyToSymbolAsync(c_sd_r5, tmp, kHoistSamples * sizeof(float), 0, cudaMemcpyDeviceToDevice, st);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
 	cudaFree(tmp);
-	if (e == cudaSuccess && dev >= 0 && dev < 64) ready[dev] = true;
+	if (e == cudaSuccess && dev >= 0 && dev < 256) ready[dev] = true;
 	return e;
 }
 cudaError_t launch_setup_views(const dvp_camera* cams, ViewConst* views, int S, cudaStream_t st) {

@@ -4,6 +4,7 @@
 #include "dvp_weak.cuh"
 #include "dvp_launch.h"
 #include <cfloat>
+#include <mutex>
 
 namespace dvp {
 
@@ -739,10 +740,7 @@ cudaError_t launch_edge_inform(const KArgs& a, cudaStream_t st) {
 	// part (a) (candidate offsets) is only ever read by the deformable NCC of WEAK pixels; with no WEAK pixel in
 	// the view it has no reader and is skipped (the reference computes it regardless: 31 % of its pass at S=4).
 	if (a.weak_count > 0) {
-		static bool table_ready[64] = {false};
-		int dev = 0; cudaGetDevice(&dev);
-		if (dev >= 0 && dev < 64 && !table_ready[dev]) { k_fill_sector_table<<<1, dim3(11, 11), 0, st>>>(); table_ready[dev] = true; }
-		dim3 b(32, 8);
+		dim3 b(32, 8);   // the sector table was filled by configure_weak_kernels at upload
 		dim3 g((a.W + 31) / 32, (a.H + 7) / 8, 1);
 		k_candidate<<<g, b, 0, st>>>(a);
 	}
@@ -763,6 +761,22 @@ cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count,
 	k_weak_sweep<<<(count + 63) / 64, 64, patch_smem_bytes(64), st>>>(a, colour_list, count, iter);
 	return cudaGetLastError();
 }
-cudaError_t configure_weak_kernels(int S) { return cudaSuccess; }
+// One-time, per-device fill of the sector table, completed before the flag is set so that contexts on other streams
+// (or host threads) of the same device can never launch k_candidate ahead of it.
+cudaError_t configure_weak_kernels(int S) {
+	(void)S;
+	static std::mutex mu;
+	static bool table_ready[256] = {false};
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	std::lock_guard<std::mutex> lock(mu);
+	if (dev >= 0 && dev < 256 && table_ready[dev]) return cudaSuccess;
+	k_fill_sector_table<<<1, dim3(11, 11)>>>();
+	if ((e = cudaGetLastError()) != cudaSuccess) return e;
+	if ((e = cudaDeviceSynchronize()) != cudaSuccess) return e;
+	if (dev >= 0 && dev < 256) table_ready[dev] = true;
+	return cudaSuccess;
+}
 
 }  // namespace dvp
