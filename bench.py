@@ -305,7 +305,11 @@ def main():
                         "note": "TEX-bound kernel: ~%d bilinear source fetches per byte of compulsory traffic; the binding roof is the texture unit "
                                 "(measured 1155 Gfetch/s coherent, profiles/r01_tex_coherence_ubench.txt), not HBM" % int(samples_per_launch / bytes_per_launch),
                         "tex_gsamples_per_s": samples_per_launch / (sweep_ms * 1e-3) / 1e9, "tex_peak_gsamples_per_s": 1155.0},
-           "per_stage_ms": [round(v, 3) for v in per_stage], "clocks": clocks}
+           "per_stage_ms": [round(v, 3) for v in per_stage],
+           "stage_share": {k: round(v / max(sum(per_stage), 1e-9), 4) for k, v in zip(
+               ("K1", "K2", "K3", "K4", "K5", "K6", "K7", "K8", "K9", "K10", "K11", "K12", "K13", "K14", "K15+K16", "K16"), per_stage) if v > 0},
+           "sweep_mpix_per_s_per_iteration": N / ((per_stage[6] + per_stage[7]) / args.iters) / 1e3,   # K7 + K8 alone
+           "clocks": clocks}
     cb = cpu_baseline(args, cores)
     if cb:
         out["cpu_baseline"] = cb

@@ -75,3 +75,26 @@ def test_product_package_never_references_the_oracle():
                 assert "libapd_" not in src, f                                   # never names an oracle library
                 assert not re.search(r"^\s*(import|from)\s+(cpu_oracle|ref_oracle)", src, flags=re.M), f
                 assert "dlopen" not in src and "/oracle/_ref" not in src, f
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """The boundary is a C ABI: include/dvp_mvs.h must compile as C99 and a C program must link against
+    libdvp_mvs.so and reach the entry points that need no GPU."""
+    import shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "dvp_mvs.h"\n'
+                   'int main(void) { dvp_params p; dvp_default_params(&p);\n'
+                   '  if (dvp_create(0, 0, 0, 0, &p) != NULL) return 2;          /* invalid size: rejected before any CUDA call */\n'
+                   '  if (dvp_restore_visibility(NULL, 8, NULL) != DVP_ERR_ARG) return 3;\n'
+                   '  if (dvp_scene_create(0, 1, 1) != NULL) return 4;           /* a scene needs at least two views */\n'
+                   '  printf("%s %d %d %.3f\\n", dvp_version(), p.max_iterations, p.strong_radius, p.ransac_threshold); return 0; }\n')
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(_lib.PRODUCT_LIB)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-l:libdvp_mvs.so", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.split()[-3:] == ["3", "5", "0.005"] and "sm_100a" in out.stdout
