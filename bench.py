@@ -235,7 +235,7 @@ def main():
         eng.run(sync=False)
 
     def step_e2e():
-        eng.upload_raw(h_in, device=False)
+        eng.upload_raw(h_in, device=False, overlapped=True)   # pinned buffers: the large maps stream in behind K1..K5
         eng.run(sync=False)
         eng._check(eng._f("download")(eng.ctx, hptr(out_planes), hptr(out_weak), hptr(out_sel), hptr(out_rad)), "download")
 

@@ -66,7 +66,7 @@ STATUS = {0: "DVP_OK", -1: "DVP_ERR_ARG", -2: "DVP_ERR_CUDA", -3: "DVP_ERR_STATE
 
 ABI_SYMBOLS = ["version", "default_params", "create", "destroy", "upload", "run", "run_stage", "download",
                "buffer_bytes", "get_buffer", "set_buffer", "last_run_times", "weak_count", "last_cuda_error", "stream"]
-PRODUCT_ONLY_SYMBOLS = ["upload_device", "restore_visibility", "rescale_map", "scene_create", "scene_destroy", "scene_level_size",
+PRODUCT_ONLY_SYMBOLS = ["upload_device", "upload_overlapped", "restore_visibility", "rescale_map", "scene_create", "scene_destroy", "scene_level_size",
                         "scene_pass_params", "scene_set_max_iterations", "scene_set_view", "scene_set_level",
                         "scene_set_initial_planes", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats",
                         "scene_run_view", "scene_depth_map", "scene_remote_depth"]
@@ -101,6 +101,7 @@ def load_library(path: str, prefix: str):
     f("stream").argtypes = [C.c_void_p]; f("stream").restype = C.c_void_p
     if prefix == "dvp_":
         f("upload_device").argtypes = [C.c_void_p, C.POINTER(Inputs), C.POINTER(Params)]; f("upload_device").restype = C.c_int
+        f("upload_overlapped").argtypes = [C.c_void_p, C.POINTER(Inputs), C.POINTER(Params)]; f("upload_overlapped").restype = C.c_int
         f("restore_visibility").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]; f("restore_visibility").restype = C.c_int
         f("rescale_map").argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]; f("rescale_map").restype = C.c_int
         f("scene_create").argtypes = [C.c_int, C.c_int, C.c_int]; f("scene_create").restype = C.c_void_p
@@ -184,7 +185,7 @@ class Engine:
             pass
 
     def upload(self, images, cameras, planes, depths=None, selected_views=None, weak_info=None, edge=None,
-               label=None, radius=None, seed=0x5EED, params: Params | None = None):
+               label=None, radius=None, seed=0x5EED, params: Params | None = None, overlapped: bool = False):
         S, H, W = self.S, self.H, self.W
         new_params = self.params
         if params is not None:
@@ -203,13 +204,14 @@ class Engine:
         )
         inp = Inputs(*[_ptr(keep[k]) for k in ("images", "depths", "cameras", "planes", "selected_views",
                                                   "weak_info", "edge", "label", "radius")], int(seed))
-        self._check(self._f("upload")(self.ctx, C.byref(inp), C.byref(new_params)), "upload")
+        name = "upload_overlapped" if overlapped else "upload"   # overlapped: the arrays stay referenced in self._keep
+        self._check(self._f(name)(self.ctx, C.byref(inp), C.byref(new_params)), name)
         self._keep = keep
         self.params = new_params
 
-    def upload_raw(self, inp: Inputs, device: bool = False):
-        fn = self._f("upload_device") if device else self._f("upload")
-        self._check(fn(self.ctx, C.byref(inp), C.byref(self.params)), "upload_device" if device else "upload")
+    def upload_raw(self, inp: Inputs, device: bool = False, overlapped: bool = False):
+        name = "upload_device" if device else ("upload_overlapped" if overlapped else "upload")
+        self._check(self._f(name)(self.ctx, C.byref(inp), C.byref(self.params)), name)
 
     def run(self, sync: bool = True, mode: int | None = None):
         arg = (1 if sync else 0) if mode is None else mode

@@ -25,6 +25,10 @@ struct dvp_ctx {
 	int W = 0, H = 0, S = 0, N = 0;
 	dvp_params prm;
 	cudaStream_t stream = nullptr;
+	// dvp_upload_overlapped: the large maps travel on a second stream while K1..K5 already run
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t ev_main_idle = nullptr, ev_planes = nullptr, ev_maps = nullptr;
+	bool copies_pending = false;
 	bool uploaded = false;
 	unsigned long long seed = 0;
 	int weak_count = 0;
@@ -110,10 +114,15 @@ KArgs make_args(const dvp_ctx* c) {
 	return a;
 }
 
-int make_texture(dvp_ctx* ctx, cudaArray_t* arr, cudaTextureObject_t* tex, const float* src, cudaMemcpyKind kind) {
+int fill_texture(dvp_ctx* ctx, cudaArray_t arr, const float* src, cudaMemcpyKind kind, cudaStream_t stream) {
+	CK(cudaMemcpy2DToArrayAsync(arr, 0, 0, src, ctx->W * sizeof(float), ctx->W * sizeof(float), ctx->H, kind, stream));
+	return DVP_OK;
+}
+
+// array + texture object, created once per context and image slot (no data yet)
+int ensure_texture(dvp_ctx* ctx, cudaArray_t* arr, cudaTextureObject_t* tex) {
 	cudaChannelFormatDesc desc = cudaCreateChannelDesc(32, 0, 0, 0, cudaChannelFormatKindFloat);
 	if (!*arr) CK(cudaMallocArray(arr, &desc, ctx->W, ctx->H));
-	CK(cudaMemcpy2DToArrayAsync(*arr, 0, 0, src, ctx->W * sizeof(float), ctx->W * sizeof(float), ctx->H, kind, ctx->stream));
 	if (!*tex) {
 		// hardware bilinear filter, unnormalised coordinates, clamp addressing: what the reference's texture
 		// objects do in effect (it asks for wrap, which degrades to clamp with unnormalised coordinates)
@@ -205,9 +214,18 @@ struct UploadSrc {
 	uint64_t seed = 0;
 };
 
-int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bool from_device);
+int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bool from_device, bool overlap = false);
 
-int upload_common(dvp_ctx* ctx, const dvp_inputs* din, const dvp_params* params, bool from_device) {
+// everything on the context stream is ordered after the copies of an overlapped upload
+int join_copies(dvp_ctx* ctx) {
+	if (ctx->copies_pending) {
+		CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_maps, 0));
+		ctx->copies_pending = false;
+	}
+	return DVP_OK;
+}
+
+int upload_common(dvp_ctx* ctx, const dvp_inputs* din, const dvp_params* params, bool from_device, bool overlap = false) {
 	if (!ctx || !din || !din->images || !din->cameras || !din->planes) return DVP_ERR_ARG;
 	UploadSrc u;
 	const size_t N = (size_t)ctx->N;
@@ -219,10 +237,10 @@ int upload_common(dvp_ctx* ctx, const dvp_inputs* din, const dvp_params* params,
 	u.cameras = din->cameras; u.cameras_on_device = from_device;
 	u.planes = din->planes; u.selected_views = din->selected_views; u.weak_info = din->weak_info;
 	u.edge = din->edge; u.label = din->label; u.radius = din->radius; u.seed = din->seed;
-	return upload_parts(ctx, &u, params, from_device);
+	return upload_parts(ctx, &u, params, from_device, overlap);
 }
 
-int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bool from_device) {
+int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bool from_device, bool overlap) {
 	if (!ctx || !in || !in->images[0] || !in->cameras || !in->planes) return DVP_ERR_ARG;
 	CK(cudaSetDevice(ctx->device));
 	{   // validate first: a rejected upload must leave the context as it was
@@ -237,23 +255,24 @@ int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bo
 	const size_t N = (size_t)ctx->N;
 	cudaStream_t st = ctx->stream;
 	ctx->seed = in->seed;
-	for (int i = 0; i <= ctx->S; ++i) {
+	for (int i = 0; i <= ctx->S; ++i)
 		if (!in->images[i] || (in->have_depths && !in->depths[i])) return DVP_ERR_ARG;
-		int r = make_texture(ctx, &ctx->img_arr[i], &ctx->img_tex[i], in->images[i], kind);
+	{   // a previous overlapped upload that was never run: its copies must not overtake this one
+		int r = join_copies(ctx);
 		if (r) return r;
-		if (in->have_depths) {
-			r = make_texture(ctx, &ctx->dep_arr[i], &ctx->dep_tex[i], in->depths[i], kind);
-			if (r) return r;
-		}
 	}
-	CK(cudaMemcpyAsync(ctx->ref_img, in->images[0], N * 4, kind, st));
+	for (int i = 0; i <= ctx->S; ++i) {
+		int r = ensure_texture(ctx, &ctx->img_arr[i], &ctx->img_tex[i]);
+		if (!r && in->have_depths) r = ensure_texture(ctx, &ctx->dep_arr[i], &ctx->dep_tex[i]);
+		if (r) return r;
+	}
 	CK(cudaMemcpyAsync(ctx->d_img_tex, ctx->img_tex, sizeof(ctx->img_tex), cudaMemcpyHostToDevice, st));
 	CK(cudaMemcpyAsync(ctx->d_dep_tex, ctx->dep_tex, sizeof(ctx->dep_tex), cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(ctx->ref_img, in->images[0], N * 4, kind, st));
 	CK(cudaMemcpyAsync(ctx->cams, in->cameras, sizeof(dvp_camera) * (ctx->S + 1), in->cameras_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
 	if (in->cameras_on_device) CK(cudaMemcpyAsync(&ctx->ref_cam, in->cameras, sizeof(dvp_camera), cudaMemcpyDeviceToHost, st));
 	else ctx->ref_cam = in->cameras[0];
 	CK(launch_setup_views(ctx->cams, ctx->views, ctx->S, st));
-	CK(cudaMemcpyAsync(ctx->planes, in->planes, N * 16, kind, st));
 	CK(cudaMemsetAsync(ctx->fit_planes, 0, N * 16, st));
 	if (in->selected_views) CK(cudaMemcpyAsync(ctx->selected, in->selected_views, N * 4, kind, st));
 	else CK(cudaMemsetAsync(ctx->selected, 0, N * 4, st));
@@ -306,10 +325,27 @@ int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bo
 	if (in->radius) CK(cudaMemcpyAsync(ctx->radius, in->radius, N * 4, kind, st));
 	else CK(launch_fill_i32(ctx->radius, ctx->prm.strong_radius, ctx->N, st));
 	if (have_weak && in->radius) CK(launch_reset_unknown_radius(ctx->weak, ctx->radius, ctx->prm.strong_radius, ctx->N, st));
+	// The large maps — plane hypotheses (first read by K4), the 1+S images (K6) and depth maps (K6/K7) — go to the
+	// copy stream when the upload is overlapped; everything K1..K3 and K5 need stays on the context stream.  They are
+	// enqueued LAST: the host-to-device DMA engine serves copies in issue order, whatever the stream.
+	cudaStream_t cs = overlap ? ctx->copy_stream : st;
+	if (overlap) {
+		CK(cudaEventRecord(ctx->ev_main_idle, st));
+		CK(cudaStreamWaitEvent(cs, ctx->ev_main_idle, 0));   // the buffers may still be in use by work queued on the context stream
+	}
+	CK(cudaMemcpyAsync(ctx->planes, in->planes, N * 16, kind, cs));
+	if (overlap) CK(cudaEventRecord(ctx->ev_planes, cs));
 	CK(launch_fill_sd_table(st));
 	CK(configure_strong_kernels(ctx->S));
 	CK(configure_weak_kernels(ctx->S));
-	CK(cudaStreamSynchronize(st));
+	if (overlap) CK(cudaStreamSynchronize(st));   // the small maps are in place; what follows is not waited for
+	for (int i = 0; i <= ctx->S; ++i) {
+		int r = fill_texture(ctx, ctx->img_arr[i], in->images[i], kind, cs);
+		if (!r && in->have_depths) r = fill_texture(ctx, ctx->dep_arr[i], in->depths[i], kind, cs);
+		if (r) return r;
+	}
+	if (overlap) { CK(cudaEventRecord(ctx->ev_maps, cs)); ctx->copies_pending = true; }
+	else CK(cudaStreamSynchronize(st));
 	ctx->uploaded = true;
 	ctx->timed_valid = false;
 	return DVP_OK;
@@ -339,6 +375,10 @@ dvp_ctx* dvp_create(int device, int width, int height, int num_src, const dvp_pa
 	c->device = device; c->W = width; c->H = height; c->S = num_src; c->N = width * height; c->prm = *params;
 	const size_t N = (size_t)c->N;
 	bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&c->ev_main_idle, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&c->ev_planes, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&c->ev_maps, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && zalloc(&c->d_img_tex, DVP_MAX_IMAGES) == cudaSuccess;
 	ok = ok && zalloc(&c->d_dep_tex, DVP_MAX_IMAGES) == cudaSuccess;
 	ok = ok && zalloc(&c->ref_img, N) == cudaSuccess;
@@ -382,6 +422,10 @@ void dvp_destroy(dvp_ctx* c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+	if (c->ev_main_idle) cudaEventDestroy(c->ev_main_idle);
+	if (c->ev_planes) cudaEventDestroy(c->ev_planes);
+	if (c->ev_maps) cudaEventDestroy(c->ev_maps);
 	for (int i = 0; i < DVP_MAX_IMAGES; ++i) {
 		if (c->img_tex[i]) cudaDestroyTextureObject(c->img_tex[i]);
 		if (c->dep_tex[i]) cudaDestroyTextureObject(c->dep_tex[i]);
@@ -401,12 +445,14 @@ void dvp_destroy(dvp_ctx* c) {
 
 int dvp_upload(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params) { return upload_common(ctx, in, params, false); }
 int dvp_upload_device(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params) { return upload_common(ctx, in, params, true); }
+int dvp_upload_overlapped(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params) { return upload_common(ctx, in, params, false, true); }
 
 int dvp_run_stage(dvp_ctx* ctx, int stage, int iter) {
 	if (!ctx) return DVP_ERR_ARG;
 	if (!ctx->uploaded) return DVP_ERR_STATE;
 	if (stage < 0 || stage > DVP_K15_K16_FUSED) return DVP_ERR_ARG;
 	CK(cudaSetDevice(ctx->device));
+	{ int r = join_copies(ctx); if (r) return r; }
 	const KArgs a = make_args(ctx);
 	cudaError_t e = launch_stage(ctx, a, stage, iter);
 	if (e == cudaErrorNotSupported) return DVP_ERR_UNSUPPORTED;
@@ -425,6 +471,10 @@ int dvp_run(dvp_ctx* ctx, int sync) {
 	int n = 0;
 	ctx->timed_valid = false;
 	auto go = [&](int stage, int iter) -> int {
+		if (ctx->copies_pending) {   // overlapped upload: K1..K3 and K5 need none of the large maps
+			if (stage == DVP_K4_GEN_NEIGHBOURS) CK(cudaStreamWaitEvent(st, ctx->ev_planes, 0));
+			else if (stage >= DVP_K6_RANDOM_INITIALIZATION) { int jr = join_copies(ctx); if (jr) return jr; }
+		}
 		CK(cudaEventRecord(ctx->ev[2 * n], st));
 		cudaError_t e = launch_stage(ctx, a, stage, iter);
 		if (e == cudaErrorNotSupported) return DVP_ERR_UNSUPPORTED;
@@ -477,6 +527,7 @@ int dvp_last_run_times(dvp_ctx* ctx, float* total_ms, float* per_stage_ms, int* 
 int dvp_download(dvp_ctx* ctx, float* planes, uint8_t* weak_info, uint32_t* selected_views, int32_t* radius) {
 	if (!ctx) return DVP_ERR_ARG;
 	CK(cudaSetDevice(ctx->device));
+	{ int r = join_copies(ctx); if (r) return r; }
 	const size_t N = (size_t)ctx->N;
 	cudaStream_t st = ctx->stream;
 	// cudaMemcpyDefault: destinations may be host (pageable / pinned) or device memory (in-memory pass chaining, row N2)
@@ -493,6 +544,7 @@ size_t dvp_buffer_bytes(dvp_ctx* ctx, int buffer) { return ctx ? buf_desc(ctx, b
 int dvp_get_buffer(dvp_ctx* ctx, int buffer, void* dst, size_t bytes) {
 	if (!ctx || !dst) return DVP_ERR_ARG;
 	CK(cudaSetDevice(ctx->device));
+	{ int r = join_copies(ctx); if (r) return r; }
 	BufDesc b = buf_desc(ctx, buffer);
 	if (!b.ptr || bytes != b.bytes) return DVP_ERR_ARG;
 	if (bytes == 0) return DVP_OK;
@@ -514,6 +566,7 @@ int dvp_get_buffer(dvp_ctx* ctx, int buffer, void* dst, size_t bytes) {
 int dvp_set_buffer(dvp_ctx* ctx, int buffer, const void* src, size_t bytes) {
 	if (!ctx || !src) return DVP_ERR_ARG;
 	CK(cudaSetDevice(ctx->device));
+	{ int r = join_copies(ctx); if (r) return r; }
 	BufDesc b = buf_desc(ctx, buffer);
 	if (!b.ptr || bytes != b.bytes) return DVP_ERR_ARG;
 	if (bytes == 0) return DVP_OK;
@@ -536,6 +589,7 @@ int dvp_restore_visibility(dvp_ctx* ctx, int scale_size, float* device_ms) {
 	if (!ctx || scale_size <= 0) return DVP_ERR_ARG;
 	if (!ctx->uploaded) return DVP_ERR_STATE;
 	CK(cudaSetDevice(ctx->device));
+	{ int r = join_copies(ctx); if (r) return r; }
 	if (!ctx->vis_parent) CK(zalloc(&ctx->vis_parent, (size_t)ctx->N));
 	if (!ctx->vis_count) CK(zalloc(&ctx->vis_count, (size_t)ctx->N));
 	const KArgs a = make_args(ctx);

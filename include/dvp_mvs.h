@@ -247,6 +247,12 @@ int dvp_scene_stats(dvp_scene* scene, double* device_ms, long long* passes);
 /* RescaleMatToTargetSize (APD.cpp:1773-1796, swapped scale factors reproduced) on device memory; elem_bytes 1, 4 or 16. */
 int dvp_rescale_map(int device, const void* src, int src_w, int src_h, void* dst, int dst_w, int dst_h, int elem_bytes);
 
+/* dvp_upload whose large maps (plane hypotheses, the 1+S images, the depth maps: ~3/4 of the bytes) travel on a second
+ * stream while the next dvp_run already executes K1..K3 and K5; K4 waits for the planes, K6 for everything.  Host
+ * buffers must be page-locked for the copies to be asynchronous and must stay valid and unchanged until a synchronising
+ * call returns (dvp_run with sync != 0, dvp_run_stage, dvp_download, dvp_get_buffer).  Results are those of dvp_upload. */
+int dvp_upload_overlapped(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params);
+
 int dvp_weak_count(dvp_ctx* ctx);
 int dvp_last_cuda_error(dvp_ctx* ctx);
 void* dvp_stream(dvp_ctx* ctx); /* cudaStream_t */

@@ -225,6 +225,40 @@ def test_fused_k15_k16_equals_the_two_kernels(geom):
         assert same.all(), (n, int((~same).sum()))
 
 
+@pytest.mark.parametrize("use_weak", [0, 1])
+def test_overlapped_upload_gives_the_same_results(use_weak):
+    """dvp_upload_overlapped streams planes, images and depth maps on a second stream behind K1..K5; with 0 iterations
+    the pass is deterministic, so every output must equal the plain upload's bit for bit (pinned and pageable hosts)."""
+    import torch
+    from dvp_mvs_b200 import REFINE_ITER
+    W, H, S = 320, 240, 3
+    sc = synth.make_scene(W, H, S)
+    p = c1_params(sc.depth_min, sc.depth_max, S, iters=1)
+    e = Engine(W, H, S, p)
+    e.upload(images=sc.images, cameras=sc.cameras, planes=sc.planes_init, edge=sc.edge, label=sc.label, seed=synth.SEED_RNG)
+    e.run()
+    planes, weak, sel, rad = e.download()
+    q = c1_params(sc.depth_min, sc.depth_max, S, iters=0, use_apd=use_weak)
+    q.state = REFINE_ITER; q.geom_consistency = 1; q.use_detail = 1; q.ransac_threshold = 0.00875; q.rotate_time = 2
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    for host in (lambda a: a, pin):
+        kw = dict(images=host(sc.images), depths=host(sc.depths), cameras=sc.cameras, planes=host(planes), selected_views=host(sel),
+                  weak_info=host(weak), edge=sc.edge, label=sc.label, radius=host(rad), seed=synth.SEED_RNG + 3, params=q)
+        outs = []
+        for overlapped in (False, True, True):      # twice overlapped: a re-upload must not race the previous one
+            e.upload(overlapped=overlapped, **kw)
+            e.run(sync=not overlapped)
+            outs.append({n: e.get(n) for n in ("planes", "costs", "selected", "weak", "radius", "rand", "view_weight")})
+        for n, a in outs[0].items():
+            for o in outs[1:]:
+                b = o[n]
+                same = (a.view(np.uint32) == b.view(np.uint32)) if a.dtype == np.float32 else (a == b)
+                assert same.all(), (n, int((~same).sum()))
+    # an overlapped upload followed by stage stepping / buffer access also sees complete data
+    e.upload(overlapped=True, **kw)
+    assert (e.get("planes").view(np.uint32) == np.ascontiguousarray(planes).view(np.uint32)).all()
+
+
 def test_product_matches_committed_golden_vectors():
     """Same stepping protocol against tests/golden/c1_64x48.npz (reference kernels, generated on B200)."""
     g = load_golden("c1_64x48.npz")
