@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -m gpu -q -k "overlapped" > gpurun_out/s18_pytest.log 2>&1; tail -12 gpurun_out/s18_pytest.log | cut -c1-300
-python bench.py --cpu-sample 0 > gpurun_out/s18_bench.log 2>&1; tail -1 gpurun_out/s18_bench.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e'])"
+nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/ubench_tex tools/ubench_tex.cu && /tmp/ubench_tex > gpurun_out/s21_ubench_tex.log 2>&1
+tail -15 gpurun_out/s21_ubench_tex.log

@@ -5,6 +5,9 @@
 //   B  lane-per-anchor : every lane walks the 9 samples of its OWN anchor (anchors scattered within +-R px of the pixel)
 //   C  9-lanes-per-anchor : lanes l -> (anchor l/9, sample l%9); 3.5 anchors per instruction
 //   D  as B, but the 32 lanes' anchors are the anchors of 3 pixels (11 anchors each) -> what a unit-per-lane warp sees
+//   E  quad-coherent: the 4 lanes of a quad sample 4 adjacent pixels of one anchor, the 8 quads of a warp are scattered
+//   F  pair-coherent: 2 adjacent lanes share an anchor neighbourhood, the 16 pairs are scattered
+//   G  quad lanes `gap` pixels apart along x (gap = spread argument); H: the same in a 2x2 arrangement (x and y)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -27,6 +30,23 @@ __global__ void __launch_bounds__(128) k_tex(cudaTextureObject_t tex, int W, int
 		float v[9];
 		if (MODE == 0) {
 			const float x = (wx + lane) * 1.01f + shift, y = wy * 0.99f + shift;
+#pragma unroll
+			for (int q = 0; q < 9; ++q) v[q] = tex2D<float>(tex, x + di[q] + 0.5f, y + dj[q] + 0.5f);
+		} else if (MODE == 4 || MODE == 5) {
+			const int grp = (MODE == 4) ? 4 : 2;
+			const unsigned key = hash(warp * 32 + lane / grp);
+			const int ax = wx + (lane / grp) * grp + (lane % grp) + (int)(key % (2 * spread + 1)) - spread;
+			const int ay = wy + (int)((key >> 12) % (2 * spread + 1)) - spread;
+			const float x = ax * 1.01f + shift, y = ay * 0.99f + shift;
+#pragma unroll
+			for (int q = 0; q < 9; ++q) v[q] = tex2D<float>(tex, x + di[q] + 0.5f, y + dj[q] + 0.5f);
+		} else if (MODE == 6 || MODE == 7) {
+			const int gap = spread;   // reused argument: distance between the quad's lanes
+			const unsigned key = hash(warp * 32 + lane / 4);
+			const int l4 = lane % 4;
+			const int ax = wx + (int)(key % 301) - 150 + (MODE == 6 ? l4 * gap : (l4 & 1) * gap);
+			const int ay = wy + (int)((key >> 12) % 301) - 150 + (MODE == 6 ? 0 : (l4 >> 1) * gap);
+			const float x = ax * 1.01f + shift, y = ay * 0.99f + shift;
 #pragma unroll
 			for (int q = 0; q < 9; ++q) v[q] = tex2D<float>(tex, x + di[q] + 0.5f, y + dj[q] + 0.5f);
 		} else if (MODE == 1 || MODE == 3) {
@@ -65,7 +85,7 @@ static void run(const char* name, cudaTextureObject_t tex, int W, int H, int rep
 	CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
 	float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= 3;
 	const double fetches = (double)nthreads * reps * 9;
-	printf("%-28s spread=%4d  %8.3f ms  %8.1f Gfetch/s\n", name, spread, ms, fetches / ms / 1e6);
+	printf("%-32s arg=%4d  %8.3f ms  %8.1f Gfetch/s\n", name, spread, ms, fetches / ms / 1e6);
 }
 
 int main() {
@@ -87,6 +107,12 @@ int main() {
 		run<1>("B lane-per-anchor", tex, W, H, reps, spread, out, nthreads);
 		run<3>("D lane-per-anchor (3 px)", tex, W, H, reps, spread, out, nthreads);
 		run<2>("C 9-lanes-per-anchor", tex, W, H, reps, spread, out, nthreads);
+		run<4>("E quad-coherent", tex, W, H, reps, spread, out, nthreads);
+		run<5>("F pair-coherent", tex, W, H, reps, spread, out, nthreads);
+	}
+	for (int gap : {1, 2, 3, 4, 5, 8, 16}) {
+		run<6>("G quad, lanes gap px apart (x)", tex, W, H, reps, gap, out, nthreads);
+		run<7>("H quad, 2x2 lanes gap px apart", tex, W, H, reps, gap, out, nthreads);
 	}
 	return 0;
 }
