@@ -96,9 +96,11 @@ def make_workload(args, seed):
     else:
         sc = synth.make_scene(W, H, S, seed=seed)
         try:
-            np.savez(cache, images=sc.images, depths=sc.depths, cameras=sc.cameras.view(np.uint8), planes_init=sc.planes_init,
+            tmp = cache + f".{os.getpid()}.tmp.npz"
+            np.savez(tmp, images=sc.images, depths=sc.depths, cameras=sc.cameras.view(np.uint8), planes_init=sc.planes_init,
                      planes_true=sc.planes_true, plane_id=sc.plane_id, edge=sc.edge, label=sc.label,
                      depth_min=sc.depth_min, depth_max=sc.depth_max)
+            os.replace(tmp, cache)
         except Exception:
             pass
     p = default_params()
@@ -160,7 +162,14 @@ def main():
     torch.cuda.set_device(local)
     from dvp_mvs_b200 import Engine, Inputs
     from dvp_mvs_b200 import _lib
-    sc, p, inputs, workload = make_workload(args, seed=rank if args.impl == "ours" else 0)
+    # Every rank processes a view of the same synthetic scene (weak scaling: one view per GPU).  Rank 0 synthesises it
+    # (threaded numpy, ~10 s) and leaves it in the /tmp cache; the other ranks load it after the barrier instead of
+    # all ranks rendering at once on the same host cores.
+    if dist is not None and rank != 0:
+        dist.barrier()
+    sc, p, inputs, workload = make_workload(args, seed=0)
+    if dist is not None and rank == 0:
+        dist.barrier()
     W, H, S = args.width, args.height, args.src
     N = W * H
     peaks = {}
