@@ -317,6 +317,9 @@ def main():
            "per_stage_ms": [round(v, 3) for v in per_stage],
            "stage_share": {k: round(v / max(sum(per_stage), 1e-9), 4) for k, v in zip(
                ("K1", "K2", "K3", "K4", "K5", "K6", "K7", "K8", "K9", "K10", "K11", "K12", "K13", "K14", "K15+K16", "K16"), per_stage) if v > 0},
+           # WEAK-pixel traffic is data dependent and reported apart from the per-pixel figure:
+           # neighbours 48 + label_boundary 32 + complex 4 + fit plane 16 bytes per WEAK pixel
+           "weak": {"pixels": weak_px, "fraction": weak_px / N, "algorithmic_bytes_per_pass": weak_px * (48 + 32 + 4 + 16)},
            "sweep_mpix_per_s_per_iteration": N / ((per_stage[6] + per_stage[7]) / args.iters) / 1e3,   # K7 + K8 alone
            "clocks": clocks}
     cb = cpu_baseline(args, cores)
