@@ -213,6 +213,8 @@ int dvp_restore_visibility(dvp_ctx* ctx, int scale_size, float* device_ms);
  * other tools: the resized grey image, the edge map and the label map; and for level 0 the FIRST_INIT plane prior.
  * All views of a scene must share one full-resolution size.  Views run in index order (the reference's order). */
 typedef struct dvp_scene dvp_scene;
+/* device < 0 creates a host-only scene: it answers dvp_scene_level_size / dvp_scene_pass_params and refuses everything
+ * that needs a GPU (DVP_ERR_STATE) — lets the schedule be checked where no GPU is present. */
 dvp_scene* dvp_scene_create(int device, int num_views, int num_levels);
 void dvp_scene_destroy(dvp_scene* scene);
 /* Level size as InuputInitialization computes it: round(full * (1 / scale)) (APD.cpp:1119-1123). */

@@ -69,6 +69,24 @@ def test_scene_symbols_are_exported():
         assert hasattr(lib, "dvp_" + n), n
 
 
+def test_library_schedule_equals_the_restatement_without_a_gpu():
+    """dvp_scene_pass_params / dvp_scene_level_size are host logic: a host-only scene (device -1) answers them."""
+    from dvp_mvs_b200 import Scene, DvpError
+    sc = Scene(3, 3, device=-1)
+    for level, scale in enumerate((8, 4, 2)):
+        assert sc.level_size(6221, 4146, level) == host_chain.level_size(6221, 4146, scale)
+        assert sc.level_size(1001, 777, level) == host_chain.level_size(1001, 777, scale)
+        for pass_ in range(4):
+            a, b = sc.pass_params(level, pass_), host_chain.schedule_params(3, level, pass_)
+            for name, _ in a._fields_:
+                if name not in ("depth_min", "depth_max", "num_images"):
+                    assert getattr(a, name) == getattr(b, name), (level, pass_, name)
+    with pytest.raises(DvpError):
+        sc.run_pass(0, 0, 1)           # no device: DVP_ERR_STATE
+    with pytest.raises(DvpError):
+        sc.pass_params(3, 0)           # level out of range
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _fill_scene(mv):
     from dvp_mvs_b200 import Scene
