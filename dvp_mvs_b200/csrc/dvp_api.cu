@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <algorithm>
 #include <new>
 
 namespace dvp { cudaError_t launch_edge_inform(const KArgs& a, cudaStream_t st); }
@@ -304,13 +305,16 @@ int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bo
 		cudaFree(ctx->colour_list[0]); cudaFree(ctx->colour_list[1]);
 		ctx->neighbours = nullptr; ctx->label_boundary = nullptr; ctx->complex_ = nullptr; ctx->weak_list = nullptr;
 		ctx->colour_list[0] = ctx->colour_list[1] = nullptr;
-		CK(zalloc(&ctx->weak_list, (size_t)weak_count));
-		CK(zalloc(&ctx->colour_list[0], (size_t)weak_count));
-		CK(zalloc(&ctx->colour_list[1], (size_t)weak_count));
-		CK(zalloc(&ctx->neighbours, (size_t)weak_count * DVP_NEIGHBOUR_NUM));
-		CK(zalloc(&ctx->label_boundary, (size_t)weak_count * DVP_LAB_BOUNDARY_NUM));
-		CK(zalloc(&ctx->complex_, (size_t)weak_count));
-		ctx->weak_capacity = weak_count;
+		// grow by at least half: a multi-pass caller's WEAK counts creep up pass after pass, and every cudaFree of
+		// maps this size synchronises the device
+		const size_t cap = std::min((size_t)ctx->N, std::max((size_t)weak_count, (size_t)ctx->weak_capacity + (size_t)ctx->weak_capacity / 2));
+		CK(zalloc(&ctx->weak_list, cap));
+		CK(zalloc(&ctx->colour_list[0], cap));
+		CK(zalloc(&ctx->colour_list[1], cap));
+		CK(zalloc(&ctx->neighbours, cap * DVP_NEIGHBOUR_NUM));
+		CK(zalloc(&ctx->label_boundary, cap * DVP_LAB_BOUNDARY_NUM));
+		CK(zalloc(&ctx->complex_, cap));
+		ctx->weak_capacity = (int)cap;
 	}
 	if (have_weak) {
 		const int yy_limit = (((ctx->H / 2) + 15) / 16) * 16;

@@ -24,11 +24,12 @@ def main():
     t_synth = time.perf_counter() - t0
     V = a.views
     # warm-up: load every kernel module and create the CUDA context outside the timed regions
-    wmv = synth.make_multiview(320, 240, 3, 1, seed=9)
-    wsc = Scene(3, 1)
+    wmv = synth.make_multiview(640, 480, 3, 2, seed=9)   # two levels: the second one exercises the WEAK-path kernels too
+    wsc = Scene(3, 2)
     for v in range(3):
-        wsc.set_view(v, wmv.cameras[v], 320, 240, wmv.src_views[v])
-        wsc.set_level(v, 0, wmv.levels[0][v]["image"], wmv.levels[0][v]["edge"], wmv.levels[0][v]["label"])
+        wsc.set_view(v, wmv.cameras[v], 640, 480, wmv.src_views[v])
+        for l in range(2):
+            wsc.set_level(v, l, wmv.levels[l][v]["image"], wmv.levels[l][v]["edge"], wmv.levels[l][v]["label"])
         wsc.set_initial_planes(v, wmv.planes_init[v])
     wsc.run(seed=1); wsc.close()
     sc = Scene(V, a.levels)

@@ -24,13 +24,14 @@ def main():
     from dvp_mvs_b200 import synth, Scene
     from dvp_mvs_b200.farm import run_scene_schedule
     # warm-up: CUDA context, kernel modules and NCCL communicator outside the timed region
-    wmv = synth.make_multiview(320, 240, 3, 1, seed=9)
-    wsc = Scene(3, 1, device=local)
+    wmv = synth.make_multiview(640, 480, 3, 2, seed=9)   # two levels: the second one exercises the WEAK-path kernels too
+    wsc = Scene(3, 2, device=local)
     for v in range(3):
-        wsc.set_view(v, wmv.cameras[v], 320, 240, wmv.src_views[v])
-        wsc.set_level(v, 0, wmv.levels[0][v]["image"], wmv.levels[0][v]["edge"], wmv.levels[0][v]["label"])
+        wsc.set_view(v, wmv.cameras[v], 640, 480, wmv.src_views[v])
+        for l in range(2):
+            wsc.set_level(v, l, wmv.levels[l][v]["image"], wmv.levels[l][v]["edge"], wmv.levels[l][v]["label"])
         wsc.set_initial_planes(v, wmv.planes_init[v])
-    run_scene_schedule(wsc, 3, 1, seed=1); wsc.close()
+    run_scene_schedule(wsc, 3, 2, seed=1); wsc.close()
     mv = synth.make_multiview(fw, fh, a.views, a.levels, seed=0, num_src=a.src)
     V = a.views
     sc = Scene(V, a.levels, device=local)
