@@ -720,10 +720,13 @@ __global__ void __launch_bounds__(64) k_weak_sweep(const __grid_constant__ KArgs
 	}
 	// "update cost with old method" (APD.cu:3072-3088): rescore the stored plane with the plain NCC at strong_radius
 	{
-		extern __shared__ __align__(16) unsigned char smem_raw[];
-		float2* wt = reinterpret_cast<float2*>(smem_raw) + threadIdx.x;
+		// No shared-memory table here: this kernel's fetches are scattered (each lane walks its own anchors), its hit rate
+		// lives on the L1/TEX cache, and a 64-thread block's table would take 18 KB of it per block (147 KB per SM).  The
+		// <= S NCCs of this rescoring recompute their 36 weights through ncc_cost's general path instead
+		// (37.2 -> 34.5 ms per iteration on the bench workload, same bits).
 		RefPatch rp;
-		rp.prepare(a, px, py, a.prm.strong_radius, wt, 64);
+		rp.prepare(a, px, py, a.prm.strong_radius, nullptr, 0);
+		const float2* wt = nullptr;
 		float c2 = 0.0f;
 		for (int i = 0; i < S; ++i) {
 			const int wv = vw.get(i);
@@ -758,7 +761,7 @@ cudaError_t launch_ransac_fit(const KArgs& a, cudaStream_t st) {
 cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count, int iter, int red, cudaStream_t st) {
 	(void)red;
 	if (count == 0) return cudaSuccess;
-	k_weak_sweep<<<(count + 63) / 64, 64, patch_smem_bytes(64), st>>>(a, colour_list, count, iter);
+	k_weak_sweep<<<(count + 63) / 64, 64, 0, st>>>(a, colour_list, count, iter);
 	return cudaGetLastError();
 }
 // One-time, per-device fill of the sector table, completed before the flag is set so that contexts on other streams

@@ -109,7 +109,7 @@ struct RefPatch {
 		inc = a.prm.strong_increment;
 		if (a.prm.use_radius) inc = DVP_MAX(2, (int)(2.0 * rad / 5.0));
 		n = (rad >= 0) ? (2 * rad) / inc + 1 : 0;
-		hoisted = (n == kHoistAxis);
+		hoisted = (n == kHoistAxis) && wt != nullptr;   // no table given: every NCC recomputes its weights (general path)
 		sigma_rcps(a.prm, rcp_s, rcp_c);
 		center = ref_pixel(a, px, py);
 		sd_const = (rad == 5 && inc == 2);
