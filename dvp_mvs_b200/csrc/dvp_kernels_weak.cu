@@ -583,25 +583,27 @@ __global__ void __launch_bounds__(64) k_weak_sweep(const __grid_constant__ KArgs
 	const int nm = a.neighbours_map[center];
 	const short2* nb = a.neighbours + (size_t)nm * DVP_NEIGHBOUR_NUM;
 
+	// the reference's cost_array[8][32] (local memory; a shared-memory column per thread was measured slower: it
+	// takes its 9*S*4 bytes per thread from the L1 this kernel's scattered fetches live on)
 	float cost_array[8][DVP_MAX_IMAGES];
-	for (int i = 0; i < 8; ++i) for (int j = 0; j < S; ++j) cost_array[i][j] = 0.0f;
-	cost_array[0][0] = 2.0f;   // B2
+#define COST(i, j) cost_array[i][j]
+	for (int i = 0; i < 8; ++i) for (int j = 0; j < S; ++j) COST(i, j) = 0.0f;
+	COST(0, 0) = 2.0f;   // B2
 	bool flag[8];
 	int positions[8];
-	float4 new_plane[8];
 	for (int i = 0; i < 8; ++i) {
-		flag[i] = false; positions[i] = 0; new_plane[i] = make_float4(0, 0, 0, 0);
+		flag[i] = false; positions[i] = 0;
 		const short2 np = nb[i + 1];
 		if (np.x == -1 || np.y == -1 || a.weak[np.x + np.y * W] != DVP_STRONG) continue;
 		positions[i] = np.x + np.y * W;
 		flag[i] = true;
 		const float4 pl = a.planes[positions[i]];
-		for (int v = 0; v < S; ++v) cost_array[i][v] = ncc_new(a, px, py, v, pl);
-		new_plane[i] = pl;
+		for (int v = 0; v < S; ++v) COST(i, v) = ncc_new(a, px, py, v, pl);
 	}
 	Rng rng; rng.load(a.rng, a.N, center);
 	ViewWeights vw; vw.clear();
 	float probs[DVP_MAX_IMAGES];
+#define PROB(i) probs[i]
 	{
 		const float cost_threshold = 0.8 * expf((iter) * (iter) / (-90.0f));
 		for (int i = 0; i < S; i++) {
@@ -613,24 +615,24 @@ __global__ void __launch_bounds__(64) k_weak_sweep(const __grid_constant__ KArgs
 			}
 			float count = 0; int count_false = 0; float tmpw = 0;
 			for (int j = 0; j < 8; j++) {
-				const float c = cost_array[j][i];
+				const float c = COST(j, i);
 				if (c < cost_threshold) { tmpw += expf(c * c / (-0.18f)); count++; }
 				if (c > 1.2f) count_false++;
 			}
 			float prob = 0.0f;
 			if (count > 2 && count_false < 3) prob = tmpw / count;
 			else if (count_false < 3) prob = expf(cost_threshold * cost_threshold / (-0.32f));
-			probs[i] = prob * prior;
+			PROB(i) = prob * prior;
 		}
 		float prob_sum = 0.0f;
-		for (int i = 0; i < S; ++i) prob_sum += probs[i];
+		for (int i = 0; i < S; ++i) prob_sum += PROB(i);
 		const float inv_prob_sum = 1.0f / prob_sum;
 		float cum_prob = 0.0f;
-		for (int i = 0; i < S; ++i) { const float prob = probs[i] * inv_prob_sum; cum_prob += prob; probs[i] = cum_prob; }
+		for (int i = 0; i < S; ++i) { const float prob = PROB(i) * inv_prob_sum; cum_prob += prob; PROB(i) = cum_prob; }
 		for (int sample = 0; sample < 15; ++sample) {
 			const float rand_prob = rng.uniform() - FLT_EPSILON;
 			for (int image_id = 0; image_id < S; ++image_id)
-				if (probs[image_id] > rand_prob) { vw.inc(image_id); break; }
+				if (PROB(image_id) > rand_prob) { vw.inc(image_id); break; }
 		}
 	}
 	vw.store(a.view_weight + (size_t)center * DVP_MAX_IMAGES);
@@ -645,9 +647,9 @@ __global__ void __launch_bounds__(64) k_weak_sweep(const __grid_constant__ KArgs
 			const int wv = vw.get(j);
 			if (wv > 0) {
 				if (a.prm.geom_consistency) {
-					if (flag[i]) fc += wv * (cost_array[i][j] + a.prm.geom_factor * geom_cost(a, a.views[j], a.tex_depth[j + 1], px, py, a.planes[positions[i]]));
-					else fc += wv * (cost_array[i][j] + a.prm.geom_factor * 3.0f);
-				} else fc += wv * cost_array[i][j];
+					if (flag[i]) fc += wv * (COST(i, j) + a.prm.geom_factor * geom_cost(a, a.views[j], a.tex_depth[j + 1], px, py, a.planes[positions[i]]));
+					else fc += wv * (COST(i, j) + a.prm.geom_factor * 3.0f);
+				} else fc += wv * COST(i, j);
 			}
 		}
 		fc /= weight_norm;
@@ -666,9 +668,10 @@ __global__ void __launch_bounds__(64) k_weak_sweep(const __grid_constant__ KArgs
 	const float cost_stored = cost_now;
 	float depth_now = depth_from_plane(a.ref, plane_now, px, py);
 	if (flag[min_cost_idx]) {
-		const float depth_before = depth_from_plane(a.ref, new_plane[min_cost_idx], px, py);
+		const float4 winner = a.planes[positions[min_cost_idx]];   // a STRONG anchor's plane: not written by this kernel
+		const float depth_before = depth_from_plane(a.ref, winner, px, py);
 		if (depth_before >= a.prm.depth_min && depth_before <= a.prm.depth_max && min_final < cost_now) {
-			depth_now = depth_before; plane_now = new_plane[min_cost_idx]; cost_now = min_final;
+			depth_now = depth_before; plane_now = winner; cost_now = min_final;
 			a.selected[center] = temp_selected;
 		}
 	}
@@ -737,6 +740,8 @@ __global__ void __launch_bounds__(64) k_weak_sweep(const __grid_constant__ KArgs
 		a.costs[center] = c2;
 	}
 }
+#undef COST
+#undef PROB
 
 // ------------------------------------------------------------------------------------------------------
 cudaError_t launch_edge_inform(const KArgs& a, cudaStream_t st) {
