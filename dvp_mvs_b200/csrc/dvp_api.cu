@@ -73,6 +73,10 @@ struct dvp_ctx {
 	int* colour_list[2] = {nullptr, nullptr};  // WEAK pixels of one checkerboard colour (dense warps in the weak sweep)
 	int colour_count[2] = {0, 0};
 	int* scan_blocks_c[2] = {nullptr, nullptr};
+	int* sort_keys[2] = {nullptr, nullptr};   // tile reordering of the WEAK lists (sized by weak_capacity)
+	int* sort_vals = nullptr;
+	void* sort_temp = nullptr;
+	size_t sort_temp_bytes = 0;
 	int* vis_parent = nullptr;  // union-find links / region sizes of dvp_restore_visibility (allocated on first use)
 	int* vis_count = nullptr;
 	// host staging
@@ -314,6 +318,11 @@ int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bo
 		CK(zalloc(&ctx->neighbours, cap * DVP_NEIGHBOUR_NUM));
 		CK(zalloc(&ctx->label_boundary, cap * DVP_LAB_BOUNDARY_NUM));
 		CK(zalloc(&ctx->complex_, cap));
+		cudaFree(ctx->sort_keys[0]); cudaFree(ctx->sort_keys[1]); cudaFree(ctx->sort_vals); cudaFree(ctx->sort_temp);
+		ctx->sort_keys[0] = ctx->sort_keys[1] = ctx->sort_vals = nullptr; ctx->sort_temp = nullptr;
+		CK(zalloc(&ctx->sort_keys[0], cap)); CK(zalloc(&ctx->sort_keys[1], cap)); CK(zalloc(&ctx->sort_vals, cap));
+		ctx->sort_temp_bytes = tile_order_temp_bytes((int)cap);
+		CK(cudaMalloc(&ctx->sort_temp, ctx->sort_temp_bytes ? ctx->sort_temp_bytes : 1));
 		ctx->weak_capacity = (int)cap;
 	}
 	if (have_weak) {
@@ -322,6 +331,14 @@ int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bo
 		if (weak_count > 0)
 			for (int k = 0; k < 2; ++k)
 				CK(launch_weak_index(ctx->weak, ctx->N, ctx->W, k, yy_limit, ctx->scan_blocks_c[k], nullptr, ctx->colour_list[k], st));
+#ifndef DVP_NO_TILE_ORDER
+		if (weak_count > 0) {
+			// one block of each kernel = one compact tile: 8x8 pixels (K4), 16 x (threads/8) pixels of one colour (K10/K11)
+			CK(launch_tile_order(ctx->weak_list, weak_count, ctx->W, ctx->H, 8, 8, ctx->sort_keys[0], ctx->sort_keys[1], ctx->sort_vals, ctx->sort_temp, ctx->sort_temp_bytes, st));
+			for (int k = 0; k < 2; ++k)
+				CK(launch_tile_order(ctx->colour_list[k], ctx->colour_count[k], ctx->W, ctx->H, 16, kWeakThreads / 8, ctx->sort_keys[0], ctx->sort_keys[1], ctx->sort_vals, ctx->sort_temp, ctx->sort_temp_bytes, st));
+		}
+#endif
 		if (weak_count > 0)
 			CK(cudaMemsetAsync(ctx->neighbours, 0xFF, (size_t)weak_count * DVP_NEIGHBOUR_NUM * sizeof(short2), st));  // (-1,-1): no anchor yet
 	}
@@ -442,6 +459,7 @@ void dvp_destroy(dvp_ctx* c) {
 	cudaFree(c->label); cudaFree(c->candidate); cudaFree(c->nearest_strong); cudaFree(c->weak_reliable);
 	cudaFree(c->neighbours_map); cudaFree(c->neighbours); cudaFree(c->label_boundary); cudaFree(c->complex_); cudaFree(c->weak_list); cudaFree(c->scan_blocks); cudaFree(c->scan_total); cudaFree(c->next_right); cudaFree(c->next_down); for (int k = 0; k < 2; ++k) { cudaFree(c->scan_blocks_c[k]); cudaFree(c->colour_list[k]); }
 	cudaFree(c->vis_parent); cudaFree(c->vis_count);
+	cudaFree(c->sort_keys[0]); cudaFree(c->sort_keys[1]); cudaFree(c->sort_vals); cudaFree(c->sort_temp);
 	for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;

@@ -2,6 +2,7 @@
 // exchange helpers (reference APD.cu:3731-3890, 4159-4193, 3713-3729).
 #include "dvp_common.cuh"
 #include "dvp_launch.h"
+#include <cub/cub.cuh>
 
 namespace dvp {
 
@@ -308,6 +309,33 @@ cudaError_t launch_weak_index(const uint8_t* weak, int n, int W, int colour, int
 	const int nb = (n + kScanBlock - 1) / kScanBlock;
 	k_weak_index<<<nb, 256, 0, st>>>(weak, n, W, colour, yy_limit, block_offsets, nmap, weak_list);
 	return cudaGetLastError();
+}
+// Reorder a raster-ordered pixel list into tiles of tile_w x tile_h pixels (stable: raster order inside a tile).  The
+// WEAK kernels take 64 consecutive list entries per block; with compact tiles the anchors and patches a block touches
+// overlap, which is what their scattered fetches need from the L1.  Results do not depend on the order (one thread
+// owns one pixel and same-colour WEAK pixels never read each other).
+__global__ void __launch_bounds__(256) k_tile_keys(const int* __restrict__ list, int count, int W, int tile_w, int tile_h, int tiles_x, int* __restrict__ keys) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	const int p = list[i];
+	const int y = p / W, x = p - y * W;
+	keys[i] = (y / tile_h) * tiles_x + (x / tile_w);
+}
+size_t tile_order_temp_bytes(int count) {
+	size_t bytes = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr, count);
+	return bytes;
+}
+cudaError_t launch_tile_order(int* list, int count, int W, int H, int tile_w, int tile_h, int* keys_in, int* keys_out, int* vals_out,
+                              void* temp, size_t temp_bytes, cudaStream_t st) {
+	if (count <= 1) return cudaSuccess;
+	const int tiles_x = (W + tile_w - 1) / tile_w, tiles_y = (H + tile_h - 1) / tile_h;
+	int bits = 1;
+	while ((1ll << bits) < (long long)tiles_x * tiles_y) ++bits;
+	k_tile_keys<<<(count + 255) / 256, 256, 0, st>>>(list, count, W, tile_w, tile_h, tiles_x, keys_in);
+	cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const int*)keys_in, keys_out, (const int*)list, vals_out, count, 0, bits, st);
+	if (e != cudaSuccess) return e;
+	return cudaMemcpyAsync(list, vals_out, (size_t)count * sizeof(int), cudaMemcpyDeviceToDevice, st);
 }
 cudaError_t launch_reset_unknown_radius(const uint8_t* weak, int32_t* radius, int32_t strong_radius, int n, cudaStream_t st) {
 	k_reset_unknown_radius<<<(n + 255) / 256, 256, 0, st>>>(weak, radius, strong_radius, n);

@@ -573,7 +573,7 @@ __device__ __forceinline__ float weak_weighted_cost(const KArgs& a, int px, int 
 
 // One thread per WEAK pixel of ONE checkerboard colour: `colour_list` (built at upload by a device prefix sum)
 // holds the pixels the reference's half grid reaches for this colour (APD.cu:3093-3106), so warps are dense.
-__global__ void __launch_bounds__(64) k_weak_sweep(const __grid_constant__ KArgs a, const int* colour_list, int count, int iter) {
+__global__ void __launch_bounds__(kWeakThreads, 512 / kWeakThreads) k_weak_sweep(const __grid_constant__ KArgs a, const int* colour_list, int count, int iter) {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= count) return;
 	const int center = colour_list[t];
@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(64) k_weak_sweep(const __grid_constant__ KArgs
 		for (int i = 0; i < S; ++i) {
 			const int wv = vw.get(i);
 			if (wv == 0) continue;
-			c2 += wv * ncc_cost<1>(a, a.views[i], a.tex_img[i + 1], px, py, plane_final, rp, wt, 64);
+			c2 += wv * ncc_cost<1>(a, a.views[i], a.tex_img[i + 1], px, py, plane_final, rp, wt, 0);
 		}
 		c2 /= weight_norm;
 		a.costs[center] = c2;
@@ -766,7 +766,7 @@ cudaError_t launch_ransac_fit(const KArgs& a, cudaStream_t st) {
 cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count, int iter, int red, cudaStream_t st) {
 	(void)red;
 	if (count == 0) return cudaSuccess;
-	k_weak_sweep<<<(count + 63) / 64, 64, 0, st>>>(a, colour_list, count, iter);
+	k_weak_sweep<<<(count + kWeakThreads - 1) / kWeakThreads, kWeakThreads, 0, st>>>(a, colour_list, count, iter);
 	return cudaGetLastError();
 }
 // One-time, per-device fill of the sector table, completed before the flag is set so that contexts on other streams

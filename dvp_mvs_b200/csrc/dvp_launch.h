@@ -24,6 +24,10 @@ constexpr bool kSweepRW = DVP_SWEEP_RW != 0;  // sweep keeps only the reference 
 #define DVP_SWEEP_RB 3
 #endif
 constexpr int kSweepRB = DVP_SWEEP_RB;         // patch rows of texture fetches in flight per thread in the sweep (all 36 samples)
+#ifndef DVP_WEAK_THREADS
+#define DVP_WEAK_THREADS 128
+#endif
+constexpr int kWeakThreads = DVP_WEAK_THREADS;   // WEAK sweep block = one tile of the per-colour list: 16 x (threads / 8) pixels
 constexpr int kWideRB = 2;          // ... in the 256-thread, 24-warp/SM kernels (K6, K15, K16)
 
 // shared memory: 36 (w, w*r) pairs per thread
@@ -57,6 +61,9 @@ cudaError_t launch_fill_i32(int32_t* dst, int32_t v, int n, cudaStream_t st);
 constexpr int kWeakScanBlock = 1024;
 cudaError_t launch_weak_count(const uint8_t* weak, int n, int W, int colour, int yy_limit, int* block_sums, int* total, cudaStream_t st);
 cudaError_t launch_weak_index(const uint8_t* weak, int n, int W, int colour, int yy_limit, const int* block_offsets, int* nmap, int* weak_list, cudaStream_t st);
+size_t tile_order_temp_bytes(int count);
+cudaError_t launch_tile_order(int* list, int count, int W, int H, int tile_w, int tile_h, int* keys_in, int* keys_out, int* vals_out,
+                              void* temp, size_t temp_bytes, cudaStream_t st);
 cudaError_t launch_reset_unknown_radius(const uint8_t* weak, int32_t* radius, int32_t strong_radius, int n, cudaStream_t st);
 
 // post-pass on the resident maps (main.cpp:297-363): dvp_kernels_post.cu
