@@ -333,8 +333,8 @@ int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bo
 				CK(launch_weak_index(ctx->weak, ctx->N, ctx->W, k, yy_limit, ctx->scan_blocks_c[k], nullptr, ctx->colour_list[k], st));
 #ifndef DVP_NO_TILE_ORDER
 		if (weak_count > 0) {
-			// one block of each kernel = one compact tile: 8x8 pixels (K4), 16 x (threads/8) pixels of one colour (K10/K11)
-			CK(launch_tile_order(ctx->weak_list, weak_count, ctx->W, ctx->H, 8, 8, ctx->sort_keys[0], ctx->sort_keys[1], ctx->sort_vals, ctx->sort_temp, ctx->sort_temp_bytes, st));
+			// one block of each kernel = one compact tile: (threads/8) x 8 pixels (K4), 16 x (threads/8) pixels of one colour (K10/K11)
+			CK(launch_tile_order(ctx->weak_list, weak_count, ctx->W, ctx->H, kK4Threads / 8, 8, ctx->sort_keys[0], ctx->sort_keys[1], ctx->sort_vals, ctx->sort_temp, ctx->sort_temp_bytes, st));
 			for (int k = 0; k < 2; ++k)
 				CK(launch_tile_order(ctx->colour_list[k], ctx->colour_count[k], ctx->W, ctx->H, 16, kWeakThreads / 8, ctx->sort_keys[0], ctx->sort_keys[1], ctx->sort_vals, ctx->sort_temp, ctx->sort_temp_bytes, st));
 		}

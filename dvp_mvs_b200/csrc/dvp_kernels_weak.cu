@@ -142,7 +142,7 @@ __device__ __forceinline__ void normalize2(float2* v) {
 	v->x *= inv; v->y *= inv;
 }
 
-__global__ void __launch_bounds__(64) k_gen_neighbours(const __grid_constant__ KArgs a, const int* weak_list) {
+__global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_constant__ KArgs a, const int* weak_list) {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= a.weak_count) return;
 	const int center = weak_list[t];
@@ -756,7 +756,7 @@ cudaError_t launch_edge_inform(const KArgs& a, cudaStream_t st) {
 }
 cudaError_t launch_gen_neighbours(const KArgs& a, const int* weak_list, cudaStream_t st) {
 	if (a.weak_count == 0) return cudaSuccess;
-	k_gen_neighbours<<<(a.weak_count + 63) / 64, 64, 0, st>>>(a, weak_list);
+	k_gen_neighbours<<<(a.weak_count + kK4Threads - 1) / kK4Threads, kK4Threads, 0, st>>>(a, weak_list);
 	return cudaGetLastError();
 }
 cudaError_t launch_ransac_fit(const KArgs& a, cudaStream_t st) {

@@ -25,9 +25,13 @@ constexpr bool kSweepRW = DVP_SWEEP_RW != 0;  // sweep keeps only the reference 
 #endif
 constexpr int kSweepRB = DVP_SWEEP_RB;         // patch rows of texture fetches in flight per thread in the sweep (all 36 samples)
 #ifndef DVP_WEAK_THREADS
-#define DVP_WEAK_THREADS 128
+#define DVP_WEAK_THREADS 256
 #endif
 constexpr int kWeakThreads = DVP_WEAK_THREADS;   // WEAK sweep block = one tile of the per-colour list: 16 x (threads / 8) pixels
+#ifndef DVP_K4_THREADS
+#define DVP_K4_THREADS 64
+#endif
+constexpr int kK4Threads = DVP_K4_THREADS;       // K4 block = one (threads / 8) x 8 pixel tile of the WEAK list
 constexpr int kWideRB = 2;          // ... in the 256-thread, 24-warp/SM kernels (K6, K15, K16)
 
 // shared memory: 36 (w, w*r) pairs per thread
