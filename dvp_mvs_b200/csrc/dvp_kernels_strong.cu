@@ -781,6 +781,9 @@ cudaError_t configure_strong_kernels(int S) {
 	if ((e = cudaFuncSetAttribute(k_local_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
 	if ((e = cudaFuncSetAttribute(k_depth_to_weak_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
 	if ((e = cudaFuncSetAttribute(k_strong_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kSweepThreads, S)))) return e;
+#ifdef DVP_SWEEP_CARVEOUT
+	if ((e = cudaFuncSetAttribute(k_strong_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, DVP_SWEEP_CARVEOUT))) return e;
+#endif
 	return cudaSuccess;
 }
 
