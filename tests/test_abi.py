@@ -20,7 +20,12 @@ def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for name in ["dvp_create", "dvp_destroy", "dvp_upload", "dvp_upload_device", "dvp_run", "dvp_run_stage",
                  "dvp_download", "dvp_get_buffer", "dvp_set_buffer", "dvp_buffer_bytes", "dvp_last_run_times",
-                 "dvp_default_params", "dvp_version", "dvp_weak_count", "dvp_last_cuda_error", "dvp_stream"]:
+                 "dvp_default_params", "dvp_version", "dvp_weak_count", "dvp_last_cuda_error", "dvp_stream",
+                 # rows N1 / N2 and the overlapped upload
+                 "dvp_restore_visibility", "dvp_upload_overlapped", "dvp_rescale_map", "dvp_scene_create", "dvp_scene_destroy",
+                 "dvp_scene_level_size", "dvp_scene_pass_params", "dvp_scene_set_max_iterations", "dvp_scene_set_view",
+                 "dvp_scene_set_level", "dvp_scene_set_initial_planes", "dvp_scene_run_pass", "dvp_scene_run_view", "dvp_scene_run",
+                 "dvp_scene_get_view", "dvp_scene_stats", "dvp_scene_depth_map", "dvp_scene_remote_depth"]:
         assert name in syms
 
 
