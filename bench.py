@@ -313,7 +313,8 @@ def main():
                         "share_of_step": (per_stage[6] + per_stage[7]) / max(total_ms, 1e-9),
                         "note": "TEX-bound kernel: ~%d bilinear source fetches per byte of compulsory traffic; the binding roof is the texture unit "
                                 "(measured 1155 Gfetch/s coherent, profiles/r01_tex_coherence_ubench.txt), not HBM" % int(samples_per_launch / bytes_per_launch),
-                        "tex_gsamples_per_s": samples_per_launch / (sweep_ms * 1e-3) / 1e9, "tex_peak_gsamples_per_s": 1155.0},
+                        "tex_gsamples_per_s": samples_per_launch / (sweep_ms * 1e-3) / 1e9, "tex_peak_gsamples_per_s": 1155.0,
+                        "tex_frac": samples_per_launch / (sweep_ms * 1e-3) / 1e9 / 1155.0},
            "per_stage_ms": [round(v, 3) for v in per_stage],
            "stage_share": {k: round(v / max(sum(per_stage), 1e-9), 4) for k, v in zip(
                ("K1", "K2", "K3", "K4", "K5", "K6", "K7", "K8", "K9", "K10", "K11", "K12", "K13", "K14", "K15+K16", "K16"), per_stage) if v > 0},
