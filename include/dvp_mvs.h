@@ -75,7 +75,7 @@ typedef struct dvp_params {
 	int32_t weak_radius;       /* 5 */
 	int32_t weak_increment;    /* 5 */
 	int32_t use_APD;
-	int32_t use_edge;
+	int32_t use_edge;          /* must be 1: with 0 the reference reads an uninitialised position array (APD.cu:2036, 2559) -> DVP_ERR_UNSUPPORTED */
 	int32_t use_limit;
 	int32_t use_label;
 	int32_t use_detail;
