@@ -172,6 +172,7 @@ int stage_kernel_count(const dvp_ctx* c, int stage) {
 	case DVP_K2_GEN_EDGE_INFORM: return (weak ? 1 : 0) + (c->prm.use_edge ? 1 : 0) + ((c->prm.use_label && weak) ? 1 : 0) + 1;
 	case DVP_K3_FIND_NEAREST_STRONG: return (weak ? 1 : 0) + 1;
 	case DVP_K4_GEN_NEIGHBOURS: return weak ? 1 : 0;
+	case DVP_K9_RANSAC_FIT_PLANE: return 1 + (weak ? 1 : 0);
 	case DVP_K10_BLACK_WEAK: return c->colour_count[0] > 0 ? 1 : 0;
 	case DVP_K11_RED_WEAK: return c->colour_count[1] > 0 ? 1 : 0;
 	default: return 1;
@@ -189,7 +190,7 @@ cudaError_t launch_stage(dvp_ctx* c, const KArgs& a, int stage, int iter) {
 	case DVP_K6_RANDOM_INITIALIZATION: return launch_random_init(a, st);
 	case DVP_K7_BLACK_STRONG: return launch_strong_sweep(a, iter, 0, st);
 	case DVP_K8_RED_STRONG: return launch_strong_sweep(a, iter, 1, st);
-	case DVP_K9_RANSAC_FIT_PLANE: return launch_ransac_fit(a, st);
+	case DVP_K9_RANSAC_FIT_PLANE: return launch_ransac_fit(a, c->weak_list, st);
 	case DVP_K10_BLACK_WEAK: return launch_weak_sweep(a, c->colour_list[0], c->colour_count[0], iter, 0, st);
 	case DVP_K11_RED_WEAK: return launch_weak_sweep(a, c->colour_list[1], c->colour_count[1], iter, 1, st);
 	case DVP_K12_DEPTH_NORMAL: return launch_depth_normal(a, st);

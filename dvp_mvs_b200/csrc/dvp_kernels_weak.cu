@@ -452,9 +452,17 @@ __global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_cons
 
 // ------------------------------------------------------------------------------------------------------
 // K9 RANSACToGetFitPlane (APD.cu:4195-4404).
-__global__ void __launch_bounds__(256) k_ransac_fit(const __grid_constant__ KArgs a) {
+// Non-WEAK pixels: fit plane = current plane (APD.cu:4204-4207), a streaming copy over the image.
+__global__ void __launch_bounds__(256) k_fit_copy_nonweak(const __grid_constant__ KArgs a) {
 	const int center = blockIdx.x * blockDim.x + threadIdx.x;
-	if (center >= a.N) return;
+	if (center < a.N && a.weak[center] != DVP_WEAK) a.fit_planes[center] = a.planes[center];
+}
+// WEAK pixels: one thread each over the tile-ordered WEAK list (a block = one 8x8-pixel tile, so the anchors' planes and
+// the edge walks of a block overlap in the L1).  Pixels demoted since the list was built fall through to the copy rule.
+__global__ void __launch_bounds__(64) k_ransac_fit(const __grid_constant__ KArgs a, const int* weak_list) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= a.weak_count) return;
+	const int center = weak_list[t];
 	const int W = a.W;
 	if (a.weak[center] != DVP_WEAK) { a.fit_planes[center] = a.planes[center]; return; }
 	const int px = center % W, py = center / W;
@@ -759,8 +767,9 @@ cudaError_t launch_gen_neighbours(const KArgs& a, const int* weak_list, cudaStre
 	k_gen_neighbours<<<(a.weak_count + kK4Threads - 1) / kK4Threads, kK4Threads, 0, st>>>(a, weak_list);
 	return cudaGetLastError();
 }
-cudaError_t launch_ransac_fit(const KArgs& a, cudaStream_t st) {
-	k_ransac_fit<<<(a.N + 255) / 256, 256, 0, st>>>(a);
+cudaError_t launch_ransac_fit(const KArgs& a, const int* weak_list, cudaStream_t st) {
+	k_fit_copy_nonweak<<<(a.N + 255) / 256, 256, 0, st>>>(a);
+	if (a.weak_count > 0) k_ransac_fit<<<(a.weak_count + 63) / 64, 64, 0, st>>>(a, weak_list);
 	return cudaGetLastError();
 }
 cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count, int iter, int red, cudaStream_t st) {

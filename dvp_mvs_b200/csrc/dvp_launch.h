@@ -52,7 +52,7 @@ cudaError_t launch_gen_neighbours(const KArgs& a, const int* weak_list, cudaStre
 cudaError_t launch_neighbour_update(const KArgs& a, cudaStream_t st);                            // K5
 cudaError_t launch_random_init(const KArgs& a, cudaStream_t st);                                 // K6
 cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, cudaStream_t st);             // K7 / K8
-cudaError_t launch_ransac_fit(const KArgs& a, cudaStream_t st);                                  // K9
+cudaError_t launch_ransac_fit(const KArgs& a, const int* weak_list, cudaStream_t st);                                  // K9
 cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count, int iter, int red, cudaStream_t st);  // K10 / K11
 cudaError_t launch_depth_normal(const KArgs& a, cudaStream_t st);                                // K12
 cudaError_t launch_filter(const KArgs& a, int red, cudaStream_t st);                             // K13 / K14

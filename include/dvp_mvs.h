@@ -182,7 +182,9 @@ int dvp_run_stage(dvp_ctx* ctx, int stage, int iter);
  * GetPixelStates / GetSelectedViews / GetRadiusMap (APD.cpp:1706-1732).  Any pointer may be NULL. */
 int dvp_download(dvp_ctx* ctx, float* planes, uint8_t* weak_info, uint32_t* selected_views, int32_t* radius);
 
-/* Raw buffer access by id (sizes in bytes must match exactly; query with dvp_buffer_bytes). */
+/* Raw buffer access by id (sizes in bytes must match exactly; query with dvp_buffer_bytes).  The compact WEAK-pixel
+ * lists are built by dvp_upload: a DVP_BUF_WEAK written afterwards may demote WEAK pixels (as K2 / K5 do) but pixels
+ * it newly marks WEAK are not picked up by K4, K9, K10 and K11 until the next upload. */
 size_t dvp_buffer_bytes(dvp_ctx* ctx, int buffer);
 int dvp_get_buffer(dvp_ctx* ctx, int buffer, void* dst, size_t bytes);
 int dvp_set_buffer(dvp_ctx* ctx, int buffer, const void* src, size_t bytes);
