@@ -62,3 +62,15 @@ def test_compare_counts_pixels_not_components():
 def test_params_mirror():
     p = c1_params(0.9, 14.4, 2)
     assert p.num_images == 3 and p.state == 0 and p.use_APD == 0 and p.max_iterations == 1
+
+
+def test_every_python_file_compiles():
+    """bench.py, the graft entry, the tools and the oracle drivers cannot be run without a GPU here; at least they parse."""
+    import glob, os, py_compile
+    from util import ROOT
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    for sub in ("tools", "oracle", "dvp_mvs_b200", "tests"):
+        files += glob.glob(os.path.join(ROOT, sub, "*.py"))
+    assert len(files) > 15
+    for f in files:
+        py_compile.compile(f, doraise=True)
