@@ -69,7 +69,38 @@ ABI_SYMBOLS = ["version", "default_params", "create", "destroy", "upload", "run"
 PRODUCT_ONLY_SYMBOLS = ["upload_device", "upload_overlapped", "restore_visibility", "rescale_map", "scene_create", "scene_destroy", "scene_level_size",
                         "scene_pass_params", "scene_set_max_iterations", "scene_set_view", "scene_set_level",
                         "scene_set_initial_planes", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats",
-                        "scene_run_view", "scene_depth_map", "scene_remote_depth"]
+                        "scene_run_view", "scene_depth_map", "scene_remote_depth",
+                        "fusion_create", "fusion_destroy", "fusion_set_view", "fusion_reset", "fusion_run_view", "fusion_run",
+                        "fusion_num_points", "fusion_get_points", "fusion_get_mask", "fusion_last_view", "fusion_write_ply"]
+
+
+class FusionView(C.Structure):
+    """Mirror of dvp_fusion_view (include/dvp_mvs.h, row N3): one view as RunFusion holds it after its loading loop
+    (reference APD.cpp:1841-1873)."""
+    _fields_ = [
+        ("camera", C.c_uint8 * 112), ("width", C.c_int32), ("height", C.c_int32), ("depth", C.c_void_p),
+        ("normal", C.c_void_p), ("image", C.c_void_p), ("weak", C.c_void_p), ("block", C.c_void_p),
+        ("num_src", C.c_int32), ("src_views", C.c_void_p),
+    ]
+
+
+def make_fusion_view(view: dict, keep: list) -> FusionView:
+    """dict(camera, depth [h,w] f32, normal [h,w,3] f32, image [h,w,3] u8, weak [h,w] u8, src_views, block=None) ->
+    FusionView; the contiguous arrays it points to are appended to `keep` (the caller keeps them alive)."""
+    depth = np.ascontiguousarray(view["depth"], np.float32)
+    H, W = depth.shape
+    normal = _carr(view["normal"], np.float32, (H, W, 3)); image = _carr(view["image"], np.uint8, (H, W, 3))
+    weak = _carr(view["weak"], np.uint8, (H, W)); block = _carr(view.get("block"), np.uint8, (H, W))
+    src = np.ascontiguousarray(view["src_views"], np.int32)
+    cam = np.ascontiguousarray(np.asarray(view["camera"], CAMERA_DTYPE).reshape(1))
+    keep += [depth, normal, image, weak, block, src, cam]
+    fv = FusionView()
+    C.memmove(fv.camera, cam.ctypes.data, 112)
+    fv.width, fv.height = W, H
+    fv.depth, fv.normal, fv.image, fv.weak = depth.ctypes.data, normal.ctypes.data, image.ctypes.data, weak.ctypes.data
+    fv.block = block.ctypes.data if block is not None else None
+    fv.num_src = len(src); fv.src_views = src.ctypes.data if len(src) else None
+    return fv
 
 
 class DvpError(RuntimeError):
@@ -119,6 +150,17 @@ def load_library(path: str, prefix: str):
         f("scene_remote_depth").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]; f("scene_remote_depth").restype = C.c_int
         f("scene_get_view").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)] + [C.c_void_p] * 4; f("scene_get_view").restype = C.c_int
         f("scene_stats").argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]; f("scene_stats").restype = C.c_int
+        f("fusion_create").argtypes = [C.c_int, C.c_int]; f("fusion_create").restype = C.c_void_p
+        f("fusion_destroy").argtypes = [C.c_void_p]; f("fusion_destroy").restype = None
+        f("fusion_set_view").argtypes = [C.c_void_p, C.c_int, C.POINTER(FusionView)]; f("fusion_set_view").restype = C.c_int
+        f("fusion_reset").argtypes = [C.c_void_p]; f("fusion_reset").restype = C.c_int
+        f("fusion_run_view").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]; f("fusion_run_view").restype = C.c_int
+        f("fusion_run").argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_float)]; f("fusion_run").restype = C.c_int
+        f("fusion_num_points").argtypes = [C.c_void_p]; f("fusion_num_points").restype = C.c_longlong
+        f("fusion_get_points").argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong]; f("fusion_get_points").restype = C.c_int
+        f("fusion_get_mask").argtypes = [C.c_void_p, C.c_int, C.c_void_p]; f("fusion_get_mask").restype = C.c_int
+        f("fusion_last_view").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]; f("fusion_last_view").restype = C.c_int
+        f("fusion_write_ply").argtypes = [C.c_void_p, C.c_char_p]; f("fusion_write_ply").restype = C.c_int
     return lib
 
 
@@ -373,3 +415,77 @@ class Scene:
         sel = np.empty((H, W), np.uint32); rad = np.empty((H, W), np.int32)
         self._check(self.lib.dvp_scene_get_view(self.h, view, C.byref(w), C.byref(h), _ptr(planes), _ptr(weak), _ptr(sel), _ptr(rad)), "get_view")
         return planes, weak, sel, rad
+
+
+class Fusion:
+    """Depth-map fusion on the device (include/dvp_mvs.h, row N3): RunFusion of the reference (APD.cpp:1809-1960) with
+    the reference's sequential visiting order reproduced by deterministic reservations."""
+
+    def __init__(self, views: list, device: int = 0):
+        self.lib = load_library(PRODUCT_LIB, "dvp_")
+        self.device = device
+        self.h = self.lib.dvp_fusion_create(device, len(views))
+        if not self.h:
+            raise DvpError(f"dvp_fusion_create failed (device {device}, {len(views)} views)")
+        self.shapes = []
+        for i, v in enumerate(views):
+            keep = []
+            fv = make_fusion_view(v, keep)
+            self._check(self.lib.dvp_fusion_set_view(self.h, i, C.byref(fv)), "set_view")
+            self.shapes.append((fv.height, fv.width, fv.num_src))
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise DvpError(f"dvp_fusion_{what} -> {STATUS.get(rc, rc)}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dvp_fusion_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._check(self.lib.dvp_fusion_reset(self.h), "reset")
+
+    def run_view(self, view: int) -> float:
+        ms = C.c_float()
+        self._check(self.lib.dvp_fusion_run_view(self.h, view, C.byref(ms)), "run_view")
+        return float(ms.value)
+
+    def run(self):
+        """-> (points [n, 6] float32 in the reference's order, device ms)."""
+        n, ms = C.c_longlong(), C.c_float()
+        self._check(self.lib.dvp_fusion_run(self.h, C.byref(n), C.byref(ms)), "run")
+        return self.points(), float(ms.value)
+
+    def num_points(self) -> int:
+        return int(self.lib.dvp_fusion_num_points(self.h))
+
+    def points(self, first: int = 0, count: int | None = None) -> np.ndarray:
+        count = self.num_points() - first if count is None else count
+        out = np.empty((count, 6), np.float32)
+        if count:
+            self._check(self.lib.dvp_fusion_get_points(self.h, _ptr(out), first, count), "get_points")
+        return out
+
+    def mask(self, view: int) -> np.ndarray:
+        H, W, _ = self.shapes[view]
+        out = np.empty((H, W), np.uint8)
+        self._check(self.lib.dvp_fusion_get_mask(self.h, view, _ptr(out)), "get_mask")
+        return out
+
+    def last_view(self, view: int):
+        """Stage outputs of the last run_view(view): candidates (cells, terms [h*w, S]), decision (used [h*w]), rounds."""
+        H, W, S = self.shapes[view]
+        cells = np.empty((H * W, S), np.int32); terms = np.empty((H * W, S), np.float32); used = np.empty(H * W, np.uint32)
+        rounds = C.c_int()
+        self._check(self.lib.dvp_fusion_last_view(self.h, _ptr(cells), _ptr(terms), _ptr(used), C.byref(rounds)), "last_view")
+        return cells, terms, used, int(rounds.value)
+
+    def write_ply(self, path: str):
+        self._check(self.lib.dvp_fusion_write_ply(self.h, os.fsencode(path)), "write_ply")

@@ -317,3 +317,41 @@ def make_multiview(full_w: int, full_h: int, num_views: int, num_levels: int, se
                 planes_init.append(_first_init_planes(dep, Kl, Rv, rng_init))
         levels.append(per_view)
     return MultiView(full_w, full_h, num_levels, cameras, src_views, levels, planes_init, 0.6 * cam_dmin, 1.2 * cam_dmax)
+
+
+def make_fusion_views(mv: MultiView, levels, seed: int = 0, depth_noise: float = 0.001, normal_noise: float = 0.015) -> list:
+    """What RunFusion holds after its loading loop (reference APD.cpp:1841-1873), synthesised from a MultiView: per view
+    a depth map (true depth with multiplicative noise, 3 % invalid, 2 % gross outliers), world normals (finite
+    differences of the true depth, perturbed), a 3-channel uint8 image, a weak map (the textureless wall is WEAK) and
+    the source list.  `levels` is one pyramid level for all views or one per view (views of different sizes make many
+    pixels claim the same source cell, which is what the fusion's visiting order decides)."""
+    V = len(mv.cameras)
+    levels = [levels] * V if np.isscalar(levels) else list(levels)
+    rng = np.random.default_rng(20250104 + seed)
+    out = []
+    for v in range(V):
+        lv = mv.levels[levels[v]][v]
+        cam = np.array(lv["camera"], dtype=CAMERA_DTYPE).reshape(())
+        H, W = lv["h"], lv["w"]
+        true = lv["depth"].astype(np.float64)
+        K = cam["K"].astype(np.float64).reshape(3, 3); R = cam["R"].astype(np.float64).reshape(3, 3)
+        xs = (np.arange(W) - K[0, 2]) / K[0, 0]; ys = (np.arange(H) - K[1, 2]) / K[1, 1]
+        X = np.stack([xs[None, :] * true, ys[:, None] * true, true], -1)
+        dx = np.zeros_like(X); dy = np.zeros_like(X)
+        dx[:, :-1] = X[:, 1:] - X[:, :-1]; dx[:, -1] = dx[:, -2]
+        dy[:-1, :] = X[1:, :] - X[:-1, :]; dy[-1, :] = dy[-2, :]
+        nrm = np.cross(dx, dy)
+        nrm /= np.maximum(np.linalg.norm(nrm, axis=-1, keepdims=True), 1e-30)
+        nrm[(nrm * X).sum(-1) > 0] *= -1.0
+        nrm = nrm @ R + rng.normal(0.0, normal_noise, (H, W, 3))
+        nrm /= np.maximum(np.linalg.norm(nrm, axis=-1, keepdims=True), 1e-30)
+        depth = true * (1.0 + rng.normal(0.0, depth_noise, (H, W)))
+        u = rng.uniform(size=(H, W))
+        depth[u < 0.03] = 0.0
+        depth[(u >= 0.03) & (u < 0.05)] *= 1.05
+        grey = np.clip(lv["image"], 0, 255)
+        image = np.stack([grey, np.clip(grey * 0.9 + 10, 0, 255), np.clip(255 - grey, 0, 255)], -1).astype(np.uint8)
+        weak = np.where(lv["label"] == 4, 0, 1).astype(np.uint8)   # plane 3 (label 4) is the textureless wall; WEAK = 0
+        out.append(dict(camera=cam, depth=depth.astype(np.float32), normal=nrm.astype(np.float32), image=image, weak=weak,
+                        src_views=list(mv.src_views[v])))
+    return out

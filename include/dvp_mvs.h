@@ -257,6 +257,51 @@ int dvp_rescale_map(int device, const void* src, int src_w, int src_h, void* dst
  * call returns (dvp_run with sync != 0, dvp_run_stage, dvp_download, dvp_get_buffer).  Results are those of dvp_upload. */
 int dvp_upload_overlapped(dvp_ctx* ctx, const dvp_inputs* in, const dvp_params* params);
 
+/* ---- "Next" row N3: depth-map fusion on the device -------------------------------------------------------------------
+ * Replaces RunFusion, the "ETH version" main() calls (APD.cpp:1809-1960, main.cpp:514): every pixel of every view is
+ * lifted to 3-D, projected into the view's sources, checked for reprojection / depth / normal consistency, and — if
+ * accepted — emitted as one coloured point while the source pixels that agreed are masked so that they do not emit
+ * the same surface point again.  The reference does this in one sequential loop (views in order, pixels in raster
+ * order) and its result depends on that order; the device path reproduces exactly that order's result (deterministic
+ * reservations: a pixel decides once no earlier undecided pixel claims one of its source cells).
+ * One view = what the reference holds after its loading loop (APD.cpp:1841-1873): camera and colour image already
+ * rescaled to the depth map's size (RescaleImageAndCamera), weak map rescaled to it (RescaleMatToTargetSize). */
+typedef struct dvp_fusion_view {
+	dvp_camera camera;        /* K, R, t at the depth map's size                                                   */
+	int32_t width, height;    /* of the depth map                                                                  */
+	const float* depth;       /* [h][w]     depths.dmb                                                             */
+	const float* normal;      /* [h][w][3]  APD_normals.dmb (world frame)                                          */
+	const uint8_t* image;     /* [h][w][3]  colour image, channel order kept as given (BGR in the reference)       */
+	const uint8_t* weak;      /* [h][w]     DVP_WEAK / DVP_STRONG / DVP_UNKNOWN (weak.bin)                         */
+	const uint8_t* block;     /* [h][w] or NULL: pixels < 128 are not fused (the optional blocks/ folder)          */
+	int32_t num_src;          /* Problem::src_image_ids.size(), <= 32                                              */
+	const int32_t* src_views; /* [num_src] view indices (imageIdToindexMap applied)                                */
+} dvp_fusion_view;
+
+typedef struct dvp_fusion dvp_fusion;
+dvp_fusion* dvp_fusion_create(int device, int num_views);
+void dvp_fusion_destroy(dvp_fusion* f);
+/* Copies one view's maps to the device (host pointers). */
+int dvp_fusion_set_view(dvp_fusion* f, int view, const dvp_fusion_view* v);
+/* Clears the fusion masks (APD.cpp:1870) and the point list. */
+int dvp_fusion_reset(dvp_fusion* f);
+/* One iteration of the reference's outer loop (APD.cpp:1879-1957): fuses view `view` against the current masks and
+ * appends its points.  `device_ms` may be NULL. */
+int dvp_fusion_run_view(dvp_fusion* f, int view, float* device_ms);
+/* dvp_fusion_reset + every view in index order. */
+int dvp_fusion_run(dvp_fusion* f, long long* num_points, float* device_ms);
+long long dvp_fusion_num_points(dvp_fusion* f);
+/* Points [first, first + count) in the reference's order: 6 floats each (coord xyz, colour in the image's channel
+ * order — PointList, main.h:69-72). */
+int dvp_fusion_get_points(dvp_fusion* f, float* dst, long long first, long long count);
+int dvp_fusion_get_mask(dvp_fusion* f, int view, uint8_t* dst);
+/* Stage stepping for parity tests, about the last dvp_fusion_run_view: the mask-independent candidates
+ * (cells / terms: [h*w][num_src], -1 = source not consistent), the per-pixel decision (used: bit j = source j
+ * contributed, 0 = no point) and the number of reservation rounds it took.  Any pointer may be NULL. */
+int dvp_fusion_last_view(dvp_fusion* f, int32_t* cells, float* terms, uint32_t* used, int* rounds);
+/* ExportPointCloud (APD.cpp:842-882): binary little-endian PLY, x y z float + 3 uchar colours. */
+int dvp_fusion_write_ply(dvp_fusion* f, const char* path);
+
 int dvp_weak_count(dvp_ctx* ctx);
 int dvp_last_cuda_error(dvp_ctx* ctx);
 void* dvp_stream(dvp_ctx* ctx); /* cudaStream_t */

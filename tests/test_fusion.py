@@ -1,0 +1,262 @@
+"""Row N3: depth-map fusion — RunFusion, the "ETH version" main() calls (reference APD.cpp:1809-1960).
+CPU part: the restatement (oracle/cpu/fusion_cpu.cpp) against hand-computed answers, its split into a mask-independent
+and a mask-dependent stage, and the reservation scheme of the CUDA path (emulated in numpy) against the sequential loop.
+GPU part: dvp_fusion_* against the restatement, stage by stage: candidates within float tolerance (exp / acos are the
+only non-IEEE operations), the order-dependent resolution bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from util import ROOT
+from dvp_mvs_b200 import synth
+from fusion_oracle import FusionOracle
+
+FREE = np.uint32(0xFFFFFFFF)
+
+
+def camera(W, H, f, c=(0.0, 0.0, 0.0)):
+    K = np.array([[f, 0, W / 2.0], [0, f, H / 2.0], [0, 0, 1.0]])
+    return synth.make_camera(K, np.eye(3), np.array(c, np.float64), W, H, 1.0, 10.0)
+
+
+def flat_view(W, H, f, depth, src, grey=100, weak=1, c=(0.0, 0.0, 0.0)):
+    """A fronto-parallel wall at z = depth seen by an axis-aligned camera."""
+    n = np.zeros((H, W, 3), np.float32); n[..., 2] = -1.0
+    img = np.full((H, W, 3), grey, np.uint8); img[..., 1] = grey // 2; img[..., 2] = 255 - grey
+    return dict(camera=camera(W, H, f, c), depth=np.full((H, W), depth, np.float32), normal=n, image=img,
+                weak=np.full((H, W), weak, np.uint8), src_views=src)
+
+
+@pytest.fixture(scope="module")
+def scene():
+    mv = synth.make_multiview(640, 480, 4, 2, seed=1)
+    return mv
+
+
+# ---------------------------------------------------------------------------------------------------------- CPU
+def test_known_answers_identical_cameras():
+    # two identical views of one wall: every pixel of view 0 agrees with view 1 exactly (index 0 -> term 1 > 0.3), is
+    # emitted with the mean colour and masks its twin, so view 1 emits nothing
+    W, H = 12, 8
+    views = [flat_view(W, H, 10.0, 4.0, [1], grey=100), flat_view(W, H, 10.0, 4.0, [0], grey=60)]
+    o = FusionOracle(views)
+    pts = o.run()
+    assert len(pts) == W * H
+    assert o.masks[1].all() and not o.masks[0].any()
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H))
+    np.testing.assert_array_equal(pts[:, 0].reshape(H, W), (np.float32(4.0) * (xs - np.float32(W / 2)).astype(np.float32)) / np.float32(10.0))
+    np.testing.assert_array_equal(pts[:, 1].reshape(H, W), (np.float32(4.0) * (ys - np.float32(H / 2)).astype(np.float32)) / np.float32(10.0))
+    assert (pts[:, 2] == 4.0).all()
+    assert (pts[:, 3] == 80.0).all() and (pts[:, 4] == 40.0).all() and (pts[:, 5] == (155 + 195) / 2).all()
+    # a 2 % depth disagreement fails the 1 % test in both directions: nothing is emitted for those pixels
+    views[1]["depth"][2:4, :] = 4.08
+    o = FusionOracle(views)
+    pts = o.run()
+    assert len(pts) == W * (H - 2)
+    assert not o.masks[1][2:4].any() and o.masks[1][:2].all() and o.masks[1][4:].all()
+    # a normal 12 degrees off fails the 10 degree test; 8 degrees passes with index 10 * 0.1396 = 1.396 -> term 0.2476,
+    # which is below the 0.3 a STRONG pixel needs
+    for deg, expect in ((12.0, 0), (8.0, 0), (2.0, W * H)):
+        views = [flat_view(W, H, 10.0, 4.0, [1]), flat_view(W, H, 10.0, 4.0, [0])]
+        a = np.deg2rad(deg)
+        views[1]["normal"][...] = np.array([np.sin(a), 0.0, -np.cos(a)], np.float32)
+        assert len(FusionOracle(views).run()) == expect, deg
+
+
+def test_known_answers_visiting_order():
+    # view 0 at twice the resolution of view 1: the four pixels of a 2x2 block project to one pixel of view 1 (or its
+    # neighbour, int(x + 0.5) truncation).  The first pixel in raster order to claim a cell is emitted and masks it; the
+    # later claimants see the mask, have no consistent source left and are dropped.
+    W, H = 16, 12
+    views = [flat_view(W, H, 20.0, 4.0, [1]), flat_view(W // 2, H // 2, 10.0, 4.0, [0])]
+    o = FusionOracle(views)
+    pts = o.run()
+    cells, terms = o.candidates(0)
+    inside = (np.arange(W * H) % W < W - 1) & (np.arange(W * H) // W < H - 1)   # the last column / row round to cell W/2, H/2
+    assert ((cells[:, 0] >= 0) == inside).all()
+    # expected by hand: pixel (x, y) claims cell (int(x/2 + .5), int(y/2 + .5)), which looks back at pixel (2cx, 2cy); the
+    # claim's index is that distance in pixels (depths and normals agree exactly), and exp(-d) > 0.3 needs d < 1.204:
+    # a diagonal neighbour (d = 1.414) is refused and leaves the cell to the next claimant
+    first = np.zeros(W * H, bool)
+    seen = set()
+    for p in np.flatnonzero(inside):
+        y, x = divmod(int(p), W)
+        cx, cy = int(x / 2 + 0.5), int(y / 2 + 0.5)
+        assert cells[p, 0] == cy * (W // 2) + cx
+        d = np.hypot(x - 2 * cx, y - 2 * cy)
+        if (cx, cy) not in seen and d < 1.2:
+            seen.add((cx, cy)); first[p] = True
+    n0 = int(first.sum())
+    assert n0 == (W // 2) * (H // 2)                 # every cell of view 1 ends up claimed exactly once
+    assert o.masks[1].sum() == n0 and len(pts) == n0  # ... so view 1 itself has nothing left to emit
+    ys, xs = np.divmod(np.flatnonzero(first), W)
+    np.testing.assert_array_equal(pts[:, 0], (np.float32(4.0) * (xs - np.float32(W / 2)).astype(np.float32)) / np.float32(20.0))
+    np.testing.assert_array_equal(pts[:, 1], (np.float32(4.0) * (ys - np.float32(H / 2)).astype(np.float32)) / np.float32(20.0))
+
+
+def test_run_equals_candidates_plus_resolve(scene):
+    for levels in (1, [1, 0, 1, 0]):
+        views = synth.make_fusion_views(scene, levels)
+        o = FusionOracle(views)
+        pts = o.run()
+        masks = [m.copy() for m in o.masks]
+        assert len(pts) > 1000
+        o.reset()
+        parts = []
+        for v in range(len(views)):
+            cells, terms = o.candidates(v)
+            used, p = o.resolve(v, cells, terms)
+            assert (used != 0).sum() == len(p)
+            parts.append(p)
+        np.testing.assert_array_equal(np.concatenate(parts), pts)
+        for a, b in zip(masks, o.masks):
+            np.testing.assert_array_equal(a, b)
+
+
+def reservations_numpy(masks, ref, src_views, cells, terms, weak):
+    """The CUDA path's resolve stage (dvp_kernels_fusion.cu: reserve_one / decide_one), vectorised per round."""
+    N, S = cells.shape
+    live = cells >= 0
+    active = live.any(1) & (masks[ref].ravel() != 1)
+    used = np.zeros(N, np.uint32)
+    resv = {s: np.full(masks[s].size, FREE, np.uint32) for s in set(src_views)}
+    rounds = 0
+    while active.any():
+        idx = np.flatnonzero(active)
+        for j, s in enumerate(src_views):                                  # (A) drop masked cells, reserve the rest
+            sel = idx[live[idx, j]]
+            c = cells[sel, j]
+            masked = masks[s].ravel()[c] == 1
+            live[sel[masked], j] = False
+            np.minimum.at(resv[s], c[~masked], sel[~masked].astype(np.uint32))
+        ready = np.ones(len(idx), bool)                                    # (B) holders of all their cells decide
+        for j, s in enumerate(src_views):
+            lj = live[idx, j]
+            ready &= ~lj | (resv[s][np.where(lj, cells[idx, j], 0)] == idx)
+        r = idx[ready]
+        assert len(r) > 0
+        num = np.zeros(len(r), np.int32); dyn = np.zeros(len(r), np.float32); bits = np.zeros(len(r), np.uint32)
+        for j in range(S):
+            lj = live[r, j]
+            dyn = np.where(lj, dyn + terms[r, j], dyn).astype(np.float32)
+            num += lj; bits |= lj.astype(np.uint32) << np.uint32(j)
+        factor = np.where(weak.ravel()[r] == 0, np.float32(0.45), np.float32(0.3)).astype(np.float32)
+        acc = (num >= 1) & (dyn > factor * num.astype(np.float32))
+        for j, s in enumerate(src_views):
+            lj = live[r, j]
+            c = cells[r[lj], j]
+            resv[s][c] = FREE
+            masks[s].ravel()[c[acc[lj]]] = 1
+        used[r[acc]] = bits[acc]
+        active[r] = False
+        rounds += 1
+    return used, rounds
+
+
+def test_reservation_scheme_equals_sequential_loop(scene):
+    # views of mixed sizes: most pixels of the fine views share their source cells with neighbours
+    views = synth.make_fusion_views(scene, [1, 0, 1, 0])
+    o = FusionOracle(views)
+    masks = [np.zeros_like(m) for m in o.masks]
+    most_rounds = 0
+    for v in range(len(views)):
+        cells, terms = o.candidates(v)
+        used_seq, _ = o.resolve(v, cells, terms)
+        used_par, rounds = reservations_numpy(masks, v, views[v]["src_views"], cells, terms, views[v]["weak"])
+        np.testing.assert_array_equal(used_par, used_seq)
+        for a, b in zip(masks, o.masks):
+            np.testing.assert_array_equal(a, b)
+        most_rounds = max(most_rounds, rounds)
+    assert most_rounds > 2     # the order did matter somewhere
+
+
+# ---------------------------------------------------------------------------------------------------------- GPU
+def _gpu_stagewise(views):
+    from dvp_mvs_b200 import Fusion
+    o = FusionOracle(views)
+    f = Fusion(views)
+    f.reset()
+    report = dict(cell_flips=0, cells=0, term_err=0.0, rounds=[])
+    parts = []
+    for v in range(len(views)):
+        f.run_view(v)
+        cells, terms, used, rounds = f.last_view(v)
+        # stage 1 against the restatement: same claims, except where acos / exp land a threshold on the other side
+        c_ref, t_ref = o.candidates(v)
+        flips = cells != c_ref
+        report["cell_flips"] += int(flips.sum()); report["cells"] += cells.size
+        same = ~flips & (cells >= 0)
+        if same.any():
+            report["term_err"] = max(report["term_err"], float(np.max(np.abs(terms[same] - t_ref[same]) / t_ref[same])))
+        # stage 2 from the device's own candidates: the sequential loop must give the same decisions bit for bit
+        used_ref, p_ref = o.resolve(v, cells, terms)
+        np.testing.assert_array_equal(used, used_ref)
+        parts.append(p_ref)
+        report["rounds"].append(rounds)
+    pts = f.points()
+    np.testing.assert_array_equal(pts, np.concatenate(parts))           # coordinates, colours and order
+    for v in range(len(views)):
+        np.testing.assert_array_equal(f.mask(v), o.masks[v])
+    f.close()
+    return report, pts
+
+
+@pytest.mark.gpu
+def test_gpu_fusion_stagewise_vs_restatement(scene):
+    views = synth.make_fusion_views(scene, 1)
+    report, pts = _gpu_stagewise(views)
+    assert len(pts) > 1000
+    assert report["cell_flips"] <= 1e-4 * report["cells"], report
+    assert report["term_err"] <= 1e-6, report        # exp(-x) in double rounded to float vs libm expf: a few ulp at most
+
+
+@pytest.mark.gpu
+def test_gpu_fusion_mixed_sizes_many_rounds(scene):
+    # fine views fused against coarse ones: shared source cells everywhere, long reservation chains, tail kernel
+    views = synth.make_fusion_views(scene, [1, 0, 1, 0])
+    report, pts = _gpu_stagewise(views)
+    assert len(pts) > 1000
+    assert max(report["rounds"]) > 4, report
+    assert report["cell_flips"] <= 1e-4 * report["cells"], report
+
+
+@pytest.mark.gpu
+def test_gpu_fusion_whole_run_vs_restatement(scene, tmp_path):
+    from dvp_mvs_b200 import Fusion
+    views = synth.make_fusion_views(scene, 1, seed=3)
+    views[2]["block"] = (np.arange(views[2]["depth"].size).reshape(views[2]["depth"].shape) % 7 != 0).astype(np.uint8) * 255
+    ref = FusionOracle(views).run()
+    f = Fusion(views)
+    pts, ms = f.run()
+    assert ms > 0
+    # whole-run agreement: identical unless an exp / acos ulp flipped a decision (then a handful of points differ)
+    a = {tuple(p) for p in np.round(pts[:, :3].astype(np.float64), 6)}
+    b = {tuple(p) for p in np.round(ref[:, :3].astype(np.float64), 6)}
+    assert len(a ^ b) <= max(4, 1e-4 * len(b)), (len(a), len(b), len(a ^ b))
+    pts2, _ = f.run()                                                    # deterministic: a second run is identical
+    np.testing.assert_array_equal(pts, pts2)
+    path = str(tmp_path / "fused.ply")
+    f.write_ply(path)
+    raw = open(path, "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    assert b"element vertex %d\n" % len(pts) in head and b"property uchar diffuse_blue" in head
+    assert len(body) == 15 * len(pts)
+    rec = np.frombuffer(body, np.dtype([("xyz", "<f4", 3), ("bgr", "u1", 3)]))
+    np.testing.assert_array_equal(rec["xyz"], pts[:, :3])
+    np.testing.assert_array_equal(rec["bgr"], pts[:, 3:].astype(np.uint8))
+    f.close()
+
+
+@pytest.mark.gpu
+def test_gpu_fusion_argument_errors(scene):
+    from dvp_mvs_b200 import Fusion, DvpError
+    views = synth.make_fusion_views(scene, 0)
+    bad = [dict(v) for v in views]
+    bad[1]["src_views"] = [1, 2]                      # a view cannot be its own source
+    with pytest.raises(DvpError):
+        Fusion(bad)
+    bad = [dict(v) for v in views]
+    bad[0]["src_views"] = [7]
+    with pytest.raises(DvpError):
+        Fusion(bad)
