@@ -70,7 +70,7 @@ PRODUCT_ONLY_SYMBOLS = ["upload_device", "upload_overlapped", "restore_visibilit
                         "scene_pass_params", "scene_set_max_iterations", "scene_set_view", "scene_set_level",
                         "scene_set_initial_planes", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats",
                         "scene_run_view", "scene_depth_map", "scene_remote_depth",
-                        "fusion_create", "fusion_destroy", "fusion_set_view", "fusion_reset", "fusion_run_view", "fusion_run",
+                        "fusion_create", "fusion_destroy", "fusion_set_view", "fusion_set_view_planes", "scene_fuse_views", "fusion_reset", "fusion_run_view", "fusion_run",
                         "fusion_num_points", "fusion_get_points", "fusion_get_mask", "fusion_last_view", "fusion_write_ply"]
 
 
@@ -153,6 +153,8 @@ def load_library(path: str, prefix: str):
         f("fusion_create").argtypes = [C.c_int, C.c_int]; f("fusion_create").restype = C.c_void_p
         f("fusion_destroy").argtypes = [C.c_void_p]; f("fusion_destroy").restype = None
         f("fusion_set_view").argtypes = [C.c_void_p, C.c_int, C.POINTER(FusionView)]; f("fusion_set_view").restype = C.c_int
+        f("fusion_set_view_planes").argtypes = [C.c_void_p, C.c_int, C.POINTER(FusionView), C.c_void_p]; f("fusion_set_view_planes").restype = C.c_int
+        f("scene_fuse_views").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]; f("scene_fuse_views").restype = C.c_int
         f("fusion_reset").argtypes = [C.c_void_p]; f("fusion_reset").restype = C.c_int
         f("fusion_run_view").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]; f("fusion_run_view").restype = C.c_int
         f("fusion_run").argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_float)]; f("fusion_run").restype = C.c_int
@@ -357,6 +359,7 @@ class Scene:
         self._check(self.lib.dvp_scene_set_max_iterations(self.h, n), "set_max_iterations")
 
     def set_view(self, view: int, camera, full_w: int, full_h: int, src_views):
+        self.src_views = getattr(self, "src_views", {}); self.src_views[view] = list(src_views)
         cam = np.ascontiguousarray(camera, dtype=CAMERA_DTYPE).reshape(1)
         src = (C.c_int * len(src_views))(*[int(s) for s in src_views])
         self._check(self.lib.dvp_scene_set_view(self.h, view, _ptr(cam), full_w, full_h, len(src_views), src), "set_view")
@@ -421,18 +424,50 @@ class Fusion:
     """Depth-map fusion on the device (include/dvp_mvs.h, row N3): RunFusion of the reference (APD.cpp:1809-1960) with
     the reference's sequential visiting order reproduced by deterministic reservations."""
 
-    def __init__(self, views: list, device: int = 0):
+    def __init__(self, views, device: int = 0):
+        """views: list of view dicts (see make_fusion_view; `planes` [h,w,4] may replace depth + normal), or the number
+        of views when they are registered later (from_scene)."""
         self.lib = load_library(PRODUCT_LIB, "dvp_")
         self.device = device
-        self.h = self.lib.dvp_fusion_create(device, len(views))
+        count = views if isinstance(views, int) else len(views)
+        self.h = self.lib.dvp_fusion_create(device, count)
         if not self.h:
-            raise DvpError(f"dvp_fusion_create failed (device {device}, {len(views)} views)")
+            raise DvpError(f"dvp_fusion_create failed (device {device}, {count} views)")
         self.shapes = []
-        for i, v in enumerate(views):
+        for i, v in enumerate([] if isinstance(views, int) else views):
             keep = []
-            fv = make_fusion_view(v, keep)
-            self._check(self.lib.dvp_fusion_set_view(self.h, i, C.byref(fv)), "set_view")
+            if "planes" in v:
+                planes = np.ascontiguousarray(v["planes"], np.float32)
+                H, W = planes.shape[:2]
+                stub = dict(v, depth=np.zeros((H, W), np.float32), normal=np.zeros((H, W, 3), np.float32))
+                fv = make_fusion_view(stub, keep)
+                self._check(self.lib.dvp_fusion_set_view_planes(self.h, i, C.byref(fv), _ptr(planes)), "set_view_planes")
+            else:
+                fv = make_fusion_view(v, keep)
+                self._check(self.lib.dvp_fusion_set_view(self.h, i, C.byref(fv)), "set_view")
             self.shapes.append((fv.height, fv.width, fv.num_src))
+
+    @classmethod
+    def from_scene(cls, scene: "Scene", images: list, blocks: list | None = None) -> "Fusion":
+        """N2 -> N3: every view's maps go from the scene's device buffers to the fusion object (dvp_scene_fuse_views);
+        images[v]: [h, w, 3] uint8 at the view's current map size."""
+        V = scene.num_views
+        f = cls(V, scene.device)
+        imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        img_ptrs = (C.c_void_p * V)(*[im.ctypes.data for im in imgs])
+        blk_ptrs = None
+        if blocks is not None:
+            blks = [None if b is None else np.ascontiguousarray(b, np.uint8) for b in blocks]
+            blk_ptrs = (C.c_void_p * V)(*[None if b is None else b.ctypes.data for b in blks])
+        rc = f.lib.dvp_scene_fuse_views(scene.h, f.h, img_ptrs, blk_ptrs)
+        if rc != 0:
+            raise DvpError(f"dvp_scene_fuse_views -> {STATUS.get(rc, rc)}")
+        for v in range(V):
+            w, h = C.c_int(), C.c_int()
+            scene._check(scene.lib.dvp_scene_get_view(scene.h, v, C.byref(w), C.byref(h), None, None, None, None), "get_view")
+            assert imgs[v].shape == (h.value, w.value, 3), (imgs[v].shape, h.value, w.value)
+            f.shapes.append((int(h.value), int(w.value), len(scene.src_views[v])))
+        return f
 
     def _check(self, rc, what):
         if rc != 0:

@@ -304,6 +304,15 @@ __global__ void __launch_bounds__(256) k_fuse_emit(const __grid_constant__ RefAr
 	o[3] = col0 / div; o[4] = col1 / div; o[5] = col2 / div;
 }
 
+// (world normal, depth) plane map -> the depth and normal maps ProcessProblem writes (main.cpp:300-306)
+__global__ void __launch_bounds__(256) k_fuse_split_planes(int n, const float4* __restrict__ planes, float* __restrict__ depth, float* __restrict__ normal) {
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n) return;
+	const float4 v = planes[p];
+	depth[p] = v.w;
+	normal[3 * (size_t)p] = v.x; normal[3 * (size_t)p + 1] = v.y; normal[3 * (size_t)p + 2] = v.z;
+}
+
 }  // namespace dvp_fuse
 
 // =====================================================================================================================
@@ -348,7 +357,7 @@ template <typename T> cudaError_t upload(const T** dst, const T* src, size_t cou
 	cudaError_t e = cudaMalloc((void**)&d, count * sizeof(T));
 	if (e != cudaSuccess) return e;
 	*dst = d;
-	return cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, st);
+	return cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyDefault, st);   // host or device source
 }
 
 int grow(dvp_fusion* f, size_t n, size_t s) {
@@ -408,9 +417,11 @@ void dvp_fusion_destroy(dvp_fusion* f) {
 	delete f;
 }
 
-int dvp_fusion_set_view(dvp_fusion* f, int view, const dvp_fusion_view* v) {
+// `planes` != NULL: depth and normal come from a [h][w][4] (world normal, depth) plane map instead of v->depth / v->normal
+static int set_view_impl(dvp_fusion* f, int view, const dvp_fusion_view* v, const float* planes) {
 	if (!f || !v || view < 0 || view >= f->V) return DVP_ERR_ARG;
-	if (v->width <= 0 || v->height <= 0 || !v->depth || !v->normal || !v->image || !v->weak) return DVP_ERR_ARG;
+	if (v->width <= 0 || v->height <= 0 || !v->image || !v->weak) return DVP_ERR_ARG;
+	if (!planes && (!v->depth || !v->normal)) return DVP_ERR_ARG;
 	if ((long long)v->width * v->height > 0x7fffffffLL / 8) return DVP_ERR_ARG;
 	if (v->num_src < 0 || v->num_src > kMaxSrc || (v->num_src > 0 && !v->src_views)) return DVP_ERR_ARG;
 	for (int j = 0; j < v->num_src; ++j)
@@ -423,8 +434,24 @@ int dvp_fusion_set_view(dvp_fusion* f, int view, const dvp_fusion_view* v) {
 	hv.w = v->width; hv.h = v->height; hv.num_src = v->num_src;
 	for (int j = 0; j < v->num_src; ++j) hv.src[j] = v->src_views[j];
 	hv.d.cam = v->camera; hv.d.w = v->width; hv.d.h = v->height;
-	FCK(upload(&hv.d.depth, v->depth, n, f->stream));
-	FCK(upload(&hv.d.normal, v->normal, 3 * n, f->stream));
+	if (planes) {
+		const float* d_planes = nullptr;
+		float* d_depth = nullptr; float* d_normal = nullptr;
+		FCK(upload(&d_planes, planes, 4 * n, f->stream));
+		cudaError_t e = cudaMalloc((void**)&d_depth, n * sizeof(float));
+		if (e == cudaSuccess) e = cudaMalloc((void**)&d_normal, 3 * n * sizeof(float));
+		hv.d.depth = d_depth; hv.d.normal = d_normal;
+		if (e == cudaSuccess) {
+			k_fuse_split_planes<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>((int)n, (const float4*)d_planes, d_depth, d_normal);
+			e = cudaGetLastError();
+		}
+		if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
+		cudaFree((void*)d_planes);
+		FCK(e);
+	} else {
+		FCK(upload(&hv.d.depth, v->depth, n, f->stream));
+		FCK(upload(&hv.d.normal, v->normal, 3 * n, f->stream));
+	}
 	FCK(upload(&hv.d.image, v->image, 3 * n, f->stream));
 	FCK(upload(&hv.d.weak, v->weak, n, f->stream));
 	if (v->block) FCK(upload(&hv.d.block, v->block, n, f->stream));
@@ -433,9 +460,16 @@ int dvp_fusion_set_view(dvp_fusion* f, int view, const dvp_fusion_view* v) {
 	FCK(cudaMemsetAsync(hv.d.mask, 0, n, f->stream));
 	FCK(cudaMemsetAsync(hv.d.resv, 0xFF, n * sizeof(unsigned), f->stream));
 	FCK(cudaMemcpyAsync(f->d_views + view, &hv.d, sizeof(ViewDev), cudaMemcpyHostToDevice, f->stream));
-	FCK(cudaStreamSynchronize(f->stream));   // the host buffers may go away after the call
+	FCK(cudaStreamSynchronize(f->stream));   // the caller's buffers may go away after the call
 	hv.set = true;
 	return DVP_OK;
+}
+
+int dvp_fusion_set_view(dvp_fusion* f, int view, const dvp_fusion_view* v) { return set_view_impl(f, view, v, nullptr); }
+
+int dvp_fusion_set_view_planes(dvp_fusion* f, int view, const dvp_fusion_view* v, const float* planes) {
+	if (!planes) return DVP_ERR_ARG;
+	return set_view_impl(f, view, v, planes);
 }
 
 int dvp_fusion_reset(dvp_fusion* f) {

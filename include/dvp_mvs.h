@@ -281,8 +281,18 @@ typedef struct dvp_fusion_view {
 typedef struct dvp_fusion dvp_fusion;
 dvp_fusion* dvp_fusion_create(int device, int num_views);
 void dvp_fusion_destroy(dvp_fusion* f);
-/* Copies one view's maps to the device (host pointers). */
+/* Copies one view's maps into the fusion object (host or device pointers). */
 int dvp_fusion_set_view(dvp_fusion* f, int view, const dvp_fusion_view* v);
+/* Same, with depth and normal taken from a [h][w][4] (world normal, depth) plane map as dvp_download / dvp_scene_get_view
+ * return it (host or device pointer) — the split ProcessProblem does before writing depths.dmb / APD_normals.dmb
+ * (main.cpp:300-306).  v->depth and v->normal are ignored. */
+int dvp_fusion_set_view_planes(dvp_fusion* f, int view, const dvp_fusion_view* v, const float* planes);
+/* N2 -> N3 hand-off: registers every view of a scene with a fusion object (same device) straight from the scene's
+ * device buffers — what the reference passes through depths.dmb / APD_normals.dmb / weak.bin (main.cpp:365-370 ->
+ * APD.cpp:1851-1858) — with the camera rescaled to the map size (RescaleImageAndCamera, APD.cpp:1750-1771) and the
+ * scene's source lists.  images[v]: [h][w][3] u8 colour image of view v at its current map size (host or device; the
+ * reference's cv::resize of the jpg); blocks (or blocks[v]) may be NULL. */
+int dvp_scene_fuse_views(dvp_scene* scene, dvp_fusion* f, const uint8_t* const* images, const uint8_t* const* blocks);
 /* Clears the fusion masks (APD.cpp:1870) and the point list. */
 int dvp_fusion_reset(dvp_fusion* f);
 /* One iteration of the reference's outer loop (APD.cpp:1879-1957): fuses view `view` against the current masks and

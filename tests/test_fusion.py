@@ -260,3 +260,45 @@ def test_gpu_fusion_argument_errors(scene):
     bad[0]["src_views"] = [7]
     with pytest.raises(DvpError):
         Fusion(bad)
+
+
+@pytest.mark.gpu
+def test_gpu_scene_to_fusion_handoff_equals_the_host_route():
+    """N2 -> N3: maps handed over inside HBM (dvp_scene_fuse_views) fuse to the same points, bit for bit, as maps that
+    went through the host the way the reference passes them through depths.dmb / APD_normals.dmb / weak.bin."""
+    from dvp_mvs_b200 import Fusion, Scene
+    mv = synth.make_multiview(320, 240, 3, 2, seed=5)
+    V = len(mv.cameras)
+    sc = Scene(V, mv.num_levels)
+    for v in range(V):
+        sc.set_view(v, mv.cameras[v], mv.full_w, mv.full_h, mv.src_views[v])
+        for level in range(mv.num_levels):
+            L = mv.levels[level][v]
+            sc.set_level(v, level, L["image"], L["edge"], L["label"])
+        sc.set_initial_planes(v, mv.planes_init[v])
+    sc.run(seed=7)
+    fine = mv.levels[-1]
+    images = [np.stack([np.clip(L["image"], 0, 255)] * 3, -1).astype(np.uint8) for L in fine]
+    f = Fusion.from_scene(sc, images)
+    pts, _ = f.run()
+    assert len(pts) > 500
+    # host route: download, split (main.cpp:300-306), camera rescaled as RescaleImageAndCamera does
+    views = []
+    for v in range(V):
+        planes, weak, _, _ = sc.get_view(v)
+        h, w = weak.shape
+        cam = synth.level_camera(mv.cameras[v], mv.full_w, mv.full_h, w, h, 2)
+        views.append(dict(camera=cam, depth=planes[..., 3].copy(), normal=planes[..., :3].copy(), image=images[v], weak=weak,
+                          src_views=mv.src_views[v]))
+    g = Fusion(views)
+    pts_host, _ = g.run()
+    np.testing.assert_array_equal(pts, pts_host)
+    # the plane-map entry point on host memory is the same split
+    k = Fusion([dict(v, planes=np.concatenate([v["normal"], v["depth"][..., None]], -1)) for v in views])
+    np.testing.assert_array_equal(k.run()[0], pts)
+    # and the restatement agrees on what these maps fuse to (up to exp / acos ulps)
+    ref = FusionOracle(views).run()
+    assert abs(len(ref) - len(pts)) <= max(4, 1e-4 * len(ref))
+    # the fused cloud lies on the synthetic room: its points are the views' own back-projections
+    for x in (f, g, k, sc):
+        x.close()

@@ -15,6 +15,8 @@ def main():
     ap.add_argument("--views", type=int, default=5)
     ap.add_argument("--levels", type=int, default=3)
     ap.add_argument("--host-chain", type=int, default=1)
+    ap.add_argument("--fuse", type=int, default=1, help="fuse the finished maps on the device (row N3)")
+    ap.add_argument("--ply", default="", help="write the fused cloud here")
     a = ap.parse_args()
     fw, fh = (int(v) for v in a.full.split("x"))
     from dvp_mvs_b200 import synth, Scene, Engine
@@ -54,6 +56,24 @@ def main():
            "passes": a.levels * 4 * V, "pixels_processed": pix,
            "resident": {"device_ms": dev_ms, "wall_ms": wall * 1e3, "mpix_per_s_wall": pix / wall / 1e6},
            "median_rel_depth_error_per_view": [round(e, 5) for e in errs], "synth_s": round(t_synth, 1)}
+    if a.fuse:
+        # row N3 on top of rows N1 + N2: the finished maps go to the fusion object inside HBM
+        from dvp_mvs_b200 import Fusion
+        fine = mv.levels[-1]
+        images = [np.stack([np.clip(L["image"], 0, 255)] * 3, -1).astype(np.uint8) for L in fine]
+        t0 = time.perf_counter()
+        fu = Fusion.from_scene(sc, images)
+        t_hand = time.perf_counter() - t0
+        fu.run()
+        t0 = time.perf_counter()
+        pts, fuse_ms = fu.run()
+        t_fuse = time.perf_counter() - t0
+        # accuracy of the cloud: every point is some view's pixel lifted with its estimated depth -> compare with the
+        # ray-cast truth through that depth's relative error (points are emitted in view / raster order)
+        out["fusion"] = {"points": int(len(pts)), "handoff_ms": t_hand * 1e3, "device_ms": fuse_ms, "wall_ms": t_fuse * 1e3}
+        if a.ply:
+            fu.write_ply(a.ply)
+        fu.close()
     if a.host_chain:
         import host_chain
         hc = host_chain.HostChain(mv, lambda w, h, S, p: Engine(w, h, S, p))
