@@ -71,7 +71,8 @@ PRODUCT_ONLY_SYMBOLS = ["upload_device", "upload_overlapped", "restore_visibilit
                         "scene_set_initial_planes", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats",
                         "scene_run_view", "scene_depth_map", "scene_remote_depth",
                         "fusion_create", "fusion_destroy", "fusion_set_view", "fusion_set_view_planes", "scene_fuse_views", "fusion_reset", "fusion_run_view", "fusion_run",
-                        "fusion_num_points", "fusion_get_points", "fusion_get_mask", "fusion_last_view", "fusion_write_ply"]
+                        "fusion_num_points", "fusion_get_points", "fusion_get_mask", "fusion_last_view", "fusion_write_ply",
+                        "edge_segment", "scene_compute_edges", "scene_get_edges"]
 
 
 class FusionView(C.Structure):
@@ -150,6 +151,9 @@ def load_library(path: str, prefix: str):
         f("scene_remote_depth").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]; f("scene_remote_depth").restype = C.c_int
         f("scene_get_view").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)] + [C.c_void_p] * 4; f("scene_get_view").restype = C.c_int
         f("scene_stats").argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]; f("scene_stats").restype = C.c_int
+        f("edge_segment").argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float)]; f("edge_segment").restype = C.c_int
+        f("scene_compute_edges").argtypes = [C.c_void_p, C.c_int, C.c_int]; f("scene_compute_edges").restype = C.c_int
+        f("scene_get_edges").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]; f("scene_get_edges").restype = C.c_int
         f("fusion_create").argtypes = [C.c_int, C.c_int]; f("fusion_create").restype = C.c_void_p
         f("fusion_destroy").argtypes = [C.c_void_p]; f("fusion_destroy").restype = None
         f("fusion_set_view").argtypes = [C.c_void_p, C.c_int, C.POINTER(FusionView)]; f("fusion_set_view").restype = C.c_int
@@ -370,6 +374,14 @@ class Scene:
         img = _carr(image, np.float32, (h, w)); e = _carr(edge, np.uint8, (h, w)); l = _carr(label, np.int32, (h, w))
         self._check(self.lib.dvp_scene_set_level(self.h, view, level, _ptr(img), _ptr(e), _ptr(l)), "set_level")
 
+    def compute_edges(self, view: int, level: int) -> np.ndarray:
+        """Row N4: the level's edge map computed on the device from the level image (it becomes the level's edge input)."""
+        self._check(self.lib.dvp_scene_compute_edges(self.h, view, level), "compute_edges")
+        w, h = self.level_size(*self._sizes[view], level)
+        out = np.empty((h, w), np.uint8)
+        self._check(self.lib.dvp_scene_get_edges(self.h, view, level, _ptr(out)), "get_edges")
+        return out
+
     def set_initial_planes(self, view: int, planes):
         w, h = self.level_size(*self._sizes[view], 0)
         p = _carr(planes, np.float32, (h, w, 4))
@@ -418,6 +430,24 @@ class Scene:
         sel = np.empty((H, W), np.uint32); rad = np.empty((H, W), np.int32)
         self._check(self.lib.dvp_scene_get_view(self.h, view, C.byref(w), C.byref(h), _ptr(planes), _ptr(weak), _ptr(sel), _ptr(rad)), "get_view")
         return planes, weak, sel, rad
+
+
+def edge_segment(image: np.ndarray, device: int = 0):
+    """The depth-edge prior of one level image (include/dvp_mvs.h, row N4): EdgeSegment(scale, image, 0, true) of the
+    reference (APD.cpp:348-466) on the device.  image: [h, w] uint8 -> (edge [h, w] uint8 0/255, (threshold1,
+    threshold2), device ms)."""
+    lib = load_library(PRODUCT_LIB, "dvp_")
+    img = np.ascontiguousarray(image, np.uint8)
+    if img.ndim != 2:
+        raise ValueError("expected a [h, w] uint8 image")
+    H, W = img.shape
+    edge = np.empty((H, W), np.uint8)
+    thr = (C.c_int32 * 2)()
+    ms = C.c_float()
+    rc = lib.dvp_edge_segment(device, _ptr(img), W, H, _ptr(edge), thr, C.byref(ms))
+    if rc != 0:
+        raise DvpError(f"dvp_edge_segment -> {STATUS.get(rc, rc)}")
+    return edge, (int(thr[0]), int(thr[1])), float(ms.value)
 
 
 class Fusion:

@@ -74,6 +74,9 @@ cudaError_t launch_reset_unknown_radius(const uint8_t* weak, int32_t* radius, in
 cudaError_t launch_invalidate_depth(const KArgs& a, cudaStream_t st);
 cudaError_t launch_rescale(const void* src, int sw, int sh, void* dst, int dw, int dh, int elem_bytes, cudaStream_t st);
 cudaError_t launch_extract_depth(const float4* planes, float* depth, int n, cudaStream_t st);
+size_t edge_scratch_bytes(int W, int H);
+cudaError_t launch_edge_segment(const uint8_t* d_img, int W, int H, uint8_t* d_edge, void* scratch, int** d_thr, cudaStream_t st);
+cudaError_t launch_edge_to_u8(const float* d_img, int n, uint8_t* d_out, cudaStream_t st);
 cudaError_t launch_restore_visibility(const KArgs& a, int scale_size, int* parent, int* count, cudaStream_t st);
 
 // canonical RNG exchange format <-> SoA planes

@@ -312,6 +312,19 @@ int dvp_fusion_last_view(dvp_fusion* f, int32_t* cells, float* terms, uint32_t* 
 /* ExportPointCloud (APD.cpp:842-882): binary little-endian PLY, x y z float + 3 uchar colours. */
 int dvp_fusion_write_ply(dvp_fusion* f, const char* path);
 
+/* ---- "Next" row N4, edge half: the depth-edge prior ------------------------------------------------------------------
+ * Replaces EdgeSegment(scale, image, mode 0, use_canny = true) (APD.cpp:348-466) as GetProblemEdges calls it per view
+ * and pyramid level (main.cpp:193-226); its result is the `edge` input of dvp_upload / dvp_scene_set_level.
+ * image: [height][width] u8 grey levels (the level image after convertTo(CV_8UC1)), host or device; edge: [height][width]
+ * u8, 0 / 255, host or device.  thresholds (may be NULL): the two Canny thresholds derived from the histogram median
+ * (APD.cpp:405-432).  Bit-exact with OpenCV's Canny (3x3 Sobel, L2 gradient) followed by the reference's border
+ * clean-up.  width, height >= 3.  Stateless and synchronous. */
+int dvp_edge_segment(int device, const uint8_t* image, int width, int height, uint8_t* edge, int32_t* thresholds, float* device_ms);
+/* The same for a level of a scene, from the level image given to dvp_scene_set_level (rounded to 8 bits as
+ * main.cpp:208 does): the edge map stays in HBM as that level's edge input.  dvp_scene_get_edges copies it out. */
+int dvp_scene_compute_edges(dvp_scene* scene, int view, int level);
+int dvp_scene_get_edges(dvp_scene* scene, int view, int level, uint8_t* edge);
+
 int dvp_weak_count(dvp_ctx* ctx);
 int dvp_last_cuda_error(dvp_ctx* ctx);
 void* dvp_stream(dvp_ctx* ctx); /* cudaStream_t */
