@@ -154,4 +154,69 @@ private:
 	}
 };
 
+// ---- rows N3 / N4 of the scope table: the two other device-side replacements a maintainer can switch to ---------------
+#include <unordered_map>
+
+// Replaces the fusing loop of RunFusion (APD.cpp:1876-1958).  Call it where that loop stands, with the vectors the
+// loading loop above it (APD.cpp:1841-1873) filled; points are appended to PointCloud in the reference's order
+// (views in index order, pixels in raster order).  `blocks` is only read when use_block is set.
+inline void DvpRunFusionLoop(const std::vector<Problem>& problems, std::unordered_map<int, int>& imageIdToindexMap,
+		const std::vector<cv::Mat>& images, const std::vector<Camera>& cameras, const std::vector<cv::Mat>& depths,
+		const std::vector<cv::Mat>& normals, const std::vector<cv::Mat>& weaks, const std::vector<cv::Mat>& blocks,
+		bool use_block, std::vector<PointList>& PointCloud) {
+	const int num_images = (int)problems.size();
+	int device = 0;
+	cudaGetDevice(&device);
+	dvp_fusion* f = dvp_fusion_create(device, num_images);
+	if (!f) { std::fprintf(stderr, "[APD/dvp] dvp_fusion_create failed\n"); std::exit(EXIT_FAILURE); }
+	auto pack = [](const cv::Mat& m, size_t elem, std::vector<unsigned char>& out) {   // cv::Mat rows may be padded
+		out.resize((size_t)m.rows * m.cols * elem);
+		for (int r = 0; r < m.rows; ++r) std::memcpy(&out[(size_t)r * m.cols * elem], m.ptr<unsigned char>(r), (size_t)m.cols * elem);
+	};
+	std::vector<unsigned char> depth, normal, image, weak, block;
+	for (int i = 0; i < num_images; ++i) {
+		const int ref_index = imageIdToindexMap[problems[i].ref_image_id];
+		std::vector<int32_t> src;
+		for (size_t j = 0; j < problems[i].src_image_ids.size(); ++j) src.push_back(imageIdToindexMap[problems[i].src_image_ids[j]]);
+		pack(depths[ref_index], 4, depth); pack(normals[ref_index], 12, normal); pack(images[ref_index], 3, image); pack(weaks[ref_index], 1, weak);
+		if (use_block) pack(blocks[ref_index], 1, block);
+		dvp_fusion_view v;
+		std::memset(&v, 0, sizeof(v));
+		static_assert(sizeof(dvp_camera) == sizeof(Camera), "Camera layout (main.h:58-67)");
+		std::memcpy(&v.camera, &cameras[ref_index], sizeof(Camera));
+		v.width = depths[ref_index].cols; v.height = depths[ref_index].rows;
+		v.depth = reinterpret_cast<const float*>(depth.data()); v.normal = reinterpret_cast<const float*>(normal.data());
+		v.image = image.data(); v.weak = weak.data(); v.block = use_block ? block.data() : nullptr;
+		v.num_src = (int32_t)src.size(); v.src_views = src.data();
+		if (dvp_fusion_set_view(f, ref_index, &v) != DVP_OK) { std::fprintf(stderr, "[APD/dvp] dvp_fusion_set_view failed\n"); std::exit(EXIT_FAILURE); }
+	}
+	long long n = 0;
+	if (dvp_fusion_run(f, &n, nullptr) != DVP_OK) { std::fprintf(stderr, "[APD/dvp] dvp_fusion_run failed\n"); std::exit(EXIT_FAILURE); }
+	std::vector<float> pts((size_t)n * 6);
+	if (n) dvp_fusion_get_points(f, pts.data(), 0, n);
+	for (long long k = 0; k < n; ++k) {
+		PointList point3D;
+		point3D.coord = make_float3(pts[6 * k], pts[6 * k + 1], pts[6 * k + 2]);
+		point3D.color = make_float3(pts[6 * k + 3], pts[6 * k + 4], pts[6 * k + 5]);
+		PointCloud.emplace_back(point3D);
+	}
+	dvp_fusion_destroy(f);
+}
+
+// Replaces EdgeSegment(scale, src_img, 0, true) as GetProblemEdges calls it (main.cpp:218; APD.cpp:348-466, the
+// use_canny branch): src_image is the 8-bit level image; returns the CV_8UC1 edge map (0 / 255).
+inline cv::Mat DvpEdgeSegmentCanny(const cv::Mat& src_image) {
+	int device = 0;
+	cudaGetDevice(&device);
+	std::vector<unsigned char> in((size_t)src_image.rows * src_image.cols), out(in.size());
+	for (int r = 0; r < src_image.rows; ++r) std::memcpy(&in[(size_t)r * src_image.cols], src_image.ptr<unsigned char>(r), (size_t)src_image.cols);
+	if (dvp_edge_segment(device, in.data(), src_image.cols, src_image.rows, out.data(), nullptr, nullptr) != DVP_OK) {
+		std::fprintf(stderr, "[APD/dvp] dvp_edge_segment failed\n");
+		std::exit(EXIT_FAILURE);
+	}
+	cv::Mat edge(src_image.rows, src_image.cols, CV_8UC1);
+	for (int r = 0; r < edge.rows; ++r) std::memcpy(edge.ptr<unsigned char>(r), &out[(size_t)r * edge.cols], (size_t)edge.cols);
+	return edge;
+}
+
 #endif  // DVP_APD_ADAPTER_HPP

@@ -27,3 +27,20 @@ int process_problem_like(const Problem& problem) {
 	cv::Mat states = apd.GetPixelStates(), sel = apd.GetSelectedViews(), rad = apd.GetRadiusMap(), edge = apd.GetEdge();
 	return acc + states.rows + sel.rows + rad.rows + edge.rows;
 }
+
+// the fusing loop of RunFusion (APD.cpp:1876-1958) and the edge prior of GetProblemEdges (main.cpp:218) on the device
+int fusion_and_edges_like(const std::vector<Problem>& problems) {
+	std::unordered_map<int, int> imageIdToindexMap;
+	std::vector<cv::Mat> images, depths, normals, weaks, blocks;
+	std::vector<Camera> cameras;
+	for (size_t i = 0; i < problems.size(); ++i) {
+		imageIdToindexMap.emplace(problems[i].ref_image_id, (int)i);
+		images.emplace_back(cv::Mat(8, 8, CV_8UC1)); depths.emplace_back(cv::Mat(8, 8, CV_32FC1));
+		normals.emplace_back(cv::Mat(8, 8, CV_32FC3)); weaks.emplace_back(cv::Mat(8, 8, CV_8UC1));
+		cameras.emplace_back(Camera());
+	}
+	std::vector<PointList> PointCloud;
+	DvpRunFusionLoop(problems, imageIdToindexMap, images, cameras, depths, normals, weaks, blocks, false, PointCloud);
+	cv::Mat edge = DvpEdgeSegmentCanny(cv::Mat(8, 8, CV_8UC1));
+	return (int)PointCloud.size() + edge.rows;
+}
