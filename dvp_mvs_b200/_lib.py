@@ -70,7 +70,7 @@ PRODUCT_ONLY_SYMBOLS = ["upload_device", "upload_overlapped", "restore_visibilit
                         "scene_pass_params", "scene_set_max_iterations", "scene_set_view", "scene_set_level",
                         "scene_set_initial_planes", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats",
                         "scene_run_view", "scene_depth_map", "scene_remote_depth",
-                        "fusion_create", "fusion_destroy", "fusion_set_view", "fusion_set_view_planes", "scene_fuse_views", "fusion_reset", "fusion_run_view", "fusion_run",
+                        "fusion_create", "fusion_destroy", "fusion_set_view", "fusion_set_view_planes", "scene_fuse_views", "fusion_set_mode", "fusion_reset", "fusion_run_view", "fusion_run",
                         "fusion_num_points", "fusion_get_points", "fusion_get_mask", "fusion_last_view", "fusion_write_ply",
                         "edge_segment", "scene_compute_edges", "scene_get_edges"]
 
@@ -91,14 +91,15 @@ def make_fusion_view(view: dict, keep: list) -> FusionView:
     depth = np.ascontiguousarray(view["depth"], np.float32)
     H, W = depth.shape
     normal = _carr(view["normal"], np.float32, (H, W, 3)); image = _carr(view["image"], np.uint8, (H, W, 3))
-    weak = _carr(view["weak"], np.uint8, (H, W)); block = _carr(view.get("block"), np.uint8, (H, W))
+    weak = _carr(view.get("weak"), np.uint8, (H, W)); block = _carr(view.get("block"), np.uint8, (H, W))
     src = np.ascontiguousarray(view["src_views"], np.int32)
     cam = np.ascontiguousarray(np.asarray(view["camera"], CAMERA_DTYPE).reshape(1))
     keep += [depth, normal, image, weak, block, src, cam]
     fv = FusionView()
     C.memmove(fv.camera, cam.ctypes.data, 112)
     fv.width, fv.height = W, H
-    fv.depth, fv.normal, fv.image, fv.weak = depth.ctypes.data, normal.ctypes.data, image.ctypes.data, weak.ctypes.data
+    fv.depth, fv.normal, fv.image = depth.ctypes.data, normal.ctypes.data, image.ctypes.data
+    fv.weak = weak.ctypes.data if weak is not None else None
     fv.block = block.ctypes.data if block is not None else None
     fv.num_src = len(src); fv.src_views = src.ctypes.data if len(src) else None
     return fv
@@ -160,6 +161,7 @@ def load_library(path: str, prefix: str):
         f("fusion_set_view_planes").argtypes = [C.c_void_p, C.c_int, C.POINTER(FusionView), C.c_void_p]; f("fusion_set_view_planes").restype = C.c_int
         f("scene_fuse_views").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]; f("scene_fuse_views").restype = C.c_int
         f("fusion_reset").argtypes = [C.c_void_p]; f("fusion_reset").restype = C.c_int
+        f("fusion_set_mode").argtypes = [C.c_void_p, C.c_int]; f("fusion_set_mode").restype = C.c_int
         f("fusion_run_view").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]; f("fusion_run_view").restype = C.c_int
         f("fusion_run").argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_float)]; f("fusion_run").restype = C.c_int
         f("fusion_num_points").argtypes = [C.c_void_p]; f("fusion_num_points").restype = C.c_longlong
@@ -517,6 +519,10 @@ class Fusion:
     def reset(self):
         self._check(self.lib.dvp_fusion_reset(self.h), "reset")
 
+    def set_mode(self, mode: int):
+        """0 RunFusion (ETH, default), 1 RunFusion_TAT_Intermediate, 2 RunFusion_TAT_advanced."""
+        self._check(self.lib.dvp_fusion_set_mode(self.h, mode), "set_mode")
+
     def run_view(self, view: int) -> float:
         ms = C.c_float()
         self._check(self.lib.dvp_fusion_run_view(self.h, view, C.byref(ms)), "run_view")
@@ -551,6 +557,13 @@ class Fusion:
         rounds = C.c_int()
         self._check(self.lib.dvp_fusion_last_view(self.h, _ptr(cells), _ptr(terms), _ptr(used), C.byref(rounds)), "last_view")
         return cells, terms, used, int(rounds.value)
+
+    def last_used(self, view: int) -> np.ndarray:
+        """Per-pixel decision of the last run_view(view) in any mode: bit j = source j counted, 0 = no point."""
+        H, W, _ = self.shapes[view]
+        used = np.empty(H * W, np.uint32)
+        self._check(self.lib.dvp_fusion_last_view(self.h, None, None, _ptr(used), None), "last_view")
+        return used
 
     def write_ply(self, path: str):
         self._check(self.lib.dvp_fusion_write_ply(self.h, os.fsencode(path)), "write_ply")

@@ -90,6 +90,30 @@ __device__ __forceinline__ int to_int(float v) {
 	return (int)v;
 }
 
+// The mask-independent part of one (pixel, source) evaluation, shared by the three fusion variants (APD.cpp:1901-1921,
+// 2067-2085, 2231-2251): the source cell the pixel projects to and, if that cell holds a depth, the three measures.
+// Returns the cell or -1 where the reference skips the source.
+__device__ __forceinline__ int measures(const ViewDev& rv, const ViewDev& sv, int r, int c, float ref_depth, const F3& X,
+		float n0, float n1, float n2, float& reproj_error, float& relative_depth_diff, float& angle) {
+	float px, py, proj_depth;
+	project(X, sv.cam, px, py, proj_depth);
+	const int src_r = to_int(py + 0.5f), src_c = to_int(px + 0.5f);
+	if (!(src_c >= 0 && src_c < sv.w && src_r >= 0 && src_r < sv.h)) return -1;
+	const int q = src_r * sv.w + src_c;
+	const float src_depth = sv.depth[q];
+	if (src_depth <= 0.0f) return -1;
+	const F3 Y = point_on_world(src_c, src_r, src_depth, sv.cam);
+	float qx, qy;
+	project(Y, rv.cam, qx, qy, proj_depth);
+	const double dx = (double)((float)c - qx), dy = (double)((float)r - qy);
+	reproj_error = (float)sqrt(dx * dx + dy * dy);
+	relative_depth_diff = fabsf(proj_depth - ref_depth) / ref_depth;
+	const float dot = n0 * sv.normal[3 * (size_t)q] + n1 * sv.normal[3 * (size_t)q + 1] + n2 * sv.normal[3 * (size_t)q + 2];
+	angle = (float)acos((double)dot);
+	if (angle != angle) angle = 0.0f;                                  // APD.cpp:1802-1803
+	return q;
+}
+
 // ---- stage 1: candidates ------------------------------------------------------------------------------------------
 // cells / terms are [S][N] (one coalesced plane per source).  live[p]: bit j = cell j is a candidate.
 __global__ void __launch_bounds__(256) k_fuse_candidates(const __grid_constant__ RefArgs a, const ViewDev* __restrict__ views,
@@ -113,30 +137,13 @@ __global__ void __launch_bounds__(256) k_fuse_candidates(const __grid_constant__
 			int cell = -1;
 			float term = 0.0f;
 			if (!skip) {
-				const ViewDev& sv = views[a.src[j]];
-				float px, py, proj_depth;
-				project(X, sv.cam, px, py, proj_depth);
-				const int src_r = to_int(py + 0.5f), src_c = to_int(px + 0.5f);
-				if (src_c >= 0 && src_c < sv.w && src_r >= 0 && src_r < sv.h) {
-					const int q = src_r * sv.w + src_c;
-					const float src_depth = sv.depth[q];
-					if (!(src_depth <= 0.0f)) {
-						const F3 Y = point_on_world(src_c, src_r, src_depth, sv.cam);
-						float qx, qy;
-						project(Y, rv.cam, qx, qy, proj_depth);
-						const double dx = (double)((float)c - qx), dy = (double)((float)r - qy);
-						const float reproj_error = (float)sqrt(dx * dx + dy * dy);
-						const float relative_depth_diff = fabsf(proj_depth - ref_depth) / ref_depth;
-						const float dot = n0 * sv.normal[3 * (size_t)q] + n1 * sv.normal[3 * (size_t)q + 1] + n2 * sv.normal[3 * (size_t)q + 2];
-						float angle = (float)acos((double)dot);
-						if (angle != angle) angle = 0.0f;                                  // APD.cpp:1802-1803
-						if (reproj_error < 2.0f && relative_depth_diff < 0.01f && angle < 0.174533f) {
-							const float tmp_index = reproj_error + 200.0f * relative_depth_diff + angle * 10.0f;
-							term = (float)exp((double)(-tmp_index));
-							cell = q;
-							bits |= 1u << j;
-						}
-					}
+				float reproj_error, relative_depth_diff, angle;
+				const int q = measures(rv, views[a.src[j]], r, c, ref_depth, X, n0, n1, n2, reproj_error, relative_depth_diff, angle);
+				if (q >= 0 && reproj_error < 2.0f && relative_depth_diff < 0.01f && angle < 0.174533f) {
+					const float tmp_index = reproj_error + 200.0f * relative_depth_diff + angle * 10.0f;
+					term = (float)exp((double)(-tmp_index));
+					cell = q;
+					bits |= 1u << j;
 				}
 			}
 			cells[(size_t)j * a.N + p] = cell;
@@ -304,6 +311,108 @@ __global__ void __launch_bounds__(256) k_fuse_emit(const __grid_constant__ RefAr
 	o[3] = col0 / div; o[4] = col1 / div; o[5] = col2 / div;
 }
 
+// ---- the two Tanks-and-Temples variants (RunFusion_TAT_Intermediate APD.cpp:1962-2130, RunFusion_TAT_advanced
+// APD.cpp:2132-2279; mode 1 / 2) ---------------------------------------------------------------------------------------
+// An emitted pixel masks itself and masks are only looked at on source views, so inside one view no pixel depends on
+// another through the masks.  The one sequential thing is the reference's `diff` vector, declared once per view
+// (APD.cpp:2052, 2216): a source that is not evaluated for a pixel keeps the measures of the last pixel in raster order
+// that did evaluate it.  That is a running "last evaluated pixel" per source: a max-scan.
+//   k_fuse_tat_measures   per (pixel, source): measures + cell if evaluated; last = pixel index or -1
+//   cub inclusive max-scan of `last` per source -> carry
+//   k_fuse_tat_decide     per pixel: measures at carry, the k = 2..S test, own mask, used bits
+//   k_fuse_tat_emit       points in raster order (colour: mode 1 mean with the counted sources' cells, mode 2 own colour)
+struct MaxOp { __host__ __device__ __forceinline__ int operator()(int x, int y) const { return x > y ? x : y; } };
+
+__device__ __forceinline__ bool tat_skipped(const ViewDev& rv, int p) {
+	return (rv.block && rv.block[p] < 128) || rv.depth[p] <= 0.0f;     // APD.cpp:2055-2061
+}
+
+__global__ void __launch_bounds__(256) k_fuse_tat_measures(const __grid_constant__ RefArgs a, const ViewDev* __restrict__ views,
+		int* __restrict__ cells, float* __restrict__ m_dist, float* __restrict__ m_depth, float* __restrict__ m_angle, int* __restrict__ last) {
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= a.N) return;
+	const ViewDev& rv = views[a.ref];
+	const int r = p / rv.w, c = p - r * rv.w;
+	const bool skip = tat_skipped(rv, p);
+	const float ref_depth = rv.depth[p];
+	F3 X = {0.f, 0.f, 0.f};
+	float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+	if (!skip) {
+		X = point_on_world(c, r, ref_depth, rv.cam);
+		n0 = rv.normal[3 * (size_t)p]; n1 = rv.normal[3 * (size_t)p + 1]; n2 = rv.normal[3 * (size_t)p + 2];
+	}
+	for (int j = 0; j < a.S; ++j) {
+		int q = -1;
+		float e = 0.f, d = 0.f, g = 0.f;
+		if (!skip) {
+			const ViewDev& sv = views[a.src[j]];
+			q = measures(rv, sv, r, c, ref_depth, X, n0, n1, n2, e, d, g);
+			if (q >= 0 && sv.mask[q] == 1) q = -1;                      // APD.cpp:2075-2076
+		}
+		const size_t at = (size_t)j * a.N + p;
+		cells[at] = q; m_dist[at] = e; m_depth[at] = d; m_angle[at] = g;
+		last[at] = q >= 0 ? p : -1;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_fuse_tat_decide(const __grid_constant__ RefArgs a, int mode, const ViewDev* __restrict__ views,
+		const float* __restrict__ m_dist, const float* __restrict__ m_depth, const float* __restrict__ m_angle,
+		const int* __restrict__ carry, unsigned* __restrict__ used, int* __restrict__ flags) {
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= a.N) return;
+	const ViewDev& rv = views[a.ref];
+	unsigned bits = 0;
+	if (!tat_skipped(rv, p)) {
+		const float dist_base = 0.25f;
+		const float depth_base = mode == 1 ? 1.0f / 3500.0f : 1.0f / 3000.0f;
+		const float angle_base = 0.06981317007977318f, angle_grad = 0.05235987755982988f;
+		for (int k = 2; k <= a.S && !bits; ++k) {
+			int count = 0;
+			unsigned ok_bits = 0;
+			const float lim_dist = (float)k * dist_base, lim_depth = (float)k * depth_base, lim_angle = (float)k * angle_grad + angle_base;
+			for (int j = 0; j < a.S; ++j) {
+				const int q = carry[(size_t)j * a.N + p];
+				if (q < 0) continue;                                        // still FLT_MAX: fails every test
+				const size_t at = (size_t)j * a.N + q;
+				const bool ok = mode == 1 ? (m_dist[at] < lim_dist && m_depth[at] < lim_depth && m_angle[at] < lim_angle)
+				                          : (m_dist[at] < lim_dist && m_depth[at] < lim_depth);
+				if (ok) { count++; ok_bits |= 1u << j; }
+			}
+			if (count >= k) bits = ok_bits;
+		}
+		if (bits) rv.mask[p] = 1;                                           // APD.cpp:2121, 2271
+	}
+	used[p] = bits;
+	flags[p] = bits != 0u;
+}
+
+__global__ void __launch_bounds__(256) k_fuse_tat_emit(const __grid_constant__ RefArgs a, int mode, const ViewDev* __restrict__ views,
+		const int* __restrict__ cells, const int* __restrict__ carry, const unsigned* __restrict__ used, const int* __restrict__ offs, float* __restrict__ points) {
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= a.N) return;
+	const unsigned bits = used[p];
+	if (!bits) return;
+	const ViewDev& rv = views[a.ref];
+	const int r = p / rv.w, c = p - r * rv.w;
+	const F3 X = point_on_world(c, r, rv.depth[p], rv.cam);
+	float col0 = (float)rv.image[3 * (size_t)p], col1 = (float)rv.image[3 * (size_t)p + 1], col2 = (float)rv.image[3 * (size_t)p + 2];
+	if (mode == 1) {                                                        // APD.cpp:2106-2116
+		int count = 0;
+		for (unsigned rest = bits; rest;) {
+			const int j = __ffs(rest) - 1;
+			rest &= rest - 1;
+			const int q = carry[(size_t)j * a.N + p];
+			const uint8_t* s = views[a.src[j]].image + 3 * (size_t)cells[(size_t)j * a.N + q];
+			col0 += (float)s[0]; col1 += (float)s[1]; col2 += (float)s[2];
+			count++;
+		}
+		const float div = (float)count + 1.0f;
+		col0 = col0 / div; col1 = col1 / div; col2 = col2 / div;
+	}
+	float* o = points + 6 * (size_t)offs[p];
+	o[0] = X.x; o[1] = X.y; o[2] = X.z; o[3] = col0; o[4] = col1; o[5] = col2;
+}
+
 // (world normal, depth) plane map -> the depth and normal maps ProcessProblem writes (main.cpp:300-306)
 __global__ void __launch_bounds__(256) k_fuse_split_planes(int n, const float4* __restrict__ planes, float* __restrict__ depth, float* __restrict__ normal) {
 	const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,6 +444,9 @@ struct dvp_fusion {
 	int* flags = nullptr; int* offs = nullptr;
 	void* scan_temp = nullptr; size_t scan_temp_bytes = 0;
 	float* d_points = nullptr;
+	int mode = 0;                  // 0 RunFusion (ETH), 1 RunFusion_TAT_Intermediate, 2 RunFusion_TAT_advanced
+	size_t cap_tat = 0;            // elements of the four [S][N] planes below (modes 1 and 2 only)
+	float* m_depth = nullptr; float* m_angle = nullptr; int* last = nullptr; int* carry = nullptr;
 	std::vector<float> points;     // 6 floats per point, the reference's order
 	int last_view = -1, last_rounds = 0;
 	int last_err = 0;
@@ -369,9 +481,11 @@ int grow(dvp_fusion* f, size_t n, size_t s) {
 		FCK(cudaMalloc((void**)&f->list[0], n * 4)); FCK(cudaMalloc((void**)&f->list[1], n * 4));
 		FCK(cudaMalloc((void**)&f->flags, n * 4)); FCK(cudaMalloc((void**)&f->offs, n * 4));
 		FCK(cudaMalloc((void**)&f->d_points, n * 6 * sizeof(float)));
-		f->scan_temp_bytes = 0;
-		FCK(cub::DeviceScan::ExclusiveSum(nullptr, f->scan_temp_bytes, (const int*)nullptr, (int*)nullptr, (int)n));
-		FCK(cudaMalloc(&f->scan_temp, f->scan_temp_bytes ? f->scan_temp_bytes : 1));
+		size_t sum_bytes = 0, max_bytes = 0;   // one temporary serves the exclusive sum and the max-scan of modes 1 / 2
+		FCK(cub::DeviceScan::ExclusiveSum(nullptr, sum_bytes, (const int*)nullptr, (int*)nullptr, (int)n));
+		FCK(cub::DeviceScan::InclusiveScan(nullptr, max_bytes, (const int*)nullptr, (int*)nullptr, MaxOp(), (int)n));
+		f->scan_temp_bytes = (sum_bytes > max_bytes ? sum_bytes : max_bytes) + 1;
+		FCK(cudaMalloc(&f->scan_temp, f->scan_temp_bytes));
 		f->cap_n = n;
 	}
 	if (n * s > f->cap_ns) {
@@ -379,6 +493,13 @@ int grow(dvp_fusion* f, size_t n, size_t s) {
 		f->cap_ns = 0;
 		FCK(cudaMalloc((void**)&f->cells, n * s * 4)); FCK(cudaMalloc((void**)&f->terms, n * s * 4));
 		f->cap_ns = n * s;
+	}
+	if (f->mode != 0 && n * s > f->cap_tat) {
+		cudaFree(f->m_depth); cudaFree(f->m_angle); cudaFree(f->last); cudaFree(f->carry);
+		f->cap_tat = 0;
+		FCK(cudaMalloc((void**)&f->m_depth, n * s * 4)); FCK(cudaMalloc((void**)&f->m_angle, n * s * 4));
+		FCK(cudaMalloc((void**)&f->last, n * s * 4)); FCK(cudaMalloc((void**)&f->carry, n * s * 4));
+		f->cap_tat = n * s;
 	}
 	return DVP_OK;
 }
@@ -411,6 +532,7 @@ void dvp_fusion_destroy(dvp_fusion* f) {
 	cudaFree(f->d_views); cudaFree(f->cells); cudaFree(f->terms); cudaFree(f->live); cudaFree(f->used); cudaFree(f->state);
 	cudaFree(f->list[0]); cudaFree(f->list[1]); cudaFree(f->counters); cudaFree(f->flags); cudaFree(f->offs);
 	cudaFree(f->scan_temp); cudaFree(f->d_points);
+	cudaFree(f->m_depth); cudaFree(f->m_angle); cudaFree(f->last); cudaFree(f->carry);
 	if (f->ev0) cudaEventDestroy(f->ev0);
 	if (f->ev1) cudaEventDestroy(f->ev1);
 	if (f->stream) cudaStreamDestroy(f->stream);
@@ -420,7 +542,7 @@ void dvp_fusion_destroy(dvp_fusion* f) {
 // `planes` != NULL: depth and normal come from a [h][w][4] (world normal, depth) plane map instead of v->depth / v->normal
 static int set_view_impl(dvp_fusion* f, int view, const dvp_fusion_view* v, const float* planes) {
 	if (!f || !v || view < 0 || view >= f->V) return DVP_ERR_ARG;
-	if (v->width <= 0 || v->height <= 0 || !v->image || !v->weak) return DVP_ERR_ARG;
+	if (v->width <= 0 || v->height <= 0 || !v->image) return DVP_ERR_ARG;
 	if (!planes && (!v->depth || !v->normal)) return DVP_ERR_ARG;
 	if ((long long)v->width * v->height > 0x7fffffffLL / 8) return DVP_ERR_ARG;
 	if (v->num_src < 0 || v->num_src > kMaxSrc || (v->num_src > 0 && !v->src_views)) return DVP_ERR_ARG;
@@ -453,7 +575,7 @@ static int set_view_impl(dvp_fusion* f, int view, const dvp_fusion_view* v, cons
 		FCK(upload(&hv.d.normal, v->normal, 3 * n, f->stream));
 	}
 	FCK(upload(&hv.d.image, v->image, 3 * n, f->stream));
-	FCK(upload(&hv.d.weak, v->weak, n, f->stream));
+	if (v->weak) FCK(upload(&hv.d.weak, v->weak, n, f->stream));
 	if (v->block) FCK(upload(&hv.d.block, v->block, n, f->stream));
 	FCK(cudaMalloc((void**)&hv.d.mask, n));
 	FCK(cudaMalloc((void**)&hv.d.resv, n * sizeof(unsigned)));
@@ -472,6 +594,12 @@ int dvp_fusion_set_view_planes(dvp_fusion* f, int view, const dvp_fusion_view* v
 	return set_view_impl(f, view, v, planes);
 }
 
+int dvp_fusion_set_mode(dvp_fusion* f, int mode) {
+	if (!f || mode < 0 || mode > 2) return DVP_ERR_ARG;
+	f->mode = mode;
+	return DVP_OK;
+}
+
 int dvp_fusion_reset(dvp_fusion* f) {
 	if (!f) return DVP_ERR_ARG;
 	FCK(cudaSetDevice(f->device));
@@ -483,6 +611,22 @@ int dvp_fusion_reset(dvp_fusion* f) {
 	FCK(cudaStreamSynchronize(f->stream));
 	f->points.clear();
 	f->last_view = -1; f->last_rounds = 0;
+	return DVP_OK;
+}
+
+// the end of a view: how many points the emit kernel wrote, copy them behind the ones already held
+static int finish_view(dvp_fusion* f, int view, int n, int rounds) {
+	cudaStream_t st = f->stream;
+	int tail[2] = {0, 0};
+	FCK(cudaMemcpyAsync(&tail[0], f->offs + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+	FCK(cudaMemcpyAsync(&tail[1], f->flags + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+	FCK(cudaEventRecord(f->ev1, st));
+	FCK(cudaStreamSynchronize(st));
+	const size_t emitted = (size_t)tail[0] + (size_t)tail[1];
+	const size_t at = f->points.size();
+	f->points.resize(at + 6 * emitted);
+	if (emitted) FCK(cudaMemcpy(f->points.data() + at, f->d_points, 6 * emitted * sizeof(float), cudaMemcpyDeviceToHost));
+	f->last_view = view; f->last_rounds = rounds;
 	return DVP_OK;
 }
 
@@ -502,6 +646,20 @@ int dvp_fusion_run_view(dvp_fusion* f, int view, float* device_ms) {
 	cudaStream_t st = f->stream;
 	const int blocks = (n + 255) / 256;
 	FCK(cudaEventRecord(f->ev0, st));
+	if (f->mode != 0) {
+		k_fuse_tat_measures<<<blocks, 256, 0, st>>>(a, f->d_views, f->cells, f->terms, f->m_depth, f->m_angle, f->last);
+		FCK(cudaGetLastError());
+		for (int j = 0; j < S; ++j)
+			FCK(cub::DeviceScan::InclusiveScan(f->scan_temp, f->scan_temp_bytes, (const int*)(f->last + (size_t)j * n), f->carry + (size_t)j * n, MaxOp(), n, st));
+		k_fuse_tat_decide<<<blocks, 256, 0, st>>>(a, f->mode, f->d_views, f->terms, f->m_depth, f->m_angle, f->carry, f->used, f->flags);
+		FCK(cub::DeviceScan::ExclusiveSum(f->scan_temp, f->scan_temp_bytes, (const int*)f->flags, f->offs, n, st));
+		k_fuse_tat_emit<<<blocks, 256, 0, st>>>(a, f->mode, f->d_views, f->cells, f->carry, f->used, f->offs, f->d_points);
+		FCK(cudaGetLastError());
+		{ const int r = finish_view(f, view, n, 0); if (r) return r; }
+		if (device_ms) FCK(cudaEventElapsedTime(device_ms, f->ev0, f->ev1));
+		return DVP_OK;
+	}
+	if (!hv.d.weak) return DVP_ERR_STATE;   // RunFusion reads weak.bin (APD.cpp:1933)
 	FCK(cudaMemsetAsync(f->counters, 0, 4 * sizeof(int), st));
 	k_fuse_candidates<<<blocks, 256, 0, st>>>(a, f->d_views, f->cells, f->terms, f->live, f->used, f->state, f->list[0], f->counters);
 	FCK(cudaGetLastError());
@@ -540,17 +698,8 @@ int dvp_fusion_run_view(dvp_fusion* f, int view, float* device_ms) {
 	FCK(cub::DeviceScan::ExclusiveSum(f->scan_temp, f->scan_temp_bytes, (const int*)f->flags, f->offs, n, st));
 	k_fuse_emit<<<blocks, 256, 0, st>>>(a, f->d_views, f->cells, f->used, f->offs, f->d_points);
 	FCK(cudaGetLastError());
-	int tail[2] = {0, 0};
-	FCK(cudaMemcpyAsync(&tail[0], f->offs + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-	FCK(cudaMemcpyAsync(&tail[1], f->flags + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-	FCK(cudaEventRecord(f->ev1, st));
-	FCK(cudaStreamSynchronize(st));
-	const size_t emitted = (size_t)tail[0] + (size_t)tail[1];
-	const size_t at = f->points.size();
-	f->points.resize(at + 6 * emitted);
-	if (emitted) FCK(cudaMemcpy(f->points.data() + at, f->d_points, 6 * emitted * sizeof(float), cudaMemcpyDeviceToHost));
+	{ const int r = finish_view(f, view, n, rounds); if (r) return r; }
 	if (device_ms) FCK(cudaEventElapsedTime(device_ms, f->ev0, f->ev1));
-	f->last_view = view; f->last_rounds = rounds;
 	return DVP_OK;
 }
 
@@ -591,6 +740,7 @@ int dvp_fusion_get_mask(dvp_fusion* f, int view, uint8_t* dst) {
 int dvp_fusion_last_view(dvp_fusion* f, int32_t* cells, float* terms, uint32_t* used, int* rounds) {
 	if (!f) return DVP_ERR_ARG;
 	if (f->last_view < 0) return DVP_ERR_STATE;
+	if (f->mode != 0 && (cells || terms)) return DVP_ERR_STATE;   // candidates are a stage of RunFusion (mode 0) only
 	const dvp_fusion::HostView& hv = f->views[f->last_view];
 	const size_t n = (size_t)hv.w * hv.h, S = (size_t)hv.num_src;
 	FCK(cudaSetDevice(f->device));

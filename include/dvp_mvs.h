@@ -293,6 +293,11 @@ int dvp_fusion_set_view_planes(dvp_fusion* f, int view, const dvp_fusion_view* v
  * scene's source lists.  images[v]: [h][w][3] u8 colour image of view v at its current map size (host or device; the
  * reference's cv::resize of the jpg); blocks (or blocks[v]) may be NULL. */
 int dvp_scene_fuse_views(dvp_scene* scene, dvp_fusion* f, const uint8_t* const* images, const uint8_t* const* blocks);
+/* Which of the reference's three fusion routines runs: 0 RunFusion (ETH, the one main() calls; default),
+ * 1 RunFusion_TAT_Intermediate (APD.cpp:1962-2130), 2 RunFusion_TAT_advanced (APD.cpp:2132-2279).  Modes 1 and 2 need no
+ * weak map (v->weak may be NULL) and reproduce the reference's per-view `diff` vector, which keeps a source's measures
+ * from the last pixel that evaluated it (APD.cpp:2052, 2216). */
+int dvp_fusion_set_mode(dvp_fusion* f, int mode);
 /* Clears the fusion masks (APD.cpp:1870) and the point list. */
 int dvp_fusion_reset(dvp_fusion* f);
 /* One iteration of the reference's outer loop (APD.cpp:1879-1957): fuses view `view` against the current masks and

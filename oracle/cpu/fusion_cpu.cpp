@@ -21,6 +21,7 @@
 //                           pixel would claim and its exp(-index) term, or -1.
 //   fusion_cpu_resolve    — the mask-dependent part, sequential, from given candidates.  run == candidates + resolve
 //                           (checked in the CPU suite); the CUDA path is compared stage by stage against these.
+#include <cfloat>
 #include <climits>
 #include <cmath>
 #include <cstdint>
@@ -77,9 +78,10 @@ int to_int(float v) {
 	return (int)v;
 }
 
-// The mask-independent half of APD.cpp:1899-1931 for pixel (r, c) of view `ref` and its j-th source.
-// Returns the source cell (src_r * src_w + src_c) and the term exp(-tmp_index), or -1.
-int candidate(const dvp_fusion_view* views, int ref, int j, int r, int c, float ref_depth, const F3& X, float* term) {
+// The mask-independent part of one (pixel, source) evaluation, shared by the three fusion variants
+// (APD.cpp:1901-1921, 2067-2085, 2231-2251): the source cell the pixel projects to and, if that cell holds a depth, the
+// three consistency measures.  Returns the cell (src_r * src_w + src_c) or -1 when the reference `continue`s / skips.
+int measures(const dvp_fusion_view* views, int ref, int j, int r, int c, float ref_depth, const F3& X, float* reproj_error, float* relative_depth_diff, float* angle) {
 	const dvp_fusion_view& rv = views[ref];
 	const dvp_fusion_view& sv = views[rv.src_views[j]];
 	float px, py, proj_depth;
@@ -94,13 +96,22 @@ int candidate(const dvp_fusion_view* views, int ref, int j, int r, int c, float 
 	float qx, qy;
 	project(Y, rv.camera, qx, qy, proj_depth);
 	const double dx = (double)(c - qx), dy = (double)(r - qy);
-	const float reproj_error = (float)std::sqrt(dx * dx + dy * dy);
-	const float relative_depth_diff = std::fabs(proj_depth - ref_depth) / ref_depth;
-	const float angle = get_angle(rv.normal + 3 * ((size_t)r * rv.width + c), sv.normal + 3 * cell);
+	*reproj_error = (float)std::sqrt(dx * dx + dy * dy);
+	*relative_depth_diff = std::fabs(proj_depth - ref_depth) / ref_depth;
+	*angle = get_angle(rv.normal + 3 * ((size_t)r * rv.width + c), sv.normal + 3 * cell);
+	return (int)cell;
+}
+
+// The mask-independent half of APD.cpp:1899-1931 for pixel (r, c) of view `ref` and its j-th source.
+// Returns the source cell and the term exp(-tmp_index), or -1.
+int candidate(const dvp_fusion_view* views, int ref, int j, int r, int c, float ref_depth, const F3& X, float* term) {
+	float reproj_error, relative_depth_diff, angle;
+	const int cell = measures(views, ref, j, r, c, ref_depth, X, &reproj_error, &relative_depth_diff, &angle);
+	if (cell < 0) return -1;
 	if (reproj_error < 2.0f && relative_depth_diff < 0.01f && angle < 0.174533f) {
 		const float tmp_index = reproj_error + 200 * relative_depth_diff + angle * 10;
 		*term = expf(-tmp_index);
-		return (int)cell;
+		return cell;
 	}
 	return -1;
 }
@@ -217,6 +228,73 @@ long long fusion_cpu_resolve(const dvp_fusion_view* views, int ref, const int32_
 				++n;
 			}
 		}
+	return n;
+}
+
+// RunFusion_TAT_Intermediate (mode 1, APD.cpp:1962-2130) and RunFusion_TAT_advanced (mode 2, APD.cpp:2132-2279): neither
+// is called by main() (main.cpp:514 calls RunFusion).  A point needs k >= 2 sources within k-scaled limits; an emitted
+// pixel masks ITSELF (APD.cpp:2121, 2271) and masked pixels are skipped when they are looked at as a source, so within a
+// view nothing depends on the visiting order — except through `diff`: the vector of per-source measures is declared
+// once per view (APD.cpp:2052, 2216), so a source that is not evaluated for a pixel (projects outside, hits a masked or
+// empty cell) keeps the measures, and in mode 1 the colour cell, of the last pixel in raster order that did evaluate it.
+// Reproduced as written.  used[p] (may be NULL): bit j = source j counted at the accepting k.
+long long fusion_cpu_run_tat(int mode, int num_views, const dvp_fusion_view* views, uint8_t* const* masks, float* points, long long capacity, uint32_t* const* used_out) {
+	const float dist_base = 0.25f;
+	const float depth_base = mode == 1 ? 1.0f / 3500.0f : 1.0f / 3000.0f;
+	const float angle_base = 0.06981317007977318f, angle_grad = 0.05235987755982988f;
+	struct CostData { float dist, depth, angle; int cell; bool use; };
+	long long n = 0;
+	for (int i = 0; i < num_views; ++i) {
+		const dvp_fusion_view& rv = views[i];
+		const int num_ngb = rv.num_src;
+		std::vector<CostData> diff(num_ngb, CostData{FLT_MAX, FLT_MAX, FLT_MAX, -1, false});
+		for (int r = 0; r < rv.height; ++r)
+			for (int c = 0; c < rv.width; ++c) {
+				const size_t p = (size_t)r * rv.width + c;
+				if (used_out) used_out[i][p] = 0;
+				if (rv.block && rv.block[p] < 128) continue;
+				const float ref_depth = rv.depth[p];
+				if (ref_depth <= 0.0) continue;
+				const F3 X = point_on_world(c, r, ref_depth, rv.camera);
+				for (int j = 0; j < num_ngb; ++j) {
+					float e, d, a;
+					const int cell = measures(views, i, j, r, c, ref_depth, X, &e, &d, &a);
+					// the mask test stands between the bounds test and the depth test (APD.cpp:2075-2079); both skip
+					if (cell < 0 || masks[rv.src_views[j]][cell] == 1) continue;
+					diff[j].dist = e; diff[j].depth = d; diff[j].angle = a; diff[j].cell = cell;
+				}
+				for (int k = 2; k <= num_ngb; ++k) {
+					int count = 0;
+					for (int j = 0; j < num_ngb; ++j) {
+						diff[j].use = false;
+						const bool ok = mode == 1 ? (diff[j].dist < k * dist_base && diff[j].depth < k * depth_base && diff[j].angle < (k * angle_grad + angle_base))
+						                          : (diff[j].dist < k * dist_base && diff[j].depth < k * depth_base);
+						if (ok) { count++; diff[j].use = true; }
+					}
+					if (count >= k) {
+						float color[3] = {(float)rv.image[3 * p], (float)rv.image[3 * p + 1], (float)rv.image[3 * p + 2]};
+						uint32_t used = 0;
+						for (int j = 0; j < num_ngb; ++j)
+							if (diff[j].use) {
+								used |= 1u << j;
+								if (mode == 1) {
+									const uint8_t* col = views[rv.src_views[j]].image + 3 * (size_t)diff[j].cell;
+									color[0] += (float)col[0]; color[1] += (float)col[1]; color[2] += (float)col[2];
+								}
+							}
+						if (mode == 1) { color[0] /= (count + 1.0f); color[1] /= (count + 1.0f); color[2] /= (count + 1.0f); }
+						if (n < capacity) {
+							float* o = points + 6 * n;
+							o[0] = X.x; o[1] = X.y; o[2] = X.z; o[3] = color[0]; o[4] = color[1]; o[5] = color[2];
+						}
+						++n;
+						if (used_out) used_out[i][p] = used;
+						masks[i][p] = 1;
+						break;
+					}
+				}
+			}
+	}
 	return n;
 }
 

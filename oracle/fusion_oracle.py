@@ -24,7 +24,19 @@ class FusionOracle:
         self.lib.fusion_cpu_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         self.lib.fusion_cpu_resolve.restype = C.c_longlong
         self.lib.fusion_cpu_resolve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
+        self.lib.fusion_cpu_run_tat.restype = C.c_longlong
+        self.lib.fusion_cpu_run_tat.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
         self.reset()
+
+    def run_tat(self, mode: int):
+        """RunFusion_TAT_Intermediate (mode 1) / RunFusion_TAT_advanced (mode 2) as written -> (points, used per view)."""
+        self.reset()
+        cap = sum(h * w for h, w, _ in self.shapes)
+        pts = np.empty((cap, 6), np.float32)
+        used = [np.zeros(h * w, np.uint32) for h, w, _ in self.shapes]
+        used_ptrs = (C.c_void_p * self.V)(*[u.ctypes.data for u in used])
+        n = self.lib.fusion_cpu_run_tat(mode, self.V, self.arr, self.mask_ptrs, pts.ctypes.data, cap, used_ptrs)
+        return pts[:n].copy(), used
 
     def reset(self):
         self.masks = [np.zeros((h, w), np.uint8) for h, w, _ in self.shapes]

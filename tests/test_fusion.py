@@ -302,3 +302,89 @@ def test_gpu_scene_to_fusion_handoff_equals_the_host_route():
     # the fused cloud lies on the synthetic room: its points are the views' own back-projections
     for x in (f, g, k, sc):
         x.close()
+
+
+# ------------------------------------------------------------------------------------------- T&T variants (modes 1, 2)
+def _tat_views(W=12, H=8):
+    return [flat_view(W, H, 10.0, 4.0, [1, 2], grey=100), flat_view(W, H, 10.0, 4.0, [2, 0], grey=60),
+            flat_view(W, H, 10.0, 4.0, [0, 1], grey=20)]
+
+
+def test_tat_known_answers_and_the_stale_diff_vector():
+    W, H = 12, 8
+    for mode in (1, 2):
+        # three identical views: every pixel of view 0 has two sources in exact agreement (k = 2 needs two) and masks
+        # itself; views 1 and 2 then find view 0's pixels masked, are left with one source and emit nothing
+        o = FusionOracle(_tat_views())
+        pts, used = o.run_tat(mode)
+        assert len(pts) == W * H and (used[0] == 3).all() and not used[1].any() and not used[2].any()
+        assert o.masks[0].all() and not o.masks[1].any() and not o.masks[2].any()
+        want = (100 + 60 + 20) / 3 if mode == 1 else 100.0          # mode 2 keeps the reference pixel's own colour
+        assert (pts[:, 3] == np.float32(want)).all()
+        # holes in source 2: a pixel that cannot evaluate a source keeps the measures of the last pixel (raster order) that
+        # did — so it is still emitted — unless no pixel evaluated that source before it
+        views = _tat_views()
+        views[2]["depth"][0, 0:3] = 0.0       # start of the image: nothing to inherit
+        views[2]["depth"][3, 5:8] = 0.0       # inherits from (3, 4)
+        views[2]["depth"][5, 0] = 0.0         # inherits across the row end, from (4, W - 1)
+        o = FusionOracle(views)
+        pts, used = o.run_tat(mode)
+        u0 = used[0].reshape(H, W)
+        assert not u0[0, 0:3].any() and (u0[3, 5:8] == 3).all() and u0[5, 0] == 3
+        assert (u0 != 0).sum() == W * H - 3
+        if mode == 1:                           # ... and mode 1 averages in the colour of the INHERITED cell: all greys equal here
+            assert (pts[:, 3] == np.float32(60.0)).all()
+    # a single source can never satisfy k >= 2
+    v = [flat_view(W, H, 10.0, 4.0, [1]), flat_view(W, H, 10.0, 4.0, [0])]
+    assert len(FusionOracle(v).run_tat(1)[0]) == 0
+
+
+def _gpu_tat(views, mode):
+    from dvp_mvs_b200 import Fusion
+    o = FusionOracle(views)
+    ref, used_ref = o.run_tat(mode)
+    f = Fusion(views)
+    f.set_mode(mode)
+    f.reset()
+    used = []
+    for v in range(len(views)):
+        f.run_view(v)
+        used.append(f.last_used(v))
+    pts = f.points()
+    masks = [f.mask(v) for v in range(len(views))]
+    f.close()
+    return pts, used, masks, ref, used_ref, o.masks
+
+
+@pytest.mark.gpu
+def test_gpu_tat_known_answers():
+    for mode in (1, 2):
+        views = _tat_views()
+        views[2]["depth"][0, 0:3] = 0.0; views[2]["depth"][3, 5:8] = 0.0; views[2]["depth"][5, 0] = 0.0
+        pts, used, masks, ref, used_ref, masks_ref = _gpu_tat(views, mode)
+        np.testing.assert_array_equal(pts, ref)
+        for a, b in zip(used, used_ref):
+            np.testing.assert_array_equal(a, b)
+        for a, b in zip(masks, masks_ref):
+            np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_gpu_tat_variants_vs_restatement(scene):
+    for levels in (1, [1, 0, 1, 0]):
+        views = synth.make_fusion_views(scene, levels, seed=2, depth_noise=0.0003, normal_noise=0.01)
+        for v in views:
+            v.pop("weak")                                       # the T&T variants never read weak.bin
+        # mode 2 tests reprojection error and depth only (IEEE operations): bit-exact, points and masks
+        pts, used, masks, ref, used_ref, masks_ref = _gpu_tat(views, 2)
+        assert len(ref) > 1000
+        np.testing.assert_array_equal(pts, ref)
+        for a, b in zip(masks, masks_ref):
+            np.testing.assert_array_equal(a, b)
+        # mode 1 also tests the angle (acos): a decision may flip where an angle sits within an ulp of its limit
+        pts, used, masks, ref, used_ref, masks_ref = _gpu_tat(views, 1)
+        assert len(ref) > 1000
+        flips = sum(int((a != b).sum()) for a, b in zip(used, used_ref))
+        assert flips <= max(4, 1e-4 * len(ref)), flips
+        if flips == 0:
+            np.testing.assert_array_equal(pts, ref)
