@@ -98,6 +98,56 @@ def run_scene_schedule(scene, num_views: int, num_levels: int, seed: int, costs:
     return owner
 
 
+def fuse_farmed_scene(scene, owner: Dict[int, int], views_static: Sequence[dict], fuse_rank: int = 0, mode: int = 0, make_fusion=None):
+    """Row N3 after a farmed schedule: the finished plane and pixel-state maps of every view meet on `fuse_rank`, which
+    fuses them (RunFusion, APD.cpp:1809-1960; `mode` 1 / 2 for the T&T variants).  Fusion costs well under a millisecond
+    of device time per megapixel view, so it runs on ONE GPU ("replicas only"); the exchange is a broadcast
+    of each view's maps from its owner — the in-memory form of the depths.dmb / APD_normals.dmb / weak.bin files the
+    reference's RunFusion reads (APD.cpp:1851-1858).
+
+    `scene.get_view(v) -> (planes [h,w,4], weak [h,w], ...)` on the owner; `views_static[v]` = dict(camera=<camera at the
+    map size>, image=<[h,w,3] uint8>, src_views=[...], block=None) known to every rank.  Returns the point list
+    [n, 6] on `fuse_rank`, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    num_views = len(views_static)
+    device = torch.device("cpu")
+    if world > 1 and dist.get_backend() == "nccl":
+        device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    gathered = []
+    for v in range(num_views):
+        src = owner[v] if world > 1 else 0
+        planes = weak = None
+        if rank == src:
+            got = scene.get_view(v)
+            planes = np.ascontiguousarray(got[0], np.float32); weak = np.ascontiguousarray(got[1], np.uint8)
+        if world > 1:
+            shape = [tuple(planes.shape[:2]) if rank == src else None]
+            dist.broadcast_object_list(shape, src=src)
+            h, w = shape[0]
+            tp = torch.from_numpy(planes).to(device) if rank == src else torch.empty((h, w, 4), dtype=torch.float32, device=device)
+            tw = torch.from_numpy(weak).to(device) if rank == src else torch.empty((h, w), dtype=torch.uint8, device=device)
+            dist.broadcast(tp, src=src); dist.broadcast(tw, src=src)
+            if rank == fuse_rank and rank != src:
+                planes, weak = tp.cpu().numpy(), tw.cpu().numpy()
+        if rank == fuse_rank:
+            st = views_static[v]
+            gathered.append(dict(camera=st["camera"], planes=planes, image=st["image"], weak=weak, src_views=list(st["src_views"]),
+                                 block=st.get("block")))
+    if rank != fuse_rank:
+        return None
+    if make_fusion is None:
+        from . import Fusion
+        make_fusion = lambda views: Fusion(views, device=int(os.environ.get("LOCAL_RANK", "0")))
+    f = make_fusion(gathered)
+    if mode:
+        f.set_mode(mode)
+    points, _ = f.run()
+    return points
+
+
 def make_gpu_view_processor(scenes, params, iters_hint: int | None = None):
     """process_view for synthetic scenes: one Engine per rank, reused across its views."""
     from . import Engine

@@ -146,3 +146,56 @@ def test_scene_schedule_two_ranks_exchange_depth_maps(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     a = json.loads((tmp_path / "rank0.json").read_text()); b = json.loads((tmp_path / "rank1.json").read_text())
     assert a == b and len(set(a)) == 5          # every rank ends with every view's depth map, and they are the same maps
+
+
+def test_two_ranks_gather_their_views_for_fusion(tmp_path):
+    """Row N3 after a farmed schedule: every view's plane and pixel-state maps reach the fusing rank unchanged, in view
+    order, whoever owned them (stand-in scene and stand-in fusion object; gloo)."""
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch.distributed as dist
+        from dvp_mvs_b200.farm import fuse_farmed_scene, partition
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        V = 5
+        owner = {{v: r for r in range(world) for v in partition(V, world, r)}}
+        def maps(v):
+            h, w = 4 + v, 6
+            planes = (np.arange(h * w * 4, dtype=np.float32).reshape(h, w, 4) + 1000 * v)
+            return planes, np.full((h, w), v % 3, np.uint8), None, None
+        class Scene:
+            def get_view(self, v):
+                assert owner[v] == rank, "a rank may only be asked for the views it owns"
+                return maps(v)
+        class Fusion:
+            def __init__(self, views): self.views = views; self.mode = 0
+            def set_mode(self, m): self.mode = m
+            def run(self): return np.array([[len(self.views), self.mode, 0, 0, 0, 0]], np.float32), 0.0
+        static = [dict(camera=v, image=np.zeros((4 + v, 6, 3), np.uint8), src_views=[(v + 1) % V]) for v in range(V)]
+        seen = []
+        def make(views):
+            seen.extend(views)
+            return Fusion(views)
+        pts = fuse_farmed_scene(Scene(), owner, static, fuse_rank=0, mode=2, make_fusion=make)
+        if rank == 0:
+            assert pts.tolist() == [[5.0, 2.0, 0, 0, 0, 0]]
+            for v, got in enumerate(seen):
+                planes, weak, _, _ = maps(v)
+                assert np.array_equal(got["planes"], planes) and np.array_equal(got["weak"], weak)
+                assert got["camera"] == v and got["src_views"] == [(v + 1) % V] and got["block"] is None
+        else:
+            assert pts is None and not seen
+        open(os.path.join({str(tmp_path)!r}, f"rank{{rank}}.txt"), "w").write("RANK_OK")
+        dist.destroy_process_group()
+    """))
+    import socket
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "rank0.txt").read_text() == "RANK_OK" and (tmp_path / "rank1.txt").read_text() == "RANK_OK"

@@ -15,6 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", default="1280x960"); ap.add_argument("--views", type=int, default=6); ap.add_argument("--levels", type=int, default=2)
     ap.add_argument("--src", type=int, default=4)
+    ap.add_argument("--fuse", type=int, default=1, help="gather the finished maps on rank 0 and fuse them there (row N3)")
     a = ap.parse_args()
     fw, fh = (int(v) for v in a.full.split("x"))
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -61,8 +62,23 @@ def main():
         d = sc.depth_tensor(v, a.levels - 1, owner[v] == rank).cpu().numpy()
         truth = mv.levels[-1][v]["depth"]; ok = d > 0
         errs[v] = float(np.median(np.abs(d[ok] - truth[ok]) / truth[ok]))
+    fusion = None
+    if a.fuse:
+        from dvp_mvs_b200.farm import fuse_farmed_scene
+        fine = mv.levels[-1]
+        static = [dict(camera=fine[v]["camera"], image=np.stack([np.clip(fine[v]["image"], 0, 255)] * 3, -1).astype(np.uint8),
+                       src_views=mv.src_views[v]) for v in range(V)]
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        pts = fuse_farmed_scene(sc, owner, static, fuse_rank=0)
+        if world > 1:
+            dist.barrier()
+        fusion = {"gather_and_fuse_wall_s": round(time.perf_counter() - t0, 3), "points": None if pts is None else int(len(pts))}
+        if pts is not None and len(pts):
+            fusion["bbox"] = [[round(float(x), 2) for x in pts[:, :3].min(0)], [round(float(x), 2) for x in pts[:, :3].max(0)]]
     if rank == 0:
-        print(json.dumps({"world": world, "views": V, "levels": a.levels, "finest": [mv.levels[-1][0]["w"], mv.levels[-1][0]["h"]],
+        print(json.dumps({"world": world, "fusion": fusion, "views": V, "levels": a.levels, "finest": [mv.levels[-1][0]["w"], mv.levels[-1][0]["h"]],
                           "wall_s": round(wall, 3), "depth_maps_identical_across_ranks": bool(torch.equal(lo, hi)),
                           "owner": owner, "median_rel_depth_error": {k: round(e, 5) for k, e in errs.items()}}))
     if world > 1:
