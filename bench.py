@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--state", default="refine_iter", choices=["first_init", "refine_init", "refine_iter"])
     ap.add_argument("--geom", type=int, default=1)
     ap.add_argument("--cpu-sample", default="640x480", help="WxH of the bounded CPU-baseline sample (0 = skip)")
+    ap.add_argument("--next-rows", type=int, default=1, help="also time the callers' rows N3 (fusion) and N4 (edge prior) after the timed region")
     return ap.parse_args()
 
 
@@ -145,6 +146,31 @@ def cpu_baseline(args, cores):
     return {"value": w * h / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
             "sample": f"one full RunPatchMatch pass of the same configuration (STRONG and WEAK paths) on a {w}x{h} view "
                       f"({dt:.1f} s, OpenMP over pixels)"}
+
+
+def next_rows(local):
+    """Device times of the two callers' rows that are not part of a RunPatchMatch pass, measured after the
+    timed region on rank 0: N3 fusion of 5 synthetic views of 1555x1037 (4 sources each) and N4 edge prior of one
+    1555x1037 level image.  Never allowed to break the bench line: any failure is reported as text."""
+    try:
+        import numpy as np
+        from dvp_mvs_b200 import Fusion, edge_segment, synth
+        mv = synth.make_multiview(3110, 2074, 5, 2, seed=2)
+        views = synth.make_fusion_views(mv, 1)
+        f = Fusion(views, device=local)
+        f.run()
+        pts, ms = f.run()
+        f.close()
+        img = np.clip(np.rint(mv.levels[1][0]["image"]), 0, 255).astype(np.uint8)
+        edge_segment(img, device=local)
+        edge, thr, edge_ms = edge_segment(img, device=local)
+        npx = sum(v["depth"].size for v in views)
+        return {"N3_fusion": {"views": 5, "view_size": [1555, 1037], "sources": 4, "points": int(len(pts)), "device_ms": ms,
+                              "mpix_per_s": npx / 1e3 / max(ms, 1e-9)},
+                "N4_edge_prior": {"size": [1555, 1037], "device_ms": edge_ms, "mpix_per_s": img.size / 1e3 / max(edge_ms, 1e-9),
+                                  "edge_fraction": float((edge > 0).mean())}}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def main():
@@ -323,9 +349,11 @@ def main():
            "weak": {"pixels": weak_px, "fraction": weak_px / N, "algorithmic_bytes_per_pass": weak_px * (48 + 32 + 4 + 16)},
            "sweep_mpix_per_s_per_iteration": N / ((per_stage[6] + per_stage[7]) / args.iters) / 1e3,   # K7 + K8 alone
            "clocks": clocks}
-    cb = cpu_baseline(args, cores)
+    cb = cpu_baseline(args, cores) if world == 1 else None   # rank 0 at N = 1 only
     if cb:
         out["cpu_baseline"] = cb
+    if args.next_rows and world == 1:
+        out["next_rows"] = next_rows(local)
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
