@@ -4,7 +4,7 @@
 //
 // The reference is one sequential loop: views in order, pixels in raster order; a pixel that is accepted masks the
 // source pixels that agreed with it, and a masked source pixel is ignored by every later pixel — so the result
-// depends on the visiting order.  That order's result is reproduced exactly, in parallel, in two stages per view:
+// depends on the visiting order.  That order's result is reproduced exactly, in parallel, in three stages per view:
 //
 //   candidates  everything that does not depend on the masks: per (pixel, source) the source cell the pixel would
 //               claim and its exp(-index) term.  One thread per pixel, 2*S projections, the only floating-point stage.

@@ -272,7 +272,7 @@ typedef struct dvp_fusion_view {
 	const float* depth;       /* [h][w]     depths.dmb                                                             */
 	const float* normal;      /* [h][w][3]  APD_normals.dmb (world frame)                                          */
 	const uint8_t* image;     /* [h][w][3]  colour image, channel order kept as given (BGR in the reference)       */
-	const uint8_t* weak;      /* [h][w]     DVP_WEAK / DVP_STRONG / DVP_UNKNOWN (weak.bin)                         */
+	const uint8_t* weak;      /* [h][w]     DVP_WEAK / DVP_STRONG / DVP_UNKNOWN (weak.bin); may be NULL in modes 1, 2 */
 	const uint8_t* block;     /* [h][w] or NULL: pixels < 128 are not fused (the optional blocks/ folder)          */
 	int32_t num_src;          /* Problem::src_image_ids.size(), <= 32                                              */
 	const int32_t* src_views; /* [num_src] view indices (imageIdToindexMap applied)                                */
