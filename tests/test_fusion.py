@@ -171,6 +171,39 @@ def test_reservation_scheme_equals_sequential_loop(scene):
     assert most_rounds > 2     # the order did matter somewhere
 
 
+def test_reservation_scheme_on_adversarial_candidates():
+    """Random claims with heavy collisions (many pixels per source cell, several views marking each other's cells, terms
+    straddling the acceptance limit): the round-based scheme must still equal the sequential loop, whatever the chains."""
+    rng = np.random.default_rng(21)
+    for trial in range(30):
+        V = int(rng.integers(2, 5))
+        shapes = [(int(rng.integers(3, 9)), int(rng.integers(3, 9))) for _ in range(V)]
+        views = []
+        for v, (h, w) in enumerate(shapes):
+            others = [u for u in range(V) if u != v]
+            src = list(rng.permutation(others)[: int(rng.integers(1, len(others) + 1))])
+            fv = flat_view(w, h, 10.0, 4.0, [int(u) for u in src])
+            fv["weak"] = rng.integers(0, 3, (h, w)).astype(np.uint8)
+            fv["depth"][rng.random((h, w)) < 0.1] = 0.0
+            views.append(fv)
+        o = FusionOracle(views)
+        masks = [np.zeros_like(m) for m in o.masks]
+        for v, (h, w) in enumerate(shapes):
+            S = len(views[v]["src_views"])
+            cells = np.full((h * w, S), -1, np.int32); terms = np.zeros((h * w, S), np.float32)
+            for j, u in enumerate(views[v]["src_views"]):
+                n_u = shapes[u][0] * shapes[u][1]
+                claim = rng.random(h * w) < 0.8
+                cells[claim, j] = rng.integers(0, max(1, n_u // 3), int(claim.sum()))     # few cells, many claimants
+                terms[claim, j] = rng.choice(np.array([0.2, 0.3, 0.31, 0.45, 0.46, 0.9], np.float32), int(claim.sum()))
+            cells[views[v]["depth"].ravel() <= 0] = -1        # a pixel without a depth has no candidates (stage 1 skips it)
+            used_seq, _ = o.resolve(v, cells, terms)
+            used_par, rounds = reservations_numpy(masks, v, views[v]["src_views"], cells, terms, views[v]["weak"])
+            np.testing.assert_array_equal(used_par, used_seq)
+            for a, b in zip(masks, o.masks):
+                np.testing.assert_array_equal(a, b)
+
+
 # ---------------------------------------------------------------------------------------------------------- GPU
 def _gpu_stagewise(views):
     from dvp_mvs_b200 import Fusion
