@@ -94,6 +94,10 @@ def test_header_is_plain_c_and_a_c_program_links(tmp_path):
                    '  if (dvp_create(0, 0, 0, 0, &p) != NULL) return 2;          /* invalid size: rejected before any CUDA call */\n'
                    '  if (dvp_restore_visibility(NULL, 8, NULL) != DVP_ERR_ARG) return 3;\n'
                    '  if (dvp_scene_create(0, 1, 1) != NULL) return 4;           /* a scene needs at least two views */\n'
+                   '  if (dvp_fusion_create(0, 0) != NULL) return 5;             /* rows N3 / N4: argument checks need no GPU */\n'
+                   '  if (dvp_fusion_run(NULL, NULL, NULL) != DVP_ERR_ARG || dvp_fusion_set_mode(NULL, 1) != DVP_ERR_ARG) return 6;\n'
+                   '  { dvp_fusion_view v; unsigned char px[9] = {0}; v.width = 3; v.height = 3; (void)v;\n'
+                   '    if (dvp_edge_segment(0, px, 2, 3, px, NULL, NULL) != DVP_ERR_ARG) return 7; }  /* images below 3 x 3 are refused */\n'
                    '  printf("%s %d %d %.3f\\n", dvp_version(), p.max_iterations, p.strong_radius, p.ransac_threshold); return 0; }\n')
     exe = tmp_path / "t"
     libdir = os.path.dirname(_lib.PRODUCT_LIB)
