@@ -10,6 +10,7 @@ Only what the hot path needs lives here:
 from ._lib import (Engine, Scene, Fusion, FusionView, make_fusion_view, edge_segment, Params, Inputs, DvpError, default_params, FIRST_INIT, REFINE_INIT, REFINE_ITER,
                    WEAK, STRONG, UNKNOWN, STAGES, PRODUCT_LIB)
 from . import synth
+from . import formats
 
 __all__ = ["Engine", "Scene", "Fusion", "FusionView", "make_fusion_view", "edge_segment", "Params", "Inputs", "DvpError", "default_params", "FIRST_INIT", "REFINE_INIT", "REFINE_ITER",
-           "WEAK", "STRONG", "UNKNOWN", "STAGES", "PRODUCT_LIB", "synth"]
+           "WEAK", "STRONG", "UNKNOWN", "STAGES", "PRODUCT_LIB", "synth", "formats"]

@@ -72,7 +72,8 @@ PRODUCT_ONLY_SYMBOLS = ["upload_device", "upload_overlapped", "restore_visibilit
                         "scene_run_view", "scene_depth_map", "scene_remote_depth",
                         "fusion_create", "fusion_destroy", "fusion_set_view", "fusion_set_view_planes", "scene_fuse_views", "fusion_set_mode", "fusion_reset", "fusion_run_view", "fusion_run",
                         "fusion_num_points", "fusion_get_points", "fusion_get_mask", "fusion_last_view", "fusion_write_ply",
-                        "edge_segment", "scene_compute_edges", "scene_get_edges"]
+                        "edge_segment", "scene_compute_edges", "scene_get_edges",
+                        "io_binmat_header", "io_read_binmat", "io_write_binmat", "io_write_dmb", "io_read_camera", "io_read_pairs"]
 
 
 class FusionView(C.Structure):

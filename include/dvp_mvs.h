@@ -330,6 +330,21 @@ int dvp_edge_segment(int device, const uint8_t* image, int width, int height, ui
 int dvp_scene_compute_edges(dvp_scene* scene, int view, int level);
 int dvp_scene_get_edges(dvp_scene* scene, int view, int level, uint8_t* edge);
 
+/* ---- Row N4, second half: the reference's on-disk exchange formats (host code, no GPU) ------------------------------
+ * .bin / .dmb files of WriteBinMat / ReadBinMat (APD.cpp:548-573, 630-648): int32 version = 1, rows, cols, OpenCV type
+ * code (CV_8U 0, CV_32S 4, CV_32F 5, CV_32FC3 21, ...), then rows * cols * elemSize bytes.  DVP_ERR_STATE: cannot open /
+ * short file; DVP_ERR_UNSUPPORTED: version != 1 (the reference's "Version error"). */
+int dvp_io_binmat_header(const char* path, int32_t* rows, int32_t* cols, int32_t* cv_type);
+int dvp_io_read_binmat(const char* path, void* data, size_t bytes);          /* bytes must equal the payload size */
+int dvp_io_write_binmat(const char* path, int32_t rows, int32_t cols, int32_t cv_type, const void* data);
+/* writeDepthDmb (channels 1) / writeNormalDmb (channels 3), APD.cpp:575-628: int32 1, h, w, channels, then floats. */
+int dvp_io_write_dmb(const char* path, int32_t rows, int32_t cols, int32_t channels, const float* data);
+/* ReadCamera (APD.cpp:651-692), the TAT & ETH cam.txt layout; the centre is computed as the reference does. */
+int dvp_io_read_camera(const char* path, dvp_camera* cam);
+/* GenerateSampleList (main.cpp:127-170): pair.txt.  With ref_ids == NULL only *num_views is returned.  src_ids is
+ * [max_views][DVP_MAX_IMAGES]; sources with score <= 0 are dropped as in the reference. */
+int dvp_io_read_pairs(const char* path, int32_t max_views, int32_t* num_views, int32_t* ref_ids, int32_t* num_src, int32_t* src_ids);
+
 int dvp_weak_count(dvp_ctx* ctx);
 int dvp_last_cuda_error(dvp_ctx* ctx);
 void* dvp_stream(dvp_ctx* ctx); /* cudaStream_t */
