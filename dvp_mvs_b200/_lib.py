@@ -485,21 +485,24 @@ class Fusion:
         """N2 -> N3: every view's maps go from the scene's device buffers to the fusion object (dvp_scene_fuse_views);
         images[v]: [h, w, 3] uint8 at the view's current map size."""
         V = scene.num_views
-        f = cls(V, scene.device)
         imgs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        blks = None if blocks is None else [None if b is None else np.ascontiguousarray(b, np.uint8) for b in blocks]
+        shapes = []
+        for v in range(V):          # the library reads h * w * 3 bytes per image: check the sizes before handing pointers over
+            w, h = C.c_int(), C.c_int()
+            scene._check(scene.lib.dvp_scene_get_view(scene.h, v, C.byref(w), C.byref(h), None, None, None, None), "get_view")
+            if imgs[v].shape != (h.value, w.value, 3):
+                raise ValueError(f"view {v}: image {imgs[v].shape} does not match the map size {(h.value, w.value, 3)}")
+            if blks is not None and blks[v] is not None and blks[v].shape != (h.value, w.value):
+                raise ValueError(f"view {v}: block mask {blks[v].shape} does not match the map size {(h.value, w.value)}")
+            shapes.append((int(h.value), int(w.value), len(scene.src_views[v])))
+        f = cls(V, scene.device)
         img_ptrs = (C.c_void_p * V)(*[im.ctypes.data for im in imgs])
-        blk_ptrs = None
-        if blocks is not None:
-            blks = [None if b is None else np.ascontiguousarray(b, np.uint8) for b in blocks]
-            blk_ptrs = (C.c_void_p * V)(*[None if b is None else b.ctypes.data for b in blks])
+        blk_ptrs = None if blks is None else (C.c_void_p * V)(*[None if b is None else b.ctypes.data for b in blks])
         rc = f.lib.dvp_scene_fuse_views(scene.h, f.h, img_ptrs, blk_ptrs)
         if rc != 0:
             raise DvpError(f"dvp_scene_fuse_views -> {STATUS.get(rc, rc)}")
-        for v in range(V):
-            w, h = C.c_int(), C.c_int()
-            scene._check(scene.lib.dvp_scene_get_view(scene.h, v, C.byref(w), C.byref(h), None, None, None, None), "get_view")
-            assert imgs[v].shape == (h.value, w.value, 3), (imgs[v].shape, h.value, w.value)
-            f.shapes.append((int(h.value), int(w.value), len(scene.src_views[v])))
+        f.shapes = shapes
         return f
 
     def _check(self, rc, what):
