@@ -74,3 +74,47 @@ def test_every_python_file_compiles():
     assert len(files) > 15
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+def test_closed_form_of_the_reference_edge_walk():
+    """Groundwork for K4 / K9: the positions BresenhamLine tests (reference APD.cu:281-313) have a
+    closed form, so a warp can evaluate 32 steps of one walk at once.  The loop tests exactly min(max(dx, dy) + 1, max_step)
+    positions — it overshoots the end point by one step — and position k (1-based) is
+        x-major:  (x0 + sx k,  y0 + sy floor((k dy - e0 + dx - 1) / dx))
+        y-major:  (x0 + sx min(k, floor((e0 + k dx - 1 + dy) / dy)),  y0 + sy k)        e0 = max(dx, dy) / 2
+        diagonal: (x0 + sx k,  y0 + sy k);   A == B: the start point itself, once."""
+    def walk_ref(x0, y0, x1, y1, max_step):
+        dx, sx = abs(x1 - x0), (1 if x0 < x1 else -1)
+        dy, sy = abs(y1 - y0), (1 if y0 < y1 else -1)
+        erro = (dx if dx > dy else dy) // 2
+        step, tagx, tagy, out = 0, True, True, []
+        while tagx or tagy:
+            if x0 == x1: tagx = False
+            if y0 == y1: tagy = False
+            e2 = erro
+            if e2 > -dx: erro -= dy; x0 += sx
+            if e2 < dy: erro += dx; y0 += sy
+            out.append((x0, y0)); step += 1
+            if step >= max_step: break
+        return out
+
+    def walk_closed(x0, y0, x1, y1, max_step):
+        dx, sx = abs(x1 - x0), (1 if x0 < x1 else -1)
+        dy, sy = abs(y1 - y0), (1 if y0 < y1 else -1)
+        m = max(dx, dy); e0 = m // 2
+        if m == 0:
+            return [(x0, y0)]
+        out = []
+        for k in range(1, min(m + 1, max_step) + 1):
+            if dx > dy:
+                out.append((x0 + sx * k, y0 + sy * ((k * dy - e0 + dx - 1) // dx)))
+            elif dy > dx:
+                out.append((x0 + sx * min(k, (e0 + k * dx - 1 + dy) // dy), y0 + sy * k))
+            else:
+                out.append((x0 + sx * k, y0 + sy * k))
+        return out
+
+    for ddx in range(-36, 37):
+        for ddy in range(-36, 37):
+            for max_step in (1, 2, 5, 16, 200):
+                assert walk_ref(3, -2, 3 + ddx, -2 + ddy, max_step) == walk_closed(3, -2, 3 + ddx, -2 + ddy, max_step), (ddx, ddy, max_step)
