@@ -107,3 +107,25 @@ def test_header_is_plain_c_and_a_c_program_links(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert out.stdout.split()[-3:] == ["3", "5", "0.005"] and "sm_100a" in out.stdout
+
+
+def test_documents_only_name_entry_points_that_exist():
+    """Every dvp_* function INTEGRATION.md, DESIGN.md or README.md mentions is declared in include/dvp_mvs.h (or is a
+    type / file / wildcard of the same family) — the documents are part of the boundary."""
+    import re
+    header = open(os.path.join(ROOT, "include", "dvp_mvs.h")).read()
+    declared = set(re.findall(r"\b(dvp_[a-z0-9_]+)\s*\(", header)) | set(re.findall(r"\b(dvp_[a-z0-9_]+)\b(?=;|\s*\{|\s+[a-z_*]+[;,)])", header))
+    known_other = {"dvp_mvs", "dvp_mvs_b200", "dvp_ctx", "dvp_scene", "dvp_fusion", "dvp_params", "dvp_inputs", "dvp_camera", "dvp_status",
+                   "dvp_fusion_view", "dvp_apd_adapter", "dvp_stage", "dvp_buffer", "dvp_api", "dvp_ncc", "dvp_strong", "dvp_weak", "dvp_common",
+                   "dvp_launch", "dvp_unionfind", "dvp_io", "dvp_kernels_post", "dvp_kernels_edge", "dvp_kernels_fusion", "dvp_kernels_prep",
+                   "dvp_kernels_strong", "dvp_kernels_weak", "dvp_kernels_", "dvp_b200", "dvp_fuse"}
+    missing = {}
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md"):
+        text = open(os.path.join(ROOT, doc)).read()
+        for name in set(re.findall(r"\b(dvp_[a-z0-9_]+)\b", text)):
+            if name in declared or name in known_other or name.endswith("_"):
+                continue
+            if any(d.startswith(name) for d in declared):      # a family prefix such as dvp_scene_* / dvp_io_*
+                continue
+            missing.setdefault(doc, []).append(name)
+    assert not missing, missing
