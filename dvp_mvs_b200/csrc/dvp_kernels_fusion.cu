@@ -43,7 +43,7 @@ struct ViewDev {
 	const uint8_t* image;
 	const uint8_t* weak;
 	const uint8_t* block;
-	uint8_t* mask;       // fusion mask, APD.cpp:1870
+	uint8_t* mask;       // fusion mask, APD.cpp:1867
 	unsigned* resv;      // reservation word per pixel: raster index of the smallest undecided claimant, or kFree
 };
 
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) k_fuse_candidates(const __grid_constant__
 		const int r = p / rv.w, c = p - r * rv.w;
 		unsigned bits = 0;
 		const float ref_depth = rv.depth[p];
-		const bool skip = (rv.block && rv.block[p] < 128) || ref_depth <= 0.0f;   // APD.cpp:1886-1888, 1894-1896
+		const bool skip = (rv.block && rv.block[p] < 128) || ref_depth <= 0.0f;   // APD.cpp:1884-1886, 1892-1894
 		F3 X = {0.f, 0.f, 0.f};
 		float n0 = 0.f, n1 = 0.f, n2 = 0.f;
 		if (!skip) {
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_fuse_candidates(const __grid_constant__
 		}
 		live[p] = bits;
 		used[p] = 0;
-		active = bits != 0 && rv.mask[p] != 1;    // a pixel masked by an earlier view is skipped, APD.cpp:1890-1892
+		active = bits != 0 && rv.mask[p] != 1;    // a pixel masked by an earlier view is skipped, APD.cpp:1888-1890
 		state[p] = active ? ST_ACTIVE : ST_DECIDED;
 	}
 	// warp-aggregated append to the undecided list (its order does not matter: priority is the pixel index)
@@ -175,7 +175,7 @@ __device__ __forceinline__ void reserve_one(const RefArgs& a, const ViewDev* vie
 		rest &= rest - 1;
 		const ViewDev& sv = views[a.src[j]];
 		const int cell = cells[(size_t)j * a.N + p];
-		if (__ldcg(&sv.mask[cell]) == 1) bits &= ~(1u << j);           // claimed by an earlier pixel: APD.cpp:1910-1911
+		if (__ldcg(&sv.mask[cell]) == 1) bits &= ~(1u << j);           // claimed by an earlier pixel: APD.cpp:1911-1912
 		else atomicMin(&sv.resv[cell], (unsigned)p);
 	}
 	if (bits != before) __stcg(&live[p], bits);
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256) k_fuse_tat_decide(const __grid_constant__
 			}
 			if (count >= k) bits = ok_bits;
 		}
-		if (bits) rv.mask[p] = 1;                                           // APD.cpp:2121, 2271
+		if (bits) rv.mask[p] = 1;                                           // APD.cpp:2121, 2270
 	}
 	used[p] = bits;
 	flags[p] = bits != 0u;

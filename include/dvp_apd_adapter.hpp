@@ -157,7 +157,7 @@ private:
 // ---- rows N3 / N4 of the scope table: the two other device-side replacements a maintainer can switch to ---------------
 #include <unordered_map>
 
-// Replaces the fusing loop of RunFusion (APD.cpp:1876-1958).  Call it where that loop stands, with the vectors the
+// Replaces the fusing loop of RunFusion (APD.cpp:1875-1957).  Call it where that loop stands, with the vectors the
 // loading loop above it (APD.cpp:1841-1873) filled; points are appended to PointCloud in the reference's order
 // (views in index order, pixels in raster order).  `blocks` is only read when use_block is set.
 inline void DvpRunFusionLoop(const std::vector<Problem>& problems, std::unordered_map<int, int>& imageIdToindexMap,

@@ -298,9 +298,9 @@ int dvp_scene_fuse_views(dvp_scene* scene, dvp_fusion* f, const uint8_t* const* 
  * weak map (v->weak may be NULL) and reproduce the reference's per-view `diff` vector, which keeps a source's measures
  * from the last pixel that evaluated it (APD.cpp:2052, 2216). */
 int dvp_fusion_set_mode(dvp_fusion* f, int mode);
-/* Clears the fusion masks (APD.cpp:1870) and the point list. */
+/* Clears the fusion masks (APD.cpp:1867) and the point list. */
 int dvp_fusion_reset(dvp_fusion* f);
-/* One iteration of the reference's outer loop (APD.cpp:1879-1957): fuses view `view` against the current masks and
+/* One iteration of the reference's outer loop (APD.cpp:1875-1957): fuses view `view` against the current masks and
  * appends its points.  `device_ms` may be NULL. */
 int dvp_fusion_run_view(dvp_fusion* f, int view, float* device_ms);
 /* dvp_fusion_reset + every view in index order. */

@@ -142,16 +142,16 @@ uint32_t accept(const dvp_fusion_view* views, int ref, int r, int c, const int32
 }
 
 bool skipped(const dvp_fusion_view& rv, size_t p, uint8_t* const* masks, int ref) {
-	if (rv.block && rv.block[p] < 128) return true;   // APD.cpp:1886-1888
-	if (masks[ref][p] == 1) return true;                // APD.cpp:1890-1892
-	return rv.depth[p] <= 0.0;                          // APD.cpp:1894-1896
+	if (rv.block && rv.block[p] < 128) return true;   // APD.cpp:1884-1886
+	if (masks[ref][p] == 1) return true;                // APD.cpp:1888-1890
+	return rv.depth[p] <= 0.0;                          // APD.cpp:1892-1894
 }
 
 }  // namespace
 
 extern "C" {
 
-// RunFusion, APD.cpp:1876-1958.  masks[v]: height*width bytes per view, zeroed by the caller (APD.cpp:1870).
+// RunFusion, APD.cpp:1875-1957.  masks[v]: height*width bytes per view, zeroed by the caller (APD.cpp:1867).
 // points: [capacity][6] floats (coord xyz, colour in the image's channel order), in the reference's push order.
 // Returns the number of points the reference would hold (may exceed capacity; the excess is not stored).
 long long fusion_cpu_run(int num_views, const dvp_fusion_view* views, uint8_t* const* masks, float* points, long long capacity) {
@@ -170,7 +170,7 @@ long long fusion_cpu_run(int num_views, const dvp_fusion_view* views, uint8_t* c
 				const F3 X = point_on_world(c, r, ref_depth, rv.camera);
 				for (int j = 0; j < rv.num_src; ++j) {
 					cells[j] = candidate(views, i, j, r, c, ref_depth, X, &terms[j]);
-					if (cells[j] >= 0 && masks[rv.src_views[j]][cells[j]] == 1) cells[j] = -1;   // APD.cpp:1910-1911
+					if (cells[j] >= 0 && masks[rv.src_views[j]][cells[j]] == 1) cells[j] = -1;   // APD.cpp:1911-1912
 				}
 				float color[3];
 				if (accept(views, i, r, c, cells.data(), terms.data(), masks, color)) {
@@ -233,7 +233,7 @@ long long fusion_cpu_resolve(const dvp_fusion_view* views, int ref, const int32_
 
 // RunFusion_TAT_Intermediate (mode 1, APD.cpp:1962-2130) and RunFusion_TAT_advanced (mode 2, APD.cpp:2132-2279): neither
 // is called by main() (main.cpp:514 calls RunFusion).  A point needs k >= 2 sources within k-scaled limits; an emitted
-// pixel masks ITSELF (APD.cpp:2121, 2271) and masked pixels are skipped when they are looked at as a source, so within a
+// pixel masks ITSELF (APD.cpp:2121, 2270) and masked pixels are skipped when they are looked at as a source, so within a
 // view nothing depends on the visiting order — except through `diff`: the vector of per-source measures is declared
 // once per view (APD.cpp:2052, 2216), so a source that is not evaluated for a pixel (projects outside, hits a masked or
 // empty cell) keeps the measures, and in mode 1 the colour cell, of the last pixel in raster order that did evaluate it.

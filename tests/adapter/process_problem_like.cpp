@@ -28,7 +28,7 @@ int process_problem_like(const Problem& problem) {
 	return acc + states.rows + sel.rows + rad.rows + edge.rows;
 }
 
-// the fusing loop of RunFusion (APD.cpp:1876-1958) and the edge prior of GetProblemEdges (main.cpp:218) on the device
+// the fusing loop of RunFusion (APD.cpp:1875-1957) and the edge prior of GetProblemEdges (main.cpp:218) on the device
 int fusion_and_edges_like(const std::vector<Problem>& problems) {
 	std::unordered_map<int, int> imageIdToindexMap;
 	std::vector<cv::Mat> images, depths, normals, weaks, blocks;
