@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) k_edge_border_rows(int W, int H, uint8_t*
 	if (edge[(size_t)(H - 2) * W + x] == 0) edge[(size_t)(H - 1) * W + x] = 0;
 }
 
-// GetProblemEdges: scaled_image_float.convertTo(src_img, CV_8UC1) (main.cpp:208) = saturate_cast<uchar>(cvRound(v)),
+// GetProblemEdges: scaled_image_float.convertTo(src_img, CV_8UC1) (main.cpp:209) = saturate_cast<uchar>(cvRound(v)),
 // round half to even
 __global__ void __launch_bounds__(256) k_edge_to_u8(const float* __restrict__ img, int n, uint8_t* __restrict__ out) {
 	const int p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -326,7 +326,7 @@ int dvp_fusion_write_ply(dvp_fusion* f, const char* path);
  * clean-up.  width, height >= 3.  Stateless and synchronous. */
 int dvp_edge_segment(int device, const uint8_t* image, int width, int height, uint8_t* edge, int32_t* thresholds, float* device_ms);
 /* The same for a level of a scene, from the level image given to dvp_scene_set_level (rounded to 8 bits as
- * main.cpp:208 does): the edge map stays in HBM as that level's edge input.  dvp_scene_get_edges copies it out. */
+ * main.cpp:209 does): the edge map stays in HBM as that level's edge input.  dvp_scene_get_edges copies it out. */
 int dvp_scene_compute_edges(dvp_scene* scene, int view, int level);
 int dvp_scene_get_edges(dvp_scene* scene, int view, int level, uint8_t* edge);
 

@@ -5,7 +5,7 @@
 //   1. grey-level histogram (in float, as the reference keeps it) -> "median" = first level < 255 whose cumulative count
 //      exceeds rows*cols/2, else -1 (APD.cpp:405-428);
 //   2. threshold1 = (1 - 0.67f) * median, threshold2 = median, both truncated to int (APD.cpp:430-432);
-//   3. cv::Canny(src, dst, threshold1, threshold2, 3, L2gradient = true) (APD.cpp:434);
+//   3. cv::Canny(src, dst, threshold1, threshold2, 3, L2gradient = true) (APD.cpp:433);
 //   4. cv::resize to the image's own size (a copy), cv::threshold(> 4 -> 255) (APD.cpp:437-446): no-ops on a 0/255 map;
 //   5. border clean-up: a border pixel whose inner neighbour is 0 becomes 0, columns first, then rows (APD.cpp:452-463).
 // Step 3 lives in a third-party dependency that is not under /root/reference: OpenCV (the reference asks for >= 3.3,
