@@ -71,8 +71,9 @@ PRODUCT_ONLY_SYMBOLS = ["upload_device", "upload_overlapped", "restore_visibilit
                         "scene_set_initial_planes", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats",
                         "scene_run_view", "scene_depth_map", "scene_remote_depth",
                         "fusion_create", "fusion_destroy", "fusion_set_view", "fusion_set_view_planes", "scene_fuse_views", "fusion_set_mode", "fusion_reset", "fusion_run_view", "fusion_run",
-                        "fusion_num_points", "fusion_get_points", "fusion_get_mask", "fusion_last_view", "fusion_write_ply",
+                        "fusion_num_points", "fusion_get_points", "fusion_get_mask", "fusion_last_view", "fusion_last_view_index", "fusion_write_ply",
                         "edge_segment", "scene_compute_edges", "scene_get_edges",
+                        "debug_set_plane_snapshots", "debug_sweep_forced_d4", "debug_fetch_count",
                         "io_binmat_header", "io_read_binmat", "io_write_binmat", "io_write_dmb", "io_read_camera", "io_read_pairs"]
 
 
@@ -170,6 +171,10 @@ def load_library(path: str, prefix: str):
         f("fusion_get_mask").argtypes = [C.c_void_p, C.c_int, C.c_void_p]; f("fusion_get_mask").restype = C.c_int
         f("fusion_last_view").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]; f("fusion_last_view").restype = C.c_int
         f("fusion_write_ply").argtypes = [C.c_void_p, C.c_char_p]; f("fusion_write_ply").restype = C.c_int
+        f("fusion_last_view_index").argtypes = [C.c_void_p]; f("fusion_last_view_index").restype = C.c_int
+        f("debug_set_plane_snapshots").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]; f("debug_set_plane_snapshots").restype = C.c_int
+        f("debug_sweep_forced_d4").argtypes = [C.c_void_p] + [C.c_int] * 5; f("debug_sweep_forced_d4").restype = C.c_int
+        f("debug_fetch_count").argtypes = [C.c_void_p, C.c_int]; f("debug_fetch_count").restype = C.c_longlong
     return lib
 
 
@@ -282,6 +287,21 @@ class Engine:
         ms = C.c_float()
         self._check(self._f("restore_visibility")(self.ctx, int(scale_size), C.byref(ms)), "restore_visibility")
         return float(ms.value)
+
+    def set_plane_snapshots(self, before: np.ndarray, after: np.ndarray):
+        """Parity instrumentation (include/dvp_mvs.h): the two plane maps direction 4 of a forced sweep may read."""
+        b = _carr(before, np.float32, (self.H, self.W, 4)); a = _carr(after, np.float32, (self.H, self.W, 4))
+        self._check(self._f("debug_set_plane_snapshots")(self.ctx, _ptr(b), _ptr(a)), "debug_set_plane_snapshots")
+
+    def sweep_forced_d4(self, iteration: int, red: int, m: int, ncc_from_after: int, accept_from_after: int):
+        self._check(self._f("debug_sweep_forced_d4")(self.ctx, iteration, red, m, ncc_from_after, accept_from_after), "debug_sweep_forced_d4")
+
+    def fetch_count(self, reset: bool = True) -> int:
+        """Texture fetches since the last reset (instrumented build only: DVP_MVS_LIB=.../libdvp_mvs_count.so)."""
+        n = int(self._f("debug_fetch_count")(self.ctx, 1 if reset else 0))
+        if n < 0:
+            raise DvpError(f"debug_fetch_count -> {STATUS.get(n, n)} (this library is not the instrumented build)")
+        return n
 
     def weak_count(self) -> int:
         return int(self._f("weak_count")(self.ctx))
@@ -554,8 +574,16 @@ class Fusion:
         self._check(self.lib.dvp_fusion_get_mask(self.h, view, _ptr(out)), "get_mask")
         return out
 
+    def _require_last(self, view: int):
+        """dvp_fusion_last_view copies the buffers of the view that ran LAST, sized by that view: asking for another one
+        would overrun the numpy buffers allocated for `view`."""
+        last = int(self.lib.dvp_fusion_last_view_index(self.h))
+        if last != view:
+            raise DvpError(f"fusion stage outputs are those of view {last if last >= 0 else None} (the last one run), not of view {view}")
+
     def last_view(self, view: int):
         """Stage outputs of the last run_view(view): candidates (cells, terms [h*w, S]), decision (used [h*w]), rounds."""
+        self._require_last(view)
         H, W, S = self.shapes[view]
         cells = np.empty((H * W, S), np.int32); terms = np.empty((H * W, S), np.float32); used = np.empty(H * W, np.uint32)
         rounds = C.c_int()
@@ -564,6 +592,7 @@ class Fusion:
 
     def last_used(self, view: int) -> np.ndarray:
         """Per-pixel decision of the last run_view(view) in any mode: bit j = source j counted, 0 = no point."""
+        self._require_last(view)
         H, W, _ = self.shapes[view]
         used = np.empty(H * W, np.uint32)
         self._check(self.lib.dvp_fusion_last_view(self.h, None, None, _ptr(used), None), "last_view")

@@ -77,6 +77,8 @@ struct dvp_ctx {
 	int* sort_vals = nullptr;
 	void* sort_temp = nullptr;
 	size_t sort_temp_bytes = 0;
+	unsigned long long* fetch_counter = nullptr;   // instrumented build only (DVP_COUNT_FETCHES)
+	float4* dbg_planes[2] = {nullptr, nullptr};  // plane snapshots of dvp_debug_sweep_forced_d4 (allocated on first use)
 	int* vis_parent = nullptr;  // union-find links / region sizes of dvp_restore_visibility (allocated on first use)
 	int* vis_count = nullptr;
 	// host staging
@@ -115,7 +117,7 @@ KArgs make_args(const dvp_ctx* c) {
 	a.edge = c->edge; a.edge_neigh = c->edge_neigh; a.label = c->label; a.candidate = c->candidate;
 	a.nearest_strong = c->nearest_strong; a.weak_reliable = c->weak_reliable; a.neighbours_map = c->neighbours_map;
 	a.neighbours = c->neighbours; a.label_boundary = c->label_boundary; a.complex_ = c->complex_;
-	a.scratch = nullptr; a.weak_count = c->weak_count;
+	a.scratch = nullptr; a.weak_count = c->weak_count; a.fetch_counter = c->fetch_counter;
 	return a;
 }
 
@@ -459,7 +461,7 @@ void dvp_destroy(dvp_ctx* c) {
 	cudaFree(c->radius); cudaFree(c->view_weight); cudaFree(c->rng); cudaFree(c->edge); cudaFree(c->edge_neigh);
 	cudaFree(c->label); cudaFree(c->candidate); cudaFree(c->nearest_strong); cudaFree(c->weak_reliable);
 	cudaFree(c->neighbours_map); cudaFree(c->neighbours); cudaFree(c->label_boundary); cudaFree(c->complex_); cudaFree(c->weak_list); cudaFree(c->scan_blocks); cudaFree(c->scan_total); cudaFree(c->next_right); cudaFree(c->next_down); for (int k = 0; k < 2; ++k) { cudaFree(c->scan_blocks_c[k]); cudaFree(c->colour_list[k]); }
-	cudaFree(c->vis_parent); cudaFree(c->vis_count);
+	cudaFree(c->vis_parent); cudaFree(c->vis_count); cudaFree(c->dbg_planes[0]); cudaFree(c->dbg_planes[1]); cudaFree(c->fetch_counter);
 	cudaFree(c->sort_keys[0]); cudaFree(c->sort_keys[1]); cudaFree(c->sort_vals); cudaFree(c->sort_temp);
 	for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -624,6 +626,51 @@ int dvp_restore_visibility(dvp_ctx* ctx, int scale_size, float* device_ms) {
 	CK(cudaEventRecord(ctx->ev[e1], st));
 	CK(cudaStreamSynchronize(st));
 	if (device_ms) CK(cudaEventElapsedTime(device_ms, ctx->ev[e0], ctx->ev[e1]));
+	return DVP_OK;
+}
+
+long long dvp_debug_fetch_count(dvp_ctx* ctx, int reset) {
+#ifdef DVP_COUNT_FETCHES
+	if (!ctx) return DVP_ERR_ARG;
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return DVP_ERR_CUDA;
+	if (!ctx->fetch_counter) {
+		if (zalloc(&ctx->fetch_counter, (size_t)kFetchSlots) != cudaSuccess) return DVP_ERR_CUDA;
+		return 0;
+	}
+	cudaStreamSynchronize(ctx->stream);
+	std::vector<unsigned long long> h(kFetchSlots);
+	if (cudaMemcpy(h.data(), ctx->fetch_counter, kFetchSlots * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return DVP_ERR_CUDA;
+	unsigned long long sum = 0;
+	for (unsigned long long v : h) sum += v;
+	if (reset) cudaMemset(ctx->fetch_counter, 0, kFetchSlots * sizeof(unsigned long long));
+	return (long long)sum;
+#else
+	(void)ctx; (void)reset;
+	return DVP_ERR_UNSUPPORTED;   // only libdvp_mvs_count.so counts
+#endif
+}
+
+int dvp_debug_set_plane_snapshots(dvp_ctx* ctx, const float* planes_before, const float* planes_after) {
+	if (!ctx || !planes_before || !planes_after) return DVP_ERR_ARG;
+	CK(cudaSetDevice(ctx->device));
+	const float* src[2] = {planes_before, planes_after};
+	for (int k = 0; k < 2; ++k) {
+		if (!ctx->dbg_planes[k]) CK(cudaMalloc((void**)&ctx->dbg_planes[k], (size_t)ctx->N * 16));
+		CK(cudaMemcpyAsync(ctx->dbg_planes[k], src[k], (size_t)ctx->N * 16, cudaMemcpyDefault, ctx->stream));
+	}
+	CK(cudaStreamSynchronize(ctx->stream));
+	return DVP_OK;
+}
+
+int dvp_debug_sweep_forced_d4(dvp_ctx* ctx, int iter, int red, int m, int ncc_from_after, int accept_from_after) {
+	if (!ctx || m < 0 || m > 65535) return DVP_ERR_ARG;
+	if (!ctx->uploaded || !ctx->dbg_planes[0] || !ctx->dbg_planes[1]) return DVP_ERR_STATE;
+	CK(cudaSetDevice(ctx->device));
+	{ int r = join_copies(ctx); if (r) return r; }
+	const KArgs a = make_args(ctx);
+	const D4Force f{m, ctx->dbg_planes[ncc_from_after ? 1 : 0], ctx->dbg_planes[accept_from_after ? 1 : 0]};
+	CK(launch_strong_sweep_forced(a, iter, red ? 1 : 0, f, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
 	return DVP_OK;
 }
 

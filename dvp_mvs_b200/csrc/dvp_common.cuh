@@ -70,7 +70,18 @@ struct KArgs {
 	float* complex_;        // [weak_count]
 	float* scratch;         // per-pixel spill area for large S (cost arrays)
 	int weak_count;
+	unsigned long long* fetch_counter;   // [kFetchSlots] texture-fetch tally of the instrumented build (-DDVP_COUNT_FETCHES), else null
 };
+
+// Instrumented build only (libdvp_mvs_count.so, `make count`): every texture fetch site adds its fetches to one of
+// kFetchSlots counters so that bench.py can report MEASURED fetches per launch next to the measured texture roof.
+// The production build compiles this to nothing.
+constexpr int kFetchSlots = 4096;
+#ifdef DVP_COUNT_FETCHES
+#define DVP_COUNT(a, n) do { if ((a).fetch_counter) atomicAdd((a).fetch_counter + ((blockIdx.x * 131u + blockIdx.y * 17u + threadIdx.x) & (kFetchSlots - 1)), (unsigned long long)(n)); } while (0)
+#else
+#define DVP_COUNT(a, n) do { } while (0)
+#endif
 
 // ---- approximate MUFU ops exactly as the reference build emits them -----------------------------------
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }

@@ -737,6 +737,8 @@ int dvp_fusion_get_mask(dvp_fusion* f, int view, uint8_t* dst) {
 	return DVP_OK;
 }
 
+int dvp_fusion_last_view_index(dvp_fusion* f) { return (f && f->last_view >= 0) ? f->last_view : DVP_ERR_STATE; }
+
 int dvp_fusion_last_view(dvp_fusion* f, int32_t* cells, float* terms, uint32_t* used, int* rounds) {
 	if (!f) return DVP_ERR_ARG;
 	if (f->last_view < 0) return DVP_ERR_STATE;

@@ -143,7 +143,12 @@ __global__ void __launch_bounds__(256, 3) k_random_init(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------------
 // K7/K8: red-black propagation sweep for non-WEAK pixels (edge-adaptive branch, params.use_edge).
 // shared memory per thread: 36 float2 (w, w r) + 9*S floats (8 direction cost vectors + 1 spare) + 8 u16 ladder offsets.
-__global__ void __launch_bounds__(kSweepThreads, kSweepMinBlocks) k_strong_sweep(const __grid_constant__ KArgs a, int iter, int red, int yy_limit) {
+// FORCE_D4 (parity instrumentation, never launched by dvp_run): direction 4 — the one whose ladder reads pixels of the
+// colour being written — takes its candidate from ladder offset `force.m` with the plane read from a snapshot,
+// and re-reads it at acceptance from a second snapshot.  Enumerating (m, snapshot, snapshot) reproduces every outcome the
+// reference's race can have for a pixel: tests/test_gpu_parity.py proves the full-image differences lie inside that set.
+template <bool FORCE_D4>
+__global__ void __launch_bounds__(kSweepThreads, kSweepMinBlocks) k_strong_sweep(const __grid_constant__ KArgs a, int iter, int red, int yy_limit, const D4Force force) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	constexpr int T = kSweepThreads;   // compile-time stride: shared-memory offsets become immediates
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -184,6 +189,17 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinBlocks) k_strong_sweep
 		const int sx = 5 * dx, sy = 5 * dy;
 		int fx = 0, fy = 0;
 		if (d > 4) { if (d % 2) fx = dx; else fy = dy; }  // colour fix on directions 5,6,7 only (B6: 4 is racy)
+		if (FORCE_D4 && d == 4) {
+			const int tx = x + sx - force.m, ty = y + sy - force.m;
+			if (tx >= 0 && ty >= 0) {
+				flag |= 1u << d;
+				pos_arr[d * T] = (uint16_t)force.m;
+				const float4 pl = force.planes_ncc[tx + ty * W];
+				for (int v = 0; v < S; ++v)
+					cost_arr[(d * S + v) * T] = ncc_cost<kSweepRB, kSweepRW>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+			}
+			continue;
+		}
 		// ---- edge-adaptive ladder (APD.cu:2053-2087) ----
 		{
 			const short2 edge_pt = edge_neigh[d];
@@ -348,7 +364,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinBlocks) k_strong_sweep
 			if (min_cost_idx > 4) { if (min_cost_idx % 2) fx = dx; else fy = dy; }
 			cx = x + 5 * dx + k * dx + fx; cy = y + 5 * dy + k * dy + fy;
 		}
-		const float4 cand = a.planes[cx + cy * W];
+		const float4 cand = (FORCE_D4 && min_cost_idx == 4) ? force.planes_accept[cx + cy * W] : a.planes[cx + cy * W];
 		const float depth_before = depth_from_plane(a.ref, cand, x, y);
 		if (depth_before >= a.prm.depth_min && depth_before <= a.prm.depth_max && min_final < cost_now) {
 			depth_now = depth_before;
@@ -446,6 +462,7 @@ __device__ __forceinline__ float profile_cost_sum(const KArgs& a, int x, int y, 
 	for (int v = 0; v < a.S; ++v) {
 		if (!is_set(sel, v)) continue;
 		const int wv = vw.get(v);
+		if (wv == 0) continue;   // a selected view the last sweep never drew: its (finite) cost is multiplied by 0 and added — exactly +0
 		if (k16_form) {
 			acc += (ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T) * wv);
 			if (a.prm.geom_consistency) acc += (a.prm.geom_factor * geom_cost(a, a.views[v], a.tex_depth[v + 1], x, y, pl) * wv);
@@ -458,6 +475,13 @@ __device__ __forceinline__ float profile_cost_sum(const KArgs& a, int x, int y, 
 	}
 	return acc;
 }
+
+// DepthToWeak's peak analysis (APD.cu:3999-4016) looks for local minima on indices 2..58 of the 61-entry profile, so it
+// reads entries 1..59 and entry [min_peak] with min_peak in {0, 2..58}: the last entry is never read, and entry 0 only
+// through `abs(min_peak - 30) > weak_peak_radius || p_costs[0] > 0.5f` when no peak exists — which the first operand
+// already decides for every weak_peak_radius < 30 (the reference's schedules use 2, 4, 6).  Dead entries are not
+// evaluated: 2 of 61 hypotheses, i.e. 2 * S_sel NCCs per pixel.
+__device__ __forceinline__ int profile_first_live(const KArgs& a) { return a.prm.weak_peak_radius < 30 ? 1 : 0; }
 
 template <bool WITH_COST>   // DepthToWeak never uses the cost of the current depth (APD.cu:3957 is dead there): K15 skips those NCCs
 __device__ __forceinline__ void profile_front(const KArgs& a, int x, int y, int center, uint32_t sel, const ViewWeights& vw,
@@ -478,7 +502,7 @@ __device__ __forceinline__ void profile_front(const KArgs& a, int x, int y, int 
 	for (int v = 0; v < a.S; ++v) {
 		if (!is_set(sel, v)) continue;
 		const int wv = vw.get(v);
-		if (WITH_COST) {
+		if (WITH_COST && wv != 0) {   // zero-weight view: contributes exactly +0
 			float4 t = pc.plane;
 			t.w = w_front;
 			float temp_cost = ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, t, rp, wt, T);
@@ -526,7 +550,9 @@ __global__ void __launch_bounds__(256, 3) k_depth_to_weak(const __grid_constant_
 	const int radius = 30;
 	const int p_costs_size = 2 * radius + 1;
 	float p_costs[p_costs_size];  // 244 B of local memory per thread, touched ~240 times per ~8000 texture samples
-	for (int idx = 0; idx < p_costs_size; ++idx) {
+	const int idx_lo = profile_first_live(a);
+	p_costs[0] = 2.0f; p_costs[p_costs_size - 1] = 2.0f;
+	for (int idx = idx_lo; idx < p_costs_size - 1; ++idx) {
 		const int p_disp = idx - radius;
 		const float p_depth = a.ref.K[0] * pc.base_line / (disp + p_disp);
 		if (p_depth < a.prm.depth_min || p_depth > a.prm.depth_max) { p_costs[idx] = 2.0f; continue; }
@@ -642,7 +668,9 @@ __global__ void __launch_bounds__(256, 3) k_depth_to_weak_refine(const __grid_co
 	const int p_costs_size = 2 * radius + 1;
 	float p_costs[p_costs_size];
 	float refine_min = 2.0f, refine_depth = pc.depth;   // LocalRefine's running minimum over p_disp = -5..5, in its order
-	for (int idx = 0; idx < p_costs_size; ++idx) {
+	const int idx_lo = profile_first_live(a);
+	p_costs[0] = 2.0f; p_costs[p_costs_size - 1] = 2.0f;
+	for (int idx = idx_lo; idx < p_costs_size - 1; ++idx) {
 		const int p_disp = idx - radius;
 		const float p_depth = a.ref.K[0] * pc.base_line / (disp + p_disp);
 		if (p_depth < a.prm.depth_min || p_depth > a.prm.depth_max) { p_costs[idx] = 2.0f; continue; }
@@ -653,6 +681,7 @@ __global__ void __launch_bounds__(256, 3) k_depth_to_weak_refine(const __grid_co
 			float acc15 = 0.0f, acc16 = 0.0f;
 			for (int v = 0; v < a.S; ++v) {
 				if (!is_set(sel, v)) continue;
+				if (vw.get(v) == 0) continue;   // adds exactly +0 to both folds
 				const float wvf = (float)vw.get(v);
 				const float ncc = ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, t, rp, wt, T);
 				float temp = __fadd_rn(0.0f, ncc);
@@ -744,7 +773,14 @@ cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, cudaStream_t 
 	dim3 b(kSweepBlockX, kSweepThreads / kSweepBlockX);
 	const int yy_limit = ref_half_rows(a.H);
 	dim3 g((a.W + b.x - 1) / b.x, (yy_limit + b.y - 1) / b.y, 1);
-	k_strong_sweep<<<g, b, sweep_smem_bytes(kSweepThreads, a.S), st>>>(a, iter, red, yy_limit);
+	k_strong_sweep<false><<<g, b, sweep_smem_bytes(kSweepThreads, a.S), st>>>(a, iter, red, yy_limit, D4Force{0, nullptr, nullptr});
+	return cudaGetLastError();
+}
+cudaError_t launch_strong_sweep_forced(const KArgs& a, int iter, int red, const D4Force& force, cudaStream_t st) {
+	dim3 b(kSweepBlockX, kSweepThreads / kSweepBlockX);
+	const int yy_limit = ref_half_rows(a.H);
+	dim3 g((a.W + b.x - 1) / b.x, (yy_limit + b.y - 1) / b.y, 1);
+	k_strong_sweep<true><<<g, b, sweep_smem_bytes(kSweepThreads, a.S), st>>>(a, iter, red, yy_limit, force);
 	return cudaGetLastError();
 }
 cudaError_t launch_depth_normal(const KArgs& a, cudaStream_t st) {
@@ -780,9 +816,10 @@ cudaError_t configure_strong_kernels(int S) {
 	if ((e = cudaFuncSetAttribute(k_depth_to_weak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
 	if ((e = cudaFuncSetAttribute(k_local_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
 	if ((e = cudaFuncSetAttribute(k_depth_to_weak_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
-	if ((e = cudaFuncSetAttribute(k_strong_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kSweepThreads, S)))) return e;
+	if ((e = cudaFuncSetAttribute(k_strong_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kSweepThreads, S)))) return e;
+	if ((e = cudaFuncSetAttribute(k_strong_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kSweepThreads, S)))) return e;
 #ifdef DVP_SWEEP_CARVEOUT
-	if ((e = cudaFuncSetAttribute(k_strong_sweep, cudaFuncAttributePreferredSharedMemoryCarveout, DVP_SWEEP_CARVEOUT))) return e;
+	if ((e = cudaFuncSetAttribute(k_strong_sweep<false>, cudaFuncAttributePreferredSharedMemoryCarveout, DVP_SWEEP_CARVEOUT))) return e;
 #endif
 	return cudaSuccess;
 }

@@ -565,14 +565,18 @@ __global__ void __launch_bounds__(64) k_ransac_fit(const __grid_constant__ KArgs
 
 // ------------------------------------------------------------------------------------------------------
 // K10/K11 CheckerboardPropagationWeak + PlaneHypothesisRefinementWeak (APD.cu:2739-3089, 1897-2008).
-__device__ __forceinline__ float weak_weighted_cost(const KArgs& a, int px, int py, const float4 pl, const ViewWeights& vw, float weight_norm) {
+// `reject_at`: see weighted_cost (dvp_strong.cuh) — the terms are non-negative (NCC in [0, 2], reprojection error in [0, 3],
+// geom_factor >= 0), so the views left over are skipped once the scaled partial sum has reached the cost to beat.
+__device__ __forceinline__ float weak_weighted_cost(const KArgs& a, int px, int py, const float4 pl, const ViewWeights& vw, float weight_norm, float reject_at) {
 	float temp_cost = 0.0f;
+	const bool can_reject = !(a.prm.geom_factor < 0.0f);
 	for (int j = 0; j < a.S; ++j) {
 		const int wv = vw.get(j);
 		if (wv > 0) {
 			const float c = ncc_new(a, px, py, j, pl);
 			if (a.prm.geom_consistency) temp_cost += wv * (c + a.prm.geom_factor * geom_cost(a, a.views[j], a.tex_depth[j + 1], px, py, pl));
 			else temp_cost += wv * c;
+			if (can_reject && !(temp_cost / weight_norm < reject_at)) break;
 		}
 	}
 	temp_cost /= weight_norm;
@@ -691,9 +695,11 @@ __global__ void __launch_bounds__(kWeakThreads, 512 / kWeakThreads) k_weak_sweep
 		const float4 fit = a.fit_planes[center];
 		if (fit.x == 0 && fit.y == 0 && fit.z == 0) skip_all = true;   // `return` before the random refinement (APD.cu:1923-1925)
 		if (!skip_all) {
-			const float temp_cost = weak_weighted_cost(a, px, py, fit, vw, weight_norm);
 			const float depth_before = depth_from_plane(a.ref, fit, px, py);
-			if (depth_before >= depth_min && depth_before <= depth_max && temp_cost < cost_now) { depth_now = depth_before; plane_now = fit; cost_now = temp_cost; }
+			if (depth_before >= depth_min && depth_before <= depth_max) {   // else rejected whatever it costs
+				const float temp_cost = weak_weighted_cost(a, px, py, fit, vw, weight_norm, cost_now);
+				if (temp_cost < cost_now) { depth_now = depth_before; plane_now = fit; cost_now = temp_cost; }
+			}
 			const float depth_rand = rng.uniform() * (depth_max - depth_min) + depth_min;
 			const float4 plane_rand = random_normal(a, px, py, rng, depth_now, sel_now);
 			float depth_perturbed = depth_now;
@@ -715,9 +721,10 @@ __global__ void __launch_bounds__(kWeakThreads, 512 / kWeakThreads) k_weak_sweep
 				default: d = depth_perturbed; tpl = plane0; break;
 				}
 				tpl.w = get_distance2origin(a.ref, px, py, d, tpl);
-				const float tc = weak_weighted_cost(a, px, py, tpl, vw, weight_norm);
 				const float db = depth_from_plane(a.ref, tpl, px, py);
-				if (db >= depth_min && db <= depth_max && tc < cost_now) { depth_now = db; plane_now = tpl; cost_now = tc; }
+				if (!(db >= depth_min && db <= depth_max)) continue;
+				const float tc = weak_weighted_cost(a, px, py, tpl, vw, weight_norm, cost_now);
+				if (tc < cost_now) { depth_now = db; plane_now = tpl; cost_now = tc; }
 			}
 		}
 	}

@@ -52,6 +52,9 @@ cudaError_t launch_gen_neighbours(const KArgs& a, const int* weak_list, cudaStre
 cudaError_t launch_neighbour_update(const KArgs& a, cudaStream_t st);                            // K5
 cudaError_t launch_random_init(const KArgs& a, cudaStream_t st);                                 // K6
 cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, cudaStream_t st);             // K7 / K8
+// parity instrumentation: direction 4's candidate forced to ladder offset m, planes from snapshots (see k_strong_sweep)
+struct D4Force { int m; const float4* planes_ncc; const float4* planes_accept; };
+cudaError_t launch_strong_sweep_forced(const KArgs& a, int iter, int red, const D4Force& force, cudaStream_t st);
 cudaError_t launch_ransac_fit(const KArgs& a, const int* weak_list, cudaStream_t st);                                  // K9
 cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count, int iter, int red, cudaStream_t st);  // K10 / K11
 cudaError_t launch_depth_normal(const KArgs& a, cudaStream_t st);                                // K12

@@ -173,6 +173,7 @@ __device__ __forceinline__ float ncc_cost(const KArgs& a, const ViewConst& vc, c
 	if (rp.degenerate) return kCostMax;
 
 	float s_s = 0.f, s_ss = 0.f, s_rs = 0.f;
+	DVP_COUNT(a, rp.n * rp.n);
 	if (rp.hoisted) {
 		static_assert(kHoistAxis % RB == 0, "row batch must divide the patch height");
 #pragma unroll 1
@@ -261,6 +262,7 @@ __device__ __forceinline__ float geom_cost(const KArgs& a, const ViewConst& vc, 
 	float2 src_pt; float src_d;
 	project_on_camera(fwd, vc.sK, vc.sR, vc.st, src_pt, src_d);
 	const float src_depth = tex2D<float>(depth_tex, (int)src_pt.x + 0.5f, (int)src_pt.y + 0.5f);
+	DVP_COUNT(a, 1);
 	if (src_depth == 0.0f) return max_cost;
 	float3 back = point_to_world(src_pt.x, src_pt.y, src_depth, vc.sK, vc.sR, vc.sc);
 	float2 bpt; float ref_d;

@@ -60,7 +60,7 @@ static __device__ __noinline__ float4 random_normal(const KArgs& a, int px, int 
 			// out-of-image projections leave src_depth uninitialised in the reference (UB); 1.0 gives the
 			// same direction as any positive value because the direction is normalised.
 			if (sx >= 0 && sx < a.W && sy >= 0 && sy < a.H)
-				src_depth = tex2D<float>(a.tex_depth[v + 1], (int)src_pt.x + 0.5f, (int)src_pt.y + 0.5f);
+				{ src_depth = tex2D<float>(a.tex_depth[v + 1], (int)src_pt.x + 0.5f, (int)src_pt.y + 0.5f); DVP_COUNT(a, 1); }
 		}
 		const dvp_camera& sc = a.cams[v + 1];
 		const float4 d = get_view_direction(sc, sx, sy, src_depth);
@@ -133,14 +133,19 @@ static __device__ __noinline__ float4 perturbed_normal(const KArgs& a, int px, i
 
 // Weighted multi-view cost of one hypothesis over the views with a positive weight.
 // (the reference evaluates all S views and multiplies the unused ones by 0 — identical sum.)
+// `reject_at`: the caller only asks whether the result is < reject_at (refinement, APD.cu:1373).  Every term is
+// >= 0 (an NCC lies in [0, 2]), float addition of a non-negative term never lowers the sum and the scaling by
+// 1 / weight_norm is monotone, so as soon as the scaled partial sum is no longer below reject_at the full cost cannot
+// be either: the remaining views are not evaluated.  The value returned then only has to fail the same test.
 __device__ __forceinline__ float weighted_cost(const KArgs& a, int px, int py, const float4 pl, const RefPatch& rp,
-                                               const float2* wt, int stride, const ViewWeights& vw, float weight_norm) {
+                                               const float2* wt, int stride, const ViewWeights& vw, float weight_norm, float reject_at) {
 	float acc = 0.0f;
 	for (int v = 0; v < a.S; ++v) {
 		const int wv = vw.get(v);
 		if (wv > 0) {
 			const float c = ncc_cost<kSweepRB, kSweepRW>(a, a.views[v], a.tex_img[v + 1], px, py, pl, rp, wt, stride);
 			acc += wv * c;
+			if (!(acc / weight_norm < reject_at)) break;
 		}
 	}
 	acc /= weight_norm;
@@ -185,9 +190,10 @@ __device__ __forceinline__ void refine_strong(const KArgs& a, int px, int py, fl
 		default: d = depth_perturbed; t = plane0; break;
 		}
 		t.w = get_distance2origin(a.ref, px, py, d, t);
-		const float temp_cost = weighted_cost(a, px, py, t, rp, wt, stride, vw, weight_norm);
 		const float depth_before = depth_from_plane(a.ref, t, px, py);
-		if (depth_before >= depth_min && depth_before <= depth_max && temp_cost < *cost) {
+		if (!(depth_before >= depth_min && depth_before <= depth_max)) continue;   // rejected whatever it costs
+		const float temp_cost = weighted_cost(a, px, py, t, rp, wt, stride, vw, weight_norm, *cost);
+		if (temp_cost < *cost) {
 			*depth = depth_before;
 			*plane = t;
 			*cost = temp_cost;

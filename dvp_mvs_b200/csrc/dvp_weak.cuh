@@ -163,6 +163,7 @@ __device__ __forceinline__ float ncc_new(const KArgs& a, int px, int py, int v /
 		if (k == 0) {
 			int radius = a.prm.strong_radius, inc = a.prm.strong_increment;
 			if (a.prm.use_radius) { radius = a.radius[center]; inc = DVP_MAX(2, (int)(2.0 * radius / 5.0)); }
+			DVP_COUNT(a, radius >= 0 ? ((2 * radius) / inc + 1) * ((2 * radius) / inc + 1) : 0);
 			for (int i = -radius; i <= radius; i += inc) {
 				const float xf = (float)(np.x + i);
 				const float hx = __fmul_rn(H[0], xf), hy = __fmul_rn(H[3], xf), hz = __fmul_rn(H[6], xf);
@@ -195,6 +196,7 @@ __device__ __forceinline__ float ncc_new(const KArgs& a, int px, int py, int v /
 			// all nine reference reads and texture fetches are issued before the first is consumed; the sums are
 			// then folded strictly in sample order (the reference's rounding sequence)
 			float ref_pix[9], src_pix[9];
+			DVP_COUNT(a, 9);
 #pragma unroll
 			for (int q = 0; q < 9; q++) {
 				int i = 0, j = 0;

@@ -77,8 +77,8 @@ def run_scene_schedule(scene, num_views: int, num_levels: int, seed: int, costs:
 
     `scene` holds every view's pyramid on this rank's GPU (dvp_mvs_b200.Scene, or anything with `run_view(view, level,
     pass, seed)` and `depth_tensor(view, level, owned) -> torch tensor`).  Each rank runs its own views of a pass in
-    index order; the one exchange step per pass is a broadcast of every view's depth map from its owner straight between
-    the scenes' device buffers (NCCL; gloo in the CPU tests) — depth is all a view needs from its sources.  Within a
+    index order; the one exchange step per pass is ONE all-gather of the ranks' fresh depth maps between the scenes' device
+    buffers (`exchange_depths`: NCCL; gloo in the CPU tests) — depth is all a view needs from its sources.  Within a
     pass a rank sees its own views' fresh depths and the other ranks' previous-pass depths (block Gauss-Seidel); with
     one rank this is exactly the reference's sequential order.  Returns {view: owner rank}."""
     import torch.distributed as dist
@@ -92,10 +92,38 @@ def run_scene_schedule(scene, num_views: int, num_levels: int, seed: int, costs:
             for v in mine:
                 scene.run_view(v, level, pass_, seed + 1000 * it + v)   # same seeds as dvp_scene_run
             if world > 1:
-                for v in range(num_views):
-                    dist.broadcast(scene.depth_tensor(v, level, owner[v] == rank), src=owner[v])
+                exchange_depths(scene, level, owner, rank, world)
             it += 1
     return owner
+
+
+def exchange_depths(scene, level: int, owner: Dict[int, int], rank: int, world: int):
+    """The one exchange step of a farmed pass: ONE all-gather of every rank's freshly computed depth maps
+    (all views of a level have the same size; ranks owning fewer views pad with an unused slot), then the remote maps are
+    copied into the scene's buffers.  Synchronisation: `run_view` returns only after its stream has drained, so the maps
+    packed here are complete; the collective and the unpacking copies run on torch's streams, which the scene's own
+    non-blocking stream does not order against — the device is therefore synchronised before the next pass may read a
+    remote depth map or overwrite a local one that NCCL is still sending."""
+    import torch
+    import torch.distributed as dist
+    views_of = {r: sorted(v for v, o in owner.items() if o == r) for r in range(world)}
+    slots = max(1, max(len(v) for v in views_of.values()))
+    any_view = next(iter(sorted(owner)))
+    shape = tuple(scene.depth_tensor(any_view, level, owner[any_view] == rank).shape)
+    first = scene.depth_tensor(views_of[rank][0], level, True) if views_of[rank] else scene.depth_tensor(any_view, level, False)
+    send = torch.zeros((slots,) + shape, dtype=torch.float32, device=first.device)
+    for i, v in enumerate(views_of[rank]):
+        send[i].copy_(scene.depth_tensor(v, level, True))
+    flat = torch.empty((world * slots,) + shape, dtype=torch.float32, device=first.device)   # rank-major concatenation
+    dist.all_gather_into_tensor(flat, send)
+    recv = flat.view((world, slots) + shape)
+    for r in range(world):
+        if r == rank:
+            continue
+        for i, v in enumerate(views_of[r]):
+            scene.depth_tensor(v, level, False).copy_(recv[r, i])
+    if first.is_cuda:
+        torch.cuda.synchronize(first.device)
 
 
 def fuse_farmed_scene(scene, owner: Dict[int, int], views_static: Sequence[dict], fuse_rank: int = 0, mode: int = 0, make_fusion=None):

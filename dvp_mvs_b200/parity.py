@@ -103,3 +103,34 @@ def step_compare(ref: Engine, prod: Engine, max_iterations: int, stages=None, ma
                 log(f"{stage}[{it}] {n:12s} mismatched {r['mismatched']:8d}/{r['pixels']} ({100*r['frac']:.4f}%) "
                     f"not-bit-exact {r['not_bit_exact']} first {r['first_bad']}")
     return results
+
+
+def lockstep_compare(ref: Engine, prod: Engine, max_iterations: int, racy=(), resync_extra=(), stages=None, log=None):
+    """Same protocol as step_compare for large images: both engines start from the same upload and advance together;
+    after each stage only the buffers that stage WRITES are read back (the rest of the state is identical by induction),
+    compared, and — where they differ at all — overwritten in `prod` with the reference's, so a stage is always judged
+    from the reference's pre-stage state.  `racy`: stages whose differences are expected (they are re-synchronised like
+    any other).  `resync_extra`: {stage: (buffers,)} copied from ref to prod after a stage although they are not
+    compared (K2's `candidate`, which holds uninitialised data in the reference where no pixel sees a view, B17)."""
+    results = []
+    have_weak = ref.weak_count() > 0
+    for stage, it in sequence(max_iterations):
+        if stages is not None and stage not in stages:
+            continue
+        ref.run_stage(stage, it)
+        prod.run_stage(stage, it)
+        for n in STAGE_OUTPUTS[stage]:
+            if n in WEAK_BUFS and not have_weak:
+                continue
+            a, b = ref.get(n), prod.get(n)
+            r = compare(n, a, b)
+            r.update(stage=stage, iter=it, racy=stage in racy)
+            results.append(r)
+            if log:
+                log(f"{stage}[{it}] {n:12s} mismatched {r['mismatched']:8d}/{r['pixels']} ({100*r['frac']:.4f}%) not-bit-exact {r['not_bit_exact']}")
+            if r["not_bit_exact"]:
+                prod.set(n, a)
+            del a, b
+        for n in dict(resync_extra).get(stage, ()):
+            prod.set(n, ref.get(n))
+    return results

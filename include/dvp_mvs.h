@@ -314,6 +314,9 @@ int dvp_fusion_get_mask(dvp_fusion* f, int view, uint8_t* dst);
  * (cells / terms: [h*w][num_src], -1 = source not consistent), the per-pixel decision (used: bit j = source j
  * contributed, 0 = no point) and the number of reservation rounds it took.  Any pointer may be NULL. */
 int dvp_fusion_last_view(dvp_fusion* f, int32_t* cells, float* terms, uint32_t* used, int* rounds);
+/* Index of the view dvp_fusion_last_view reports on (its buffers are sized by THAT view's h, w and num_src), or
+ * DVP_ERR_STATE when no view has run since the last reset. */
+int dvp_fusion_last_view_index(dvp_fusion* f);
 /* ExportPointCloud (APD.cpp:842-882): binary little-endian PLY, x y z float + 3 uchar colours. */
 int dvp_fusion_write_ply(dvp_fusion* f, const char* path);
 
@@ -344,6 +347,24 @@ int dvp_io_read_camera(const char* path, dvp_camera* cam);
 /* GenerateSampleList (main.cpp:127-170): pair.txt.  With ref_ids == NULL only *num_views is returned.  src_ids is
  * [max_views][DVP_MAX_IMAGES]; sources with score <= 0 are dropped as in the reference. */
 int dvp_io_read_pairs(const char* path, int32_t max_views, int32_t* num_views, int32_t* ref_ids, int32_t* num_src, int32_t* src_ids);
+
+/* ---- Parity instrumentation for the racy stage (tests only; dvp_run never takes this path) --------------------------
+ * The reference's strong sweep reads, in diagonal direction 4 only, cost and plane of pixels of the colour it is writing
+ * in the same launch (APD.cu:2039, 2071-2074: the colour fix covers `dir_index > 4`) — so what a pixel ends up with
+ * depends on which of those pixels were already rewritten when it looked.  Whatever the timing, direction 4 contributes
+ * ONE candidate: the plane of some ladder pixel (offset m along the diagonal), read before or after that pixel's update,
+ * and read again at acceptance (APD.cu:2559-2563).  dvp_debug_sweep_forced_d4 runs K7 (red = 0) / K8 (red = 1) with exactly
+ * that choice imposed on every pixel: direction 4's candidate is the pixel at (x - 5 - m, y - 5 - m), its plane taken from
+ * snapshot `planes_before` or `planes_after` (dvp_debug_set_plane_snapshots, [H][W][4], host or device) for scoring and,
+ * independently, for the acceptance re-read.  Everything else is the production kernel.  A test enumerates the choices
+ * and checks that each pixel of a racy full-image run equals one of them. */
+int dvp_debug_set_plane_snapshots(dvp_ctx* ctx, const float* planes_before, const float* planes_after);
+/* Measurement instrumentation: texture fetches issued on this context since the last reset (every fetch site of the
+ * NCC / reprojection code tallies itself).  Only the instrumented build of the same sources (libdvp_mvs_count.so, `make
+ * count` in csrc/) counts; the first call arms the counter and returns 0; the production library returns
+ * DVP_ERR_UNSUPPORTED.  bench.py uses it, outside the timed region, to report measured fetches per launch. */
+long long dvp_debug_fetch_count(dvp_ctx* ctx, int reset);
+int dvp_debug_sweep_forced_d4(dvp_ctx* ctx, int iter, int red, int m, int ncc_from_after, int accept_from_after);
 
 int dvp_weak_count(dvp_ctx* ctx);
 int dvp_last_cuda_error(dvp_ctx* ctx);

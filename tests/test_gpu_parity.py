@@ -12,7 +12,7 @@ import pytest
 
 from util import c1_params, load_golden, golden_inputs, close, per_pixel
 from dvp_mvs_b200 import Engine, synth, DvpError, STRONG, WEAK, UNKNOWN
-from dvp_mvs_b200.parity import step_compare, sequence, STAGE_OUTPUTS, STATE_BUFS, compare
+from dvp_mvs_b200.parity import step_compare, lockstep_compare, sequence, STAGE_OUTPUTS, STATE_BUFS, compare
 import ref_oracle
 import cpu_oracle
 
@@ -45,34 +45,81 @@ def test_c1_every_race_free_stage_is_bit_exact_vs_reference(c1_scene):
     assert not bad, bad[:4]
 
 
+def _d4_ladder_offsets(W, H):
+    """Every offset m (pixels along the diagonal, after the fixed 5) at which direction 4 of the strong sweep can look:
+    the edge-adaptive ladder (APD.cu:2053-2087; step count 11..22, step length >= 2) and the fixed 11 x 2 px one."""
+    out = set(range(0, 22, 2))
+    max_edge = max(H, W) / 30.0
+    dists = list(np.arange(0.0, max_edge / np.sqrt(2.0) + 0.26, 0.25)) + [22.0, max_edge / np.sqrt(2.0)]
+    for dist in dists:
+        step_num = min(max(11, int(dist / 2)), 22)
+        step_len = max(int(dist / step_num), 2)
+        out.update(k * step_len for k in range(step_num))
+    return sorted(out)
+
+
 @needs_ref
-def test_c1_racy_sweep_stays_within_the_reference_noise_floor(c1_scene):
-    """K7/K8 on the full image: the reference disagrees with ITSELF between two runs from the same state
-    (direction-4 race).  Our disagreement with it must be of the same order."""
+@pytest.mark.parametrize("stage,red", [("K7_BLACK_STRONG", 0), ("K8_RED_STRONG", 1)])
+def test_full_image_sweep_differences_are_exactly_the_direction4_race(c1_scene, stage, red):
+    """K7/K8 on the full image.  The reference disagrees with ITSELF between two runs from the same state: direction 4 of
+    its ladder reads cost and plane of pixels of the colour being written (APD.cu:2039, 2071-2074).  Whatever the
+    timing, that direction hands the pixel ONE candidate — the plane of a ladder pixel at offset m, seen before or after
+    that pixel's own update, and re-read at acceptance.  dvp_debug_sweep_forced_d4 imposes such a choice on every pixel
+    with the production arithmetic; a pixel is `explained` when some choice reproduces all five of its output buffers bit
+    for bit.  Every pixel of the reference's racy run, and of ours, must be explained — i.e. all differences between the
+    two are the reference's own race and nothing else (not a tolerance: no unexplained pixel is allowed)."""
     sc = c1_scene
+    W, H = 640, 480
     p = c1_params(sc.depth_min, sc.depth_max, 2)
-    ref = ref_oracle.engine(640, 480, 2, p); prod = Engine(640, 480, 2, p)
-    ref.upload(**c1_kwargs(sc))
-    for st in sequence(1)[:6]:
+    ref = ref_oracle.engine(W, H, 2, p); prod = Engine(W, H, 2, p)
+    ref.upload(**c1_kwargs(sc)); prod.upload(**c1_kwargs(sc))
+    for st in sequence(1)[:6 + red]:
         ref.run_stage(*st)
     pre = {n: ref.get(n) for n in STATE_BUFS}
-    outs = STAGE_OUTPUTS["K7_BLACK_STRONG"]
+    outs = STAGE_OUTPUTS[stage]
 
     def run(e):
         for n, a in pre.items():
             e.set(n, a)
-        e.run_stage("K7_BLACK_STRONG", 0)
+        e.run_stage(stage, 0)
         return {n: e.get(n) for n in outs}
-    prod.upload(**c1_kwargs(sc))
     r1, r2, p1 = run(ref), run(ref), run(prod)
     noise = max(compare(n, r1[n], r2[n])["frac"] for n in outs)
     ours = max(compare(n, r1[n], p1[n])["frac"] for n in outs)
-    assert ours < 0.02, ours                      # measured: 0.7 % (reference vs itself: 0.1 %)
-    assert ours < 20 * max(noise, 5e-4), (ours, noise)
-    # black launch must not touch red pixels
-    yy, xx = np.mgrid[0:480, 0:640]
-    red = ((xx + yy) % 2) == 1
-    assert (p1["costs"][red] == pre["costs"][red]).all() or np.isnan(pre["costs"][red]).any()
+    assert ours < 0.02, (ours, noise)
+
+    def bits(a):
+        return a.view(np.uint32) if a.dtype == np.float32 else a
+
+    def same_pixels(x, y):
+        ok = np.ones((H, W), bool)
+        for n in outs:
+            ok &= (bits(x[n]) == bits(y[n])).reshape(H, W, -1).all(-1)
+        return ok
+    prod.set_plane_snapshots(pre["planes"], r1["planes"])
+    explained_ref = np.zeros((H, W), bool); explained_ours = np.zeros((H, W), bool)
+    jacobi = None
+    for m in _d4_ladder_offsets(W, H):
+        for ncc_after in (0, 1):
+            for accept_after in (0, 1):
+                for n in outs:
+                    prod.set(n, pre[n])
+                prod.sweep_forced_d4(0, red, m, ncc_after, accept_after)
+                o = {n: prod.get(n) for n in outs}
+                explained_ref |= same_pixels(o, r1)
+                explained_ours |= same_pixels(o, p1)
+                if jacobi is None:
+                    jacobi = o
+    yy, xx = np.mgrid[0:H, 0:W]
+    other = ((xx + yy) % 2) != red
+    # the launch must not touch the other colour (NaN-aware: costs may hold NaN, SURVEY B18)
+    for n in outs:
+        assert np.array_equal(bits(p1[n])[other], bits(pre[n])[other]), n
+        assert np.array_equal(bits(r1[n])[other], bits(pre[n])[other]), n
+    n_diff = int((~same_pixels(r1, p1)).sum())
+    assert n_diff > 0 or noise == 0                    # the race is real: the two runs do differ somewhere
+    assert explained_ref.all(), (int((~explained_ref).sum()), [int(v) for v in np.argwhere(~explained_ref)[0]])
+    assert explained_ours.all(), (int((~explained_ours).sum()), [int(v) for v in np.argwhere(~explained_ours)[0]])
 
 
 @needs_ref
@@ -432,3 +479,64 @@ def test_empty_priors_and_ragged_sizes():
             res = step_compare(ref, e, 1, stages=RACE_FREE)
             bad = [r for r in res if r.get("error") or r["not_bit_exact"]]
             assert not bad, (W, H, bad[:3])
+
+
+RACY = ("K7_BLACK_STRONG", "K8_RED_STRONG")
+
+
+def _bench_workload(width, height, src, iters):
+    """The workload bench.py times (bench.make_workload): ETH3D-shaped synthetic view, REFINE_ITER with geometric
+    consistency, priors on, the textureless wall WEAK."""
+    import argparse
+    import bench
+    ns = argparse.Namespace(width=width, height=height, src=src, iters=iters, state="refine_iter", geom=1)
+    sc, p, inputs, name = bench.make_workload(ns, seed=0)
+    return p, inputs, name
+
+
+@needs_ref
+def test_bench_workload_stage_by_stage_vs_reference():
+    """The stage-wise comparison at the size and configuration bench.py reports on its C2 line (3111x2073, 4 source views,
+    REFINE_ITER + geometric consistency, 16 % WEAK pixels), one iteration: large-image behaviour that 640x480 never
+    exercises — K2's unbounded rays, K3's 100-ring search inside a wall, K4's search radii up to the image size and
+    max(H, W)/30-step edge walks, the long adaptive ladders of the sweep.  Every race-free stage and the whole WEAK path
+    bit for bit; the racy strong sweep is re-synchronised from the reference after each launch."""
+    W, H, S = 3111, 2073, 4
+    p, inputs, _ = _bench_workload(W, H, S, 1)
+    ref = ref_oracle.engine(W, H, S, p); prod = Engine(W, H, S, p)
+    ref.upload(**inputs); prod.upload(**inputs)
+    assert ref.weak_count() == prod.weak_count() > 900000
+    res = lockstep_compare(ref, prod, 1, racy=RACY, resync_extra={"K2_GEN_EDGE_INFORM": ("candidate",)})
+    assert len(res) >= 40
+    n_weak = ref.weak_count()
+    for r in res:
+        key = (r["stage"], r["buffer"])
+        if r["stage"] in RACY:
+            assert r["frac"] < 0.02, r                 # the race itself is characterised at 640x480 (direction-4 test)
+        elif r["stage"] in ("K10_BLACK_WEAK", "K11_RED_WEAK") and r["buffer"] in ("planes", "costs", "selected", "rand"):
+            # with the geometric term a 1-ulp difference in the reprojection error flips an accept decision on a few
+            # WEAK pixels in 100 000 (see test_weak_path_stagewise_vs_reference)
+            assert r["mismatched"] <= max(8, n_weak // 20000), r
+        else:
+            assert r["not_bit_exact"] == 0, r
+
+
+@needs_ref
+def test_full_resolution_race_free_stages_vs_reference():
+    """BASELINE's full size, 6221x4146 (C3): K1, K2, K3 from the upload and K12..K16 from the reference's own state after
+    one iteration, bit for bit (coordinates beyond 4096, `short2` maps, 207-step edge limits, 25.8 M RNG sequences)."""
+    W, H, S = 6221, 4146, 2
+    p, inputs, _ = _bench_workload(W, H, S, 1)
+    ref = ref_oracle.engine(W, H, S, p); prod = Engine(W, H, S, p)
+    ref.upload(**inputs); prod.upload(**inputs)
+    head = ("K1_INIT_RANDOM_STATES", "K2_GEN_EDGE_INFORM", "K3_FIND_NEAREST_STRONG")
+    res = lockstep_compare(ref, prod, 1, stages=head)
+    for st, it in sequence(1)[3:11]:
+        ref.run_stage(st, it)
+    for n in ("planes", "costs", "selected", "weak", "radius", "view_weight"):
+        prod.set(n, ref.get(n))
+    tail = ("K12_DEPTH_NORMAL", "K13_BLACK_FILTER", "K14_RED_FILTER", "K15_DEPTH_TO_WEAK", "K16_LOCAL_REFINE")
+    res += lockstep_compare(ref, prod, 1, stages=tail)
+    assert len(res) >= 10
+    bad = [r for r in res if r["not_bit_exact"]]
+    assert not bad, bad[:4]
