@@ -73,7 +73,7 @@ PRODUCT_ONLY_SYMBOLS = ["upload_device", "upload_overlapped", "restore_visibilit
                         "fusion_create", "fusion_destroy", "fusion_set_view", "fusion_set_view_planes", "scene_fuse_views", "fusion_set_mode", "fusion_reset", "fusion_run_view", "fusion_run",
                         "fusion_num_points", "fusion_get_points", "fusion_get_mask", "fusion_last_view", "fusion_last_view_index", "fusion_write_ply",
                         "edge_segment", "scene_compute_edges", "scene_get_edges",
-                        "debug_set_plane_snapshots", "debug_sweep_forced_d4", "debug_fetch_count",
+                        "debug_race_explain", "debug_fetch_count",
                         "io_binmat_header", "io_read_binmat", "io_write_binmat", "io_write_dmb", "io_read_camera", "io_read_pairs"]
 
 
@@ -172,8 +172,8 @@ def load_library(path: str, prefix: str):
         f("fusion_last_view").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]; f("fusion_last_view").restype = C.c_int
         f("fusion_write_ply").argtypes = [C.c_void_p, C.c_char_p]; f("fusion_write_ply").restype = C.c_int
         f("fusion_last_view_index").argtypes = [C.c_void_p]; f("fusion_last_view_index").restype = C.c_int
-        f("debug_set_plane_snapshots").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]; f("debug_set_plane_snapshots").restype = C.c_int
-        f("debug_sweep_forced_d4").argtypes = [C.c_void_p] + [C.c_int] * 5; f("debug_sweep_forced_d4").restype = C.c_int
+        f("debug_race_explain").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p]
+        f("debug_race_explain").restype = C.c_int
         f("debug_fetch_count").argtypes = [C.c_void_p, C.c_int]; f("debug_fetch_count").restype = C.c_longlong
     return lib
 
@@ -288,13 +288,21 @@ class Engine:
         self._check(self._f("restore_visibility")(self.ctx, int(scale_size), C.byref(ms)), "restore_visibility")
         return float(ms.value)
 
-    def set_plane_snapshots(self, before: np.ndarray, after: np.ndarray):
-        """Parity instrumentation (include/dvp_mvs.h): the two plane maps direction 4 of a forced sweep may read."""
-        b = _carr(before, np.float32, (self.H, self.W, 4)); a = _carr(after, np.float32, (self.H, self.W, 4))
-        self._check(self._f("debug_set_plane_snapshots")(self.ctx, _ptr(b), _ptr(a)), "debug_set_plane_snapshots")
-
-    def sweep_forced_d4(self, iteration: int, red: int, m: int, ncc_from_after: int, accept_from_after: int):
-        self._check(self._f("debug_sweep_forced_d4")(self.ctx, iteration, red, m, ncc_from_after, accept_from_after), "debug_sweep_forced_d4")
+    def race_explain(self, iteration: int, red: int, offsets, planes_before, observed: dict, tear: bool = True):
+        """Parity instrumentation (dvp_debug_race_explain, include/dvp_mvs.h): which pixels of an observed K7 / K8 result
+        (dict of planes, costs, selected, view_weight, rand) does some outcome of the reference's direction-4 race reproduce?
+        The context must hold the pre-launch state.  -> (explained [H, W] bool, (left after phase 1, left after phase 2, launches))."""
+        H, W = self.H, self.W
+        off = np.ascontiguousarray(offsets, np.int32)
+        before = _carr(planes_before, np.float32, (H, W, 4))
+        obs = dict(planes=_carr(observed["planes"], np.float32, (H, W, 4)), costs=_carr(observed["costs"], np.float32, (H, W)),
+                   selected=_carr(observed["selected"], np.uint32, (H, W)), view_weight=_carr(observed["view_weight"], np.uint8, (H, W, 32)),
+                   rand=_carr(observed["rand"], np.uint32, (H, W, 6)))
+        explained = np.zeros((H, W), np.uint8); stats = (C.c_longlong * 3)()
+        self._check(self._f("debug_race_explain")(self.ctx, iteration, red, _ptr(off), len(off), _ptr(before), _ptr(obs["planes"]), _ptr(obs["planes"]),
+                                                   _ptr(obs["costs"]), _ptr(obs["selected"]), _ptr(obs["view_weight"]), _ptr(obs["rand"]),
+                                                   1 if tear else 0, _ptr(explained), stats), "debug_race_explain")
+        return explained.astype(bool), tuple(int(v) for v in stats)
 
     def fetch_count(self, reset: bool = True) -> int:
         """Texture fetches since the last reset (instrumented build only: DVP_MVS_LIB=.../libdvp_mvs_count.so)."""

@@ -56,6 +56,8 @@ struct dvp_ctx {
 	uint8_t* view_weight = nullptr;
 	uint32_t* rng = nullptr;
 	uint8_t* edge = nullptr;
+	uint8_t* edge_blocks = nullptr;   // 8x8 block occupancy of `edge` and its 3x3 dilation (edge walks of K4 / K9)
+	uint8_t* edge_coarse = nullptr;
 	short2* edge_neigh = nullptr;
 	int32_t* label = nullptr;
 	short2* candidate = nullptr;
@@ -78,7 +80,6 @@ struct dvp_ctx {
 	void* sort_temp = nullptr;
 	size_t sort_temp_bytes = 0;
 	unsigned long long* fetch_counter = nullptr;   // instrumented build only (DVP_COUNT_FETCHES)
-	float4* dbg_planes[2] = {nullptr, nullptr};  // plane snapshots of dvp_debug_sweep_forced_d4 (allocated on first use)
 	int* vis_parent = nullptr;  // union-find links / region sizes of dvp_restore_visibility (allocated on first use)
 	int* vis_count = nullptr;
 	// host staging
@@ -118,6 +119,7 @@ KArgs make_args(const dvp_ctx* c) {
 	a.nearest_strong = c->nearest_strong; a.weak_reliable = c->weak_reliable; a.neighbours_map = c->neighbours_map;
 	a.neighbours = c->neighbours; a.label_boundary = c->label_boundary; a.complex_ = c->complex_;
 	a.scratch = nullptr; a.weak_count = c->weak_count; a.fetch_counter = c->fetch_counter;
+	a.edge_coarse = c->edge_coarse; a.coarse_w = (c->W + 7) / 8; a.coarse_h = (c->H + 7) / 8;
 	return a;
 }
 
@@ -285,6 +287,7 @@ int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bo
 	if (in->selected_views) CK(cudaMemcpyAsync(ctx->selected, in->selected_views, N * 4, kind, st));
 	else CK(cudaMemsetAsync(ctx->selected, 0, N * 4, st));
 	if (in->edge) CK(cudaMemcpyAsync(ctx->edge, in->edge, N, kind, st)); else CK(cudaMemsetAsync(ctx->edge, 0, N, st));
+	CK(launch_edge_coarse(ctx->edge, ctx->W, ctx->H, ctx->edge_blocks, ctx->edge_coarse, st));
 	if (in->label) CK(cudaMemcpyAsync(ctx->label, in->label, N * 4, kind, st)); else CK(cudaMemsetAsync(ctx->label, 0, N * 4, st));
 
 	// pixel states, neighbours map, WEAK list, radius (APD.cpp:1169-1204, 1647-1667) — all on the device: the
@@ -417,6 +420,8 @@ dvp_ctx* dvp_create(int device, int width, int height, int num_src, const dvp_pa
 	ok = ok && zalloc(&c->view_weight, N * DVP_MAX_IMAGES) == cudaSuccess;
 	ok = ok && zalloc(&c->rng, N * 6) == cudaSuccess;
 	ok = ok && zalloc(&c->edge, N) == cudaSuccess;
+	ok = ok && zalloc(&c->edge_blocks, (size_t)((width + 7) / 8) * ((height + 7) / 8)) == cudaSuccess;
+	ok = ok && zalloc(&c->edge_coarse, (size_t)((width + 7) / 8) * ((height + 7) / 8)) == cudaSuccess;
 	ok = ok && zalloc(&c->edge_neigh, N * DVP_EDGE_NEIGH_NUM) == cudaSuccess;
 	ok = ok && zalloc(&c->label, N) == cudaSuccess;
 	const int cand_views = num_src > DVP_NUM_IMAGES ? num_src : DVP_NUM_IMAGES;
@@ -458,10 +463,10 @@ void dvp_destroy(dvp_ctx* c) {
 	}
 	cudaFree(c->d_img_tex); cudaFree(c->d_dep_tex); cudaFree(c->ref_img); cudaFree(c->cams); cudaFree(c->views);
 	cudaFree(c->planes); cudaFree(c->fit_planes); cudaFree(c->costs); cudaFree(c->selected_alloc); cudaFree(c->weak);
-	cudaFree(c->radius); cudaFree(c->view_weight); cudaFree(c->rng); cudaFree(c->edge); cudaFree(c->edge_neigh);
+	cudaFree(c->radius); cudaFree(c->view_weight); cudaFree(c->rng); cudaFree(c->edge); cudaFree(c->edge_blocks); cudaFree(c->edge_coarse); cudaFree(c->edge_neigh);
 	cudaFree(c->label); cudaFree(c->candidate); cudaFree(c->nearest_strong); cudaFree(c->weak_reliable);
 	cudaFree(c->neighbours_map); cudaFree(c->neighbours); cudaFree(c->label_boundary); cudaFree(c->complex_); cudaFree(c->weak_list); cudaFree(c->scan_blocks); cudaFree(c->scan_total); cudaFree(c->next_right); cudaFree(c->next_down); for (int k = 0; k < 2; ++k) { cudaFree(c->scan_blocks_c[k]); cudaFree(c->colour_list[k]); }
-	cudaFree(c->vis_parent); cudaFree(c->vis_count); cudaFree(c->dbg_planes[0]); cudaFree(c->dbg_planes[1]); cudaFree(c->fetch_counter);
+	cudaFree(c->vis_parent); cudaFree(c->vis_count); cudaFree(c->fetch_counter);
 	cudaFree(c->sort_keys[0]); cudaFree(c->sort_keys[1]); cudaFree(c->sort_vals); cudaFree(c->sort_temp);
 	for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -650,27 +655,82 @@ long long dvp_debug_fetch_count(dvp_ctx* ctx, int reset) {
 #endif
 }
 
-int dvp_debug_set_plane_snapshots(dvp_ctx* ctx, const float* planes_before, const float* planes_after) {
-	if (!ctx || !planes_before || !planes_after) return DVP_ERR_ARG;
-	CK(cudaSetDevice(ctx->device));
-	const float* src[2] = {planes_before, planes_after};
-	for (int k = 0; k < 2; ++k) {
-		if (!ctx->dbg_planes[k]) CK(cudaMalloc((void**)&ctx->dbg_planes[k], (size_t)ctx->N * 16));
-		CK(cudaMemcpyAsync(ctx->dbg_planes[k], src[k], (size_t)ctx->N * 16, cudaMemcpyDefault, ctx->stream));
-	}
-	CK(cudaStreamSynchronize(ctx->stream));
-	return DVP_OK;
-}
-
-int dvp_debug_sweep_forced_d4(dvp_ctx* ctx, int iter, int red, int m, int ncc_from_after, int accept_from_after) {
-	if (!ctx || m < 0 || m > 65535) return DVP_ERR_ARG;
-	if (!ctx->uploaded || !ctx->dbg_planes[0] || !ctx->dbg_planes[1]) return DVP_ERR_STATE;
+int dvp_debug_race_explain(dvp_ctx* ctx, int iter, int red, const int32_t* offsets, int num_offsets, const float* planes_before, const float* planes_after,
+                           const float* exp_planes, const float* exp_costs, const uint32_t* exp_selected, const uint8_t* exp_view_weight, const uint32_t* exp_rand,
+                           int tear, uint8_t* explained, long long* stats) {
+	if (!ctx || !offsets || num_offsets <= 0 || !planes_before || !planes_after || !exp_planes || !exp_costs || !exp_selected || !exp_view_weight || !exp_rand || !explained)
+		return DVP_ERR_ARG;
+	if (!ctx->uploaded) return DVP_ERR_STATE;
 	CK(cudaSetDevice(ctx->device));
 	{ int r = join_copies(ctx); if (r) return r; }
+	const size_t N = (size_t)ctx->N;
+	cudaStream_t st = ctx->stream;
 	const KArgs a = make_args(ctx);
-	const D4Force f{m, ctx->dbg_planes[ncc_from_after ? 1 : 0], ctx->dbg_planes[accept_from_after ? 1 : 0]};
-	CK(launch_strong_sweep_forced(a, iter, red ? 1 : 0, f, ctx->stream));
-	CK(cudaStreamSynchronize(ctx->stream));
+	// device copies of the snapshots and of the observed result, shadow outputs, bookkeeping
+	struct Bufs {
+		float4 *before = nullptr, *after = nullptr, *e_planes = nullptr, *o_planes = nullptr;
+		float *e_costs = nullptr, *o_costs = nullptr;
+		uint32_t *e_sel = nullptr, *o_sel = nullptr, *e_rand = nullptr, *o_rng = nullptr;
+		uint8_t *e_vw = nullptr, *o_vw = nullptr, *expl = nullptr;
+		int *list = nullptr, *count = nullptr;
+		~Bufs() { cudaFree(before); cudaFree(after); cudaFree(e_planes); cudaFree(o_planes); cudaFree(e_costs); cudaFree(o_costs); cudaFree(e_sel); cudaFree(o_sel);
+		          cudaFree(e_rand); cudaFree(o_rng); cudaFree(e_vw); cudaFree(o_vw); cudaFree(expl); cudaFree(list); cudaFree(count); }
+	} b;
+	const int list_cap = 1 << 16;
+	CK(cudaMalloc((void**)&b.before, N * 16)); CK(cudaMalloc((void**)&b.after, N * 16)); CK(cudaMalloc((void**)&b.e_planes, N * 16)); CK(cudaMalloc((void**)&b.o_planes, N * 16));
+	CK(cudaMalloc((void**)&b.e_costs, N * 4)); CK(cudaMalloc((void**)&b.o_costs, N * 4)); CK(cudaMalloc((void**)&b.e_sel, N * 4)); CK(cudaMalloc((void**)&b.o_sel, N * 4));
+	CK(cudaMalloc((void**)&b.e_rand, N * 24)); CK(cudaMalloc((void**)&b.o_rng, N * 24)); CK(cudaMalloc((void**)&b.e_vw, N * DVP_MAX_IMAGES)); CK(cudaMalloc((void**)&b.o_vw, N * DVP_MAX_IMAGES));
+	CK(cudaMalloc((void**)&b.expl, N)); CK(cudaMalloc((void**)&b.list, (size_t)list_cap * 4)); CK(cudaMalloc((void**)&b.count, 4));
+	CK(cudaMemcpyAsync(b.before, planes_before, N * 16, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(b.after, planes_after, N * 16, cudaMemcpyDefault, st));
+	CK(cudaMemcpyAsync(b.e_planes, exp_planes, N * 16, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(b.e_costs, exp_costs, N * 4, cudaMemcpyDefault, st));
+	CK(cudaMemcpyAsync(b.e_sel, exp_selected, N * 4, cudaMemcpyDefault, st)); CK(cudaMemcpyAsync(b.e_vw, exp_view_weight, N * DVP_MAX_IMAGES, cudaMemcpyDefault, st));
+	CK(cudaMemcpyAsync(b.e_rand, exp_rand, N * 24, cudaMemcpyDefault, st));
+	const RaceExpected e{b.e_planes, b.e_costs, b.e_sel, b.e_vw, b.e_rand};
+	CK(launch_explain_init(a, red ? 1 : 0, e, b.expl, st));
+	D4Force f;
+	f.before = b.before; f.after = b.after;
+	f.out_planes = b.o_planes; f.out_costs = b.o_costs; f.out_selected = b.o_sel; f.out_view_weight = b.o_vw; f.out_rng = b.o_rng;
+	long long launches = 0;
+	// phase 1, whole colour: every ladder offset, each of the three reads entirely before or entirely after the update
+	for (int k = 0; k < num_offsets; ++k) {
+		if (offsets[k] < 0 || offsets[k] > 65535) return DVP_ERR_ARG;
+		f.m = offsets[k];
+		for (unsigned v = 0; v < 8; ++v) {
+			f.ncc_mask = (v & 1) ? 15u : 0u; f.dep_mask = (v & 2) ? 15u : 0u; f.acc_mask = (v & 4) ? 15u : 0u;
+			CK(launch_strong_sweep_forced(a, iter, red ? 1 : 0, f, st));
+			CK(launch_explain_compare(a, red ? 1 : 0, f, e, b.expl, st));
+			++launches;
+		}
+	}
+	int left1 = 0, left2 = 0;
+	CK(cudaMemsetAsync(b.count, 0, 4, st));
+	CK(launch_explain_collect(a, red ? 1 : 0, b.expl, b.list, b.count, list_cap, st));
+	CK(cudaMemcpyAsync(&left1, b.count, 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	left2 = left1;
+	// phase 2, only the pixels still unexplained: reads torn between components (the reference loads a plane with four
+	// 32-bit loads while its owner replaces it with one 128-bit store)
+	if (tear && left1 > 0 && left1 <= list_cap) {
+		f.pixel_list = b.list; f.list_count = left1;
+		for (int k = 0; k < num_offsets; ++k) {
+			f.m = offsets[k];
+			for (unsigned v = 0; v < 4096; ++v) {
+				f.ncc_mask = v & 15u; f.dep_mask = (v >> 4) & 15u; f.acc_mask = (v >> 8) & 15u;
+				const bool whole = (f.ncc_mask == 0 || f.ncc_mask == 15) && (f.dep_mask == 0 || f.dep_mask == 15) && (f.acc_mask == 0 || f.acc_mask == 15);
+				if (whole) continue;   // done in phase 1
+				CK(launch_strong_sweep_forced(a, iter, red ? 1 : 0, f, st));
+				CK(launch_explain_compare(a, red ? 1 : 0, f, e, b.expl, st));
+				++launches;
+			}
+		}
+		f.pixel_list = nullptr; f.list_count = 0;
+		CK(cudaMemsetAsync(b.count, 0, 4, st));
+		CK(launch_explain_collect(a, red ? 1 : 0, b.expl, b.list, b.count, list_cap, st));
+		CK(cudaMemcpyAsync(&left2, b.count, 4, cudaMemcpyDeviceToHost, st));
+	}
+	CK(cudaMemcpyAsync(explained, b.expl, N, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if (stats) { stats[0] = left1; stats[1] = left2; stats[2] = launches; }
 	return DVP_OK;
 }
 

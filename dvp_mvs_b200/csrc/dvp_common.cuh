@@ -70,6 +70,8 @@ struct KArgs {
 	float* complex_;        // [weak_count]
 	float* scratch;         // per-pixel spill area for large S (cost arrays)
 	int weak_count;
+	const uint8_t* edge_coarse;   // [coarse_h][coarse_w]: 1 iff any edge pixel lies in the 8x8 block or one of its 8 neighbours (K4 / K9 edge walks)
+	int coarse_w, coarse_h;
 	unsigned long long* fetch_counter;   // [kFetchSlots] texture-fetch tally of the instrumented build (-DDVP_COUNT_FETCHES), else null
 };
 

@@ -44,7 +44,9 @@ int dvp_io_read_binmat(const char* path, void* data, size_t bytes) {
 	int32_t rows, cols, type;
 	const int rc = dvp_io_binmat_header(path, &rows, &cols, &type);
 	if (rc != DVP_OK) return rc;
-	if (!data || bytes != (size_t)rows * cols * cv_elem_size(type)) return DVP_ERR_ARG;
+	const size_t elem = cv_elem_size(type);
+	if ((size_t)rows != 0 && (size_t)cols > SIZE_MAX / elem / (size_t)rows) return DVP_ERR_UNSUPPORTED;   // header sizes whose product overflows
+	if (!data || bytes != (size_t)rows * cols * elem) return DVP_ERR_ARG;
 	FILE* f = std::fopen(path, "rb");
 	if (!f) return DVP_ERR_STATE;
 	std::fseek(f, 16, SEEK_SET);
@@ -102,6 +104,7 @@ int dvp_io_read_pairs(const char* path, int32_t max_views, int32_t* num_views, i
 	std::getline(file, line);
 	int n = 0;
 	{ std::stringstream iss(line); iss >> n; }
+	if (n < 0) return DVP_ERR_UNSUPPORTED;                         // not a pair.txt
 	*num_views = n;
 	if (!ref_ids || !num_src || !src_ids) return DVP_OK;           // count only
 	if (n > max_views) return DVP_ERR_ARG;
@@ -116,7 +119,10 @@ int dvp_io_read_pairs(const char* path, int32_t max_views, int32_t* num_views, i
 			int id = 0; float score = 0.f;
 			iss >> id >> score;
 			if (score <= 0.0f) continue;                           // main.cpp:163-165
-			if (kept < DVP_MAX_IMAGES) src_ids[(size_t)i * DVP_MAX_IMAGES + kept++] = id;
+			// a context takes the reference view + at most DVP_MAX_IMAGES - 1 sources (main.h:39 MAX_IMAGES): a view listing more
+			// usable sources is reported, not silently cut (the reference would overrun its fixed-size arrays with it)
+			if (kept >= DVP_MAX_IMAGES - 1) return DVP_ERR_UNSUPPORTED;
+			src_ids[(size_t)i * DVP_MAX_IMAGES + kept++] = id;
 		}
 		num_src[i] = kept;
 	}

@@ -224,6 +224,41 @@ __global__ void k_fill_i32(int32_t* dst, int32_t v, int n) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) dst[i] = v;
 }
+// Coarse occupancy of the edge map for the edge walks of K4 / K9 (bresenham_crosses_edge, dvp_weak.cuh): cell (bx, by)
+// of the block map says whether the 8x8 pixel block holds an edge pixel; the dilated map ORs the 3x3 block neighbourhood.
+__global__ void __launch_bounds__(256) k_edge_blocks(const uint8_t* edge, int W, int H, uint8_t* blocks, int cw, int ch) {
+	const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
+	if (bx >= cw || by >= ch) return;
+	uint8_t any = 0;
+	for (int j = 0; j < 8; ++j) {
+		const int y = by * 8 + j;
+		if (y >= H) break;
+		for (int i = 0; i < 8; ++i) {
+			const int x = bx * 8 + i;
+			if (x < W) any |= edge[(size_t)y * W + x];
+		}
+	}
+	blocks[by * cw + bx] = any ? 1 : 0;
+}
+__global__ void __launch_bounds__(256) k_edge_blocks_dilate(const uint8_t* blocks, uint8_t* coarse, int cw, int ch) {
+	const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
+	if (bx >= cw || by >= ch) return;
+	uint8_t any = 0;
+	for (int j = -1; j <= 1; ++j)
+		for (int i = -1; i <= 1; ++i) {
+			const int x = bx + i, y = by + j;
+			if (x >= 0 && x < cw && y >= 0 && y < ch) any |= blocks[y * cw + x];
+		}
+	coarse[by * cw + bx] = any;
+}
+cudaError_t launch_edge_coarse(const uint8_t* edge, int W, int H, uint8_t* blocks, uint8_t* coarse, cudaStream_t st) {
+	const int cw = (W + 7) / 8, ch = (H + 7) / 8;
+	dim3 b(32, 8), g((cw + 31) / 32, (ch + 7) / 8);
+	k_edge_blocks<<<g, b, 0, st>>>(edge, W, H, blocks, cw, ch);
+	k_edge_blocks_dilate<<<g, b, 0, st>>>(blocks, coarse, cw, ch);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_fill_i32(int32_t* dst, int32_t v, int n, cudaStream_t st) {
 	k_fill_i32<<<(n + 255) / 256, 256, 0, st>>>(dst, v, n);
 	return cudaGetLastError();

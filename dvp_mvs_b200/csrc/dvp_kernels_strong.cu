@@ -143,10 +143,14 @@ __global__ void __launch_bounds__(256, 3) k_random_init(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------------
 // K7/K8: red-black propagation sweep for non-WEAK pixels (edge-adaptive branch, params.use_edge).
 // shared memory per thread: 36 float2 (w, w r) + 9*S floats (8 direction cost vectors + 1 spare) + 8 u16 ladder offsets.
-// FORCE_D4 (parity instrumentation, never launched by dvp_run): direction 4 — the one whose ladder reads pixels of the
-// colour being written — takes its candidate from ladder offset `force.m` with the plane read from a snapshot,
-// and re-reads it at acceptance from a second snapshot.  Enumerating (m, snapshot, snapshot) reproduces every outcome the
-// reference's race can have for a pixel: tests/test_gpu_parity.py proves the full-image differences lie inside that set.
+// FORCE_D4 (parity instrumentation, never launched by dvp_run; see dvp_debug_race_explain in include/dvp_mvs.h): direction
+// 4 — the one whose ladder reads pixels of the colour being written — takes its candidate from ladder offset
+// `force.m`; the candidate's plane is assembled component by component from a `before` and an `after` snapshot for each of
+// the three reads the reference makes of it (scoring, APD.cu:2084/2133; depth test and copy at acceptance, APD.cu:2559-2563),
+// the reference's SASS reading planes with 32-bit loads.  Outputs go to shadow buffers: the state is left untouched.
+__device__ __forceinline__ float4 mix_planes(const float4 b, const float4 a, unsigned mask) {
+	return make_float4((mask & 1) ? a.x : b.x, (mask & 2) ? a.y : b.y, (mask & 4) ? a.z : b.z, (mask & 8) ? a.w : b.w);
+}
 template <bool FORCE_D4>
 __global__ void __launch_bounds__(kSweepThreads, kSweepMinBlocks) k_strong_sweep(const __grid_constant__ KArgs a, int iter, int red, int yy_limit, const D4Force force) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -160,12 +164,26 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinBlocks) k_strong_sweep
 	uint16_t* pos_arr = reinterpret_cast<uint16_t*>(smem_raw + kTable + (size_t)9 * a.S * T * sizeof(float)) + tid;
 	const int S = a.S, W = a.W, H = a.H;
 
-	const int x = blockIdx.x * blockDim.x + threadIdx.x;
-	const int yy = blockIdx.y * blockDim.y + threadIdx.y;
-	const int y = 2 * yy + ((x & 1) ^ red);  // black: even x -> even row; red: the other colour (APD.cu:3129-3136)
-	if (x >= W || y >= H || yy >= yy_limit) return;
+	int x = blockIdx.x * blockDim.x + threadIdx.x;
+	int y;
+	if (FORCE_D4 && force.pixel_list) {   // instrumentation: a list of pixels of this colour instead of the whole half grid
+		const int i = blockIdx.x * T + tid;
+		if (i >= force.list_count) return;
+		const int c = force.pixel_list[i];
+		x = c % W; y = c / W;
+	} else {
+		const int yy = blockIdx.y * blockDim.y + threadIdx.y;
+		y = 2 * yy + ((x & 1) ^ red);  // black: even x -> even row; red: the other colour (APD.cu:3129-3136)
+		if (x >= W || y >= H || yy >= yy_limit) return;
+	}
 	const int center = y * W + x;
 	if (a.weak[center] == DVP_WEAK) return;
+	// where results go: the state itself, or (instrumentation) shadow buffers
+	float4* const o_planes = FORCE_D4 ? force.out_planes : a.planes;
+	float* const o_costs = FORCE_D4 ? force.out_costs : a.costs;
+	uint32_t* const o_selected = FORCE_D4 ? force.out_selected : a.selected;
+	uint8_t* const o_view_weight = FORCE_D4 ? force.out_view_weight : a.view_weight;
+	uint32_t* const o_rng = FORCE_D4 ? force.out_rng : a.rng;
 
 	RefPatch rp;
 	rp.prepare<kSweepRW>(a, x, y, a.prm.use_radius ? a.radius[center] : a.prm.strong_radius, wt, T);
@@ -194,7 +212,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinBlocks) k_strong_sweep
 			if (tx >= 0 && ty >= 0) {
 				flag |= 1u << d;
 				pos_arr[d * T] = (uint16_t)force.m;
-				const float4 pl = force.planes_ncc[tx + ty * W];
+				const float4 pl = mix_planes(force.before[tx + ty * W], force.after[tx + ty * W], force.ncc_mask);
 				for (int v = 0; v < S; ++v)
 					cost_arr[(d * S + v) * T] = ncc_cost<kSweepRB, kSweepRW>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
 			}
@@ -320,7 +338,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinBlocks) k_strong_sweep
 			}
 		}
 	}
-	vw.store(a.view_weight + (size_t)center * DVP_MAX_IMAGES);
+	vw.store(o_view_weight + (size_t)center * DVP_MAX_IMAGES);
 
 	uint32_t temp_selected = 0;
 	float weight_norm = 0;
@@ -364,31 +382,83 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinBlocks) k_strong_sweep
 			if (min_cost_idx > 4) { if (min_cost_idx % 2) fx = dx; else fy = dy; }
 			cx = x + 5 * dx + k * dx + fx; cy = y + 5 * dy + k * dy + fy;
 		}
-		const float4 cand = (FORCE_D4 && min_cost_idx == 4) ? force.planes_accept[cx + cy * W] : a.planes[cx + cy * W];
-		const float depth_before = depth_from_plane(a.ref, cand, x, y);
+		float4 cand = a.planes[cx + cy * W];
+		float4 cand_for_depth = cand;   // the reference reads the winner's plane twice here: for the depth test and for the copy
+		if (FORCE_D4 && min_cost_idx == 4) {
+			const float4 b = force.before[cx + cy * W], n = force.after[cx + cy * W];
+			cand_for_depth = mix_planes(b, n, force.dep_mask);
+			cand = mix_planes(b, n, force.acc_mask);
+		}
+		const float depth_before = depth_from_plane(a.ref, cand_for_depth, x, y);
 		if (depth_before >= a.prm.depth_min && depth_before <= a.prm.depth_max && min_final < cost_now) {
 			depth_now = depth_before;
 			plane_now = cand;
 			cost_now = min_final;
 			sel_now = temp_selected;
-			a.selected[center] = temp_selected;
+			o_selected[center] = temp_selected;
+		} else if (FORCE_D4) {
+			o_selected[center] = sel_now;   // shadow buffers get every output of a processed pixel, changed or not
 		}
+	} else if (FORCE_D4) {
+		o_selected[center] = sel_now;
 	}
 
+	const float4 plane_before_refine_write = FORCE_D4 ? a.planes[center] : plane_now;
 	refine_strong(a, x, y, &plane_now, &depth_now, &cost_now, rng, vw, weight_norm, sel_now, rp, wt, T);
-	rng.store(a.rng, a.N, center);
+	rng.store(o_rng, a.N, center);
 
 	if (a.prm.state == DVP_REFINE_INIT) {
 		if (cost_now < cost_stored - 0.1) {
-			a.costs[center] = cost_now;
-			a.planes[center] = plane_now;
+			o_costs[center] = cost_now;
+			o_planes[center] = plane_now;
 		} else {
-			a.costs[center] = cost_stored;
+			o_costs[center] = cost_stored;
+			if (FORCE_D4) o_planes[center] = plane_before_refine_write;
 		}
 	} else {
-		a.costs[center] = cost_now;
-		a.planes[center] = plane_now;
+		o_costs[center] = cost_now;
+		o_planes[center] = plane_now;
 	}
+}
+
+// ---- instrumentation: which pixels of an observed sweep result does a forced choice reproduce? -----------------------
+// expected rand is the canonical [N][6] layout; the shadow rng is the engine's 6 SoA planes
+__device__ __forceinline__ bool pixel_equal(const KArgs& a, int c, const float4* pl_a, const float* co_a, const uint32_t* se_a, const uint8_t* vw_a, const uint32_t* rng_soa,
+                                            const float4* pl_e, const float* co_e, const uint32_t* se_e, const uint8_t* vw_e, const uint32_t* rng_aos) {
+	const uint4 p0 = reinterpret_cast<const uint4*>(pl_a)[c], p1 = reinterpret_cast<const uint4*>(pl_e)[c];
+	bool ok = p0.x == p1.x && p0.y == p1.y && p0.z == p1.z && p0.w == p1.w;
+	ok = ok && __float_as_uint(co_a[c]) == __float_as_uint(co_e[c]) && se_a[c] == se_e[c];
+	const uint4* va = reinterpret_cast<const uint4*>(vw_a + (size_t)c * DVP_MAX_IMAGES);
+	const uint4* ve = reinterpret_cast<const uint4*>(vw_e + (size_t)c * DVP_MAX_IMAGES);
+	for (int k = 0; k < 2; ++k) { const uint4 u = va[k], v = ve[k]; ok = ok && u.x == v.x && u.y == v.y && u.z == v.z && u.w == v.w; }
+	for (int k = 0; k < 6; ++k) ok = ok && rng_soa[(size_t)k * a.N + c] == rng_aos[(size_t)c * 6 + k];
+	return ok;
+}
+__device__ __forceinline__ bool sweep_processes(const KArgs& a, int c, int red, int yy_limit) {
+	const int x = c % a.W, y = c / a.W;
+	if (((x + y) & 1) != red) return false;
+	if ((y >> 1) >= yy_limit) return false;
+	return a.weak[c] != DVP_WEAK;
+}
+// pixels the launch does not process must equal the pre-launch state; processed pixels start unexplained
+__global__ void k_explain_init(const __grid_constant__ KArgs a, int red, int yy_limit, const RaceExpected e, uint8_t* explained) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= a.N) return;
+	if (sweep_processes(a, c, red, yy_limit)) { explained[c] = 0; return; }
+	explained[c] = pixel_equal(a, c, a.planes, a.costs, a.selected, a.view_weight, a.rng, e.planes, e.costs, e.selected, e.view_weight, e.rand) ? 1 : 0;
+}
+__global__ void k_explain_compare(const __grid_constant__ KArgs a, int red, int yy_limit, const D4Force f, const RaceExpected e, uint8_t* explained) {
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f.pixel_list) { if (c >= f.list_count) return; c = f.pixel_list[c]; }
+	else if (c >= a.N || !sweep_processes(a, c, red, yy_limit)) return;
+	if (explained[c]) return;
+	if (pixel_equal(a, c, f.out_planes, f.out_costs, f.out_selected, f.out_view_weight, f.out_rng, e.planes, e.costs, e.selected, e.view_weight, e.rand)) explained[c] = 1;
+}
+__global__ void k_explain_collect(const __grid_constant__ KArgs a, int red, int yy_limit, const uint8_t* explained, int* list, int* count, int cap) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= a.N || explained[c] || !sweep_processes(a, c, red, yy_limit)) return;
+	const int i = atomicAdd(count, 1);
+	if (i < cap) list[i] = c;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -773,14 +843,30 @@ cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, cudaStream_t 
 	dim3 b(kSweepBlockX, kSweepThreads / kSweepBlockX);
 	const int yy_limit = ref_half_rows(a.H);
 	dim3 g((a.W + b.x - 1) / b.x, (yy_limit + b.y - 1) / b.y, 1);
-	k_strong_sweep<false><<<g, b, sweep_smem_bytes(kSweepThreads, a.S), st>>>(a, iter, red, yy_limit, D4Force{0, nullptr, nullptr});
+	k_strong_sweep<false><<<g, b, sweep_smem_bytes(kSweepThreads, a.S), st>>>(a, iter, red, yy_limit, D4Force{});
 	return cudaGetLastError();
 }
 cudaError_t launch_strong_sweep_forced(const KArgs& a, int iter, int red, const D4Force& force, cudaStream_t st) {
 	dim3 b(kSweepBlockX, kSweepThreads / kSweepBlockX);
 	const int yy_limit = ref_half_rows(a.H);
 	dim3 g((a.W + b.x - 1) / b.x, (yy_limit + b.y - 1) / b.y, 1);
+	if (force.pixel_list) g = dim3((force.list_count + kSweepThreads - 1) / kSweepThreads, 1, 1);
+	if (g.x == 0) return cudaSuccess;
 	k_strong_sweep<true><<<g, b, sweep_smem_bytes(kSweepThreads, a.S), st>>>(a, iter, red, yy_limit, force);
+	return cudaGetLastError();
+}
+cudaError_t launch_explain_init(const KArgs& a, int red, const RaceExpected& e, uint8_t* explained, cudaStream_t st) {
+	k_explain_init<<<(a.N + 255) / 256, 256, 0, st>>>(a, red, ref_half_rows(a.H), e, explained);
+	return cudaGetLastError();
+}
+cudaError_t launch_explain_compare(const KArgs& a, int red, const D4Force& f, const RaceExpected& e, uint8_t* explained, cudaStream_t st) {
+	const int n = f.pixel_list ? f.list_count : a.N;
+	if (n == 0) return cudaSuccess;
+	k_explain_compare<<<(n + 255) / 256, 256, 0, st>>>(a, red, ref_half_rows(a.H), f, e, explained);
+	return cudaGetLastError();
+}
+cudaError_t launch_explain_collect(const KArgs& a, int red, const uint8_t* explained, int* list, int* count, int cap, cudaStream_t st) {
+	k_explain_collect<<<(a.N + 255) / 256, 256, 0, st>>>(a, red, ref_half_rows(a.H), explained, list, count, cap);
 	return cudaGetLastError();
 }
 cudaError_t launch_depth_normal(const KArgs& a, cudaStream_t st) {

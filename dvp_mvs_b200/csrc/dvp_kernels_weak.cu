@@ -576,7 +576,9 @@ __device__ __forceinline__ float weak_weighted_cost(const KArgs& a, int px, int 
 			const float c = ncc_new(a, px, py, j, pl);
 			if (a.prm.geom_consistency) temp_cost += wv * (c + a.prm.geom_factor * geom_cost(a, a.views[j], a.tex_depth[j + 1], px, py, pl));
 			else temp_cost += wv * c;
+#ifndef DVP_NO_EARLY_REJECT
 			if (can_reject && !(temp_cost / weight_norm < reject_at)) break;
+#endif
 		}
 	}
 	temp_cost /= weight_norm;

@@ -53,8 +53,18 @@ cudaError_t launch_neighbour_update(const KArgs& a, cudaStream_t st);           
 cudaError_t launch_random_init(const KArgs& a, cudaStream_t st);                                 // K6
 cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, cudaStream_t st);             // K7 / K8
 // parity instrumentation: direction 4's candidate forced to ladder offset m, planes from snapshots (see k_strong_sweep)
-struct D4Force { int m; const float4* planes_ncc; const float4* planes_accept; };
+struct D4Force {
+	int m = 0;                                               // ladder offset of direction 4's candidate: pixel (x - 5 - m, y - 5 - m)
+	const float4* before = nullptr; const float4* after = nullptr;   // the candidate's plane before / after its own update
+	unsigned ncc_mask = 0, dep_mask = 0, acc_mask = 0;       // bit c: component c of the plane comes from `after` (scoring read, depth-test read, copy)
+	const int* pixel_list = nullptr; int list_count = 0;     // null: the whole half grid of the colour
+	float4* out_planes = nullptr; float* out_costs = nullptr; uint32_t* out_selected = nullptr; uint8_t* out_view_weight = nullptr; uint32_t* out_rng = nullptr;
+};
+struct RaceExpected { const float4* planes; const float* costs; const uint32_t* selected; const uint8_t* view_weight; const uint32_t* rand; };
 cudaError_t launch_strong_sweep_forced(const KArgs& a, int iter, int red, const D4Force& force, cudaStream_t st);
+cudaError_t launch_explain_init(const KArgs& a, int red, const RaceExpected& e, uint8_t* explained, cudaStream_t st);
+cudaError_t launch_explain_compare(const KArgs& a, int red, const D4Force& f, const RaceExpected& e, uint8_t* explained, cudaStream_t st);
+cudaError_t launch_explain_collect(const KArgs& a, int red, const uint8_t* explained, int* list, int* count, int cap, cudaStream_t st);
 cudaError_t launch_ransac_fit(const KArgs& a, const int* weak_list, cudaStream_t st);                                  // K9
 cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count, int iter, int red, cudaStream_t st);  // K10 / K11
 cudaError_t launch_depth_normal(const KArgs& a, cudaStream_t st);                                // K12
@@ -64,6 +74,7 @@ cudaError_t launch_local_refine(const KArgs& a, cudaStream_t st);               
 cudaError_t launch_depth_to_weak_refine(const KArgs& a, cudaStream_t st);                        // K15 + K16 fused (dvp_run)
 
 cudaError_t launch_fill_i32(int32_t* dst, int32_t v, int n, cudaStream_t st);
+cudaError_t launch_edge_coarse(const uint8_t* edge, int W, int H, uint8_t* blocks, uint8_t* coarse, cudaStream_t st);   // 8x8 block occupancy, 3x3 dilated
 // WEAK-pixel indexing (device-side replacement of the host loop APD.cpp:1182-1193)
 constexpr int kWeakScanBlock = 1024;
 cudaError_t launch_weak_count(const uint8_t* weak, int n, int W, int colour, int yy_limit, int* block_sums, int* total, cudaStream_t st);

@@ -25,6 +25,34 @@ __device__ __forceinline__ bool bresenham_crosses_edge(const KArgs& a, int Ax, i
 	int erro = (dx > dy ? dx : dy) / 2;
 	int step = 0;
 	bool tagx = true, tagy = true;
+#ifndef DVP_NO_COARSE_WALK
+	// Fast path.  The walk visits exactly n = min(max(dx, dy) + 1, max_step) positions and position k (1-based) has the
+	// closed form below (checked against the loop for all |dx|, |dy| <= 36 in tests/test_host_logic.py).  Consecutive
+	// positions differ by at most one pixel in x and in y, so every visited pixel lies within 4 pixels (both axes) of the
+	// position at one of the steps 4, 12, 20, ... or of the last one — hence inside the 3x3 block neighbourhood of that
+	// sample's 8x8 block.  If the dilated block map is clear at all those samples no visited pixel is an edge pixel and the
+	// answer is `false` without touching the edge map; the sample reads are independent of one another (no early exit
+	// chained through memory, which is what bounds the exact walk).  Otherwise the exact walk below decides.
+	{
+		const int m = dx > dy ? dx : dy;
+		const int n_total = m + 1 < max_step ? m + 1 : max_step;
+		const int e0 = erro;
+		auto coarse_at = [&](int k) -> uint8_t {
+			int x, y;
+			if (dx > dy) { x = x0 + sx * k; y = y0 + sy * ((k * dy - e0 + dx - 1) / dx); }
+			else if (dy > dx) { const int q = (e0 + k * dx - 1 + dy) / dy; x = x0 + sx * (k < q ? k : q); y = y0 + sy * k; }
+			else { x = x0 + sx * k; y = y0 + sy * k; }
+			x = min(max(x, 0), a.W - 1); y = min(max(y, 0), a.H - 1);
+			return __ldg(a.edge_coarse + (y >> 3) * a.coarse_w + (x >> 3));
+		};
+		uint8_t any = 0;
+		if (m > 0) {
+			for (int k = 4; k < n_total; k += 8) any |= coarse_at(k);
+			any |= coarse_at(n_total);
+		}
+		if (!any) return false;
+	}
+#endif
 	// The reference tests one pixel per iteration and returns at the first edge pixel.  Only the yes/no answer
 	// leaves this function, so BATCH iterations are advanced at a time (pure integer state, no memory) and their
 	// edge reads are issued together: a hit in any of them is a hit, and iterations the reference would not

@@ -345,20 +345,30 @@ int dvp_io_write_dmb(const char* path, int32_t rows, int32_t cols, int32_t chann
 /* ReadCamera (APD.cpp:651-692), the TAT & ETH cam.txt layout; the centre is computed as the reference does. */
 int dvp_io_read_camera(const char* path, dvp_camera* cam);
 /* GenerateSampleList (main.cpp:127-170): pair.txt.  With ref_ids == NULL only *num_views is returned.  src_ids is
- * [max_views][DVP_MAX_IMAGES]; sources with score <= 0 are dropped as in the reference. */
+ * [max_views][DVP_MAX_IMAGES]; sources with score <= 0 are dropped as in the reference.  DVP_ERR_UNSUPPORTED: a negative view
+ * count, or a view with more than DVP_MAX_IMAGES - 1 usable sources (more than a context can take; never silently cut). */
 int dvp_io_read_pairs(const char* path, int32_t max_views, int32_t* num_views, int32_t* ref_ids, int32_t* num_src, int32_t* src_ids);
 
 /* ---- Parity instrumentation for the racy stage (tests only; dvp_run never takes this path) --------------------------
  * The reference's strong sweep reads, in diagonal direction 4 only, cost and plane of pixels of the colour it is writing
  * in the same launch (APD.cu:2039, 2071-2074: the colour fix covers `dir_index > 4`) — so what a pixel ends up with
  * depends on which of those pixels were already rewritten when it looked.  Whatever the timing, direction 4 contributes
- * ONE candidate: the plane of some ladder pixel (offset m along the diagonal), read before or after that pixel's update,
- * and read again at acceptance (APD.cu:2559-2563).  dvp_debug_sweep_forced_d4 runs K7 (red = 0) / K8 (red = 1) with exactly
- * that choice imposed on every pixel: direction 4's candidate is the pixel at (x - 5 - m, y - 5 - m), its plane taken from
- * snapshot `planes_before` or `planes_after` (dvp_debug_set_plane_snapshots, [H][W][4], host or device) for scoring and,
- * independently, for the acceptance re-read.  Everything else is the production kernel.  A test enumerates the choices
- * and checks that each pixel of a racy full-image run equals one of them. */
-int dvp_debug_set_plane_snapshots(dvp_ctx* ctx, const float* planes_before, const float* planes_after);
+ * ONE candidate: some ladder pixel at offset m along the diagonal, i.e. (x - 5 - m, y - 5 - m), whose plane is read three
+ * times — for scoring (APD.cu:2084 / 2133), for the depth test and for the copy at acceptance (APD.cu:2559-2563) — each
+ * time before or after that pixel's own update, or torn between the two (the reference build loads a float4 plane with
+ * four 32-bit loads while its owner replaces it with one 128-bit store).
+ * dvp_debug_race_explain answers, for an OBSERVED result of K7 (red = 0) / K8 (red = 1) launched from the state this
+ * context currently holds: which pixels are reproduced, in all five output buffers bit for bit, by the production
+ * arithmetic under SOME such choice?  Phase 1 tries every offset in `offsets` with each read entirely before / after
+ * (8 combinations) on the whole image; with `tear` != 0 phase 2 tries the remaining 4088 component mixtures per offset
+ * on the pixels phase 1 left over.  The state is not modified (results go to shadow buffers).
+ * planes_before / planes_after: [H][W][4] plane maps before the launch and after it (the observed result's);
+ * exp_*: the observed result — planes [H][W][4], costs [H][W], selected [H][W], view_weight [H][W][32], rand [H][W][6];
+ * explained: [H][W] out, 1 = reproduced (pixels the launch does not process: 1 iff unchanged);
+ * stats (may be NULL): {unexplained after phase 1, unexplained after phase 2, forced launches}.  Host or device pointers. */
+int dvp_debug_race_explain(dvp_ctx* ctx, int iter, int red, const int32_t* offsets, int num_offsets, const float* planes_before, const float* planes_after,
+                           const float* exp_planes, const float* exp_costs, const uint32_t* exp_selected, const uint8_t* exp_view_weight, const uint32_t* exp_rand,
+                           int tear, uint8_t* explained, long long* stats);
 /* Measurement instrumentation: texture fetches issued on this context since the last reset (every fetch site of the
  * NCC / reprojection code tallies itself).  Only the instrumented build of the same sources (libdvp_mvs_count.so, `make
  * count` in csrc/) counts; the first call arms the counter and returns 0; the production library returns

@@ -1,0 +1,146 @@
+// oracle/ref_host.cu — TEST INFRASTRUCTURE ONLY.
+// HOST functions of the reference, compiled FROM THE REFERENCE'S OWN LINES: oracle/Makefile cuts the line ranges below
+// out of /root/reference/APD.cpp into oracle/_ref/src/*.inc at build time (nothing of them is committed) and this file
+// wraps them in a C ABI.  They pin the CPU restatements of the callers' rows to the reference itself:
+//   APD.cpp:120-346    Roberts, Label_Seek, Label_Update, Connect          -> row N1 (visibility restoration), N4 (labels)
+//   APD.cpp:501-546    Get3DPointonWorld, Get3DPoint, ProjectCamera          -> row N3
+//   APD.cpp:1797-1806  GetAngle                                               -> row N3
+//   APD.cpp:1875-1957  the fusing loop of RunFusion (ETH version)             -> row N3
+// The loops around them that cannot be cut out (they sit inside ProcessProblem between OpenCV and file calls,
+// main.cpp:322-363) are restated here in a few lines each, citing the lines they follow.
+// cv::Mat is the stub of oracle/stubs (rows, cols, at<T>(), clone()); OpenCV itself is not installed in this image.
+// Built twice: -O2 (IEEE, one rounding per operation) and with the reference's own host flags
+// `-O3 -ffast-math -march=native` (CMakeLists.txt:31) — the two differ where a decision sits within an ulp of a threshold.
+#include "main.h"
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <unordered_map>
+
+#include "_ref/src/apd_cpp_120_346.inc"
+#include "_ref/src/apd_cpp_501_546.inc"
+#include "_ref/src/apd_cpp_1797_1806.inc"
+
+struct refhost_view {   // == dvp_fusion_view (include/dvp_mvs.h)
+	Camera camera;
+	int32_t width, height;
+	const float* depth;
+	const float* normal;
+	const uint8_t* image;
+	const uint8_t* weak;
+	const uint8_t* block;
+	int32_t num_src;
+	const int32_t* src_views;
+};
+
+extern "C" {
+
+const char* refhost_flags(void) {
+#ifdef __FAST_MATH__
+	return "-O3 -ffast-math -march=native";
+#else
+	return "-O2";
+#endif
+}
+
+// main.cpp:322-363 around the reference's Connect + Label_Update: per source view, the pixels that do not select the
+// view are labelled; labels with fewer than 20 * (8 / scale)^2 pixels (and label 0) become "visible".
+int refhost_restore_visibility(const uint32_t* selected_in, uint32_t* selected_out, int W, int H, int S, int scale_size) {
+	if (!selected_in || !selected_out || W <= 0 || H <= 0 || S < 0 || S > 32 || scale_size <= 0) return 1;
+	const size_t n = (size_t)W * H;
+	std::memset(selected_out, 0, n * sizeof(uint32_t));
+	for (int i = 0; i < S; ++i) {
+		cv::Mat vis(H, W, CV_8UC1);
+		for (int r = 0; r < H; ++r)
+			for (int c = 0; c < W; ++c) vis.at<uchar>(r, c) = ((selected_in[(size_t)r * W + c] >> i) & 1) ? 255 : 0;   // main.cpp:310-318
+		cv::Mat lab_mask(H, W, CV_32S);
+		std::vector<int> label_cnt;
+		Connect(vis, lab_mask, label_cnt);        // main.cpp:326
+		Label_Update(lab_mask, label_cnt);        // main.cpp:327
+		const int label_num = (int)label_cnt.size();
+		std::vector<char> kept(label_num, 0);     // colors[j] != black  <=>  a region large enough to stay invisible (main.cpp:332-337)
+		for (int j = 1; j < label_num; j++) kept[j] = !(label_cnt[j] < 20 * (8 / scale_size) * (8 / scale_size));
+		for (int y = 0; y < H; y++)
+			for (int x = 0; x < W; x++)
+				if (!kept[lab_mask.at<int>(y, x)]) selected_out[(size_t)y * W + x] |= 1u << i;   // main.cpp:343-349, 354-361
+	}
+	return 0;
+}
+
+// Connect + Label_Update on a 0 / 255 image, as EdgeSegment's label mode calls them (APD.cpp:437-440): labels and counts out.
+int refhost_connect_update(const uint8_t* image, int W, int H, int32_t* labels, int32_t* counts, int counts_cap, int* num_labels) {
+	if (!image || !labels || W <= 0 || H <= 0) return 1;
+	cv::Mat img(H, W, CV_8UC1), lab(H, W, CV_32S);
+	std::memcpy(img.ptr<uchar>(0), image, (size_t)W * H);
+	std::vector<int> cnt;
+	Connect(img, lab, cnt);
+	Label_Update(lab, cnt);
+	std::memcpy(labels, lab.ptr<int>(0), (size_t)W * H * 4);
+	if (num_labels) *num_labels = (int)cnt.size();
+	if (counts) for (int i = 0; i < (int)cnt.size() && i < counts_cap; ++i) counts[i] = cnt[i];
+	return 0;
+}
+
+int refhost_roberts(const uint8_t* image, int W, int H, uint8_t* out) {
+	if (!image || !out || W <= 0 || H <= 0) return 1;
+	cv::Mat img(H, W, CV_8UC1);
+	std::memcpy(img.ptr<uchar>(0), image, (size_t)W * H);
+	const cv::Mat r = Roberts(img);
+	std::memcpy(out, r.ptr<uchar>(0), (size_t)W * H);
+	return 0;
+}
+
+// RunFusion's fusing loop (APD.cpp:1875-1957) over views laid out as dvp_fusion_view; what precedes it in the
+// reference (APD.cpp:1841-1873: file reads, RescaleImageAndCamera) is the caller's business here as it is in the product.
+// points: [cap][6] floats; masks (may be NULL): concatenated per-view [h*w] masks after the loop.  Returns the number
+// of points (which may exceed cap; only the first cap are written), or -1.
+long long refhost_run_fusion(int num_views, const refhost_view* views, float* points, long long cap, uint8_t* masks_out) {
+	if (num_views <= 0 || !views) return -1;
+	const int num_images = num_views;
+	std::vector<Problem> problems(num_views);
+	std::vector<cv::Mat> images, depths, normals, masks, blocks, weaks;
+	std::vector<Camera> cameras;
+	std::unordered_map<int, int> imageIdToindexMap;
+	bool use_block = false;
+	for (int i = 0; i < num_views; ++i) use_block = use_block || views[i].block != nullptr;
+	for (int i = 0; i < num_views; ++i) {
+		const refhost_view& v = views[i];
+		problems[i].index = i; problems[i].ref_image_id = i;
+		for (int k = 0; k < v.num_src; ++k) problems[i].src_image_ids.push_back(v.src_views[k]);
+		imageIdToindexMap.emplace(i, i);
+		const size_t n = (size_t)v.width * v.height;
+		cv::Mat image(v.height, v.width, CV_8UC3), depth(v.height, v.width, CV_32FC1), normal(v.height, v.width, CV_32FC3);
+		cv::Mat mask(v.height, v.width, CV_8UC1), weak(v.height, v.width, CV_8UC1), block(v.height, v.width, CV_8UC1);
+		std::memcpy(image.ptr<uchar>(0), v.image, n * 3);
+		std::memcpy(depth.ptr<float>(0), v.depth, n * 4);
+		std::memcpy(normal.ptr<float>(0), v.normal, n * 12);
+		if (v.weak) std::memcpy(weak.ptr<uchar>(0), v.weak, n); else std::memset(weak.ptr<uchar>(0), STRONG, n);
+		if (v.block) std::memcpy(block.ptr<uchar>(0), v.block, n); else std::memset(block.ptr<uchar>(0), 255, n);
+		images.push_back(image); depths.push_back(depth); normals.push_back(normal); masks.push_back(mask); weaks.push_back(weak);
+		blocks.push_back(block); cameras.push_back(v.camera);
+	}
+	std::vector<PointList> PointCloud;
+	std::cout.setstate(std::ios_base::failbit);   // the loop announces every view on std::cout
+	{
+#include "_ref/src/apd_cpp_1875_1957.inc"
+	}
+	std::cout.clear();
+	const long long n_pts = (long long)PointCloud.size();
+	if (points)
+		for (long long k = 0; k < n_pts && k < cap; ++k) {
+			const PointList& p = PointCloud[(size_t)k];
+			float* o = points + 6 * k;
+			o[0] = p.coord.x; o[1] = p.coord.y; o[2] = p.coord.z; o[3] = p.color.x; o[4] = p.color.y; o[5] = p.color.z;
+		}
+	if (masks_out) {
+		size_t off = 0;
+		for (int i = 0; i < num_views; ++i) {
+			const size_t n = (size_t)views[i].width * views[i].height;
+			std::memcpy(masks_out + off, masks[i].ptr<uchar>(0), n);
+			off += n;
+		}
+	}
+	return n_pts;
+}
+
+}  // extern "C"

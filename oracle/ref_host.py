@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE ONLY — opens oracle/_ref/libref_host.so: HOST functions of the reference compiled from line ranges
+of its own APD.cpp (oracle/ref_host.cu, oracle/Makefile `host`): Roberts / Connect / Label_Seek / Label_Update and the
+fusing loop of RunFusion.  They pin the CPU restatements of rows N1, N3 and N4.  `fast=True` opens the build with the
+reference's own host flags (-O3 -ffast-math -march=native, CMakeLists.txt:31); it only runs on the machine it was built
+on.  Import from tests/ only."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from dvp_mvs_b200._lib import FusionView, make_fusion_view
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path(fast: bool = False) -> str:
+    return os.path.join(HERE, "_ref", "libref_host_fast.so" if fast else "libref_host.so")
+
+
+def available(fast: bool = False) -> bool:
+    return os.path.exists(lib_path(fast))
+
+
+def _lib(fast=False):
+    lib = C.CDLL(lib_path(fast))
+    lib.refhost_flags.restype = C.c_char_p
+    lib.refhost_restore_visibility.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.refhost_connect_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.refhost_roberts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.refhost_run_fusion.restype = C.c_longlong
+    lib.refhost_run_fusion.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+    return lib
+
+
+def flags(fast=False) -> str:
+    return _lib(fast).refhost_flags().decode()
+
+
+def restore_visibility(selected: np.ndarray, S: int, scale: int) -> np.ndarray:
+    sel = np.ascontiguousarray(selected, np.uint32)
+    out = np.zeros_like(sel)
+    H, W = sel.shape
+    assert _lib().refhost_restore_visibility(sel.ctypes.data, out.ctypes.data, W, H, S, scale) == 0
+    return out
+
+
+def connect_update(image: np.ndarray):
+    """Connect + Label_Update of a 0 / 255 image -> (labels [H, W] int32, counts per label)."""
+    img = np.ascontiguousarray(image, np.uint8)
+    H, W = img.shape
+    labels = np.zeros((H, W), np.int32); counts = np.zeros(H * W + 2, np.int32); n = C.c_int()
+    assert _lib().refhost_connect_update(img.ctypes.data, W, H, labels.ctypes.data, counts.ctypes.data, counts.size, C.byref(n)) == 0
+    return labels, counts[:n.value].copy()
+
+
+def roberts(image: np.ndarray) -> np.ndarray:
+    img = np.ascontiguousarray(image, np.uint8)
+    out = np.empty_like(img)
+    assert _lib().refhost_roberts(img.ctypes.data, img.shape[1], img.shape[0], out.ctypes.data) == 0
+    return out
+
+
+def run_fusion(views: list, fast: bool = False):
+    """The reference's own fusing loop over `views` (dicts as dvp_mvs_b200.Fusion takes them) -> (points [n, 6], masks)."""
+    keep = []
+    arr = (FusionView * len(views))(*[make_fusion_view(v, keep) for v in views])
+    shapes = [(fv.height, fv.width) for fv in arr]
+    cap = sum(h * w for h, w in shapes)
+    pts = np.empty((cap, 6), np.float32)
+    masks = np.zeros(cap, np.uint8)
+    n = _lib(fast).refhost_run_fusion(len(views), arr, pts.ctypes.data, cap, masks.ctypes.data)
+    assert n >= 0
+    out_masks, off = [], 0
+    for h, w in shapes:
+        out_masks.append(masks[off:off + h * w].reshape(h, w).copy()); off += h * w
+    return pts[:n].copy(), out_masks

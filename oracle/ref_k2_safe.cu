@@ -1,7 +1,7 @@
 // ref_k2_safe.cu — TEST INFRASTRUCTURE ONLY (oracle/_ref/libapd_ref_k2.so, libapd_ref_k2_O1.so).
 //
 // ptxas 12.9 miscompiles the reference kernel GenEdgeInform (APD.cu:3731) for sm_100a at every
-// optimisation level above -O0 (measured on B200, tools/dbg_k2c.py):
+// optimisation level above -O0 (measured on B200, profiles/r02_reference_k2_miscompile.md):
 //   -O3 (default) / -O2 : inside the per-source-view loop it emits `LDL.64 R0, [R1+0x3c0]` (SASS offset
 //        +0x7750), overwriting R1 — the local-memory frame base every later LDL/STL uses — with a field
 //        of the uninitialised regions[2][0]; the kernel faults with an illegal address (even for S = 1);

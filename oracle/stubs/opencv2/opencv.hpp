@@ -28,6 +28,7 @@ typedef unsigned char uchar;
 #define CV_32SC1 4
 #define CV_32FC1 5
 #define CV_32FC3 21
+#define CV_8UC3 16
 
 namespace cv {
 struct Point {
@@ -46,6 +47,11 @@ struct Vec3f {
 	float& operator[](int i) { return val[i]; }
 	const float& operator[](int i) const { return val[i]; }
 };
+struct Vec3b {   // host code compiled from reference line ranges (oracle/ref_host.cu) reads colours through it
+	unsigned char val[3];
+	unsigned char& operator[](int i) { return val[i]; }
+	const unsigned char& operator[](int i) const { return val[i]; }
+};
 // A non-owning-or-owning dense matrix: just enough for `rows`, `cols`, `ptr<T>(r)`.
 class Mat {
 public:
@@ -56,11 +62,13 @@ public:
 	Mat(int r, int c, int type) { create(r, c, type); }
 	void create(int r, int c, int type) {
 		rows = r; cols = c;
-		elem_size = (type == CV_8U) ? 1 : (type == CV_32FC3 ? 12 : 4);
+		elem_size = (type == CV_8U) ? 1 : (type == CV_8UC3 ? 3 : (type == CV_32FC3 ? 12 : 4));
 		storage.assign((size_t)r * c * elem_size, 0);
 	}
 	bool empty() const { return rows == 0 || cols == 0; }
 	template <typename T> T& at(int r, int c) { return ptr<T>(r)[c]; }
+	template <typename T> const T& at(int r, int c) const { return ptr<T>(r)[c]; }
+	Mat clone() const { return *this; }   // storage is a std::vector: copying the object is a deep copy
 	template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(storage.data() + (size_t)r * cols * elem_size); }
 	template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(storage.data() + (size_t)r * cols * elem_size); }
 };

@@ -113,3 +113,70 @@ def test_whole_pipeline_program_equals_the_python_driven_run(tmp_path):
     n = int(out.stdout.split("points")[1])
     assert n > 500, out.stdout
     assert len((tmp_path / "cpp3.ply").read_bytes().split(b"end_header\n", 1)[1]) == 15 * n
+
+
+ADAPTER_EXE = os.path.join(ROOT, "tests", "adapter", "_build", "process_problem_run")
+
+
+def _dump_for_adapter(d, W, H, S, iters, state, geom, use_apd, seed, depth_min, depth_max, inputs, use_detail=0, rotate_time=4, ransac=0.005, wpr=6):
+    import numpy as np
+    has = lambda k: int(inputs.get(k) is not None)
+    (d / "meta.txt").write_text(f"{W} {H} {S} {iters} {state} {geom} {use_apd} {seed} {depth_min!r} {depth_max!r} {has('radius')} {has('weak_info')} "
+                                f"{has('selected_views')} {has('depths')} {use_detail} {rotate_time} {ransac!r} {wpr}\n")
+    for key, name, dt in (("images", "images.f32", np.float32), ("depths", "depths.f32", np.float32), ("planes", "planes.f32", np.float32),
+                          ("selected_views", "selected.u32", np.uint32), ("weak_info", "weak.u8", np.uint8), ("edge", "edge.u8", np.uint8),
+                          ("label", "label.i32", np.int32), ("radius", "radius.i32", np.int32)):
+        if inputs.get(key) is not None:
+            (d / name).write_bytes(np.ascontiguousarray(inputs[key], dt).tobytes())
+    (d / "cameras.bin").write_bytes(np.asarray(inputs["cameras"]).tobytes())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("second_pass", [0, 1])
+def test_adapter_class_executes_process_problem_and_equals_the_engine(tmp_path, second_pass):
+    """The `APD` adapter RUN, not just compiled: tests/adapter/process_problem_run.cpp is ProcessProblem's call sequence
+    (ctor, GetDepthMin/Max, InuputInitialization, SupportInitialization, CudaSpaceInitialization, SetDataPassHelperInCuda,
+    RunPatchMatch, getters) compiled against the reference's main.h with loaders that fill the reference's host members from
+    raw arrays.  Its planes / pixel states / selected views / radius map must equal what the ctypes `Engine` leaves for the
+    same inputs, parameters and seed: bit for bit with 0 iterations (every stage deterministic), within the sweep's race
+    with 1.  second_pass: a rounds >= 1 pass (REFINE_ITER, geometric consistency, WEAK pixels, radius map)."""
+    import numpy as np
+    import subprocess as sp
+    from dvp_mvs_b200 import Engine, synth, default_params, FIRST_INIT, REFINE_ITER
+    if not os.path.exists(ADAPTER_EXE):
+        pytest.skip("tests/adapter/_build/process_problem_run not built (needs the reference headers at build time)")
+    W, H, S, seed = 320, 240, 3, 4242
+    sc = synth.make_scene(W, H, S)
+    for iters in (0, 1):
+        p = default_params(); p.max_iterations = iters; p.num_images = S + 1
+        p.depth_min, p.depth_max = sc.depth_min, sc.depth_max
+        if not second_pass:
+            p.use_APD = 1; p.state = FIRST_INIT   # the adapter passes problem.params through; with no WEAK pixel the WEAK path idles
+            inputs = dict(images=sc.images, cameras=sc.cameras, planes=sc.planes_init, edge=sc.edge, label=sc.label)
+        else:
+            p.use_APD = 1; p.state = REFINE_ITER; p.geom_consistency = 1; p.use_detail = 1; p.rotate_time = 2; p.ransac_threshold = 0.00875; p.weak_peak_radius = 4
+            weak = np.full((H, W), 1, np.uint8); weak[sc.plane_id == 3] = 0
+            rng = np.random.default_rng(3)
+            planes = sc.planes_true.copy(); planes[..., 3] *= (1 + rng.normal(0, 0.02, (H, W))).astype(np.float32)
+            inputs = dict(images=sc.images, depths=sc.depths, cameras=sc.cameras, planes=planes, selected_views=np.full((H, W), (1 << S) - 1, np.uint32),
+                          weak_info=weak, edge=sc.edge, label=sc.label, radius=np.full((H, W), 5, np.int32))
+        d = tmp_path / f"case{second_pass}_{iters}"; d.mkdir()
+        _dump_for_adapter(d, W, H, S, iters, p.state, p.geom_consistency, p.use_APD, seed, float(np.float32(sc.depth_min)), float(np.float32(sc.depth_max)), inputs,
+                          use_detail=p.use_detail, rotate_time=p.rotate_time, ransac=float(np.float32(p.ransac_threshold)), wpr=p.weak_peak_radius)
+        r = sp.run([ADAPTER_EXE, str(d)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+        got = dict(planes=np.fromfile(d / "out_planes.bin", np.float32).reshape(H, W, 4), weak=np.fromfile(d / "out_states.bin", np.uint8).reshape(H, W),
+                   selected=np.fromfile(d / "out_selected.bin", np.uint32).reshape(H, W), radius=np.fromfile(d / "out_radius.bin", np.int32).reshape(H, W))
+        e = Engine(W, H, S, p)
+        e.upload(seed=seed, **inputs)
+        e.run()
+        planes, weak, sel, rad = e.download()
+        want = dict(planes=planes, weak=weak, selected=sel, radius=rad)
+        for n in want:
+            a, b = got[n], want[n]
+            same = (a.view(np.uint32) == b.view(np.uint32)).reshape(H, W, -1).all(-1) if a.dtype == np.float32 else (a == b)
+            if iters == 0:
+                assert same.all(), (second_pass, n, int((~same).sum()))
+            else:
+                assert same.mean() > 0.9, (second_pass, n, float(same.mean()))     # the strong sweep's race (two runs of either differ as much)
+        e.close()

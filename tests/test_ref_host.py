@@ -1,0 +1,111 @@
+"""The CPU restatements of the callers' rows pinned to the reference ITSELF: oracle/ref_host.cu compiles line ranges cut
+out of /root/reference/APD.cpp at build time (Roberts / Connect / Label_Seek / Label_Update, APD.cpp:120-346; the geometry
+helpers and the fusing loop of RunFusion, APD.cpp:501-546, 1797-1806, 1875-1957) against the stub cv::Mat.  What is
+compared with them here is what the GPU paths are compared with in tests/test_visibility.py, test_fusion.py and
+test_labels.py, so device parity for rows N1, N3 and N4 now rests on compiled reference code, not on hand-computed cases."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from util import ROOT
+import ref_host
+from fusion_oracle import FusionOracle
+from dvp_mvs_b200 import synth
+from test_visibility import oracle as visibility_restatement, random_masks, blobs
+
+pytestmark = pytest.mark.skipif(not ref_host.available(), reason="oracle/_ref/libref_host.so not built (needs /root/reference at build time)")
+CPU = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libapd_cpu.so"))
+CPU.label_cpu_roberts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+CPU.label_cpu_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+
+
+def test_built_from_the_reference_with_plain_flags():
+    assert ref_host.flags() == "-O2"
+
+
+def test_visibility_restatement_equals_the_reference_functions():
+    """Row N1: Connect + Label_Update + the small-region rule (main.cpp:322-363) — restatement vs the reference's own
+    functions on random masks of every density and on structured ones that reach the last row / column."""
+    rng = np.random.default_rng(11)
+    for trial in range(1500):
+        H, W = int(rng.integers(2, 28)), int(rng.integers(2, 28))
+        S = int(rng.integers(1, 4))
+        sel = random_masks(rng, H, W, S, rng.choice([0.05, 0.1, 0.25, 0.4, 0.55, 0.7, 0.9]))
+        scale = int(rng.choice([8, 8, 4]))
+        assert (visibility_restatement(sel, S, scale, 0) == ref_host.restore_visibility(sel, S, scale)).all(), (trial, H, W)
+    for trial in range(150):
+        H, W = int(rng.integers(8, 48)), int(rng.integers(8, 48))
+        sel = blobs(rng, H, W, 2, int(rng.integers(1, 8)), 9)
+        sel[-1, ::2] &= ~np.uint32(1); sel[::3, -1] &= ~np.uint32(2); sel[-2, :] &= ~np.uint32(rng.integers(0, 4))
+        assert (visibility_restatement(sel, 2, 8, 0) == ref_host.restore_visibility(sel, 2, 8)).all(), trial
+    # and a map of realistic size and shape: holes in otherwise visible views (Label_Seek is quadratic in the label count)
+    sel = blobs(rng, 120, 160, 3, 25, 7)
+    assert (visibility_restatement(sel, 3, 8, 0) == ref_host.restore_visibility(sel, 3, 8)).all()
+
+
+def test_roberts_and_labelling_restatements_equal_the_reference_functions():
+    """Row N4, label half: Roberts (APD.cpp:120-136) and Connect + Label_Update (APD.cpp:195-346) as EdgeSegment(mode 1)
+    uses them — same label NUMBERS and counts, not merely the same partition."""
+    rng = np.random.default_rng(5)
+    for trial in range(200):
+        H, W = int(rng.integers(3, 40)), int(rng.integers(3, 40))
+        img = rng.integers(0, 256, (H, W)).astype(np.uint8)
+        mine = np.empty_like(img)
+        CPU.label_cpu_roberts(img.ctypes.data, W, H, mine.ctypes.data)
+        assert (mine == ref_host.roberts(img)).all(), trial
+        edges = np.where(rng.random((H, W)) < rng.choice([0.1, 0.3, 0.5]), 255, 0).astype(np.uint8)
+        labels = np.empty((H, W), np.int32); counts = np.zeros(H * W + 2, np.int32)
+        n = CPU.label_cpu_connect(edges.ctypes.data, W, H, labels.ctypes.data, counts.ctypes.data, counts.size)
+        want_labels, want_counts = ref_host.connect_update(edges)
+        assert n == len(want_counts) and (labels == want_labels).all() and (counts[:n] == want_counts).all(), trial
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_fusion_restatement_equals_the_reference_loop(level):
+    """Row N3: RunFusion's fusing loop compiled from the reference (-O2) vs oracle/cpu/fusion_cpu.cpp — the same points
+    (coordinates and colours bit for bit, same order) and the same masks."""
+    mv = synth.make_multiview(640, 480, 4, 2, seed=3)
+    views = synth.make_fusion_views(mv, level)
+    o = FusionOracle(views)
+    mine = o.run()
+    want, want_masks = ref_host.run_fusion(views)
+    assert len(mine) == len(want) > 5000
+    assert (mine.view(np.uint32) == want.view(np.uint32)).all()
+    for a, b in zip(o.masks, want_masks):
+        assert (a == b).all()
+
+
+def test_fusion_restatement_on_views_of_mixed_sizes_and_blocks():
+    """Source cells shared by several pixels (views at different resolutions) and a block mask: the order-dependent part."""
+    mv = synth.make_multiview(320, 240, 3, 2, seed=9)
+    v0 = synth.make_fusion_views(mv, 0); v1 = synth.make_fusion_views(mv, 1)
+    views = [v1[0], v0[1], v1[2]]
+    blk = np.full(views[0]["depth"].shape, 255, np.uint8); blk[:, :40] = 0
+    views[0] = dict(views[0], block=blk)
+    o = FusionOracle(views)
+    mine = o.run()
+    want, want_masks = ref_host.run_fusion(views)
+    assert len(mine) == len(want) > 1000 and (mine.view(np.uint32) == want.view(np.uint32)).all()
+    assert all((a == b).all() for a, b in zip(o.masks, want_masks))
+
+
+@pytest.mark.skipif(not ref_host.available(fast=True), reason="fast-math build absent")
+def test_reference_host_flags_do_not_change_fusion_decisions_here():
+    """The reference's CMake builds APD.cpp with -O3 -ffast-math -march=native (CMakeLists.txt:31): FMA contraction and
+    reassociation move coordinates by an ulp or two and could flip a decision that sits on a threshold.  Measured on this
+    scene: how far apart the two builds of the SAME reference lines are — the bound on what 'parity' can mean for row N3."""
+    try:
+        fast_flags = ref_host.flags(fast=True)
+    except OSError:
+        pytest.skip("fast build not loadable on this host")
+    assert "ffast-math" in fast_flags
+    mv = synth.make_multiview(640, 480, 4, 2, seed=3)
+    views = synth.make_fusion_views(mv, 1)
+    a, ma = ref_host.run_fusion(views)
+    b, mb = ref_host.run_fusion(views, fast=True)
+    flipped = sum(int((x != y).sum()) for x, y in zip(ma, mb))
+    assert abs(len(a) - len(b)) <= max(2, len(a) // 10000) and flipped <= max(8, len(a) // 2500), (len(a), len(b), flipped)
+    if len(a) == len(b):
+        assert np.abs(a[:, :3] - b[:, :3]).max() < 1e-3

@@ -11,7 +11,7 @@ Files:
   c1_64x48.npz       BASELINE config C1 shrunk to 64x48: FIRST_INIT, S=2, 1 iteration, all STRONG;
                      the buffers every stage writes, in launch order (stage outputs chain into the next inputs)
   sparse_128x96.npz  K7/K8 on a sparse STRONG mask that makes the reference's racy direction-4 read
-                     harmless, so the sweep is deterministic (see tools/dbg_k7_sparse.py)
+                     harmless, so the sweep is deterministic
 """
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

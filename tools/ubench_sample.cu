@@ -96,12 +96,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 // ---- coherent shape: one NCC (36 samples) per thread per hypothesis, 32x8 adjacent pixels per block -------------
 template <int V>
 __global__ void __launch_bounds__(256, 3) k_coherent(const Args a, const __grid_constant__ CUtensorMap tmap, int reps, float* out) {
-	extern __shared__ __align__(128) unsigned char smem_raw[];
+	extern __shared__ __align__(1024) unsigned char smem_raw[];
 	constexpr int T = 256;
 	const int tid = threadIdx.y * 32 + threadIdx.x;
-	float* tiles = reinterpret_cast<float*>(smem_raw);                          // 2 x TILE_W x TILE_H (S only; first: TMA wants 128 B alignment)
-	float2* wt = reinterpret_cast<float2*>(smem_raw + (V == V_SMEM ? 2 * TILE_W * TILE_H * 4 : 0)) + tid;
-	__shared__ uint64_t bar[2];
+	// S only: [2 tiles, 128-byte aligned for TMA][2 mbarriers, padded to 128 B][(w, w r) table]
+	float* tiles = reinterpret_cast<float*>(smem_raw);
+	uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + 2 * TILE_W * TILE_H * 4);
+	float2* wt = reinterpret_cast<float2*>(smem_raw + (V == V_SMEM ? 2 * TILE_W * TILE_H * 4 + 128 : 0)) + tid;
 	const int px = 64 + blockIdx.x * 32 + threadIdx.x, py = 64 + blockIdx.y * 8 + threadIdx.y;
 	for (int k = 0; k < 36; ++k) { const float w = 1.0f / (1.0f + (k % 7)); wt[k * T] = make_float2(w, w * (float)((px + k) & 15)); }
 	const int bx0 = 64 + blockIdx.x * 32 - 5, by0 = 64 + blockIdx.y * 8 - 5;     // top-left of the block's reference footprint
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256, 3) k_coherent(const Args a, const __grid_
 		oy = min(oy, (int)floorf((H[5] + H[3] * (bx0 + 41) + H[4] * by0) / z) - 2);
 	};
 	if (V == V_SMEM) {
-		if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+		if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 		__syncthreads();
 		if (tid == 0) { int ox, oy; origin(0, ox, oy); mbar_expect_tx(&bar[0], TILE_W * TILE_H * 4); tma_load_2d(tiles, &tmap, ox, oy, &bar[0]); }
 	}
@@ -253,7 +254,9 @@ static void timed(const char* shape, const char* name, double samples, size_t n_
 	if (bad) printf("           (%zu of %zu outputs differ)\n", bad, n_out);
 }
 
-int main() {
+int main(int argc, char** argv) {
+	const char* only = argc > 1 ? argv[1] : "TQLHSX";   // which variants to run: T Q L H S (coherent), X (scattered)
+	auto want = [&](char c) { return strchr(only, c) != nullptr; };
 	const int W = 3112, H = 2073;   // TMA needs a 16-byte row pitch
 	std::vector<float> img((size_t)W * H);
 	srand(7);
@@ -281,18 +284,19 @@ int main() {
 	const size_t n_coh = (size_t)grid.x * grid.y * 256;
 	float* d_out; CK(cudaMalloc(&d_out, n_coh * 4));
 	const double samples = (double)n_coh * reps * 36;
-	const size_t sm_wt = 36 * 256 * 8, sm_tiles = 2 * TILE_W * TILE_H * 4;
+	const size_t sm_wt = 36 * 256 * 8, sm_tiles = 2 * TILE_W * TILE_H * 4 + 128;
 	CK(cudaFuncSetAttribute(k_coherent<V_TEX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_wt));
 	CK(cudaFuncSetAttribute(k_coherent<V_QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_wt));
 	CK(cudaFuncSetAttribute(k_coherent<V_LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_wt));
 	CK(cudaFuncSetAttribute(k_coherent<V_HYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_wt));
 	CK(cudaFuncSetAttribute(k_coherent<V_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm_wt + sm_tiles)));
-	printf("# tools/ubench_sample.cu on B200: NCC inner loop with five source-sample paths (Gsample/s = bilinear samples per second)\n");
-	timed("coherent", "T tex2D", samples, n_coh, d_out, [&] { k_coherent<V_TEX><<<grid, block, sm_wt>>>(a, tmap, reps, d_out); });
-	timed("coherent", "Q LDG.128 quad image + sw filter", samples, n_coh, d_out, [&] { k_coherent<V_QUAD><<<grid, block, sm_wt>>>(a, tmap, reps, d_out); });
-	timed("coherent", "L 4 x LDG.32 + sw filter", samples, n_coh, d_out, [&] { k_coherent<V_LIN><<<grid, block, sm_wt>>>(a, tmap, reps, d_out); });
-	timed("coherent", "S TMA tile in smem + 4 x LDS", samples, n_coh, d_out, [&] { k_coherent<V_SMEM><<<grid, block, sm_wt + sm_tiles>>>(a, tmap, reps, d_out); });
-	timed("coherent", "H rows alternate T / Q", samples, n_coh, d_out, [&] { k_coherent<V_HYB><<<grid, block, sm_wt>>>(a, tmap, reps, d_out); });
+	printf("# tools/ubench_sample.cu on B200 (variants %s): NCC inner loop with five source-sample paths (Gsample/s = bilinear samples per second)\n", only);
+	timed("coherent", "T tex2D", samples, n_coh, d_out, [&] { k_coherent<V_TEX><<<grid, block, sm_wt>>>(a, tmap, reps, d_out); });   // always: the checksum reference
+	if (want('Q')) timed("coherent", "Q LDG.128 quad image + sw filter", samples, n_coh, d_out, [&] { k_coherent<V_QUAD><<<grid, block, sm_wt>>>(a, tmap, reps, d_out); });
+	if (want('L')) timed("coherent", "L 4 x LDG.32 + sw filter", samples, n_coh, d_out, [&] { k_coherent<V_LIN><<<grid, block, sm_wt>>>(a, tmap, reps, d_out); });
+	if (want('H')) timed("coherent", "H rows alternate T / Q", samples, n_coh, d_out, [&] { k_coherent<V_HYB><<<grid, block, sm_wt>>>(a, tmap, reps, d_out); });
+	if (want('S')) timed("coherent", "S TMA tile in smem + 4 x LDS", samples, n_coh, d_out, [&] { k_coherent<V_SMEM><<<grid, block, sm_wt + sm_tiles>>>(a, tmap, reps, d_out); });
+	if (!want('X')) return 0;
 
 	// scattered: one anchor ring per lane and hypothesis
 	const int n_sc = 148 * 256 * 64, sreps = 64;
