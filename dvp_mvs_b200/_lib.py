@@ -68,12 +68,12 @@ ABI_SYMBOLS = ["version", "default_params", "create", "destroy", "upload", "run"
                "buffer_bytes", "get_buffer", "set_buffer", "last_run_times", "weak_count", "last_cuda_error", "stream"]
 PRODUCT_ONLY_SYMBOLS = ["upload_device", "upload_overlapped", "restore_visibility", "rescale_map", "scene_create", "scene_destroy", "scene_level_size",
                         "scene_pass_params", "scene_set_max_iterations", "scene_set_view", "scene_set_level",
-                        "scene_set_initial_planes", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats",
+                        "scene_set_initial_planes", "scene_set_image", "scene_set_label", "scene_get_image", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats",
                         "scene_run_view", "scene_depth_map", "scene_remote_depth",
                         "fusion_create", "fusion_destroy", "fusion_set_view", "fusion_set_view_planes", "scene_fuse_views", "fusion_set_mode", "fusion_reset", "fusion_run_view", "fusion_run",
                         "fusion_num_points", "fusion_get_points", "fusion_get_mask", "fusion_last_view", "fusion_last_view_index", "fusion_write_ply",
                         "edge_segment", "scene_compute_edges", "scene_get_edges",
-                        "debug_race_explain", "debug_fetch_count",
+                        "debug_race_explain", "debug_fetch_count", "resize_linear_f32",
                         "io_binmat_header", "io_read_binmat", "io_write_binmat", "io_write_dmb", "io_read_camera", "io_read_pairs"]
 
 
@@ -146,6 +146,9 @@ def load_library(path: str, prefix: str):
         f("scene_set_max_iterations").argtypes = [C.c_void_p, C.c_int]; f("scene_set_max_iterations").restype = C.c_int
         f("scene_set_view").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]; f("scene_set_view").restype = C.c_int
         f("scene_set_level").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]; f("scene_set_level").restype = C.c_int
+        f("scene_set_image").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]; f("scene_set_image").restype = C.c_int
+        f("scene_set_label").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]; f("scene_set_label").restype = C.c_int
+        f("scene_get_image").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]; f("scene_get_image").restype = C.c_int
         f("scene_set_initial_planes").argtypes = [C.c_void_p, C.c_int, C.c_void_p]; f("scene_set_initial_planes").restype = C.c_int
         f("scene_run_pass").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64]; f("scene_run_pass").restype = C.c_int
         f("scene_run").argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_float)]; f("scene_run").restype = C.c_int
@@ -172,6 +175,7 @@ def load_library(path: str, prefix: str):
         f("fusion_last_view").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]; f("fusion_last_view").restype = C.c_int
         f("fusion_write_ply").argtypes = [C.c_void_p, C.c_char_p]; f("fusion_write_ply").restype = C.c_int
         f("fusion_last_view_index").argtypes = [C.c_void_p]; f("fusion_last_view_index").restype = C.c_int
+        f("resize_linear_f32").argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]; f("resize_linear_f32").restype = C.c_int
         f("debug_race_explain").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p]
         f("debug_race_explain").restype = C.c_int
         f("debug_fetch_count").argtypes = [C.c_void_p, C.c_int]; f("debug_fetch_count").restype = C.c_longlong
@@ -405,6 +409,23 @@ class Scene:
         img = _carr(image, np.float32, (h, w)); e = _carr(edge, np.uint8, (h, w)); l = _carr(label, np.int32, (h, w))
         self._check(self.lib.dvp_scene_set_level(self.h, view, level, _ptr(img), _ptr(e), _ptr(l)), "set_level")
 
+    def set_image(self, view: int, image_u8: np.ndarray, compute_edges: bool = True):
+        """The whole pyramid of one view from its full-resolution 8-bit grey image (dvp_scene_set_image)."""
+        W, H = self._sizes[view]
+        img = _carr(image_u8, np.uint8, (H, W))
+        self._check(self.lib.dvp_scene_set_image(self.h, view, _ptr(img), 1 if compute_edges else 0), "set_image")
+
+    def set_label(self, view: int, level: int, label):
+        w, h = self.view_level_size(view, level)
+        lab = _carr(label, np.int32, (h, w))
+        self._check(self.lib.dvp_scene_set_label(self.h, view, level, _ptr(lab)), "set_label")
+
+    def get_image(self, view: int, level: int) -> np.ndarray:
+        w, h = self.view_level_size(view, level)
+        out = np.empty((h, w), np.float32)
+        self._check(self.lib.dvp_scene_get_image(self.h, view, level, _ptr(out)), "get_image")
+        return out
+
     def compute_edges(self, view: int, level: int) -> np.ndarray:
         """Row N4: the level's edge map computed on the device from the level image (it becomes the level's edge input)."""
         self._check(self.lib.dvp_scene_compute_edges(self.h, view, level), "compute_edges")
@@ -461,6 +482,19 @@ class Scene:
         sel = np.empty((H, W), np.uint32); rad = np.empty((H, W), np.int32)
         self._check(self.lib.dvp_scene_get_view(self.h, view, C.byref(w), C.byref(h), _ptr(planes), _ptr(weak), _ptr(sel), _ptr(rad)), "get_view")
         return planes, weak, sel, rad
+
+
+def resize_linear_f32(image: np.ndarray, dst_w: int, dst_h: int, device: int = 0) -> np.ndarray:
+    """cv::resize(image, Size(dst_w, dst_h), INTER_LINEAR) of a float grey image on the device (dvp_resize_linear_f32): the
+    pyramid level InuputInitialization / GetProblemEdges build (reference APD.cpp:1119-1140, main.cpp:203-209)."""
+    lib = load_library(PRODUCT_LIB, "dvp_")
+    img = np.ascontiguousarray(image, np.float32)
+    H, W = img.shape
+    out = np.empty((dst_h, dst_w), np.float32)
+    rc = lib.dvp_resize_linear_f32(device, _ptr(img), W, H, _ptr(out), dst_w, dst_h)
+    if rc != 0:
+        raise DvpError(f"dvp_resize_linear_f32 -> {STATUS.get(rc, rc)}")
+    return out
 
 
 def edge_segment(image: np.ndarray, device: int = 0):

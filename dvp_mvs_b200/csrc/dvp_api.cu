@@ -723,6 +723,21 @@ int dvp_debug_race_explain(dvp_ctx* ctx, int iter, int red, const int32_t* offse
 				++launches;
 			}
 		}
+		// and the scoring read repeated per source view (the reference's compiler may reload the plane inside the loop over the
+		// views instead of keeping the by-value copy in registers): some views see it before, the others after the update
+		if (ctx->S <= 8) {
+			for (int k = 0; k < num_offsets; ++k) {
+				f.m = offsets[k];
+				for (unsigned views = 1; views + 1 < (1u << ctx->S); ++views)
+					for (unsigned v = 0; v < 4; ++v) {
+						f.ncc_mask = 0; f.ncc_mask2 = 15u; f.ncc_views = views; f.dep_mask = (v & 1) ? 15u : 0u; f.acc_mask = (v & 2) ? 15u : 0u;
+						CK(launch_strong_sweep_forced(a, iter, red ? 1 : 0, f, st));
+						CK(launch_explain_compare(a, red ? 1 : 0, f, e, b.expl, st));
+						++launches;
+					}
+			}
+			f.ncc_views = 0; f.ncc_mask2 = 0;
+		}
 		f.pixel_list = nullptr; f.list_count = 0;
 		CK(cudaMemsetAsync(b.count, 0, 4, st));
 		CK(launch_explain_collect(a, red ? 1 : 0, b.expl, b.list, b.count, list_cap, st));

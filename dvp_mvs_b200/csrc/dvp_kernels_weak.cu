@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_cons
 	bool has_valid_plane = false;
 	short2 valid_pts[kMaxPts];
 	float3 valid_3d[kMaxPts];
+	float2 valid_factor[kMaxPts];   // ((x - cx) / fx, (y - cy) / fy) of every anchor: the reference recomputes them for each anchor in each of its 200 RANSAC tries
 	int valid_count = 0;
 	float X[3];
 	get_3d_point(a.ref, px, py, a.planes[center].w, X);
@@ -335,6 +336,7 @@ __global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_cons
 			valid_pts[valid_count] = sp;
 			get_3d_point(a.ref, sp.x, sp.y, a.planes[spc].w, X);
 			valid_3d[valid_count] = make_float3(X[0], X[1], X[2]);
+			valid_factor[valid_count] = make_float2((sp.x - a.ref.K[2]) / a.ref.K[0], (sp.y - a.ref.K[5]) / a.ref.K[4]);
 			valid_count++;
 		}
 	}
@@ -395,15 +397,11 @@ __global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_cons
 			if (a.prm.use_label && my_label > 0 && dn < 0.9f && dn < 0.9f && dn < 0.9f) is_strong_plane = false;
 			if (has_strong_plane && !is_strong_plane) continue;
 			int temp_count = 0;
-			float strong_dist = 0.0f;
 			for (int si = 0; si < valid_count; ++si) {
-				const float3 tp = valid_3d[si];
-				const short2 tpos = valid_pts[si];
-				const float factor_x = (tpos.x - a.ref.K[2]) / a.ref.K[0];
-				const float factor_y = (tpos.y - a.ref.K[5]) / a.ref.K[4];
+				const float factor_x = valid_factor[si].x, factor_y = valid_factor[si].y;
 				const float fit_depth = -cross_vec.w / (cross_vec.x * factor_x + cross_vec.y * factor_y + cross_vec.z);
-				const float distance = fabs(fit_depth - tp.z);
-				if (distance / depth_diff < ransac_threshold) { temp_count++; strong_dist += distance; }
+				const float distance = fabs(fit_depth - valid_3d[si].z);
+				if (distance / depth_diff < ransac_threshold) temp_count++;   // (the reference also sums the distances; the sum is never read)
 			}
 			if (temp_count < 6) continue;
 			if (temp_count > max_count || (!has_strong_plane && is_strong_plane)) {
@@ -430,12 +428,9 @@ __global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_cons
 
 	float weight[kMaxPts];
 	for (int i = 0; i < valid_count; ++i) {
-		const float3 tp = valid_3d[i];
-		const short2 tpos = valid_pts[i];
-		const float factor_x = (tpos.x - a.ref.K[2]) / a.ref.K[0];
-		const float factor_y = (tpos.y - a.ref.K[5]) / a.ref.K[4];
+		const float factor_x = valid_factor[i].x, factor_y = valid_factor[i].y;
 		const float fit_depth = -best_plane.w / (best_plane.x * factor_x + best_plane.y * factor_y + best_plane.z);
-		const float distance = fabs(fit_depth - tp.z);
+		const float distance = fabs(fit_depth - valid_3d[i].z);
 		if (distance / depth_diff >= ransac_threshold) { valid_pts[i] = make_short2(-1, -1); weight[i] = FLT_MAX; continue; }
 		weight[i] = distance;
 	}
@@ -576,7 +571,7 @@ __device__ __forceinline__ float weak_weighted_cost(const KArgs& a, int px, int 
 			const float c = ncc_new(a, px, py, j, pl);
 			if (a.prm.geom_consistency) temp_cost += wv * (c + a.prm.geom_factor * geom_cost(a, a.views[j], a.tex_depth[j + 1], px, py, pl));
 			else temp_cost += wv * c;
-#ifndef DVP_NO_EARLY_REJECT
+#ifdef DVP_EARLY_REJECT   // measured on B200: 7 % slower (see weighted_cost); off
 			if (can_reject && !(temp_cost / weight_norm < reject_at)) break;
 #endif
 		}

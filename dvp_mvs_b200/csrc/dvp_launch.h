@@ -57,6 +57,7 @@ struct D4Force {
 	int m = 0;                                               // ladder offset of direction 4's candidate: pixel (x - 5 - m, y - 5 - m)
 	const float4* before = nullptr; const float4* after = nullptr;   // the candidate's plane before / after its own update
 	unsigned ncc_mask = 0, dep_mask = 0, acc_mask = 0;       // bit c: component c of the plane comes from `after` (scoring read, depth-test read, copy)
+	unsigned ncc_views = 0, ncc_mask2 = 0;                   // source views whose bit is set in ncc_views score with ncc_mask2 instead (the plane re-read per view)
 	const int* pixel_list = nullptr; int list_count = 0;     // null: the whole half grid of the colour
 	float4* out_planes = nullptr; float* out_costs = nullptr; uint32_t* out_selected = nullptr; uint8_t* out_view_weight = nullptr; uint32_t* out_rng = nullptr;
 };
@@ -92,6 +93,10 @@ size_t edge_scratch_bytes(int W, int H);
 cudaError_t launch_edge_segment(const uint8_t* d_img, int W, int H, uint8_t* d_edge, void* scratch, int** d_thr, cudaStream_t st);
 cudaError_t launch_edge_to_u8(const float* d_img, int n, uint8_t* d_out, cudaStream_t st);
 cudaError_t launch_restore_visibility(const KArgs& a, int scale_size, int* parent, int* count, cudaStream_t st);
+
+// image preparation (dvp_kernels_image.cu): cv::resize(INTER_LINEAR) of float images, 8-bit -> float
+cudaError_t launch_resize_linear_f32(const float* src, int sw, int sh, float* dst, int dw, int dh, cudaStream_t st);
+cudaError_t launch_u8_to_f32(const uint8_t* src, size_t n, float* dst, cudaStream_t st);
 
 // canonical RNG exchange format <-> SoA planes
 cudaError_t launch_rng_export(const KArgs& a, uint32_t* dst_aos, cudaStream_t st);

@@ -145,7 +145,7 @@ __device__ __forceinline__ float weighted_cost(const KArgs& a, int px, int py, c
 		if (wv > 0) {
 			const float c = ncc_cost<kSweepRB, kSweepRW>(a, a.views[v], a.tex_img[v + 1], px, py, pl, rp, wt, stride);
 			acc += wv * c;
-#ifndef DVP_NO_EARLY_REJECT
+#ifdef DVP_EARLY_REJECT   // measured on B200: 10 % SLOWER than evaluating every view (the data-dependent loop exit breaks the fetch batching); off
 			if (!(acc / weight_norm < reject_at)) break;
 #endif
 		}

@@ -105,24 +105,33 @@ def step_compare(ref: Engine, prod: Engine, max_iterations: int, stages=None, ma
     return results
 
 
-def lockstep_compare(ref: Engine, prod: Engine, max_iterations: int, racy=(), resync_extra=(), stages=None, log=None):
+def lockstep_compare(ref: Engine, prod: Engine, max_iterations: int, racy=(), resync_extra=(), stages=None, log=None, before_stage=None, keep=None):
     """Same protocol as step_compare for large images: both engines start from the same upload and advance together;
     after each stage only the buffers that stage WRITES are read back (the rest of the state is identical by induction),
     compared, and — where they differ at all — overwritten in `prod` with the reference's, so a stage is always judged
     from the reference's pre-stage state.  `racy`: stages whose differences are expected (they are re-synchronised like
     any other).  `resync_extra`: {stage: (buffers,)} copied from ref to prod after a stage although they are not
-    compared (K2's `candidate`, which holds uninitialised data in the reference where no pixel sees a view, B17)."""
+    compared (K2's `candidate`, which holds uninitialised data in the reference where no pixel sees a view, B17).
+    `before_stage(stage, it)` is called ahead of every launch; `keep[(stage, it)]` (a dict) receives both engines' outputs
+    of that launch under "_ref_out" / "_prod_out"."""
     results = []
     have_weak = ref.weak_count() > 0
     for stage, it in sequence(max_iterations):
         if stages is not None and stage not in stages:
             continue
+        if before_stage:
+            before_stage(stage, it)
         ref.run_stage(stage, it)
         prod.run_stage(stage, it)
+        kept = keep.get((stage, it)) if keep else None       # caller wants both engines' outputs of this launch
+        if kept is not None:
+            kept["_ref_out"], kept["_prod_out"], kept["_rest"] = {}, {}, None
         for n in STAGE_OUTPUTS[stage]:
             if n in WEAK_BUFS and not have_weak:
                 continue
             a, b = ref.get(n), prod.get(n)
+            if kept is not None:
+                kept["_ref_out"][n], kept["_prod_out"][n] = a, b
             r = compare(n, a, b)
             r.update(stage=stage, iter=it, racy=stage in racy)
             results.append(r)
@@ -130,7 +139,6 @@ def lockstep_compare(ref: Engine, prod: Engine, max_iterations: int, racy=(), re
                 log(f"{stage}[{it}] {n:12s} mismatched {r['mismatched']:8d}/{r['pixels']} ({100*r['frac']:.4f}%) not-bit-exact {r['not_bit_exact']}")
             if r["not_bit_exact"]:
                 prod.set(n, a)
-            del a, b
         for n in dict(resync_extra).get(stage, ()):
             prod.set(n, ref.get(n))
     return results

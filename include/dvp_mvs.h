@@ -231,6 +231,14 @@ int dvp_scene_set_max_iterations(dvp_scene* scene, int iterations);
 int dvp_scene_set_view(dvp_scene* scene, int view, const dvp_camera* cam_full, int full_w, int full_h, int num_src, const int* src_views);
 /* Per-level data of one view, host or device pointers: image [h][w] f32 (required), edge u8 / label i32 (or NULL). */
 int dvp_scene_set_level(dvp_scene* scene, int view, int level, const float* image, const uint8_t* edge, const int32_t* label);
+/* Row N2, image pyramid: every level image of one view from its full-resolution grey image [full_h][full_w] u8 (what
+ * cv::imread(.., IMREAD_GRAYSCALE) returns; host or device), exactly as InuputInitialization builds them — convertTo(CV_32FC1),
+ * then cv::resize of the FULL image to each level's size (APD.cpp:1057-1060, 1119-1132; dvp_resize_linear_f32).  With
+ * compute_edges != 0 each level's edge map follows (dvp_scene_compute_edges).  Replaces the image argument of
+ * dvp_scene_set_level; labels are then given with dvp_scene_set_label (NULL = none). */
+int dvp_scene_set_image(dvp_scene* scene, int view, const uint8_t* image, int compute_edges);
+int dvp_scene_set_label(dvp_scene* scene, int view, int level, const int32_t* label);
+int dvp_scene_get_image(dvp_scene* scene, int view, int level, float* image);
 /* FIRST_INIT prior of one view at level 0: [h0][w0][4] (world normal, depth), APD.cpp:1410-1420. */
 int dvp_scene_set_initial_planes(dvp_scene* scene, int view, const float* planes);
 /* One pass over every view (one inner loop of main.cpp:452-511); view v runs with seed + v. */
@@ -333,6 +341,13 @@ int dvp_edge_segment(int device, const uint8_t* image, int width, int height, ui
 int dvp_scene_compute_edges(dvp_scene* scene, int view, int level);
 int dvp_scene_get_edges(dvp_scene* scene, int view, int level, uint8_t* edge);
 
+/* ---- Row N2, image pyramid: the level image every pass of a view reads --------------------------------------------------
+ * Replaces cv::resize(image, scaled, Size(new_cols, new_rows), 0, 0, INTER_LINEAR) of the float grey image in
+ * InuputInitialization (APD.cpp:1119-1140) and GetProblemEdges (main.cpp:203-209).  cv::resize is OpenCV's; what is
+ * reproduced is its generic bilinear path for CV_32F, bit-exact with OpenCV 4.13 when its IPP back end is off (an
+ * IPP-enabled build differs by up to 0.015 grey levels).  src [src_h][src_w], dst [dst_h][dst_w], host or device. */
+int dvp_resize_linear_f32(int device, const float* src, int src_w, int src_h, float* dst, int dst_w, int dst_h);
+
 /* ---- Row N4, second half: the reference's on-disk exchange formats (host code, no GPU) ------------------------------
  * .bin / .dmb files of WriteBinMat / ReadBinMat (APD.cpp:548-573, 630-648): int32 version = 1, rows, cols, OpenCV type
  * code (CV_8U 0, CV_32S 4, CV_32F 5, CV_32FC3 21, ...), then rows * cols * elemSize bytes.  DVP_ERR_STATE: cannot open /
@@ -360,8 +375,9 @@ int dvp_io_read_pairs(const char* path, int32_t max_views, int32_t* num_views, i
  * dvp_debug_race_explain answers, for an OBSERVED result of K7 (red = 0) / K8 (red = 1) launched from the state this
  * context currently holds: which pixels are reproduced, in all five output buffers bit for bit, by the production
  * arithmetic under SOME such choice?  Phase 1 tries every offset in `offsets` with each read entirely before / after
- * (8 combinations) on the whole image; with `tear` != 0 phase 2 tries the remaining 4088 component mixtures per offset
- * on the pixels phase 1 left over.  The state is not modified (results go to shadow buffers).
+ * (8 combinations) on the whole image; with `tear` != 0 phase 2 tries, on the pixels phase 1 left over, the remaining 4088
+ * component mixtures per offset and the scoring read repeated per source view (some views before, the others after).
+ * The state is not modified (results go to shadow buffers).
  * planes_before / planes_after: [H][W][4] plane maps before the launch and after it (the observed result's);
  * exp_*: the observed result — planes [H][W][4], costs [H][W], selected [H][W], view_weight [H][W][32], rand [H][W][6];
  * explained: [H][W] out, 1 = reproduced (pixels the launch does not process: 1 iff unchanged);

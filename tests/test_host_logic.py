@@ -118,3 +118,58 @@ def test_closed_form_of_the_reference_edge_walk():
         for ddy in range(-36, 37):
             for max_step in (1, 2, 5, 16, 200):
                 assert walk_ref(3, -2, 3 + ddx, -2 + ddy, max_step) == walk_closed(3, -2, 3 + ddx, -2 + ddy, max_step), (ddx, ddy, max_step)
+
+
+def test_closed_form_edge_walk_large_offsets_and_float_reciprocal_division():
+    """bresenham_crosses_edge (dvp_weak.cuh) evaluates the closed form with a float-reciprocal division corrected by one
+    exact integer remainder; same check as above on long walks (up to 700 pixels, step limits up to 512), with the division
+    done the device's way in float32."""
+    import numpy as np
+    rng = np.random.default_rng(12)
+
+    def walk_ref(x0, y0, x1, y1, max_step):
+        dx, sx = abs(x1 - x0), (1 if x0 < x1 else -1)
+        dy, sy = abs(y1 - y0), (1 if y0 < y1 else -1)
+        erro = (dx if dx > dy else dy) // 2
+        step, tagx, tagy, out = 0, True, True, []
+        while tagx or tagy:
+            if x0 == x1: tagx = False
+            if y0 == y1: tagy = False
+            e2 = erro
+            if e2 > -dx: erro -= dy; x0 += sx
+            if e2 < dy: erro += dx; y0 += sy
+            out.append((x0, y0)); step += 1
+            if step >= max_step: break
+        return out
+
+    def walk_device(x0, y0, x1, y1, max_step):
+        dx, sx = abs(x1 - x0), (1 if x0 < x1 else -1)
+        dy, sy = abs(y1 - y0), (1 if y0 < y1 else -1)
+        M = max(dx, dy); mn = min(dx, dy); e0 = M // 2
+        n_total = min(M + 1, max_step)
+        xmaj, diag = dx > dy, dx == dy
+        c = M - 1 - e0 if xmaj else e0 - 1 + M
+        rcp = np.float32(1.0) / np.float32(M)
+        out = []
+        for k in range(1, n_total + 1):
+            if diag:
+                mi = k
+            else:
+                n = k * mn + c
+                q = int(np.float32(n) * rcp)            # truncation, as the cast does
+                r = n - q * M
+                q += (1 if r >= M else 0) - (1 if r < 0 else 0)
+                assert 0 <= n - q * M < M               # the corrected quotient is exact
+                mi = q if xmaj else min(k, q)
+            out.append((x0 + sx * mi, y0 + sy * k) if dy > dx else (x0 + sx * k, y0 + sy * mi))
+        return out
+
+    for _ in range(1500):
+        ddx, ddy = int(rng.integers(-700, 701)), int(rng.integers(-700, 701))
+        if ddx == 0 and ddy == 0:
+            continue
+        max_step = int(rng.choice([13, 21, 103, 207, 512]))
+        assert walk_ref(5, 7, 5 + ddx, 7 + ddy, max_step) == walk_device(5, 7, 5 + ddx, 7 + ddy, max_step), (ddx, ddy, max_step)
+    for ddx, ddy in ((600, 599), (599, 600), (600, 600), (600, 1), (1, 600), (600, 0), (0, -600), (-333, 332), (64, -63)):
+        for max_step in (13, 207, 512):
+            assert walk_ref(0, 0, ddx, ddy, max_step) == walk_device(0, 0, ddx, ddy, max_step), (ddx, ddy, max_step)
