@@ -305,7 +305,9 @@ def main():
 
     if args.impl == "reference":
         import ref_oracle
-        os.environ.setdefault("DVP_REF_K2_LIB", "libapd_ref_k2_O1.so")  # K2 at a realistic optimisation level (oracle/ref_k2_safe.cu)
+        # K2 GenEdgeInform from the build whose SASS the DRIVER's JIT generates from the same PTX: correct on every ray and at
+        # full speed, where ptxas 12.9's own -O3 / -O2 code faults and its -O1 code is wrong (profiles/r02_reference_k2_miscompile.md)
+        os.environ.setdefault("DVP_REF_K2_LIB", "libapd_ref_k2_jit.so")
         if not ref_oracle.available():
             if rank == 0:
                 print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libapd_ref.so was not built (needs /root/reference at build time)"}))
@@ -341,8 +343,8 @@ def main():
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                "notes": "the reference's own APD.cu kernels (unmodified, sm_100a, its build flags) in its own launch order with a "
                         "cudaDeviceSynchronize after each, one view per GPU; time = sum of CUDA-event times of its 11 + 5*iters launches; "
-                        "K2 GenEdgeInform comes from the -Xptxas -O1 build of the same source because the -O3 build faults on sm_100a "
-                        "(profiles/r02_reference_k2_miscompile.md); e2e repeats value: uploads and the 25 B/pixel the real "
+                        "K2 GenEdgeInform runs from the same source and flags compiled to PTX and finished by the driver's JIT (ptxas 12.9's own "
+                        "-O3 SASS of that kernel faults on sm_100a, profiles/r02_reference_k2_miscompile.md); e2e repeats value: uploads and the 25 B/pixel the real "
                         "RunPatchMatch copies back (APD.cu:4525-4530) are left OUT of this arm's time, which favours the reference",
                "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": 0, "kind": "reference",
                                 "sample": "the reference has no CPU path: this arm is its own CUDA kernels (APD.cu unmodified, sm_100a) on the same B200(s)"},
@@ -482,8 +484,9 @@ def main():
                                       "per_stage_ratio": {k: round(sum(rp[i] for i in ix) / max(sum(per_stage[i] for i in ix), 1e-9), 2)
                                                           for k, ix in groups.items() if sum(per_stage[i] for i in ix) > 0},
                                       "note": "reference stage times of the --impl reference run that preceded this one on the same box; "
-                                              "K2 + K3 are excluded in ratio_excl_k2_k3 because the reference's K2 is timed from its -O1 build and "
-                                              "its K3 ring search is near its worst case inside the solid WEAK wall"}
+                                              "ratio_excl_k2_k3 leaves out the two stages whose reference time depends least on the kernels themselves: "
+                                              "K2 runs from a JIT-finished build (ptxas 12.9 miscompiles it) and K3's ring search is near its worst case "
+                                              "inside the solid WEAK wall of this synthetic scene"}
     except Exception:
         pass
     if args.extras and world == 1:

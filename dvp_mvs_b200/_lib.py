@@ -73,7 +73,7 @@ PRODUCT_ONLY_SYMBOLS = ["upload_device", "upload_overlapped", "restore_visibilit
                         "fusion_create", "fusion_destroy", "fusion_set_view", "fusion_set_view_planes", "scene_fuse_views", "fusion_set_mode", "fusion_reset", "fusion_run_view", "fusion_run",
                         "fusion_num_points", "fusion_get_points", "fusion_get_mask", "fusion_last_view", "fusion_last_view_index", "fusion_write_ply",
                         "edge_segment", "scene_compute_edges", "scene_get_edges",
-                        "debug_race_explain", "debug_fetch_count", "resize_linear_f32",
+                        "debug_race_explain", "debug_fetch_count", "resize_linear_f32", "label_size", "label_segment",
                         "io_binmat_header", "io_read_binmat", "io_write_binmat", "io_write_dmb", "io_read_camera", "io_read_pairs"]
 
 
@@ -175,6 +175,8 @@ def load_library(path: str, prefix: str):
         f("fusion_last_view").argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]; f("fusion_last_view").restype = C.c_int
         f("fusion_write_ply").argtypes = [C.c_void_p, C.c_char_p]; f("fusion_write_ply").restype = C.c_int
         f("fusion_last_view_index").argtypes = [C.c_void_p]; f("fusion_last_view_index").restype = C.c_int
+        f("label_size").argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]; f("label_size").restype = C.c_int
+        f("label_segment").argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]; f("label_segment").restype = C.c_int
         f("resize_linear_f32").argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]; f("resize_linear_f32").restype = C.c_int
         f("debug_race_explain").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p]
         f("debug_race_explain").restype = C.c_int
@@ -495,6 +497,25 @@ def resize_linear_f32(image: np.ndarray, dst_w: int, dst_h: int, device: int = 0
     if rc != 0:
         raise DvpError(f"dvp_resize_linear_f32 -> {STATUS.get(rc, rc)}")
     return out
+
+
+def label_segment(image: np.ndarray, scale: int, device: int = 0):
+    """EdgeSegment(scale, image, 1) on the device (dvp_label_segment): -> (labels [new_rows, new_cols] int32, the quarter-size
+    edge image after the Hough lines, device time in ms)."""
+    lib = load_library(PRODUCT_LIB, "dvp_")
+    img = np.ascontiguousarray(image, np.uint8)
+    H, W = img.shape
+    nc, nr = C.c_int(), C.c_int()
+    rc = lib.dvp_label_size(W, H, int(scale), C.byref(nc), C.byref(nr))
+    if rc != 0:
+        raise DvpError(f"dvp_label_size -> {STATUS.get(rc, rc)}")
+    labels = np.empty((nr.value, nc.value), np.int32)
+    small = np.empty(((H // 2) // 2, (W // 2) // 2), np.uint8)
+    ms = C.c_float()
+    rc = lib.dvp_label_segment(device, _ptr(img), W, H, int(scale), _ptr(labels), _ptr(small), C.byref(ms))
+    if rc != 0:
+        raise DvpError(f"dvp_label_segment -> {STATUS.get(rc, rc)}")
+    return labels, small, float(ms.value)
 
 
 def edge_segment(image: np.ndarray, device: int = 0):

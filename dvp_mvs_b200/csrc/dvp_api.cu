@@ -56,8 +56,8 @@ struct dvp_ctx {
 	uint8_t* view_weight = nullptr;
 	uint32_t* rng = nullptr;
 	uint8_t* edge = nullptr;
-	uint8_t* edge_blocks = nullptr;   // 8x8 block occupancy of `edge` and its 3x3 dilation (edge walks of K4 / K9)
-	uint8_t* edge_coarse = nullptr;
+	int* edge_sat = nullptr;          // summed-area table of `edge` and the chessboard distance map built from it (edge walks of K4 / K9)
+	uint8_t* edge_dist = nullptr;
 	short2* edge_neigh = nullptr;
 	int32_t* label = nullptr;
 	short2* candidate = nullptr;
@@ -119,7 +119,7 @@ KArgs make_args(const dvp_ctx* c) {
 	a.nearest_strong = c->nearest_strong; a.weak_reliable = c->weak_reliable; a.neighbours_map = c->neighbours_map;
 	a.neighbours = c->neighbours; a.label_boundary = c->label_boundary; a.complex_ = c->complex_;
 	a.scratch = nullptr; a.weak_count = c->weak_count; a.fetch_counter = c->fetch_counter;
-	a.edge_coarse = c->edge_coarse; a.coarse_w = (c->W + 7) / 8; a.coarse_h = (c->H + 7) / 8;
+	a.edge_dist = c->edge_dist;
 	return a;
 }
 
@@ -287,7 +287,7 @@ int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bo
 	if (in->selected_views) CK(cudaMemcpyAsync(ctx->selected, in->selected_views, N * 4, kind, st));
 	else CK(cudaMemsetAsync(ctx->selected, 0, N * 4, st));
 	if (in->edge) CK(cudaMemcpyAsync(ctx->edge, in->edge, N, kind, st)); else CK(cudaMemsetAsync(ctx->edge, 0, N, st));
-	CK(launch_edge_coarse(ctx->edge, ctx->W, ctx->H, ctx->edge_blocks, ctx->edge_coarse, st));
+	CK(launch_edge_distance(ctx->edge, ctx->W, ctx->H, ctx->edge_sat, ctx->edge_dist, st));
 	if (in->label) CK(cudaMemcpyAsync(ctx->label, in->label, N * 4, kind, st)); else CK(cudaMemsetAsync(ctx->label, 0, N * 4, st));
 
 	// pixel states, neighbours map, WEAK list, radius (APD.cpp:1169-1204, 1647-1667) — all on the device: the
@@ -420,8 +420,8 @@ dvp_ctx* dvp_create(int device, int width, int height, int num_src, const dvp_pa
 	ok = ok && zalloc(&c->view_weight, N * DVP_MAX_IMAGES) == cudaSuccess;
 	ok = ok && zalloc(&c->rng, N * 6) == cudaSuccess;
 	ok = ok && zalloc(&c->edge, N) == cudaSuccess;
-	ok = ok && zalloc(&c->edge_blocks, (size_t)((width + 7) / 8) * ((height + 7) / 8)) == cudaSuccess;
-	ok = ok && zalloc(&c->edge_coarse, (size_t)((width + 7) / 8) * ((height + 7) / 8)) == cudaSuccess;
+	ok = ok && zalloc(&c->edge_sat, (size_t)(width + 1) * (height + 1)) == cudaSuccess;
+	ok = ok && zalloc(&c->edge_dist, N) == cudaSuccess;
 	ok = ok && zalloc(&c->edge_neigh, N * DVP_EDGE_NEIGH_NUM) == cudaSuccess;
 	ok = ok && zalloc(&c->label, N) == cudaSuccess;
 	const int cand_views = num_src > DVP_NUM_IMAGES ? num_src : DVP_NUM_IMAGES;
@@ -463,7 +463,7 @@ void dvp_destroy(dvp_ctx* c) {
 	}
 	cudaFree(c->d_img_tex); cudaFree(c->d_dep_tex); cudaFree(c->ref_img); cudaFree(c->cams); cudaFree(c->views);
 	cudaFree(c->planes); cudaFree(c->fit_planes); cudaFree(c->costs); cudaFree(c->selected_alloc); cudaFree(c->weak);
-	cudaFree(c->radius); cudaFree(c->view_weight); cudaFree(c->rng); cudaFree(c->edge); cudaFree(c->edge_blocks); cudaFree(c->edge_coarse); cudaFree(c->edge_neigh);
+	cudaFree(c->radius); cudaFree(c->view_weight); cudaFree(c->rng); cudaFree(c->edge); cudaFree(c->edge_sat); cudaFree(c->edge_dist); cudaFree(c->edge_neigh);
 	cudaFree(c->label); cudaFree(c->candidate); cudaFree(c->nearest_strong); cudaFree(c->weak_reliable);
 	cudaFree(c->neighbours_map); cudaFree(c->neighbours); cudaFree(c->label_boundary); cudaFree(c->complex_); cudaFree(c->weak_list); cudaFree(c->scan_blocks); cudaFree(c->scan_total); cudaFree(c->next_right); cudaFree(c->next_down); for (int k = 0; k < 2; ++k) { cudaFree(c->scan_blocks_c[k]); cudaFree(c->colour_list[k]); }
 	cudaFree(c->vis_parent); cudaFree(c->vis_count); cudaFree(c->fetch_counter);
@@ -691,15 +691,21 @@ int dvp_debug_race_explain(dvp_ctx* ctx, int iter, int red, const int32_t* offse
 	f.before = b.before; f.after = b.after;
 	f.out_planes = b.o_planes; f.out_costs = b.o_costs; f.out_selected = b.o_sel; f.out_view_weight = b.o_vw; f.out_rng = b.o_rng;
 	long long launches = 0;
+	const int S = ctx->S;
+	auto all_views = [&](unsigned m4) { unsigned long long w = 0; for (int v = 0; v < S && v < 16; ++v) w |= (unsigned long long)(m4 & 15u) << (4 * v); return w; };
+	auto try_choice = [&]() -> int {
+		CK(launch_strong_sweep_forced(a, iter, red ? 1 : 0, f, st));
+		CK(launch_explain_compare(a, red ? 1 : 0, f, e, b.expl, st));
+		++launches;
+		return DVP_OK;
+	};
 	// phase 1, whole colour: every ladder offset, each of the three reads entirely before or entirely after the update
 	for (int k = 0; k < num_offsets; ++k) {
 		if (offsets[k] < 0 || offsets[k] > 65535) return DVP_ERR_ARG;
 		f.m = offsets[k];
 		for (unsigned v = 0; v < 8; ++v) {
-			f.ncc_mask = (v & 1) ? 15u : 0u; f.dep_mask = (v & 2) ? 15u : 0u; f.acc_mask = (v & 4) ? 15u : 0u;
-			CK(launch_strong_sweep_forced(a, iter, red ? 1 : 0, f, st));
-			CK(launch_explain_compare(a, red ? 1 : 0, f, e, b.expl, st));
-			++launches;
+			f.ncc_masks = all_views((v & 1) ? 15u : 0u); f.dep_mask = (v & 2) ? 15u : 0u; f.acc_mask = (v & 4) ? 15u : 0u;
+			const int r = try_choice(); if (r) return r;
 		}
 	}
 	int left1 = 0, left2 = 0;
@@ -708,35 +714,47 @@ int dvp_debug_race_explain(dvp_ctx* ctx, int iter, int red, const int32_t* offse
 	CK(cudaMemcpyAsync(&left1, b.count, 4, cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
 	left2 = left1;
-	// phase 2, only the pixels still unexplained: reads torn between components (the reference loads a plane with four
-	// 32-bit loads while its owner replaces it with one 128-bit store)
+	// phase 2, only the pixels still unexplained: reads torn between components.  The reference build loads a plane with
+	// four 32-bit loads (SASS: 840 LD.E against 14 LD.E.128 in BlackPixelUpdateStrong) while its owner replaces it with wider
+	// stores, and it loads the candidate's plane anew for every source view it scores (the NCC is an out-of-line call).
 	if (tear && left1 > 0 && left1 <= list_cap) {
 		f.pixel_list = b.list; f.list_count = left1;
+		// (a) one mixture for all views x every mixture of the two acceptance reads
 		for (int k = 0; k < num_offsets; ++k) {
 			f.m = offsets[k];
 			for (unsigned v = 0; v < 4096; ++v) {
-				f.ncc_mask = v & 15u; f.dep_mask = (v >> 4) & 15u; f.acc_mask = (v >> 8) & 15u;
-				const bool whole = (f.ncc_mask == 0 || f.ncc_mask == 15) && (f.dep_mask == 0 || f.dep_mask == 15) && (f.acc_mask == 0 || f.acc_mask == 15);
+				const unsigned n4 = v & 15u;
+				f.ncc_masks = all_views(n4); f.dep_mask = (v >> 4) & 15u; f.acc_mask = (v >> 8) & 15u;
+				const bool whole = (n4 == 0 || n4 == 15) && (f.dep_mask == 0 || f.dep_mask == 15) && (f.acc_mask == 0 || f.acc_mask == 15);
 				if (whole) continue;   // done in phase 1
-				CK(launch_strong_sweep_forced(a, iter, red ? 1 : 0, f, st));
-				CK(launch_explain_compare(a, red ? 1 : 0, f, e, b.expl, st));
-				++launches;
+				const int r = try_choice(); if (r) return r;
 			}
 		}
-		// and the scoring read repeated per source view (the reference's compiler may reload the plane inside the loop over the
-		// views instead of keeping the by-value copy in registers): some views see it before, the others after the update
-		if (ctx->S <= 8) {
+		// (b) a mixture per view, the acceptance reads whole.  Up to two views: all 16 per view; more views: the mixtures four
+		// loads in ascending or descending component order can see when one store lands between them
+		static const unsigned ordered[8] = {0x0, 0xF, 0x8, 0xC, 0xE, 0x1, 0x3, 0x7};
+		const int per_view = S <= 2 ? 16 : 8;
+		if (S <= 4) {
+			long long combos = 1;
+			for (int v = 0; v < S; ++v) combos *= per_view;
 			for (int k = 0; k < num_offsets; ++k) {
 				f.m = offsets[k];
-				for (unsigned views = 1; views + 1 < (1u << ctx->S); ++views)
-					for (unsigned v = 0; v < 4; ++v) {
-						f.ncc_mask = 0; f.ncc_mask2 = 15u; f.ncc_views = views; f.dep_mask = (v & 1) ? 15u : 0u; f.acc_mask = (v & 2) ? 15u : 0u;
-						CK(launch_strong_sweep_forced(a, iter, red ? 1 : 0, f, st));
-						CK(launch_explain_compare(a, red ? 1 : 0, f, e, b.expl, st));
-						++launches;
+				for (long long cmb = 0; cmb < combos; ++cmb) {
+					unsigned long long w = 0; long long rest = cmb; bool uniform = true; unsigned first = 0;
+					for (int v = 0; v < S; ++v) {
+						const unsigned m4 = S <= 2 ? (unsigned)(rest % per_view) : ordered[rest % per_view];
+						rest /= per_view;
+						if (v == 0) first = m4; else if (m4 != first) uniform = false;
+						w |= (unsigned long long)m4 << (4 * v);
 					}
+					if (uniform) continue;   // the same mixture for every view: covered by (a)
+					f.ncc_masks = w;
+					for (unsigned v = 0; v < 4; ++v) {
+						f.dep_mask = (v & 1) ? 15u : 0u; f.acc_mask = (v & 2) ? 15u : 0u;
+						const int r = try_choice(); if (r) return r;
+					}
+				}
 			}
-			f.ncc_views = 0; f.ncc_mask2 = 0;
 		}
 		f.pixel_list = nullptr; f.list_count = 0;
 		CK(cudaMemsetAsync(b.count, 0, 4, st));

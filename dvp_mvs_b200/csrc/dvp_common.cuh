@@ -70,8 +70,7 @@ struct KArgs {
 	float* complex_;        // [weak_count]
 	float* scratch;         // per-pixel spill area for large S (cost arrays)
 	int weak_count;
-	const uint8_t* edge_coarse;   // [coarse_h][coarse_w]: 1 iff any edge pixel lies in the 8x8 block or one of its 8 neighbours (K4 / K9 edge walks)
-	int coarse_w, coarse_h;
+	const uint8_t* edge_dist;     // [N] chessboard distance to the nearest edge pixel, capped at 255 (0 on edge pixels): lets the edge walks of K4 / K9 skip ahead
 	unsigned long long* fetch_counter;   // [kFetchSlots] texture-fetch tally of the instrumented build (-DDVP_COUNT_FETCHES), else null
 };
 

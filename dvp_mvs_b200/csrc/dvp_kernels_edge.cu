@@ -197,6 +197,13 @@ cudaError_t launch_edge_segment(const uint8_t* d_img, int W, int H, uint8_t* d_e
 	return cudaGetLastError();
 }
 
+// APD.cpp:452-463 on a 0 / 255 image (shared with the label half, dvp_kernels_image.cu)
+cudaError_t launch_border_cleanup(uint8_t* d_img, int W, int H, cudaStream_t st) {
+	k_edge_border_cols<<<(H + 255) / 256, 256, 0, st>>>(W, H, d_img);
+	k_edge_border_rows<<<(W + 255) / 256, 256, 0, st>>>(W, H, d_img);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_edge_to_u8(const float* d_img, int n, uint8_t* d_out, cudaStream_t st) {
 	k_edge_to_u8<<<(n + 255) / 256, 256, 0, st>>>(d_img, n, d_out);
 	return cudaGetLastError();

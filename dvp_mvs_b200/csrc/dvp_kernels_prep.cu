@@ -224,38 +224,52 @@ __global__ void k_fill_i32(int32_t* dst, int32_t v, int n) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) dst[i] = v;
 }
-// Coarse occupancy of the edge map for the edge walks of K4 / K9 (bresenham_crosses_edge, dvp_weak.cuh): cell (bx, by)
-// of the block map says whether the 8x8 pixel block holds an edge pixel; the dilated map ORs the 3x3 block neighbourhood.
-__global__ void __launch_bounds__(256) k_edge_blocks(const uint8_t* edge, int W, int H, uint8_t* blocks, int cw, int ch) {
-	const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
-	if (bx >= cw || by >= ch) return;
-	uint8_t any = 0;
-	for (int j = 0; j < 8; ++j) {
-		const int y = by * 8 + j;
-		if (y >= H) break;
-		for (int i = 0; i < 8; ++i) {
-			const int x = bx * 8 + i;
-			if (x < W) any |= edge[(size_t)y * W + x];
-		}
+// Chessboard (L-infinity) distance from every pixel to the nearest edge pixel, capped at 255, for the edge walks of K4 / K9
+// (bresenham_crosses_edge, dvp_weak.cuh): a walk standing on a pixel at distance d knows its next d - 1 steps are edge-free.
+// Built from a summed-area table of the edge map: "is the (2r+1)^2 box around p edge-free" is four reads, the largest such
+// r is found by bisection.
+__global__ void __launch_bounds__(128) k_edge_sat_rows(const uint8_t* __restrict__ edge, int W, int H, int* __restrict__ sat) {
+	// one warp per image row: inclusive prefix count of edge pixels, stored at sat[(y + 1) * (W + 1) + x + 1]; row 0 and column 0 are zero
+	const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (warp > H) return;
+	int* out = sat + (size_t)warp * (W + 1);
+	if (warp == 0) { for (int x = lane; x <= W; x += 32) out[x] = 0; return; }
+	const uint8_t* row = edge + (size_t)(warp - 1) * W;
+	int carry = 0;
+	if (lane == 0) out[0] = 0;
+	for (int x0 = 0; x0 < W; x0 += 32) {
+		const int x = x0 + lane;
+		int v = (x < W && row[x]) ? 1 : 0;
+		for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+		if (x < W) out[x + 1] = carry + v;
+		carry += __shfl_sync(0xffffffffu, v, 31);
 	}
-	blocks[by * cw + bx] = any ? 1 : 0;
 }
-__global__ void __launch_bounds__(256) k_edge_blocks_dilate(const uint8_t* blocks, uint8_t* coarse, int cw, int ch) {
-	const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
-	if (bx >= cw || by >= ch) return;
-	uint8_t any = 0;
-	for (int j = -1; j <= 1; ++j)
-		for (int i = -1; i <= 1; ++i) {
-			const int x = bx + i, y = by + j;
-			if (x >= 0 && x < cw && y >= 0 && y < ch) any |= blocks[y * cw + x];
-		}
-	coarse[by * cw + bx] = any;
+__global__ void __launch_bounds__(128) k_edge_sat_cols(int W, int H, int* __restrict__ sat) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	if (x > W) return;
+	int acc = 0;
+	for (int y = 0; y <= H; ++y) { acc += sat[(size_t)y * (W + 1) + x]; sat[(size_t)y * (W + 1) + x] = acc; }
 }
-cudaError_t launch_edge_coarse(const uint8_t* edge, int W, int H, uint8_t* blocks, uint8_t* coarse, cudaStream_t st) {
-	const int cw = (W + 7) / 8, ch = (H + 7) / 8;
-	dim3 b(32, 8), g((cw + 31) / 32, (ch + 7) / 8);
-	k_edge_blocks<<<g, b, 0, st>>>(edge, W, H, blocks, cw, ch);
-	k_edge_blocks_dilate<<<g, b, 0, st>>>(blocks, coarse, cw, ch);
+__global__ void __launch_bounds__(256) k_edge_distance(const uint8_t* __restrict__ edge, int W, int H, const int* __restrict__ sat, uint8_t* __restrict__ dist) {
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= W || y >= H) return;
+	if (edge[(size_t)y * W + x]) { dist[(size_t)y * W + x] = 0; return; }
+	auto clear = [&](int r) -> bool {   // no edge pixel with max(|dx|, |dy|) <= r (pixels outside the image hold no edge)
+		const int x1 = max(x - r, 0), x2 = min(x + r, W - 1) + 1, y1 = max(y - r, 0), y2 = min(y + r, H - 1) + 1;
+		const int* a = sat + (size_t)y1 * (W + 1); const int* b = sat + (size_t)y2 * (W + 1);
+		return b[x2] - b[x1] - a[x2] + a[x1] == 0;
+	};
+	int lo = 0, hi = 254;          // clear(0) holds (the pixel itself is no edge); find the largest r <= 254 with clear(r)
+	if (clear(hi)) lo = hi;
+	else while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (clear(mid)) lo = mid; else hi = mid; }
+	dist[(size_t)y * W + x] = (uint8_t)(lo + 1);   // the nearest edge pixel is lo + 1 away (or farther: capped at 255)
+}
+cudaError_t launch_edge_distance(const uint8_t* edge, int W, int H, int* sat, uint8_t* dist, cudaStream_t st) {
+	k_edge_sat_rows<<<((H + 1) * 32 + 127) / 128, 128, 0, st>>>(edge, W, H, sat);
+	k_edge_sat_cols<<<(W + 1 + 127) / 128, 128, 0, st>>>(W, H, sat);
+	dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+	k_edge_distance<<<g, b, 0, st>>>(edge, W, H, sat, dist);
 	return cudaGetLastError();
 }
 

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinBlocks) k_strong_sweep
 				pos_arr[d * T] = (uint16_t)force.m;
 				const float4 pb = force.before[tx + ty * W], pa = force.after[tx + ty * W];
 				for (int v = 0; v < S; ++v) {
-					const float4 pl = mix_planes(pb, pa, ((force.ncc_views >> v) & 1) ? force.ncc_mask2 : force.ncc_mask);
+					const float4 pl = mix_planes(pb, pa, (unsigned)(force.ncc_masks >> (4 * (v & 15))) & 15u);
 					cost_arr[(d * S + v) * T] = ncc_cost<kSweepRB, kSweepRW>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
 				}
 			}

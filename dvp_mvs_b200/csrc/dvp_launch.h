@@ -56,8 +56,9 @@ cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, cudaStream_t 
 struct D4Force {
 	int m = 0;                                               // ladder offset of direction 4's candidate: pixel (x - 5 - m, y - 5 - m)
 	const float4* before = nullptr; const float4* after = nullptr;   // the candidate's plane before / after its own update
-	unsigned ncc_mask = 0, dep_mask = 0, acc_mask = 0;       // bit c: component c of the plane comes from `after` (scoring read, depth-test read, copy)
-	unsigned ncc_views = 0, ncc_mask2 = 0;                   // source views whose bit is set in ncc_views score with ncc_mask2 instead (the plane re-read per view)
+	unsigned long long ncc_masks = 0;                        // 4 bits per source view (views 0..15): bit c set = component c of the plane scored for
+	                                                         // that view comes from `after` (the reference re-reads the plane, 32 bits at a time, for every view)
+	unsigned dep_mask = 0, acc_mask = 0;                     // the same for the depth-test read and for the copy at acceptance
 	const int* pixel_list = nullptr; int list_count = 0;     // null: the whole half grid of the colour
 	float4* out_planes = nullptr; float* out_costs = nullptr; uint32_t* out_selected = nullptr; uint8_t* out_view_weight = nullptr; uint32_t* out_rng = nullptr;
 };
@@ -75,7 +76,7 @@ cudaError_t launch_local_refine(const KArgs& a, cudaStream_t st);               
 cudaError_t launch_depth_to_weak_refine(const KArgs& a, cudaStream_t st);                        // K15 + K16 fused (dvp_run)
 
 cudaError_t launch_fill_i32(int32_t* dst, int32_t v, int n, cudaStream_t st);
-cudaError_t launch_edge_coarse(const uint8_t* edge, int W, int H, uint8_t* blocks, uint8_t* coarse, cudaStream_t st);   // 8x8 block occupancy, 3x3 dilated
+cudaError_t launch_edge_distance(const uint8_t* edge, int W, int H, int* sat, uint8_t* dist, cudaStream_t st);   // chessboard distance to the nearest edge, capped at 255
 // WEAK-pixel indexing (device-side replacement of the host loop APD.cpp:1182-1193)
 constexpr int kWeakScanBlock = 1024;
 cudaError_t launch_weak_count(const uint8_t* weak, int n, int W, int colour, int yy_limit, int* block_sums, int* total, cudaStream_t st);
@@ -92,6 +93,7 @@ cudaError_t launch_extract_depth(const float4* planes, float* depth, int n, cuda
 size_t edge_scratch_bytes(int W, int H);
 cudaError_t launch_edge_segment(const uint8_t* d_img, int W, int H, uint8_t* d_edge, void* scratch, int** d_thr, cudaStream_t st);
 cudaError_t launch_edge_to_u8(const float* d_img, int n, uint8_t* d_out, cudaStream_t st);
+cudaError_t launch_border_cleanup(uint8_t* d_img, int W, int H, cudaStream_t st);
 cudaError_t launch_restore_visibility(const KArgs& a, int scale_size, int* parent, int* count, cudaStream_t st);
 
 // image preparation (dvp_kernels_image.cu): cv::resize(INTER_LINEAR) of float images, 8-bit -> float

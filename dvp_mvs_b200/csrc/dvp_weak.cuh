@@ -11,7 +11,7 @@ namespace dvp {
 
 // reference BresenhamLine, APD.cu:267-311: does the segment B->A cross an edge pixel within max(H,W)/30 steps?
 // BATCH = iterations advanced per round of edge reads (1 = the reference's loop shape).
-constexpr int kCoarseWalkMin = 12;   // shorter walks keep the plain loop (the set-up of the closed form would cost more than it saves)
+constexpr int kCoarseWalkMin = 4;   // shorter walks keep the plain loop (the set-up of the closed form would cost more than it saves)
 template <int BATCH = 1>
 __device__ __forceinline__ bool bresenham_crosses_edge(const KArgs& a, int Ax, int Ay, int Bx, int By) {
 	const int width = a.W;
@@ -27,57 +27,43 @@ __device__ __forceinline__ bool bresenham_crosses_edge(const KArgs& a, int Ax, i
 	int step = 0;
 	bool tagx = true, tagy = true;
 #ifndef DVP_NO_COARSE_WALK
-	// Walks longer than a few steps are answered from a coarse block map and the walk's closed form instead of one dependent
-	// edge read per step.  The loop below visits exactly n = min(max(dx, dy) + 1, max_step) positions (it oversteps the end
-	// point by one) and position k (1-based) is
+	// Walks longer than a few steps skip ahead on a distance map instead of reading the edge map once per step.  The loop
+	// below visits exactly n = min(max(dx, dy) + 1, max_step) positions (it oversteps the end point by one) and position k
+	// (1-based; k = 0 is the start) is
 	//     x-major (dx > dy):  (x0 + sx k,            y0 + sy floor((k dy + dx - 1 - e0) / dx))
 	//     y-major (dy > dx):  (x0 + sx min(k, floor((k dx + dy - 1 + e0) / dy)),   y0 + sy k)          e0 = max(dx, dy) / 2
 	//     diagonal:           (x0 + sx k, y0 + sy k)
-	// (checked against the loop in tests/test_host_logic.py).  Consecutive positions differ by at most one pixel per axis, so
-	// every position of the 8-step chunk c (steps 8c+1 .. 8c+8) lies within 4 pixels of the position at step 8c+4 — inside
-	// the 3x3 block neighbourhood of that sample's 8x8 block.  Pass 1 reads the dilated block map at one sample per chunk
-	// (independent loads); chunks whose sample is clear hold no edge pixel.  Pass 2 tests the positions of the flagged
-	// chunks exactly, in walk order.  The answer is the loop's; only the number and the dependency of the reads change.
+	// (checked against the loop in tests/test_host_logic.py).  Consecutive positions differ by at most one pixel per axis.
+	// a.edge_dist holds the chessboard distance d to the nearest edge pixel: standing on position k with d > 0, positions
+	// k+1 .. k+d-1 lie within chessboard distance d-1 and cannot be edge pixels, so the walk continues at k+d.  The answer is
+	// the loop's; in an edge-free region a 200-step walk takes a handful of reads.
 	{
 		const int M = dx > dy ? dx : dy;
 		const int n_total = M + 1 < max_step ? M + 1 : max_step;
-		if (M > 0 && n_total > kCoarseWalkMin && n_total <= 512) {   // 512 steps = 64 chunks: images up to 15 360 pixels a side
+		if (M > 0 && n_total > kCoarseWalkMin) {
 			const bool xmaj = dx > dy, diag = dx == dy;
 			const int mn = dx > dy ? dy : dx, e0 = M / 2;
 			const int c = xmaj ? M - 1 - e0 : e0 - 1 + M;
 			const float rcp_m = __frcp_rn((float)M);
-			auto minor_steps = [&](int k) -> int {   // how far the minor axis has moved after k steps
-				if (diag) return k;
-				const int n = k * mn + c;             // < 2^24: exact in float; the estimate is off by at most one
-				int q = (int)(__fmul_rn((float)n, rcp_m));
-				const int r = n - q * M;
-				q += (r >= M) - (r < 0);
-				return xmaj ? q : (k < q ? k : q);
-			};
-			auto position = [&](int k, int& x, int& y) {
-				const int mi = minor_steps(k);
-				if (dy > dx) { x = x0 + sx * mi; y = y0 + sy * k; }
-				else { x = x0 + sx * k; y = y0 + sy * mi; }
-			};
-			const int nchunks = (n_total + 7) >> 3;      // <= 26 for images up to 6240 pixels wide; a 64-bit mask covers every legal size
-			unsigned long long flagged = 0;
-			for (int ch = 0; ch < nchunks; ++ch) {
-				int x, y; position(8 * ch + 4, x, y);
-				x = min(max(x, 0), a.W - 1); y = min(max(y, 0), a.H - 1);
-				flagged |= (unsigned long long)__ldg(a.edge_coarse + (y >> 3) * a.coarse_w + (x >> 3)) << ch;
-			}
-			while (flagged) {
-				const int ch = __ffsll((long long)flagged) - 1;
-				flagged &= flagged - 1;
-				const int k_end = 8 * ch + 8 < n_total ? 8 * ch + 8 : n_total;
-				uint8_t hit = 0;
-				for (int k = 8 * ch + 1; k <= k_end; ++k) {
-					int x, y; position(k, x, y);
-					if (x >= 0 && x < a.W && y >= 0 && y < a.H) hit |= a.edge[x + y * width];   // the walk may overstep the map by one pixel
+			int k = 0, d = a.edge_dist[x0 + y0 * width];    // > 0: the start pixel is no edge pixel (tested above)
+			for (;;) {
+				k += d;
+				if (k > n_total) return false;
+				int mi = k;                                   // how far the minor axis has moved after k steps
+				if (!diag) {
+					const int n = k * mn + c;                 // < 2^24: exact in float; the estimate is off by at most one
+					int q = (int)(__fmul_rn((float)n, rcp_m));
+					const int r = n - q * M;
+					q += (r >= M) - (r < 0);
+					mi = xmaj ? q : (k < q ? k : q);
 				}
-				if (hit) return true;
+				const int x = dy > dx ? x0 + sx * mi : x0 + sx * k, y = dy > dx ? y0 + sy * k : y0 + sy * mi;
+				d = 1;                                        // the walk may overstep the map by one pixel: nothing to test there
+				if (x >= 0 && x < a.W && y >= 0 && y < a.H) {
+					d = a.edge_dist[x + y * width];
+					if (d == 0) return true;
+				}
 			}
-			return false;
 		}
 	}
 #endif

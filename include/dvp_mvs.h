@@ -341,6 +341,18 @@ int dvp_edge_segment(int device, const uint8_t* image, int width, int height, ui
 int dvp_scene_compute_edges(dvp_scene* scene, int view, int level);
 int dvp_scene_get_edges(dvp_scene* scene, int view, int level, uint8_t* edge);
 
+/* ---- Row N4, label half: the region-label prior ----------------------------------------------------------------------------
+ * Replaces EdgeSegment(scale, image_uint, 1) (APD.cpp:348-402, 437-499) as GetProblemEdges calls it on the FULL-resolution
+ * 8-bit grey image (main.cpp:229-241; `scale` = log2 of Problem::scale_size); its result is the `label` input of
+ * dvp_upload / dvp_scene_set_label: 0 on region boundaries, -1 in regions of at most weak_tex_num pixels, a positive id
+ * elsewhere.  The hot path only compares labels for equality and tests `> 0`, `== 0`, `== -1` (APD.cu:3461, 3629,
+ * 3857-3886), so the ids are this library's own (root pixel + 1): the PARTITION and the classes are the reference's.
+ * labels: [new_rows][new_cols] int32 with (new_cols, new_rows) = dvp_label_size(cols, rows, scale); edge_small (may be
+ * NULL): the (rows/2)/2 x (cols/2)/2 edge image after the Hough lines were drawn, for stage-wise checks.  Host or device
+ * pointers.  cols, rows >= 16.  Stateless and synchronous. */
+int dvp_label_size(int cols, int rows, int scale, int* new_cols, int* new_rows);
+int dvp_label_segment(int device, const uint8_t* image, int cols, int rows, int scale, int32_t* labels, uint8_t* edge_small, float* device_ms);
+
 /* ---- Row N2, image pyramid: the level image every pass of a view reads --------------------------------------------------
  * Replaces cv::resize(image, scaled, Size(new_cols, new_rows), 0, 0, INTER_LINEAR) of the float grey image in
  * InuputInitialization (APD.cpp:1119-1140) and GetProblemEdges (main.cpp:203-209).  cv::resize is OpenCV's; what is

@@ -173,3 +173,77 @@ def test_closed_form_edge_walk_large_offsets_and_float_reciprocal_division():
     for ddx, ddy in ((600, 599), (599, 600), (600, 600), (600, 1), (1, 600), (600, 0), (0, -600), (-333, 332), (64, -63)):
         for max_step in (13, 207, 512):
             assert walk_ref(0, 0, ddx, ddy, max_step) == walk_device(0, 0, ddx, ddy, max_step), (ddx, ddy, max_step)
+
+
+def test_distance_map_walk_gives_the_loop_answer():
+    """bresenham_crosses_edge's skip-ahead (dvp_weak.cuh): standing on a pixel whose chessboard distance to the nearest edge
+    pixel is d, the next d - 1 positions cannot be edge pixels.  Emulated here on random edge maps against the reference's
+    loop (APD.cu:281-313, which skips positions outside the map): same yes / no on every segment."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+
+    def loop_answer(edge, ax, ay, bx, by, max_step):
+        H, W = edge.shape
+        x0, y0, x1, y1 = bx, by, ax, ay
+        dx, sx = abs(x1 - x0), (1 if x0 < x1 else -1)
+        dy, sy = abs(y1 - y0), (1 if y0 < y1 else -1)
+        erro = (dx if dx > dy else dy) // 2
+        step, tagx, tagy = 0, True, True
+        while tagx or tagy:
+            if x0 == x1: tagx = False
+            if y0 == y1: tagy = False
+            e2 = erro
+            if e2 > -dx: erro -= dy; x0 += sx
+            if e2 < dy: erro += dx; y0 += sy
+            if 0 <= x0 < W and 0 <= y0 < H and edge[y0, x0]:
+                return True
+            step += 1
+            if step >= max_step: break
+        return False
+
+    def skip_answer(edge, dist, ax, ay, bx, by, max_step):
+        H, W = edge.shape
+        x0, y0, x1, y1 = bx, by, ax, ay
+        dx, sx = abs(x1 - x0), (1 if x0 < x1 else -1)
+        dy, sy = abs(y1 - y0), (1 if y0 < y1 else -1)
+        M, mn = max(dx, dy), min(dx, dy)
+        e0 = M // 2
+        n_total = min(M + 1, max_step)
+        if M == 0:
+            return False
+        c = M - 1 - e0 if dx > dy else e0 - 1 + M
+        k, d = 0, int(dist[y0, x0])
+        while True:
+            k += d
+            if k > n_total:
+                return False
+            mi = k if dx == dy else ((k * mn + c) // M if dx > dy else min(k, (k * mn + c) // M))
+            x, y = (x0 + sx * mi, y0 + sy * k) if dy > dx else (x0 + sx * k, y0 + sy * mi)
+            d = 1
+            if 0 <= x < W and 0 <= y < H:
+                d = int(dist[y, x])
+                if d == 0:
+                    return True
+
+    checked = crossing = 0
+    for trial in range(60):
+        H, W = int(rng.integers(20, 70)), int(rng.integers(20, 90))
+        edge = (rng.random((H, W)) < rng.choice([0.002, 0.01, 0.05])).astype(np.uint8) * 255
+        if trial % 5 == 0:
+            edge[:, W // 2] = 255                      # a wall to cross
+        ys, xs = np.nonzero(edge)
+        yy, xx = np.mgrid[0:H, 0:W]
+        if len(ys):
+            dist = np.minimum(np.max(np.maximum(np.abs(yy[..., None] - ys), np.abs(xx[..., None] - xs)), axis=-1) * 0 +
+                              np.min(np.maximum(np.abs(yy[..., None] - ys), np.abs(xx[..., None] - xs)), axis=-1), 255)
+        else:
+            dist = np.full((H, W), 255)
+        for _ in range(120):
+            ax, ay, bx, by = int(rng.integers(0, W)), int(rng.integers(0, H)), int(rng.integers(0, W)), int(rng.integers(0, H))
+            if edge[ay, ax] or edge[by, bx]:
+                continue                               # the function answers `false` before walking
+            max_step = int(rng.choice([5, 13, 40, 200]))
+            want = loop_answer(edge, ax, ay, bx, by, max_step)
+            assert skip_answer(edge, dist, ax, ay, bx, by, max_step) == want, (trial, ax, ay, bx, by, max_step)
+            checked += 1; crossing += int(want)
+    assert checked > 3000 and crossing > 200

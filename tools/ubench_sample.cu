@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256, 3) k_coherent(const Args a, const __grid_
 		float H[9]; make_h(rep, H);
 		// H is close to the identity with positive scale: the top-left corner maps to the smallest coordinates
 		const float z = H[8] + H[6] * bx0 + H[7] * by0;
-		ox = (int)floorf((H[2] + H[0] * bx0 + H[1] * by0) / z) - 2;
+		ox = ((int)floorf((H[2] + H[0] * bx0 + H[1] * by0) / z) - 2) & ~3;   // TMA: the innermost box coordinate has to be 16-byte aligned (a misaligned one traps as an illegal instruction)
 		oy = (int)floorf((H[5] + H[3] * bx0 + H[4] * (by0 + 17)) / z) - 2;   // H[3] < 0: the right edge is lower; conservative
 		oy = min(oy, (int)floorf((H[5] + H[3] * (bx0 + 41) + H[4] * by0) / z) - 2);
 	};
