@@ -7,10 +7,10 @@ Only what the hot path needs lives here:
   synth.py     deterministic synthetic scenes (the reference ships no data)
   farm.py      per-view sharding across the GPUs of one box (NCCL-free)
 """
-from ._lib import (Engine, Scene, Fusion, FusionView, make_fusion_view, edge_segment, label_segment, resize_linear_f32, Params, Inputs, DvpError, default_params, FIRST_INIT, REFINE_INIT, REFINE_ITER,
+from ._lib import (Engine, Scene, Farm, Fusion, FusionView, make_fusion_view, edge_segment, label_segment, resize_linear_f32, Params, Inputs, DvpError, default_params, FIRST_INIT, REFINE_INIT, REFINE_ITER,
                    WEAK, STRONG, UNKNOWN, STAGES, PRODUCT_LIB)
 from . import synth
 from . import formats
 
-__all__ = ["Engine", "Scene", "Fusion", "FusionView", "make_fusion_view", "edge_segment", "label_segment", "resize_linear_f32", "Params", "Inputs", "DvpError", "default_params", "FIRST_INIT", "REFINE_INIT", "REFINE_ITER",
+__all__ = ["Engine", "Scene", "Farm", "Fusion", "FusionView", "make_fusion_view", "edge_segment", "label_segment", "resize_linear_f32", "Params", "Inputs", "DvpError", "default_params", "FIRST_INIT", "REFINE_INIT", "REFINE_ITER",
            "WEAK", "STRONG", "UNKNOWN", "STAGES", "PRODUCT_LIB", "synth", "formats"]

@@ -68,11 +68,13 @@ ABI_SYMBOLS = ["version", "default_params", "create", "destroy", "upload", "run"
                "buffer_bytes", "get_buffer", "set_buffer", "last_run_times", "weak_count", "last_cuda_error", "stream"]
 PRODUCT_ONLY_SYMBOLS = ["upload_device", "upload_overlapped", "restore_visibility", "rescale_map", "scene_create", "scene_destroy", "scene_level_size",
                         "scene_pass_params", "scene_set_max_iterations", "scene_set_view", "scene_set_level",
-                        "scene_set_initial_planes", "scene_set_image", "scene_set_label", "scene_get_image", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats",
+                        "scene_set_initial_planes", "scene_set_image", "scene_set_label", "scene_get_label", "scene_get_image", "scene_run_pass", "scene_run", "scene_get_view", "scene_stats",
                         "scene_run_view", "scene_depth_map", "scene_remote_depth",
                         "fusion_create", "fusion_destroy", "fusion_set_view", "fusion_set_view_planes", "scene_fuse_views", "fusion_set_mode", "fusion_reset", "fusion_run_view", "fusion_run",
                         "fusion_num_points", "fusion_get_points", "fusion_get_mask", "fusion_last_view", "fusion_last_view_index", "fusion_write_ply",
                         "edge_segment", "scene_compute_edges", "scene_get_edges",
+                        "farm_create", "farm_destroy", "farm_num_devices", "farm_owner", "farm_set_max_iterations", "farm_set_view", "farm_set_level", "farm_set_image",
+                        "farm_compute_edges", "farm_set_initial_planes", "farm_run", "farm_exchange_bytes", "farm_get_view",
                         "debug_race_explain", "debug_fetch_count", "resize_linear_f32", "label_size", "label_segment",
                         "io_binmat_header", "io_read_binmat", "io_write_binmat", "io_write_dmb", "io_read_camera", "io_read_pairs"]
 
@@ -148,6 +150,7 @@ def load_library(path: str, prefix: str):
         f("scene_set_level").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]; f("scene_set_level").restype = C.c_int
         f("scene_set_image").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]; f("scene_set_image").restype = C.c_int
         f("scene_set_label").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]; f("scene_set_label").restype = C.c_int
+        f("scene_get_label").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]; f("scene_get_label").restype = C.c_int
         f("scene_get_image").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]; f("scene_get_image").restype = C.c_int
         f("scene_set_initial_planes").argtypes = [C.c_void_p, C.c_int, C.c_void_p]; f("scene_set_initial_planes").restype = C.c_int
         f("scene_run_pass").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64]; f("scene_run_pass").restype = C.c_int
@@ -178,6 +181,19 @@ def load_library(path: str, prefix: str):
         f("label_size").argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]; f("label_size").restype = C.c_int
         f("label_segment").argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]; f("label_segment").restype = C.c_int
         f("resize_linear_f32").argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]; f("resize_linear_f32").restype = C.c_int
+        f("farm_create").argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]; f("farm_create").restype = C.c_void_p
+        f("farm_destroy").argtypes = [C.c_void_p]; f("farm_destroy").restype = None
+        f("farm_num_devices").argtypes = [C.c_void_p]; f("farm_num_devices").restype = C.c_int
+        f("farm_owner").argtypes = [C.c_void_p, C.c_int]; f("farm_owner").restype = C.c_int
+        f("farm_set_max_iterations").argtypes = [C.c_void_p, C.c_int]; f("farm_set_max_iterations").restype = C.c_int
+        f("farm_set_view").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]; f("farm_set_view").restype = C.c_int
+        f("farm_set_level").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]; f("farm_set_level").restype = C.c_int
+        f("farm_set_image").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]; f("farm_set_image").restype = C.c_int
+        f("farm_compute_edges").argtypes = [C.c_void_p, C.c_int, C.c_int]; f("farm_compute_edges").restype = C.c_int
+        f("farm_set_initial_planes").argtypes = [C.c_void_p, C.c_int, C.c_void_p]; f("farm_set_initial_planes").restype = C.c_int
+        f("farm_run").argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_float)]; f("farm_run").restype = C.c_int
+        f("farm_exchange_bytes").argtypes = [C.c_void_p]; f("farm_exchange_bytes").restype = C.c_longlong
+        f("farm_get_view").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)] + [C.c_void_p] * 4; f("farm_get_view").restype = C.c_int
         f("debug_race_explain").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_void_p]
         f("debug_race_explain").restype = C.c_int
         f("debug_fetch_count").argtypes = [C.c_void_p, C.c_int]; f("debug_fetch_count").restype = C.c_longlong
@@ -411,11 +427,18 @@ class Scene:
         img = _carr(image, np.float32, (h, w)); e = _carr(edge, np.uint8, (h, w)); l = _carr(label, np.int32, (h, w))
         self._check(self.lib.dvp_scene_set_level(self.h, view, level, _ptr(img), _ptr(e), _ptr(l)), "set_level")
 
-    def set_image(self, view: int, image_u8: np.ndarray, compute_edges: bool = True):
-        """The whole pyramid of one view from its full-resolution 8-bit grey image (dvp_scene_set_image)."""
+    def set_image(self, view: int, image_u8: np.ndarray, compute_edges: bool = True, compute_labels: bool = False):
+        """The whole pyramid of one view from its full-resolution 8-bit grey image (dvp_scene_set_image), optionally with the
+        edge and label maps GetProblemEdges derives from it."""
         W, H = self._sizes[view]
         img = _carr(image_u8, np.uint8, (H, W))
-        self._check(self.lib.dvp_scene_set_image(self.h, view, _ptr(img), 1 if compute_edges else 0), "set_image")
+        self._check(self.lib.dvp_scene_set_image(self.h, view, _ptr(img), (1 if compute_edges else 0) | (2 if compute_labels else 0)), "set_image")
+
+    def get_label(self, view: int, level: int) -> np.ndarray:
+        w, h = self.view_level_size(view, level)
+        out = np.empty((h, w), np.int32)
+        self._check(self.lib.dvp_scene_get_label(self.h, view, level, _ptr(out)), "get_label")
+        return out
 
     def set_label(self, view: int, level: int, label):
         w, h = self.view_level_size(view, level)
@@ -483,6 +506,77 @@ class Scene:
         planes = np.empty((H, W, 4), np.float32); weak = np.empty((H, W), np.uint8)
         sel = np.empty((H, W), np.uint32); rad = np.empty((H, W), np.int32)
         self._check(self.lib.dvp_scene_get_view(self.h, view, C.byref(w), C.byref(h), _ptr(planes), _ptr(weak), _ptr(sel), _ptr(rad)), "get_view")
+        return planes, weak, sel, rad
+
+
+class Farm:
+    """The per-view farm inside the library (dvp_farm_*): one resident scene and one host thread per GPU, views
+    dealt round robin, depth maps exchanged by peer copies.  Mirrors `Scene`; inputs are replicated on every GPU."""
+
+    def __init__(self, devices, num_views: int, num_levels: int):
+        self.lib = load_library(PRODUCT_LIB, "dvp_")
+        self.devices = [int(d) for d in devices]
+        self.num_views, self.num_levels = num_views, num_levels
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        self.h = self.lib.dvp_farm_create(len(self.devices), arr, num_views, num_levels)
+        if not self.h:
+            raise DvpError(f"dvp_farm_create failed (devices {self.devices}, {num_views} views, {num_levels} levels)")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise DvpError(f"dvp_farm_{what} -> {STATUS.get(rc, rc)}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dvp_farm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_max_iterations(self, n: int):
+        self._check(self.lib.dvp_farm_set_max_iterations(self.h, n), "set_max_iterations")
+
+    def set_view(self, view: int, camera, full_w: int, full_h: int, src_views):
+        cam = np.ascontiguousarray(camera, dtype=CAMERA_DTYPE).reshape(1)
+        src = (C.c_int * len(src_views))(*[int(s) for s in src_views])
+        self._check(self.lib.dvp_farm_set_view(self.h, view, _ptr(cam), full_w, full_h, len(src_views), src), "set_view")
+
+    def set_level(self, view: int, level: int, image, edge=None, label=None):
+        img = np.ascontiguousarray(image, np.float32)
+        e = None if edge is None else np.ascontiguousarray(edge, np.uint8)
+        lab = None if label is None else np.ascontiguousarray(label, np.int32)
+        self._check(self.lib.dvp_farm_set_level(self.h, view, level, _ptr(img), _ptr(e), _ptr(lab)), "set_level")
+
+    def set_image(self, view: int, image_u8, compute_edges: bool = True, compute_labels: bool = False):
+        img = np.ascontiguousarray(image_u8, np.uint8)
+        self._check(self.lib.dvp_farm_set_image(self.h, view, _ptr(img), (1 if compute_edges else 0) | (2 if compute_labels else 0)), "set_image")
+
+    def compute_edges(self, view: int, level: int):
+        self._check(self.lib.dvp_farm_compute_edges(self.h, view, level), "compute_edges")
+
+    def set_initial_planes(self, view: int, planes):
+        pl = np.ascontiguousarray(planes, np.float32)
+        self._check(self.lib.dvp_farm_set_initial_planes(self.h, view, _ptr(pl)), "set_initial_planes")
+
+    def owner(self, view: int) -> int:
+        return int(self.lib.dvp_farm_owner(self.h, view))
+
+    def run(self, seed: int):
+        """-> (wall ms, ms the slowest GPU thread spent in the exchange steps, bytes moved between GPUs)"""
+        wall, exch = C.c_float(), C.c_float()
+        self._check(self.lib.dvp_farm_run(self.h, int(seed), C.byref(wall), C.byref(exch)), "run")
+        return float(wall.value), float(exch.value), int(self.lib.dvp_farm_exchange_bytes(self.h))
+
+    def get_view(self, view: int):
+        w, h = C.c_int(), C.c_int()
+        self._check(self.lib.dvp_farm_get_view(self.h, view, C.byref(w), C.byref(h), None, None, None, None), "get_view")
+        W, H = int(w.value), int(h.value)
+        planes = np.empty((H, W, 4), np.float32); weak = np.empty((H, W), np.uint8); sel = np.empty((H, W), np.uint32); rad = np.empty((H, W), np.int32)
+        self._check(self.lib.dvp_farm_get_view(self.h, view, C.byref(w), C.byref(h), _ptr(planes), _ptr(weak), _ptr(sel), _ptr(rad)), "get_view")
         return planes, weak, sel, rad
 
 

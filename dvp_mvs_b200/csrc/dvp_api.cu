@@ -79,6 +79,7 @@ struct dvp_ctx {
 	int* sort_vals = nullptr;
 	void* sort_temp = nullptr;
 	size_t sort_temp_bytes = 0;
+	void* sweep_scratch = nullptr;                  // K7 / K8: candidate costs and winners between k_sweep_score and k_sweep_update (allocated on first use)
 	unsigned long long* fetch_counter = nullptr;   // instrumented build only (DVP_COUNT_FETCHES)
 	int* vis_parent = nullptr;  // union-find links / region sizes of dvp_restore_visibility (allocated on first use)
 	int* vis_count = nullptr;
@@ -176,6 +177,7 @@ int stage_kernel_count(const dvp_ctx* c, int stage) {
 	case DVP_K2_GEN_EDGE_INFORM: return (weak ? 1 : 0) + (c->prm.use_edge ? 1 : 0) + ((c->prm.use_label && weak) ? 1 : 0) + 1;
 	case DVP_K3_FIND_NEAREST_STRONG: return (weak ? 1 : 0) + 1;
 	case DVP_K4_GEN_NEIGHBOURS: return weak ? 1 : 0;
+	case DVP_K7_BLACK_STRONG: case DVP_K8_RED_STRONG: return 2;   // k_sweep_score + k_sweep_update
 	case DVP_K9_RANSAC_FIT_PLANE: return 1 + (weak ? 1 : 0);
 	case DVP_K10_BLACK_WEAK: return c->colour_count[0] > 0 ? 1 : 0;
 	case DVP_K11_RED_WEAK: return c->colour_count[1] > 0 ? 1 : 0;
@@ -192,8 +194,11 @@ cudaError_t launch_stage(dvp_ctx* c, const KArgs& a, int stage, int iter) {
 	case DVP_K4_GEN_NEIGHBOURS: return launch_gen_neighbours(a, c->weak_list, st);
 	case DVP_K5_NEIGHBOUR_UPDATE: return launch_neighbour_update(a, st);
 	case DVP_K6_RANDOM_INITIALIZATION: return launch_random_init(a, st);
-	case DVP_K7_BLACK_STRONG: return launch_strong_sweep(a, iter, 0, st);
-	case DVP_K8_RED_STRONG: return launch_strong_sweep(a, iter, 1, st);
+	case DVP_K7_BLACK_STRONG:
+	case DVP_K8_RED_STRONG: {
+		if (!c->sweep_scratch) { cudaError_t e = cudaMalloc(&c->sweep_scratch, sweep_scratch_bytes(c->W, c->H, c->S)); if (e != cudaSuccess) return e; }
+		return launch_strong_sweep(a, iter, stage == DVP_K8_RED_STRONG ? 1 : 0, c->sweep_scratch, st);
+	}
 	case DVP_K9_RANSAC_FIT_PLANE: return launch_ransac_fit(a, c->weak_list, st);
 	case DVP_K10_BLACK_WEAK: return launch_weak_sweep(a, c->colour_list[0], c->colour_count[0], iter, 0, st);
 	case DVP_K11_RED_WEAK: return launch_weak_sweep(a, c->colour_list[1], c->colour_count[1], iter, 1, st);
@@ -466,7 +471,7 @@ void dvp_destroy(dvp_ctx* c) {
 	cudaFree(c->radius); cudaFree(c->view_weight); cudaFree(c->rng); cudaFree(c->edge); cudaFree(c->edge_sat); cudaFree(c->edge_dist); cudaFree(c->edge_neigh);
 	cudaFree(c->label); cudaFree(c->candidate); cudaFree(c->nearest_strong); cudaFree(c->weak_reliable);
 	cudaFree(c->neighbours_map); cudaFree(c->neighbours); cudaFree(c->label_boundary); cudaFree(c->complex_); cudaFree(c->weak_list); cudaFree(c->scan_blocks); cudaFree(c->scan_total); cudaFree(c->next_right); cudaFree(c->next_down); for (int k = 0; k < 2; ++k) { cudaFree(c->scan_blocks_c[k]); cudaFree(c->colour_list[k]); }
-	cudaFree(c->vis_parent); cudaFree(c->vis_count); cudaFree(c->fetch_counter);
+	cudaFree(c->vis_parent); cudaFree(c->vis_count); cudaFree(c->fetch_counter); cudaFree(c->sweep_scratch);
 	cudaFree(c->sort_keys[0]); cudaFree(c->sort_keys[1]); cudaFree(c->sort_vals); cudaFree(c->sort_temp);
 	for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -774,3 +779,4 @@ void* dvp_stream(dvp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 }  // extern "C"
 
 #include "dvp_scene.inc"
+#include "dvp_farm.inc"

@@ -423,6 +423,290 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinBlocks) k_strong_sweep
 	}
 }
 
+// ------------------------------------------------------------------------------------------------------
+// K7/K8 as dvp_run launches them: two kernels per colour.
+//   k_sweep_score   the 8-direction candidate search and the 16 x S (minus duplicates) NCCs that score the candidates — 70 %
+//                   of the sweep's texture fetches, no RNG, no refinement state: 256-thread blocks, 3 per SM (24 warps / SM,
+//                   against 12 for the single kernel, whose per-thread cost columns and RNG / refinement registers cap it).
+//                   Candidate costs, the winning ladder offsets and the direction flags go to a scratch area in HBM
+//                   ((9 S + 9) words per pixel of the colour, written and read once, coalesced).
+//   k_sweep_update  view selection, the current plane's cost, acceptance, refinement, write-back: 128-thread blocks, 4 per SM.
+// Results are those of the reference kernel for ONE outcome of its direction-4 race, the same on every run: every pixel
+// of the colour scores its candidates before any pixel of the colour is rewritten, and direction 4's winner is kept as it
+// was scored (the reference reads it again at acceptance, APD.cu:2559-2563).  tests/test_gpu_parity.py checks that this is
+// an outcome the reference can produce (dvp_debug_race_explain) and that race-free launches equal the reference bit for bit.
+struct SweepScratch {
+	float* cost;        // [(9 S)][slots]: rows d * S + v = cost of direction d's candidate in view v; rows 8 S + v = spare (second ladder, then the CDF)
+	uint32_t* flag;     // [slots] bit d: direction d has a candidate
+	uint4* pos;         // [slots] eight 16-bit ladder offsets of the winners
+	float4* d4_plane;   // [slots] plane of direction 4's winner as scored
+	int slots;          // W * ceil(H / 2): pixel (x, y) of the colour <-> slot (y >> 1) * W + x
+};
+
+__global__ void __launch_bounds__(256, 3) k_sweep_score(const __grid_constant__ KArgs a, int iter, int red, int yy_limit, const SweepScratch sc) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	constexpr int T = 256;
+	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
+	const int S = a.S, W = a.W, H = a.H;
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int yy = blockIdx.y * blockDim.y + threadIdx.y;
+	const int y = 2 * yy + ((x & 1) ^ red);
+	if (x >= W || y >= H || yy >= yy_limit) return;
+	const int center = y * W + x;
+	if (a.weak[center] == DVP_WEAK) return;
+	const size_t slot = (size_t)yy * W + x;
+	float* const cost = sc.cost + slot;
+	const size_t row = (size_t)sc.slots;
+#define SCOST(i) cost[(size_t)(i) * row]
+
+	RefPatch rp;
+	rp.prepare<false>(a, x, y, a.prm.use_radius ? a.radius[center] : a.prm.strong_radius, wt, T);
+
+	// `float cost_array[8][32] = {2.0f}` : element [0][0] is 2, everything else 0 (bug B2, reproduced)
+	for (int i = 0; i < 8 * S; ++i) SCOST(i) = 0.0f;
+	SCOST(0) = 2.0f;
+	uint32_t flag = 0;
+	uint32_t posw[4] = {0, 0, 0, 0};   // eight 16-bit offsets
+	auto set_pos = [&](int d, int k) { posw[d >> 1] = (posw[d >> 1] & ~(0xffffu << (16 * (d & 1)))) | ((uint32_t)k << (16 * (d & 1))); };
+	auto get_pos = [&](int d) -> int { return (int)((posw[d >> 1] >> (16 * (d & 1))) & 0xffffu); };
+	float4 d4_plane = make_float4(0.f, 0.f, 0.f, 0.f);
+
+	const bool on_edge = a.edge[center] != 0;
+	const short2* edge_neigh = a.edge_neigh + (size_t)center * DVP_EDGE_NEIGH_NUM;
+	const float max_edge_dist = DVP_MAX(H, W) / 30.0f;
+	const int min_step_len = 2;
+	const float good_threshold = 0.8f * expf((iter) * (iter) / (-90.0f));
+	const float bad_threshold = 1.2f;
+
+#pragma unroll 1
+	for (int d = 0; d < 8; ++d) {
+		const int dx = c_dir[d][0], dy = c_dir[d][1];
+		const int sx = 5 * dx, sy = 5 * dy;
+		int fx = 0, fy = 0;
+		if (d > 4) { if (d % 2) fx = dx; else fy = dy; }  // colour fix on directions 5,6,7 only (B6)
+		// ---- edge-adaptive ladder (APD.cu:2053-2087) ----
+		{
+			const short2 edge_pt = edge_neigh[d];
+			const int ex = edge_pt.x - x, ey = edge_pt.y - y;
+			float dist = (float)sqrt((double)(ex * ex) + (double)(ey * ey));
+			if (d >= 4) dist = (float)((double)dist / sqrt(2.0));
+			if (on_edge) {
+				dist = 11 * min_step_len;
+			} else if (edge_pt.y == -1 || dist >= max_edge_dist) {  // `!edge_pt.x == -1` is always false (B5)
+				dist = max_edge_dist;
+				if (d >= 4) dist = (float)((double)dist / sqrt(2.0));
+			}
+			const int step_num = DVP_MIN(DVP_MAX(11, (int)(1.0f * dist / min_step_len)), 22);
+			int step_len = DVP_MAX((int)(1.0f * dist / step_num), min_step_len);
+			if (d < 4 && step_len % 2 == 1) step_len -= 1;
+			int min_pos = -1, min_k = 0;
+			float min_cost = FLT_MAX;
+			for (int step = 0; step < step_num; ++step) {
+				const int tx = x + sx + step * step_len * dx + fx, ty = y + sy + step * step_len * dy + fy;
+				if (!(tx >= 0 && ty >= 0 && tx < W && ty < H)) continue;
+				const int tc = tx + ty * W;
+				const float c = a.costs[tc];
+				if (min_cost > c) { min_pos = tc; min_k = step * step_len; min_cost = c; }
+			}
+			if (min_cost < FLT_MAX) {
+				flag |= 1u << d;
+				set_pos(d, min_k);
+				const float4 pl = a.planes[min_pos];
+				if (d == 4) d4_plane = pl;
+				for (int v = 0; v < S; ++v)
+					SCOST(d * S + v) = ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+			}
+		}
+		// ---- fixed 11 x 2 px ladder for non-edge pixels; keep the better of the two (APD.cu:2090-2140) ----
+		if (!on_edge) {
+			const bool has_before = (flag >> d) & 1;
+			int min_pos = -1, min_k = 0;
+			float min_cost = FLT_MAX;
+			for (int step = 0; step < 11; ++step) {
+				const int tx = x + sx + step * min_step_len * dx + fx, ty = y + sy + step * min_step_len * dy + fy;
+				if (!(tx >= 0 && ty >= 0 && tx < W && ty < H)) continue;
+				const int tc = tx + ty * W;
+				const float c = a.costs[tc];
+				if (min_cost > c) { min_pos = tc; min_k = step * min_step_len; min_cost = c; }
+			}
+			// same winner as the adaptive ladder: same plane, same costs, nothing is replaced (APD.cu:2126) — not rescored
+			const bool same_winner = has_before && min_k == get_pos(d);
+			if (min_cost < FLT_MAX && !same_winner) {
+				flag |= 1u << d;
+				const float4 pl = a.planes[min_pos];
+				int good0 = 0, good1 = 0, bad0 = 0, bad1 = 0;
+				for (int v = 0; v < S; ++v) {
+					const float c1 = ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
+					SCOST(8 * S + v) = c1;
+					const float c0 = SCOST(d * S + v);
+					if (c0 < good_threshold) good0++;
+					if (c0 > bad_threshold) bad0++;
+					if (c1 < good_threshold) good1++;
+					if (c1 > bad_threshold) bad1++;
+				}
+				if (!has_before || good1 > good0 || (good1 == good0 && bad1 < bad0)) {
+					set_pos(d, min_k);
+					if (d == 4) d4_plane = pl;
+					for (int v = 0; v < S; ++v) SCOST(d * S + v) = SCOST(8 * S + v);
+				}
+			}
+		}
+	}
+	sc.flag[slot] = flag;
+	sc.pos[slot] = make_uint4(posw[0], posw[1], posw[2], posw[3]);
+	sc.d4_plane[slot] = d4_plane;
+#undef SCOST
+}
+
+__global__ void __launch_bounds__(128, 4) k_sweep_update(const __grid_constant__ KArgs a, int iter, int red, int yy_limit, const SweepScratch sc) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	constexpr int T = 128;
+	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
+	const int S = a.S, W = a.W, H = a.H;
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int yy = blockIdx.y * blockDim.y + threadIdx.y;
+	const int y = 2 * yy + ((x & 1) ^ red);
+	if (x >= W || y >= H || yy >= yy_limit) return;
+	const int center = y * W + x;
+	if (a.weak[center] == DVP_WEAK) return;
+	const size_t slot = (size_t)yy * W + x;
+	float* const cost = sc.cost + slot;
+	const size_t row = (size_t)sc.slots;
+#define SCOST(i) cost[(size_t)(i) * row]
+
+	RefPatch rp;
+	rp.prepare<false>(a, x, y, a.prm.use_radius ? a.radius[center] : a.prm.strong_radius, wt, T);
+	const uint32_t flag = sc.flag[slot];
+	const uint4 posq = sc.pos[slot];
+	const uint32_t posw[4] = {posq.x, posq.y, posq.z, posq.w};
+
+	// ---- multi-hypothesis joint view selection (APD.cu:2462-2530) ----
+	Rng rng; rng.load(a.rng, a.N, center);
+	ViewWeights vw; vw.clear();
+	{
+		// priors from the 4-neighbours, guarded by flag[0], flag[2], flag[4], flag[6] (B16, reproduced;
+		// `selected` has one padded row on each side so the border reads are defined)
+		const int npos[4] = {center - W, center + W, center - 1, center + 1};
+		uint32_t nsel[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) nsel[i] = ((flag >> (2 * i)) & 1) ? a.selected[npos[i]] : 0u;
+		const float cost_threshold = 0.8 * expf((iter) * (iter) / (-90.0f));
+		for (int i = 0; i < S; i++) {
+			float prior = 0.0f;
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				if ((flag >> (2 * k)) & 1) prior += is_set(nsel[k], i) ? 0.9f : 0.1f;
+			float count = 0;
+			int count_false = 0;
+			float tmpw = 0;
+			for (int j = 0; j < 8; j++) {
+				const float c = SCOST(j * S + i);
+				if (c < cost_threshold) {
+					tmpw += expf(c * c / (-0.18f));
+					count++;
+				}
+				if (c > 1.2f) count_false++;
+			}
+			float prob = 0.0f;
+			if (count > 2 && count_false < 3) prob = tmpw / count;
+			else if (count_false < 3) prob = expf(cost_threshold * cost_threshold / (-0.32f));
+			prob = prob * prior;
+			SCOST(8 * S + i) = prob;
+		}
+		// TransformPDFToCDF (APD.cu:356-370); all-zero probabilities give NaN here (B18, reproduced)
+		float prob_sum = 0.0f;
+		for (int i = 0; i < S; ++i) prob_sum += SCOST(8 * S + i);
+		const float inv_prob_sum = 1.0f / prob_sum;
+		float cum_prob = 0.0f;
+		for (int i = 0; i < S; ++i) {
+			const float prob = SCOST(8 * S + i) * inv_prob_sum;
+			cum_prob += prob;
+			SCOST(8 * S + i) = cum_prob;
+		}
+		for (int sample = 0; sample < 15; ++sample) {
+			const float rand_prob = rng.uniform() - FLT_EPSILON;
+			for (int image_id = 0; image_id < S; ++image_id) {
+				if (SCOST(8 * S + image_id) > rand_prob) { vw.inc(image_id); break; }
+			}
+		}
+	}
+	vw.store(a.view_weight + (size_t)center * DVP_MAX_IMAGES);
+
+	uint32_t temp_selected = 0;
+	float weight_norm = 0;
+	for (int i = 0; i < S; ++i) {
+		const int wv = vw.get(i);
+		if (wv > 0) { temp_selected |= 1u << i; weight_norm += wv; }
+	}
+
+	// ---- aggregated candidate costs and the current plane (APD.cu:2532-2567) ----
+	int min_cost_idx = 0;
+	float min_final = 0.f;
+	for (int i = 0; i < 8; ++i) {
+		float fc = 0.0f;
+		for (int j = 0; j < S; ++j) {
+			const int wv = vw.get(j);
+			if (wv > 0) fc += wv * SCOST(i * S + j);
+		}
+		fc /= weight_norm;
+		if (i == 0 || fc <= min_final) { min_final = fc; min_cost_idx = i; }  // FindMinCostIndex: '<=' keeps the last
+	}
+
+	float4 plane_now = a.planes[center];
+	float cost_now = 0.0f;
+	for (int v = 0; v < S; ++v) {
+		const int wv = vw.get(v);
+		if (wv > 0) {  // zero-weight views contribute exactly 0 in the reference
+			const float c = ncc_cost<kSweepRB>(a, a.views[v], a.tex_img[v + 1], x, y, plane_now, rp, wt, T);
+			cost_now += wv * c;
+		}
+	}
+	cost_now /= weight_norm;
+	const float cost_stored = cost_now;  // costs[center] = cost_now (APD.cu:2554)
+	float depth_now = depth_from_plane(a.ref, plane_now, x, y);
+	uint32_t sel_now = a.selected[center];
+
+	if ((flag >> min_cost_idx) & 1) {
+		float4 cand;
+		if (min_cost_idx == 4) {
+			cand = sc.d4_plane[slot];   // the same-colour candidate, as it was scored (see the header of this pair of kernels)
+		} else {
+			const int dx = c_dir[min_cost_idx][0], dy = c_dir[min_cost_idx][1];
+			const int k = (int)((posw[min_cost_idx >> 1] >> (16 * (min_cost_idx & 1))) & 0xffffu);
+			int fx = 0, fy = 0;
+			if (min_cost_idx > 4) { if (min_cost_idx % 2) fx = dx; else fy = dy; }
+			const int cx = x + 5 * dx + k * dx + fx, cy = y + 5 * dy + k * dy + fy;
+			cand = a.planes[cx + cy * W];   // a pixel of the other colour: not written by this launch
+		}
+		const float depth_before = depth_from_plane(a.ref, cand, x, y);
+		if (depth_before >= a.prm.depth_min && depth_before <= a.prm.depth_max && min_final < cost_now) {
+			depth_now = depth_before;
+			plane_now = cand;
+			cost_now = min_final;
+			sel_now = temp_selected;
+			a.selected[center] = temp_selected;
+		}
+	}
+
+	refine_strong(a, x, y, &plane_now, &depth_now, &cost_now, rng, vw, weight_norm, sel_now, rp, wt, T);
+	rng.store(a.rng, a.N, center);
+
+	if (a.prm.state == DVP_REFINE_INIT) {
+		if (cost_now < cost_stored - 0.1) {
+			a.costs[center] = cost_now;
+			a.planes[center] = plane_now;
+		} else {
+			a.costs[center] = cost_stored;
+		}
+	} else {
+		a.costs[center] = cost_now;
+		a.planes[center] = plane_now;
+	}
+#undef SCOST
+}
+
 // ---- instrumentation: which pixels of an observed sweep result does a forced choice reproduce? -----------------------
 // expected rand is the canonical [N][6] layout; the shadow rng is the engine's 6 SoA planes
 __device__ __forceinline__ bool pixel_equal(const KArgs& a, int c, const float4* pl_a, const float* co_a, const uint32_t* se_a, const uint8_t* vw_a, const uint32_t* rng_soa,
@@ -841,12 +1125,37 @@ cudaError_t launch_random_init(const KArgs& a, cudaStream_t st) {
 	k_random_init<<<full_grid(a, b), b, patch_smem_bytes(256), st>>>(a);
 	return cudaGetLastError();
 }
-cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, cudaStream_t st) {
-	dim3 b(kSweepBlockX, kSweepThreads / kSweepBlockX);
+size_t sweep_scratch_bytes(int W, int H, int S) {
+	const size_t slots = (size_t)W * ((H + 1) / 2);
+	return slots * ((size_t)9 * S * sizeof(float) + sizeof(uint32_t) + sizeof(uint4) + sizeof(float4)) + 256;
+}
+cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, void* scratch, cudaStream_t st) {
 	const int yy_limit = ref_half_rows(a.H);
+#ifdef DVP_SWEEP_FUSED   // the single-kernel form (kept for A/B measurements and as the body of the forced instrumentation variant)
+	(void)scratch;
+	dim3 b(kSweepBlockX, kSweepThreads / kSweepBlockX);
 	dim3 g((a.W + b.x - 1) / b.x, (yy_limit + b.y - 1) / b.y, 1);
 	k_strong_sweep<false><<<g, b, sweep_smem_bytes(kSweepThreads, a.S), st>>>(a, iter, red, yy_limit, D4Force{});
 	return cudaGetLastError();
+#else
+	if (!scratch) return cudaErrorInvalidValue;
+	SweepScratch sc;
+	sc.slots = a.W * ((a.H + 1) / 2);
+	char* base = reinterpret_cast<char*>(scratch);
+	sc.d4_plane = reinterpret_cast<float4*>(base);          base += (size_t)sc.slots * sizeof(float4);
+	sc.pos = reinterpret_cast<uint4*>(base);                base += (size_t)sc.slots * sizeof(uint4);
+	sc.cost = reinterpret_cast<float*>(base);               base += (size_t)sc.slots * 9 * a.S * sizeof(float);
+	sc.flag = reinterpret_cast<uint32_t*>(base);
+	{
+		dim3 b(32, 8), g((a.W + 31) / 32, (yy_limit + 7) / 8, 1);
+		k_sweep_score<<<g, b, patch_smem_bytes(256), st>>>(a, iter, red, yy_limit, sc);
+	}
+	{
+		dim3 b(32, 4), g((a.W + 31) / 32, (yy_limit + 3) / 4, 1);
+		k_sweep_update<<<g, b, patch_smem_bytes(128), st>>>(a, iter, red, yy_limit, sc);
+	}
+	return cudaGetLastError();
+#endif
 }
 cudaError_t launch_strong_sweep_forced(const KArgs& a, int iter, int red, const D4Force& force, cudaStream_t st) {
 	dim3 b(kSweepBlockX, kSweepThreads / kSweepBlockX);
@@ -905,6 +1214,8 @@ cudaError_t configure_strong_kernels(int S) {
 	if ((e = cudaFuncSetAttribute(k_local_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
 	if ((e = cudaFuncSetAttribute(k_depth_to_weak_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
 	if ((e = cudaFuncSetAttribute(k_strong_sweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kSweepThreads, S)))) return e;
+	if ((e = cudaFuncSetAttribute(k_sweep_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(256)))) return e;
+	if ((e = cudaFuncSetAttribute(k_sweep_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_smem_bytes(128)))) return e;
 	if ((e = cudaFuncSetAttribute(k_strong_sweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_smem_bytes(kSweepThreads, S)))) return e;
 #ifdef DVP_SWEEP_CARVEOUT
 	if ((e = cudaFuncSetAttribute(k_strong_sweep<false>, cudaFuncAttributePreferredSharedMemoryCarveout, DVP_SWEEP_CARVEOUT))) return e;

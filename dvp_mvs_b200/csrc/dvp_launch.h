@@ -51,7 +51,8 @@ cudaError_t launch_nearest_strong(const KArgs& a, short* next_right, short* next
 cudaError_t launch_gen_neighbours(const KArgs& a, const int* weak_list, cudaStream_t st);        // K4
 cudaError_t launch_neighbour_update(const KArgs& a, cudaStream_t st);                            // K5
 cudaError_t launch_random_init(const KArgs& a, cudaStream_t st);                                 // K6
-cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, cudaStream_t st);             // K7 / K8
+size_t sweep_scratch_bytes(int W, int H, int S);                                                 // candidate costs / winners between the two kernels of a sweep
+cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, void* scratch, cudaStream_t st);   // K7 / K8
 // parity instrumentation: direction 4's candidate forced to ladder offset m, planes from snapshots (see k_strong_sweep)
 struct D4Force {
 	int m = 0;                                               // ladder offset of direction 4's candidate: pixel (x - 5 - m, y - 5 - m)

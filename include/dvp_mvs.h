@@ -233,10 +233,13 @@ int dvp_scene_set_view(dvp_scene* scene, int view, const dvp_camera* cam_full, i
 int dvp_scene_set_level(dvp_scene* scene, int view, int level, const float* image, const uint8_t* edge, const int32_t* label);
 /* Row N2, image pyramid: every level image of one view from its full-resolution grey image [full_h][full_w] u8 (what
  * cv::imread(.., IMREAD_GRAYSCALE) returns; host or device), exactly as InuputInitialization builds them — convertTo(CV_32FC1),
- * then cv::resize of the FULL image to each level's size (APD.cpp:1057-1060, 1119-1132; dvp_resize_linear_f32).  With
- * compute_edges != 0 each level's edge map follows (dvp_scene_compute_edges).  Replaces the image argument of
- * dvp_scene_set_level; labels are then given with dvp_scene_set_label (NULL = none). */
-int dvp_scene_set_image(dvp_scene* scene, int view, const uint8_t* image, int compute_edges);
+ * then cv::resize of the FULL image to each level's size (APD.cpp:1057-1060, 1119-1132; dvp_resize_linear_f32).
+ * compute_priors: bit 0 = every level's edge map (dvp_scene_compute_edges), bit 1 = every level's label map
+ * (dvp_label_segment of the full image with the level's scale) — together what GetProblemEdges prepares (main.cpp:193-246).
+ * With both bits a view needs nothing but its image, camera and source list.  dvp_scene_set_label overrides a level's
+ * label map (NULL = none); dvp_scene_get_label copies it out. */
+int dvp_scene_set_image(dvp_scene* scene, int view, const uint8_t* image, int compute_priors);
+int dvp_scene_get_label(dvp_scene* scene, int view, int level, int32_t* label);
 int dvp_scene_set_label(dvp_scene* scene, int view, int level, const int32_t* label);
 int dvp_scene_get_image(dvp_scene* scene, int view, int level, float* image);
 /* FIRST_INIT prior of one view at level 0: [h0][w0][4] (world normal, depth), APD.cpp:1410-1420. */
@@ -258,6 +261,30 @@ int dvp_scene_get_view(dvp_scene* scene, int view, int* w, int* h, float* planes
 int dvp_scene_stats(dvp_scene* scene, double* device_ms, long long* passes);
 /* RescaleMatToTargetSize (APD.cpp:1773-1796, swapped scale factors reproduced) on device memory; elem_bytes 1, 4 or 16. */
 int dvp_rescale_map(int device, const void* src, int src_w, int src_h, void* dst, int dst_w, int dst_h, int elem_bytes);
+
+/* ---- the per-view farm inside the library -----------------------------------------------------------------
+ * One resident scene and one host thread per GPU of the box; the views of every pass are dealt round robin (view v runs on
+ * devices[v % num_devices]), the data path has no collective.  The one exchange step per pass — a view's fresh depth map
+ * goes to the GPUs that own a view listing it as a source — is a peer copy (NVLink) straight between the scenes' device
+ * buffers.  The reference picks ONE GPU by argv[2] and loops over all views in one process (main.cpp:430-434, 452-507).
+ * Within a pass a GPU sees its own views' fresh maps and the other GPUs' previous-pass maps (block Gauss-Seidel); with one
+ * device this is dvp_scene_run exactly.  The setters mirror the dvp_scene_* ones and replicate their input on every GPU. */
+typedef struct dvp_farm dvp_farm;
+dvp_farm* dvp_farm_create(int num_devices, const int* devices, int num_views, int num_levels);
+void dvp_farm_destroy(dvp_farm* farm);
+int dvp_farm_num_devices(dvp_farm* farm);
+int dvp_farm_owner(dvp_farm* farm, int view);     /* the CUDA device that runs this view */
+int dvp_farm_set_max_iterations(dvp_farm* farm, int iterations);
+int dvp_farm_set_view(dvp_farm* farm, int view, const dvp_camera* cam_full, int full_w, int full_h, int num_src, const int* src_views);
+int dvp_farm_set_level(dvp_farm* farm, int view, int level, const float* image, const uint8_t* edge, const int32_t* label);
+int dvp_farm_set_image(dvp_farm* farm, int view, const uint8_t* image, int compute_priors);
+int dvp_farm_compute_edges(dvp_farm* farm, int view, int level);
+int dvp_farm_set_initial_planes(dvp_farm* farm, int view, const float* planes);
+/* The whole schedule (main.cpp:449-511).  wall_ms: host wall clock of the call; exchange_ms: what the slowest GPU thread
+ * spent in the exchange steps (peer copies and their two barriers).  Either may be NULL. */
+int dvp_farm_run(dvp_farm* farm, uint64_t seed, float* wall_ms, float* exchange_ms);
+long long dvp_farm_exchange_bytes(dvp_farm* farm);   /* bytes the last dvp_farm_run moved between GPUs */
+int dvp_farm_get_view(dvp_farm* farm, int view, int* w, int* h, float* planes, uint8_t* weak_info, uint32_t* selected_views, int32_t* radius);
 
 /* dvp_upload whose large maps (plane hypotheses, the 1+S images, the depth maps: ~3/4 of the bytes) travel on a second
  * stream while the next dvp_run already executes K1..K3 and K5; K4 waits for the planes, K6 for everything.  Host

@@ -5,7 +5,9 @@
 // is read from flat binary files that tests/test_adapter.py dumps from a synthetic scene:
 //   <dir>/meta.txt                      num_views num_levels full_w full_h iterations seed
 //   <dir>/view<v>.cam                   dvp_camera (112 bytes), then int32 num_src, then int32 src[num_src]
-//   <dir>/view<v>_level<l>.image|.label float32 / int32 [h][w] at the level's size (dvp_scene_level_size)
+//   <dir>/view<v>.gray                  uint8 [full_h][full_w]: the grey image.  If present it is ALL a view needs besides camera
+//                                       and prior: pyramid, edge maps and label maps are built on the device (dvp_scene_set_image);
+//   <dir>/view<v>_level<l>.image|.label otherwise: float32 / int32 [h][w] at the level's size (dvp_scene_level_size)
 //   <dir>/view<v>.planes                float32 [h0][w0][4]
 //   <dir>/view<v>.color                 uint8 [h][w][3] at the finest level
 // usage: pipeline_main_like <dir> <out.ply> [device]
@@ -54,14 +56,24 @@ int main(int argc, char** argv) {
 		const int* src = reinterpret_cast<const int*>(cam.data() + sizeof(dvp_camera) + 4);
 		CHECK(dvp_scene_set_view(sc, v, camera, full_w, full_h, num_src, src));                    // cam.txt, pair.txt
 		int w = 0, h = 0;
+		bool from_image = false;
+		if (FILE* g = std::fopen((base + ".gray").c_str(), "rb")) {
+			std::fclose(g);
+			std::vector<unsigned char> gray((size_t)full_w * full_h);
+			if (!read_file(base + ".gray", gray.data(), gray.size())) return 5;
+			CHECK(dvp_scene_set_image(sc, v, gray.data(), /*edges + labels*/ 3));                      // InuputInitialization's pyramid + GetProblemEdges
+			from_image = true;
+		}
 		for (int level = 0; level < num_levels; ++level) {
 			CHECK(dvp_scene_level_size(sc, full_w, full_h, level, &w, &h));
-			std::vector<float> image((size_t)w * h);
-			std::vector<int32_t> label((size_t)w * h);
-			if (!read_file(base + "_level" + std::to_string(level) + ".image", image.data(), image.size() * 4)) return 5;
-			if (!read_file(base + "_level" + std::to_string(level) + ".label", label.data(), label.size() * 4)) return 5;
-			CHECK(dvp_scene_set_level(sc, v, level, image.data(), /*edge=*/nullptr, label.data()));
-			CHECK(dvp_scene_compute_edges(sc, v, level));                                             // GetProblemEdges, main.cpp:443-447
+			if (!from_image) {
+				std::vector<float> image((size_t)w * h);
+				std::vector<int32_t> label((size_t)w * h);
+				if (!read_file(base + "_level" + std::to_string(level) + ".image", image.data(), image.size() * 4)) return 5;
+				if (!read_file(base + "_level" + std::to_string(level) + ".label", label.data(), label.size() * 4)) return 5;
+				CHECK(dvp_scene_set_level(sc, v, level, image.data(), /*edge=*/nullptr, label.data()));
+				CHECK(dvp_scene_compute_edges(sc, v, level));                                         // GetProblemEdges, main.cpp:443-447
+			}
 			if (level == 0) {
 				std::vector<float> planes((size_t)w * h * 4);
 				if (!read_file(base + ".planes", planes.data(), planes.size() * 4)) return 6;

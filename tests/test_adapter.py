@@ -180,3 +180,46 @@ def test_adapter_class_executes_process_problem_and_equals_the_engine(tmp_path, 
             else:
                 assert same.mean() > 0.9, (second_pass, n, float(same.mean()))     # the strong sweep's race (two runs of either differ as much)
         e.close()
+
+
+@pytest.mark.gpu
+def test_whole_pipeline_program_from_grey_images_only(tmp_path):
+    """The C++ program given nothing per view but the full-resolution grey image, the camera, the source list and the FIRST_INIT
+    prior: pyramid (row N2), edge maps and label maps (both halves of row N4) are built on the device by dvp_scene_set_image.
+    Byte-identical PLY with the Python-driven run of the same scene (0 iterations: every stage deterministic), and the
+    scene's label maps are dvp_label_segment of the full image at each level's scale."""
+    import numpy as np
+    from dvp_mvs_b200 import Fusion, Scene, synth, label_segment
+    mv = synth.make_multiview(320, 240, 3, 2, seed=6)
+    V, L = 3, 2
+    d = tmp_path / "scene"; d.mkdir()
+    (d / "meta.txt").write_text(f"{V} {L} {mv.full_w} {mv.full_h} 0 77\n")
+    sc0 = synth.make_scene(mv.full_w, mv.full_h, V - 1, seed=6)     # full-resolution grey images with the room's textureless wall
+    grey = [np.clip(np.rint(sc0.images[v]), 0, 255).astype(np.uint8) for v in range(V)]
+    sc = Scene(V, L)
+    sc.set_max_iterations(0)
+    for v in range(V):
+        src = np.asarray(mv.src_views[v], np.int32)
+        (d / f"view{v}.cam").write_bytes(np.asarray(mv.cameras[v]).tobytes() + np.int32(len(src)).tobytes() + src.tobytes())
+        (d / f"view{v}.gray").write_bytes(grey[v].tobytes())
+        (d / f"view{v}.planes").write_bytes(np.ascontiguousarray(mv.planes_init[v], np.float32).tobytes())
+        sc.set_view(v, mv.cameras[v], mv.full_w, mv.full_h, mv.src_views[v])
+        sc.set_image(v, grey[v], compute_edges=True, compute_labels=True)
+        sc.set_initial_planes(v, mv.planes_init[v])
+        for l in range(L):
+            want, _, _ = label_segment(grey[v], L - l)
+            assert (sc.get_label(v, l) == want).all(), (v, l)
+    fw, fh = sc.view_level_size(0, L - 1)
+    colors = [np.stack([np.full((fh, fw), 40 + 50 * v, np.uint8)] * 3, -1) for v in range(V)]
+    for v in range(V):
+        (d / f"view{v}.color").write_bytes(colors[v].tobytes())
+    exe = _build_pipeline_exe(tmp_path)
+    out = subprocess.run([str(exe), str(d), str(tmp_path / "cpp.ply")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    sc.run(seed=77)
+    f = Fusion.from_scene(sc, colors)
+    pts, _ = f.run()
+    f.write_ply(str(tmp_path / "py.ply"))
+    a, b = (tmp_path / "cpp.ply").read_bytes(), (tmp_path / "py.ply").read_bytes()
+    assert a == b and (f"points {len(pts)}" in out.stdout), (len(a), len(b), out.stdout)
+    f.close(); sc.close()
