@@ -22,7 +22,7 @@ derived_states: a second workload whose pixel states, planes, selected views and
 Under torchrun (N > 1) every rank runs its own view on its own GPU (NCCL-free sharding, weak scaling) in BOTH arms —
 the reference picks its device by argv (main.cpp:430-434) and farms as trivially; rank 0 prints ONE JSON line.
 `--workload farm` (BASELINE config C4) strong-scales a whole multi-view, multi-scale schedule with the depth-map
-exchange inside the timed region (dvp_mvs_b200/farm.py).
+exchange inside the timed region (bench_farm.py, dvp_mvs_b200/farm.py).
 """
 from __future__ import annotations
 
@@ -266,8 +266,8 @@ def timed_passes(eng, inputs, steps, warmup, ref_mode):
 def main():
     args = parse()
     if args.workload == "farm":
-        from dvp_mvs_b200 import farm_bench
-        return farm_bench.main(args)
+        import bench_farm
+        return bench_farm.main(args)
     import torch
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None

@@ -559,7 +559,10 @@ __global__ void __launch_bounds__(256, 3) k_sweep_score(const __grid_constant__ 
 #undef SCOST
 }
 
-__global__ void __launch_bounds__(128, 4) k_sweep_update(const __grid_constant__ KArgs a, int iter, int red, int yy_limit, const SweepScratch sc) {
+#ifndef DVP_UPDATE_MIN_BLOCKS
+#define DVP_UPDATE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, DVP_UPDATE_MIN_BLOCKS) k_sweep_update(const __grid_constant__ KArgs a, int iter, int red, int yy_limit, const SweepScratch sc) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	constexpr int T = 128;
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;

@@ -32,7 +32,10 @@ constexpr int kWeakThreads = DVP_WEAK_THREADS;   // WEAK sweep block = one tile 
 #define DVP_K4_THREADS 64
 #endif
 constexpr int kK4Threads = DVP_K4_THREADS;       // K4 block = one (threads / 8) x 8 pixel tile of the WEAK list
-constexpr int kWideRB = 2;          // ... in the 256-thread, 24-warp/SM kernels (K6, K15, K16)
+#ifndef DVP_WIDE_RB
+#define DVP_WIDE_RB 2
+#endif
+constexpr int kWideRB = DVP_WIDE_RB;          // ... in the 256-thread, 24-warp/SM kernels (K6, K15, K16)
 
 // shared memory: 36 (w, w*r) pairs per thread
 inline size_t patch_smem_bytes(int threads) { return (size_t)kHoistSamples * threads * sizeof(float2); }
