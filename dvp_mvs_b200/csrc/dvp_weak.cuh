@@ -172,6 +172,11 @@ __device__ __forceinline__ float ncc_tail(float s_w, float s_r, float s_rr, floa
 // reference ComputeBilateralNCCNew, APD.cu:835-1021: 0.25 * centre patch (6x6 at the adaptive radius, colour-only
 // weights) + 0.75 * mean over the <= 11 anchor pixels of a 9-sample NCC whose offsets are the anchor's
 // visibility-aware `candidate` offsets for this view (fallback: the +-5 ring).
+// Tried on B200 and rejected (bench workload, K10 + K11 = 53.8 ms; all bit-exact): scoring the hypotheses of a pixel in batches
+// with the reference side formed once per (anchor, view) — 12 % fewer instructions, but 2.2 KB of stack per thread and 2.3 GB
+// of local-memory DRAM traffic per launch (64.4 ms); a two-deep software pipeline over the anchors with the centre patch read a
+// row at a time — long-scoreboard stalls 4.3 -> 3.4 per issue, but 200 KB of SASS and instruction-fetch stalls (61.0 ms;
+// __noinline__: 61.8 ms).  ncu (profiles/r02_top_kernels_ncu.txt): TEX data pipe 54 %, LSU data pipe 41 %, issue 45 %, 24 warps.
 __device__ __forceinline__ float ncc_new(const KArgs& a, int px, int py, int v /*0-based view*/, const float4 pl) {
 	const int W = a.W, H_ = a.H;
 	const ViewConst& vc = a.views[v];
@@ -205,6 +210,10 @@ __device__ __forceinline__ float ncc_new(const KArgs& a, int px, int py, int v /
 		if (k == 0) {
 			int radius = a.prm.strong_radius, inc = a.prm.strong_increment;
 			if (a.prm.use_radius) { radius = a.radius[center]; inc = DVP_MAX(2, (int)(2.0 * radius / 5.0)); }
+			// radius 0 (what K9 stores for every pixel with a fit plane): ONE sample, the pixel itself.  Its weight is
+			// ex2(-0) = 1, the sum of weights 1, rcp.approx(1) = 1, so the reference-side variance is fma(1, r*r, -(r*r)) = 0
+			// < 1e-5 whatever the source holds: the reference returns cost_max.  Decided without the load and the fetch.
+			if (radius == 0 && np.x == px && np.y == py) { center_cost = kCostMax; continue; }
 			DVP_COUNT(a, radius >= 0 ? ((2 * radius) / inc + 1) * ((2 * radius) / inc + 1) : 0);
 			for (int i = -radius; i <= radius; i += inc) {
 				const float xf = (float)(np.x + i);
@@ -275,166 +284,5 @@ __device__ __forceinline__ float ncc_new(const KArgs& a, int px, int py, int v /
 	return cost;
 }
 
-// ---- the deformable NCC of SEVERAL plane hypotheses of one WEAK pixel against one source view ---------------------------
-// ncc_new above follows the reference call by call: every (hypothesis, view) walks the pixel's <= 11 anchors and, per
-// anchor, loads its selected-view word, its 8 sample offsets for the view, the 9 reference pixels at those offsets and
-// evaluates 9 colour weights — all of which depend on (pixel, anchor, view) only, not on the hypothesis.  A sweep evaluates
-// 8 + 2 + 5 hypotheses per pixel and view; these scattered, dependent loads (not the texture fetches) are what bounds the
-// kernel (ncu: long-scoreboard stalls on the first use of a reference pixel, texture path 20 % busy).
-// ncc_new_batch turns the loops inside out: anchors outside, hypotheses inside.  Per (anchor, view) the reference side —
-// offsets, reference pixels, weights w, products t = w r and the sums of w, t, r t — is formed once and every hypothesis
-// of the batch reuses it; only the homography, the 9 source fetches and the source-side sums are per hypothesis.
-// Each hypothesis still sees exactly the operations of ncc_new in ncc_new's order (anchors ascending, samples ascending),
-// so the results are bit-identical.
-constexpr int kWeakBatchMax = 8;
-
-struct WeakPixel {   // per pixel, loaded once per kernel instead of once per (hypothesis, view)
-	short2 nb[DVP_NEIGHBOUR_NUM];
-	uint32_t nsel[DVP_NEIGHBOUR_NUM];   // selected-view words of the anchors (entry 0 unused)
-	float ref_center_pix, rcp_c;
-	int radius, inc;
-	__device__ __forceinline__ void load(const KArgs& a, int px, int py, int center) {
-		const short2* src = a.neighbours + (size_t)a.neighbours_map[center] * DVP_NEIGHBOUR_NUM;
-#pragma unroll
-		for (int k = 0; k < DVP_NEIGHBOUR_NUM; ++k) nb[k] = src[k];
-#pragma unroll
-		for (int k = 0; k < DVP_NEIGHBOUR_NUM; ++k) {
-			nsel[k] = 0;
-			if (k > 0 && nb[k].x != -1 && nb[k].y != -1) nsel[k] = a.selected[nb[k].x + nb[k].y * a.W];
-		}
-		float rcp_s; RefPatch::sigma_rcps(a.prm, rcp_s, rcp_c);
-		ref_center_pix = RefPatch::ref_pixel(a, px, py);
-		radius = a.prm.strong_radius; inc = a.prm.strong_increment;
-		if (a.prm.use_radius) { radius = a.radius[center]; inc = DVP_MAX(2, (int)(2.0 * radius / 5.0)); }
-	}
-};
-
-// out[p] = ncc_new(a, px, py, v, planes[p]) for the hypotheses whose bit is set in `want` (count <= kWeakBatchMax)
-__device__ __noinline__ void ncc_new_batch(const KArgs& a, int px, int py, int v, const WeakPixel& wp, const float4* planes, int count, uint32_t want, float* out) {
-	const int W = a.W, H_ = a.H;
-	const ViewConst& vc = a.views[v];
-	const cudaTextureObject_t src = a.tex_img[v + 1];
-	float Hc[kWeakBatchMax][9];
-	float center_cost[kWeakBatchMax], strong_cost[kWeakBatchMax];
-	int strong_count[kWeakBatchMax];
-	uint32_t alive = 0;   // hypotheses still being evaluated (the others already returned cost_max)
-	for (int p = 0; p < count; ++p) {
-		center_cost[p] = 0.0f; strong_cost[p] = 0.0f; strong_count[p] = 0;
-		if (!((want >> p) & 1)) continue;
-		compute_homography(a.ref, vc, planes[p], Hc[p]);
-		float u, w; warp_point(Hc[p], (float)px, (float)py, u, w);
-		if (u >= (float)W || u < 0.0f || w >= (float)H_ || w < 0.0f) out[p] = kCostMax;
-		else alive |= 1u << p;
-	}
-	const float empty_cost = ncc_tail(0.f, 0.f, 0.f, 0.f, 0.f, 0.f);   // an anchor that does not select the view (the reference folds zero sums)
-	for (int k = 0; k < DVP_NEIGHBOUR_NUM && alive; ++k) {
-		const short2 np = wp.nb[k];
-		if (np.x == -1 || np.y == -1) continue;
-		if (k == 0) {
-			for (int p = 0; p < count; ++p) {
-				if (!((alive >> p) & 1)) continue;
-				const float* H = Hc[p];
-				{
-					float u, w; warp_point(H, (float)np.x, (float)np.y, u, w);
-					if (u < 0 || w < 0 || u >= (float)W || w >= (float)H_) { out[p] = kCostMax; alive &= ~(1u << p); continue; }
-				}
-				float s_r = 0.f, s_rr = 0.f, s_s = 0.f, s_ss = 0.f, s_rs = 0.f, s_w = 0.f;
-				for (int i = -wp.radius; i <= wp.radius; i += wp.inc) {
-					const float xf = (float)(np.x + i);
-					const float hx = __fmul_rn(H[0], xf), hy = __fmul_rn(H[3], xf), hz = __fmul_rn(H[6], xf);
-					float r_r = 0.f, r_rr = 0.f, r_s = 0.f, r_ss = 0.f, r_rs = 0.f, r_w = 0.f;
-					for (int j = -wp.radius; j <= wp.radius; j += wp.inc) {
-						const float yf = (float)(np.y + j);
-						const float ref_pix = RefPatch::ref_pixel(a, np.x + i, np.y + j);
-						const float z = __fadd_rn(H[8], __fmaf_rn(H[7], yf, hz));
-						const float x = __fadd_rn(H[2], __fmaf_rn(H[1], yf, hx));
-						const float y = __fadd_rn(H[5], __fmaf_rn(H[4], yf, hy));
-						const float rz = rcp_approx(z);
-						const float src_pix = tex2D<float>(src, __fmaf_rn(x, rz, 0.5f), __fmaf_rn(y, rz, 0.5f));
-						DVP_COUNT(a, 1);
-						const float w = weight_colour(ref_pix, wp.ref_center_pix, wp.rcp_c);
-						const float t = __fmul_rn(ref_pix, w), u = __fmul_rn(src_pix, w);
-						r_r = __fadd_rn(t, r_r); r_rr = __fmaf_rn(ref_pix, t, r_rr);
-						r_s = __fadd_rn(u, r_s); r_ss = __fmaf_rn(src_pix, u, r_ss);
-						r_rs = __fmaf_rn(src_pix, t, r_rs);
-						r_w = __fadd_rn(w, r_w);
-					}
-					s_r = __fadd_rn(r_r, s_r); s_rr = __fadd_rn(r_rr, s_rr); s_s = __fadd_rn(r_s, s_s);
-					s_ss = __fadd_rn(r_ss, s_ss); s_rs = __fadd_rn(r_rs, s_rs); s_w = __fadd_rn(r_w, s_w);
-				}
-				center_cost[p] = ncc_tail(s_w, s_r, s_rr, s_s, s_ss, s_rs);
-			}
-			continue;
-		}
-		const bool sel = is_set(wp.nsel[k], v) == 1;
-		// reference side of this (anchor, view), once for all hypotheses
-		short rx[9], ry[9];
-		float wq[9], tq[9];
-		float s_w = 0.f, s_r = 0.f, s_rr = 0.f;
-		if (sel) {
-			const int nei_center = np.x + np.y * W;
-			const uint4* cand4 = reinterpret_cast<const uint4*>(a.candidate + ((size_t)nei_center * DVP_NUM_IMAGES + v) * DVP_LAB_BOUNDARY_NUM);
-			const uint4 c_lo = __ldg(cand4), c_hi = __ldg(cand4 + 1);
-			const uint32_t cw[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
-			const int def_i[9] = {-5, -5, -5, 0, 0, 5, 5, 5, 0}, def_j[9] = {-5, 0, 5, -5, 5, -5, 0, 5, 0};
-			float ref_pix[9];
-#pragma unroll
-			for (int q = 0; q < 9; q++) {
-				int i = 0, j = 0;
-				if (q != 8) { i = (int)(short)(cw[q] & 0xffffu); j = (int)(short)(cw[q] >> 16); }
-				if (i == 0 && j == 0) { i = def_i[q]; j = def_j[q]; }
-				rx[q] = (short)(np.x + i); ry[q] = (short)(np.y + j);
-				ref_pix[q] = RefPatch::ref_pixel(a, rx[q], ry[q]);
-			}
-#pragma unroll
-			for (int q = 0; q < 9; q++) {
-				wq[q] = weight_colour(ref_pix[q], wp.ref_center_pix, wp.rcp_c);
-				tq[q] = __fmul_rn(ref_pix[q], wq[q]);
-				s_r = __fadd_rn(__fadd_rn(0.f, tq[q]), s_r);
-				s_rr = __fadd_rn(__fmaf_rn(ref_pix[q], tq[q], 0.f), s_rr);
-				s_w = __fadd_rn(__fadd_rn(0.f, wq[q]), s_w);
-			}
-		}
-		for (int p = 0; p < count; ++p) {
-			if (!((alive >> p) & 1)) continue;
-			const float* H = Hc[p];
-			{
-				float u, w; warp_point(H, (float)np.x, (float)np.y, u, w);
-				if (u < 0 || w < 0 || u >= (float)W || w >= (float)H_) {
-					if (sel) { strong_cost[p] += kCostMax; strong_count[p]++; }
-					continue;
-				}
-			}
-			float temp_cost = empty_cost;
-			if (sel) {
-				float src_pix[9];
-#pragma unroll
-				for (int q = 0; q < 9; q++) src_pix[q] = sample_src_warped(H, src, (float)rx[q], (float)ry[q]);
-				DVP_COUNT(a, 9);
-				float s_s = 0.f, s_ss = 0.f, s_rs = 0.f;
-#pragma unroll
-				for (int q = 0; q < 9; q++) {
-					const float u = __fmul_rn(src_pix[q], wq[q]);
-					s_s = __fadd_rn(__fadd_rn(0.f, u), s_s);
-					s_ss = __fadd_rn(__fmaf_rn(src_pix[q], u, 0.f), s_ss);
-					s_rs = __fadd_rn(__fmaf_rn(src_pix[q], tq[q], 0.f), s_rs);
-				}
-				temp_cost = ncc_tail(s_w, s_r, s_rr, s_s, s_ss, s_rs);
-			}
-			strong_cost[p] += temp_cost; strong_count[p]++;
-		}
-	}
-	for (int p = 0; p < count; ++p) {
-		if (!((alive >> p) & 1)) continue;
-		float cost;
-		if (strong_count[p] == 0) cost = center_cost[p];
-		else {
-			float sc = strong_cost[p] / strong_count[p];
-			sc = DVP_MIN(sc, kCostMax);
-			cost = 0.25 * center_cost[p] + 0.75 * sc;
-		}
-		out[p] = cost;
-	}
-}
 
 }  // namespace dvp
