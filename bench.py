@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "farm"])
+    ap.add_argument("--farm-driver", default="torchrun", choices=["torchrun", "library"],
+                    help="--workload farm: one process per GPU + NCCL exchange (default), or ONE process whose library farm (dvp_farm_*) runs one host thread per GPU with peer copies")
     ap.add_argument("--width", type=int, default=0, help="override the workload's width")
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--src", type=int, default=4)

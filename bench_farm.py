@@ -48,7 +48,45 @@ def make_scene(seed=0):
     return mv
 
 
+def main_library(args):
+    """`--farm-driver library`: the same schedule through dvp_farm_* (dvp_mvs_b200/csrc/dvp_farm.inc) — ONE process, one host
+    thread and one resident scene per GPU inside the library, depth maps exchanged by peer copies; what a C++ host would call."""
+    import torch
+    from dvp_mvs_b200 import Farm
+    n = min(args.gpus, torch.cuda.device_count())
+    if n < 1:
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    mv = make_scene(0)
+    fa = Farm(list(range(n)), V_VIEWS, LEVELS)
+    for v in range(V_VIEWS):
+        fa.set_view(v, mv.cameras[v], mv.full_w, mv.full_h, mv.src_views[v])
+        for l in range(LEVELS):
+            fa.set_level(v, l, mv.levels[l][v]["image"], None, mv.levels[l][v]["label"])
+            fa.compute_edges(v, l)
+    pixels = sum(mv.levels[l][v]["w"] * mv.levels[l][v]["h"] for l in range(LEVELS) for v in range(V_VIEWS)) * 4
+    walls, exchs, moved = [], [], 0
+    for step in range(args.warmup + args.steps):
+        for v in range(V_VIEWS):
+            fa.set_initial_planes(v, mv.planes_init[v])
+        for d in range(n):
+            torch.cuda.synchronize(d)
+        wall, exch, moved = fa.run(seed=7)
+        if step >= args.warmup:
+            walls.append(wall); exchs.append(exch)
+    ms = float(np.mean(walls))
+    print(json.dumps({"metric": "scene_schedule_mpix_per_s", "value": pixels / (ms / 1e3) / 1e6, "unit": "Mpix/s", "n_gpus": n, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "driver": "library farm (dvp_farm_run: one host thread + one scene per GPU, peer copies)",
+                      "config": {"workload": f"tnt_shaped_schedule_V{V_VIEWS}_{FULL_W}x{FULL_H}_L{LEVELS}_S{NUM_SRC}_it3", "views": V_VIEWS,
+                                 "full_size": [FULL_W, FULL_H], "src_views": NUM_SRC, "passes_per_view": 4 * LEVELS, "view_pass_jobs": 4 * LEVELS * V_VIEWS,
+                                 "timing": "wall clock of dvp_farm_run (host-driven schedule, all GPU threads joined)"},
+                      "exchange_ms_per_step": float(np.mean(exchs)), "exchange_share": float(np.mean(exchs)) / ms, "exchange_bytes_per_step": moved}))
+    fa.close()
+
+
 def main(args):
+    if getattr(args, "farm_driver", "torchrun") == "library" and args.impl != "reference":
+        return main_library(args)
     import torch
     import torch.distributed as dist
     root = os.path.dirname(os.path.abspath(__file__))

@@ -140,7 +140,9 @@ class HostChain:
         e = self._engine(w, h, S, p)
         e.upload(images=images, depths=depths, cameras=cams, planes=planes, selected_views=selected, weak_info=weak,
                  edge=L["edge"], label=L["label"], radius=radius, seed=seed, params=p)
-        e.run()
+        # the reference engine replays RunPatchMatch's launch sequence with K2 from the build that runs on sm_100a (mode 0):
+        # its own APD::RunPatchMatch() (mode 1) faults in the miscompiled GenEdgeInform (profiles/r02_reference_k2_miscompile.md)
+        e.run(**({"mode": 0} if getattr(e, "prefix", "") == "ref_" else {}))
         planes, weak, sel, rad = e.download()
         # ProcessProblem, main.cpp:297-363
         bad = (planes[..., 3] < p.depth_min) | (planes[..., 3] > p.depth_max)
