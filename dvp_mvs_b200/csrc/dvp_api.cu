@@ -264,6 +264,9 @@ int upload_parts(dvp_ctx* ctx, const UploadSrc* in, const dvp_params* params, bo
 		if (q.geom_consistency && !in->have_depths) return DVP_ERR_ARG;
 		if (q.max_iterations < 0 || q.max_iterations > 64) return DVP_ERR_ARG;
 		if (!q.use_edge) return DVP_ERR_UNSUPPORTED;  // the ACMH-style branch (APD.cu:2142-2460) is never enabled by main.cpp
+		// GenNeighbours gives every one of its 8 origin directions 4 slots ("max is 4 from [1, 2, 4]", APD.cu:3375):
+		// rotate_time is 1, 2 or 4 in every schedule (main.cpp:467, 500); more than 4 would overlap the slots of the next direction
+		if (q.use_APD && (q.rotate_time < 1 || q.rotate_time > 4)) return DVP_ERR_ARG;
 	}
 	if (params) ctx->prm = *params;
 	const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;

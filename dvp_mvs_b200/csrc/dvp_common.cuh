@@ -184,6 +184,20 @@ __device__ __forceinline__ void project_on_camera(const float3 P, const float* K
 	pt.y = (K[3] * tmp.x + K[4] * tmp.y + K[5] * tmp.z) / depth;
 }
 
+// x % m for a divisor fixed over a loop, exact for every 32-bit x and m >= 1: q = floor(x * floor((2^32 - 1) / m) / 2^32)
+// underestimates floor(x / m) by at most 2 (x M / 2^32 > x / m - 1 - x / 2^32), so two conditional subtractions finish it
+// (tests/test_host_logic.py checks the arithmetic against % on adversarial and random operands).
+struct FastMod {
+	unsigned int m, M;
+	__host__ __device__ explicit FastMod(unsigned int m_) : m(m_), M(0xFFFFFFFFu / m_) {}
+	__device__ __forceinline__ unsigned int mod(unsigned int x) const {
+		unsigned int r = x - __umulhi(x, M) * m;
+		if (r >= m) r -= m;
+		if (r >= m) r -= m;
+		return r;
+	}
+};
+
 __device__ __forceinline__ int is_set(uint32_t v, int n) { return (v >> n) & 1; }
 // reference APD.cu:186-189 — clears bit n AND every lower bit (bug B1, reproduced on purpose)
 __device__ __forceinline__ void unset_bit_ref(uint32_t* v, int n) { (*v) &= (uint32_t)(0xFFFFFFFEu << n); }

@@ -142,7 +142,10 @@ __device__ __forceinline__ void normalize2(float2* v) {
 	v->x *= inv; v->y *= inv;
 }
 
-__global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_constant__ KArgs a, const int* weak_list) {
+#ifndef DVP_K4_MIN_BLOCKS
+#define DVP_K4_MIN_BLOCKS (768 / DVP_K4_THREADS)   // 24 warps per SM (80 registers)
+#endif
+__global__ void __launch_bounds__(kK4Threads, DVP_K4_MIN_BLOCKS) k_gen_neighbours(const __grid_constant__ KArgs a, const int* weak_list) {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= a.weak_count) return;
 	const int center = weak_list[t];
@@ -156,9 +159,13 @@ __global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_cons
 	Rng rng; rng.load(a.rng, a.N, center);
 	for (int i = 0; i < DVP_NEIGHBOUR_NUM; ++i) neighbours[i] = make_short2(-1, -1);
 	neighbours[0] = make_short2((short)px, (short)py);
+	// Slots 0..31 belong to the 8 x 4 search directions (valid or not: `dir_valid`, one bit each); slots 32..extend_index are
+	// appended by the label-boundary extension and are all valid.  Nothing above extend_index is ever read, so only the
+	// direction slots are initialised (the reference initialises, and later scans, all 160: 1.4 KB of stack writes per pixel).
+	constexpr int kDirSlots = 32;
 	short2 strong_points[kMaxPts];
-	bool dir_valid[kMaxPts];
-	for (int i = 0; i < kMaxPts; ++i) { strong_points[i] = make_short2(-1, -1); dir_valid[i] = false; }
+	uint32_t dir_valid = 0;
+	for (int i = 0; i < kDirSlots; ++i) strong_points[i] = make_short2(-1, -1);
 	int origin_direction_index = -1;
 	int strong_point_size = 0;
 
@@ -168,6 +175,7 @@ __global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_cons
 	const float sin_angle = sin(angle * 3.14159265358979323846 / 180.f);
 	const float threshhold = cos((angle / 2.0f) * 3.14159265358979323846 / 180.0f);
 	const int shift_range = DVP_MAX((int)(tan((angle / 2.0f) * 3.14159265358979323846 / 180.0f) * 20), 1);
+	const FastMod shift_mod((unsigned int)shift_range);   // x % shift_range for the 4 draws of every try: a multiply instead of the generic 32-bit division
 	const float ransac_threshold = a.prm.ransac_threshold;
 
 	bool edge_limit = false;
@@ -202,9 +210,9 @@ __global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_cons
 					for (int radius_iter = 0; radius_iter < 4; ++radius_iter) {
 						// (cond ? 1 : -1) * curand() % range : unsigned arithmetic, two draws per shift, left operand first
 						const unsigned int c0 = rng.next(); const unsigned int c1 = rng.next();
-						const int rand_x_shift = (int)(((unsigned int)(c0 % 2 == 0 ? 1 : -1) * c1) % (unsigned int)shift_range);
+						const int rand_x_shift = (int)shift_mod.mod((unsigned int)(c0 % 2 == 0 ? 1 : -1) * c1);
 						const unsigned int c2 = rng.next(); const unsigned int c3 = rng.next();
-						const int rand_y_shift = (int)(((unsigned int)(c2 % 2 == 0 ? 1 : -1) * c3) % (unsigned int)shift_range);
+						const int rand_y_shift = (int)shift_mod.mod((unsigned int)(c2 % 2 == 0 ? 1 : -1) * c3);
 						float2 direction = make_float2(origin_direction.x * 20 + rand_x_shift, origin_direction.y * 20 + rand_y_shift);
 						normalize2(&direction);
 						const short2 np = make_short2(px + direction.x * radius, py + direction.y * radius);
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_cons
 					}
 #pragma unroll
 					for (int radius_iter = 0; radius_iter < 4; ++radius_iter) {
-						if (dir_valid[dir_index]) continue;   // an earlier try of this batch succeeded: the reference has left the loop
+						if ((dir_valid >> dir_index) & 1) continue;   // an earlier try of this batch succeeded: the reference has left the loop
 						if (probe_idx[radius_iter] < 0) continue;
 						short2 np = probe[radius_iter];
 						if (probe_state[radius_iter] != DVP_STRONG) {
@@ -241,12 +249,12 @@ __global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_cons
 						if (has_same_pt) continue;
 						if (!edge_limit || !bresenham_crosses_edge(a, px, py, np.x, np.y)) {
 							strong_points[dir_index] = np;
-							dir_valid[dir_index] = true;
+							dir_valid |= 1u << dir_index;
 							strong_point_size++;
 							rng.restore(after[radius_iter]);
 						}
 					}
-					if (dir_valid[dir_index]) break;
+					if ((dir_valid >> dir_index) & 1) break;
 				}
 				float2 rotated;
 				rotated.x = origin_direction.x * cos_angle - origin_direction.y * sin_angle;
@@ -310,7 +318,6 @@ __global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_cons
 				if (extend_index + 1 >= kMaxPts) continue;  // cannot happen with rotate_time <= 4 (31 + 128 slots)
 				extend_index++;
 				strong_points[extend_index] = np;
-				dir_valid[extend_index] = true;
 				strong_point_size++;
 			}
 		}
@@ -328,9 +335,9 @@ __global__ void __launch_bounds__(kK4Threads) k_gen_neighbours(const __grid_cons
 	float X[3];
 	get_3d_point(a.ref, px, py, a.planes[center].w, X);
 	const float center_z = X[2];
-	for (int i = 0; i < kMaxPts; ++i) {
-		valid_pts[i] = make_short2(-1, -1);
-		if (dir_valid[i]) {
+	for (int i = 0; i < DVP_NEIGHBOUR_NUM - 1; ++i) valid_pts[i] = make_short2(-1, -1);   // read back below even when fewer anchors survive
+	for (int i = 0; i <= extend_index; ++i) {
+		if (i >= kDirSlots || ((dir_valid >> i) & 1)) {
 			const short2 sp = strong_points[i];
 			const int spc = sp.x + sp.y * W;
 			valid_pts[valid_count] = sp;

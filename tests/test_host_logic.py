@@ -247,3 +247,21 @@ def test_distance_map_walk_gives_the_loop_answer():
             assert skip_answer(edge, dist, ax, ay, bx, by, max_step) == want, (trial, ax, ay, bx, by, max_step)
             checked += 1; crossing += int(want)
     assert checked > 3000 and crossing > 200
+
+
+def test_fast_modulo_of_the_neighbour_search_is_exact():
+    """dvp_common.cuh FastMod (K4's `curand() % shift_range`, APD.cu:3408-3411): q = umulhi(x, floor((2^32 - 1) / m)) plus two
+    conditional subtractions equals x % m for every 32-bit x — checked on adversarial operands (multiples of m and their
+    neighbours, both ends of the range) and a million random ones for every divisor the schedules can produce and beyond."""
+    rng = np.random.default_rng(5)
+    for m in list(range(1, 70)) + [127, 255, 256, 1000, 65535, 65536, 2 ** 31 - 1, 2 ** 31, 2 ** 32 - 1]:
+        M = (2 ** 32 - 1) // m
+        x = np.concatenate([rng.integers(0, 2 ** 32, 1_000_000, dtype=np.uint64),
+                            np.arange(0, 4 * min(m, 10 ** 5) + 4, dtype=np.uint64),
+                            (2 ** 32 - 1 - np.arange(0, 4 * min(m, 10 ** 5) + 4, dtype=np.uint64)),
+                            (rng.integers(0, 2 ** 32 // m + 1, 100_000).astype(np.int64) * m + rng.integers(-1, 2, 100_000)).clip(0, 2 ** 32 - 1).astype(np.uint64)])
+        q = (x * np.uint64(M)) >> np.uint64(32)
+        r = (x - q * np.uint64(m)) & np.uint64(0xFFFFFFFF)
+        r = np.where(r >= m, r - np.uint64(m), r)
+        r = np.where(r >= m, r - np.uint64(m), r)
+        assert (r == x % np.uint64(m)).all(), m
