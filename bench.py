@@ -448,14 +448,12 @@ def main():
     achieved = bytes_per_launch / (sweep_ms * 1e-3) / 1e9
     weak_px = 0 if inputs.get("weak_info") is None else int((inputs["weak_info"] == 0).sum())   # WEAK pixels leave the sweep at once (K10/K11 own them)
     traffic = None   # measured DRAM bytes per sweep launch, from the committed ncu capture of this very workload
-    for prof in ("r02_traffic.json", "r01_traffic.json"):
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", prof))).get(workload, {}).get("k_strong_sweep")
-            if tr:
-                traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
-                break
-        except Exception:
-            pass
+    try:   # profiles/r02_traffic.json: ncu --set full of the two kernels of a sweep launch (tools/ncu_traffic.py), per workload
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(workload, {}).get("k_sweep_pair")
+        if tr:
+            traffic = tr["dram_read_bytes"] + tr["dram_write_bytes"]
+    except Exception:
+        pass
     out = {"metric": "patchmatch_mpix_per_s_per_view", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic", "config": config,
@@ -464,11 +462,12 @@ def main():
            "e2e": {"value": e2e_value, "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": e2e_wall_ms / args.steps},
            "gpu_launches": int(launches * args.steps),
-           "roofline": {"kernel": "k_strong_sweep (K7/K8)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+           "roofline": {"kernel": "k_sweep_score + k_sweep_update (one K7 / K8 launch = this pair)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": bytes_per_launch, "peak_source": peak_src, "avg_launch_ms": sweep_ms,
                         "share_of_step": (per_stage[6] + per_stage[7]) / max(total_ms, 1e-9),
-                        "note": "TEX-bound kernel: the binding roof is the texture unit (measured 1155 Gfetch/s for coherent bilinear fp32 fetches, "
-                                "profiles/r01_tex_coherence_ubench.txt), not HBM; see `tex`"},
+                        "note": "TEX-bound kernels: the binding roof is the texture unit (measured 1155 Gfetch/s for coherent bilinear fp32 fetches, "
+                                "profiles/r01_tex_coherence_ubench.txt; software sampling measured slower, profiles/r02_sampling_path_ubench.txt), not HBM; "
+                                "see `tex`.  traffic = measured DRAM bytes of the pair (ncu), which include the scratch area the two kernels hand over"},
            "per_stage_ms": [round(v, 3) for v in per_stage], "ms_excl_k2_k3": round(excl_k2_k3(per_stage), 3),
            "stage_share": {k: round(v / max(sum(per_stage), 1e-9), 4) for k, v in zip(
                ("K1", "K2", "K3", "K4", "K5", "K6", "K7", "K8", "K9", "K10", "K11", "K12", "K13", "K14", "K15+K16", "K16"), per_stage) if v > 0},

@@ -179,8 +179,8 @@ int stage_kernel_count(const dvp_ctx* c, int stage) {
 	case DVP_K4_GEN_NEIGHBOURS: return weak ? 1 : 0;
 	case DVP_K7_BLACK_STRONG: case DVP_K8_RED_STRONG: return 2;   // k_sweep_score + k_sweep_update
 	case DVP_K9_RANSAC_FIT_PLANE: return 1 + (weak ? 1 : 0);
-	case DVP_K10_BLACK_WEAK: return c->colour_count[0] > 0 ? 1 : 0;
-	case DVP_K11_RED_WEAK: return c->colour_count[1] > 0 ? 1 : 0;
+	case DVP_K10_BLACK_WEAK: return c->colour_count[0] > 0 ? kWeakSweepKernels : 0;   // k_weak_score + k_weak_sweep
+	case DVP_K11_RED_WEAK: return c->colour_count[1] > 0 ? kWeakSweepKernels : 0;
 	default: return 1;
 	}
 }
@@ -200,8 +200,12 @@ cudaError_t launch_stage(dvp_ctx* c, const KArgs& a, int stage, int iter) {
 		return launch_strong_sweep(a, iter, stage == DVP_K8_RED_STRONG ? 1 : 0, c->sweep_scratch, st);
 	}
 	case DVP_K9_RANSAC_FIT_PLANE: return launch_ransac_fit(a, c->weak_list, st);
-	case DVP_K10_BLACK_WEAK: return launch_weak_sweep(a, c->colour_list[0], c->colour_count[0], iter, 0, st);
-	case DVP_K11_RED_WEAK: return launch_weak_sweep(a, c->colour_list[1], c->colour_count[1], iter, 1, st);
+	case DVP_K10_BLACK_WEAK:
+	case DVP_K11_RED_WEAK: {   // the anchors' hypotheses are scored into the (idle) K7 / K8 scratch area first
+		const int col = stage == DVP_K11_RED_WEAK ? 1 : 0;
+		if (c->colour_count[col] > 0 && !c->sweep_scratch) { cudaError_t e = cudaMalloc(&c->sweep_scratch, sweep_scratch_bytes(c->W, c->H, c->S)); if (e != cudaSuccess) return e; }
+		return launch_weak_sweep(a, c->colour_list[col], c->colour_count[col], iter, col, c->sweep_scratch, st);
+	}
 	case DVP_K12_DEPTH_NORMAL: return launch_depth_normal(a, st);
 	case DVP_K13_BLACK_FILTER: return launch_filter(a, 0, st);
 	case DVP_K14_RED_FILTER: return launch_filter(a, 1, st);

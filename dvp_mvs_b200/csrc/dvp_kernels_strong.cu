@@ -1130,7 +1130,9 @@ cudaError_t launch_random_init(const KArgs& a, cudaStream_t st) {
 }
 size_t sweep_scratch_bytes(int W, int H, int S) {
 	const size_t slots = (size_t)W * ((H + 1) / 2);
-	return slots * ((size_t)9 * S * sizeof(float) + sizeof(uint32_t) + sizeof(uint4) + sizeof(float4)) + 256;
+	const size_t strong = slots * ((size_t)9 * S * sizeof(float) + sizeof(uint32_t) + sizeof(uint4) + sizeof(float4));
+	const size_t weak = (slots + 32) * (size_t)8 * S * sizeof(float);   // k_weak_score: 8 S rows of the colour's WEAK count rounded up to 32 (<= slots + 31)
+	return (strong > weak ? strong : weak) + 256;
 }
 cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, void* scratch, cudaStream_t st) {
 	const int yy_limit = ref_half_rows(a.H);

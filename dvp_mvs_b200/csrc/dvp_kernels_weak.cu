@@ -587,12 +587,40 @@ __device__ __forceinline__ float weak_weighted_cost(const KArgs& a, int px, int 
 	return temp_cost;
 }
 
+// K10/K11, part 1 — the propagation hypotheses, scored coherently.  A WEAK pixel tries the planes of its first eight anchors
+// (APD.cu:2771-2797): 8 x S deformable NCCs, more than half of the 15 x S the kernel evaluates per pixel, and they need nothing
+// but the pixel, the anchor's plane and the view.  Thread-per-pixel, every lane of a warp walks its own anchors: the reference
+// pixel reads and the source fetches of the 32 lanes are scattered (ncu: TEX and LSU data pipes half busy each behind
+// dependent loads, 207 Gfetch/s against the 1 142 the texture unit sustains when the four lanes of a quad fetch neighbouring
+// texels, profiles/r01_tex_coherence_ubench.txt).  Here EIGHT ADJACENT LANES take the eight hypotheses of ONE pixel: they walk
+// the same anchors at the same sample offsets, so their anchor / selected-view / offset / reference-pixel loads are one
+// broadcast transaction instead of eight, and their source fetches — one reference position warped by eight neighbouring
+// planes — land a few texels apart, which is what the texture unit's quad path wants.  Every lane still folds its own NCC in
+// the reference's sample order: no cross-lane arithmetic, same bits.  Costs go to the sweep scratch area (free between K8 and
+// the next K7), rows (i * S + v) of `stride` floats indexed by the pixel's position in the colour list.
+#ifndef DVP_WEAK_SCORE_MIN_BLOCKS
+#define DVP_WEAK_SCORE_MIN_BLOCKS 4   // 64 registers, 32 warps per SM: 3 % faster than 3 blocks at 80
+#endif
+__global__ void __launch_bounds__(256, DVP_WEAK_SCORE_MIN_BLOCKS) k_weak_score(const __grid_constant__ KArgs a, const int* colour_list, int count, float* __restrict__ scored, int stride) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int slot = t >> 3, i = t & 7;
+	if (slot >= count) return;
+	const int center = colour_list[slot];
+	if (a.weak[center] != DVP_WEAK) return;   // demoted to UNKNOWN by K2/K5 since the list was built
+	const int W = a.W, S = a.S;
+	const int px = center % W, py = center / W;
+	const short2 np = a.neighbours[(size_t)a.neighbours_map[center] * DVP_NEIGHBOUR_NUM + i + 1];
+	if (np.x == -1 || np.y == -1 || a.weak[np.x + np.y * W] != DVP_STRONG) return;   // the consumer applies the same test and never reads this row
+	const float4 pl = a.planes[np.x + np.y * W];   // a STRONG pixel's plane: K10 / K11 write WEAK pixels only
+	for (int v = 0; v < S; ++v) scored[(size_t)(i * S + v) * stride + slot] = ncc_new(a, px, py, v, pl);
+}
+
 // One thread per WEAK pixel of ONE checkerboard colour: `colour_list` (built at upload by a device prefix sum)
 // holds the pixels the reference's half grid reaches for this colour (APD.cu:3093-3106), so warps are dense.
 #ifndef DVP_WEAK_MIN_BLOCKS
 #define DVP_WEAK_MIN_BLOCKS (768 / DVP_WEAK_THREADS)   // 24 warps per SM at 80 registers: measured 7 % faster than 16 warps at 127
 #endif
-__global__ void __launch_bounds__(kWeakThreads, DVP_WEAK_MIN_BLOCKS) k_weak_sweep(const __grid_constant__ KArgs a, const int* colour_list, int count, int iter) {
+__global__ void __launch_bounds__(kWeakThreads, DVP_WEAK_MIN_BLOCKS) k_weak_sweep(const __grid_constant__ KArgs a, const int* colour_list, int count, int iter, const float* __restrict__ scored, int stride) {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= count) return;
 	const int center = colour_list[t];
@@ -616,8 +644,12 @@ __global__ void __launch_bounds__(kWeakThreads, DVP_WEAK_MIN_BLOCKS) k_weak_swee
 		if (np.x == -1 || np.y == -1 || a.weak[np.x + np.y * W] != DVP_STRONG) continue;
 		positions[i] = np.x + np.y * W;
 		flag[i] = true;
-		const float4 pl = a.planes[positions[i]];
-		for (int v = 0; v < S; ++v) COST(i, v) = ncc_new(a, px, py, v, pl);
+		if (scored) {   // k_weak_score has been here
+			for (int v = 0; v < S; ++v) COST(i, v) = scored[(size_t)(i * S + v) * stride + t];
+		} else {
+			const float4 pl = a.planes[positions[i]];
+			for (int v = 0; v < S; ++v) COST(i, v) = ncc_new(a, px, py, v, pl);
+		}
 	}
 	Rng rng; rng.load(a.rng, a.N, center);
 	ViewWeights vw; vw.clear();
@@ -786,10 +818,16 @@ cudaError_t launch_ransac_fit(const KArgs& a, const int* weak_list, cudaStream_t
 	if (a.weak_count > 0) k_ransac_fit<<<(a.weak_count + 63) / 64, 64, 0, st>>>(a, weak_list);
 	return cudaGetLastError();
 }
-cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count, int iter, int red, cudaStream_t st) {
+cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count, int iter, int red, void* scratch, cudaStream_t st) {
 	(void)red;
 	if (count == 0) return cudaSuccess;
-	k_weak_sweep<<<(count + kWeakThreads - 1) / kWeakThreads, kWeakThreads, 0, st>>>(a, colour_list, count, iter);
+#ifdef DVP_WEAK_NO_SCORE_KERNEL   // A/B: everything in the thread-per-pixel kernel
+	scratch = nullptr;
+#endif
+	float* scored = static_cast<float*>(scratch);   // the K7 / K8 scratch area: >= (9 S + 9) words per pixel of a colour, idle now
+	const int stride = (count + 31) & ~31;
+	if (scored) k_weak_score<<<(int)(((size_t)count * 8 + 255) / 256), 256, 0, st>>>(a, colour_list, count, scored, stride);
+	k_weak_sweep<<<(count + kWeakThreads - 1) / kWeakThreads, kWeakThreads, 0, st>>>(a, colour_list, count, iter, scored, stride);
 	return cudaGetLastError();
 }
 // One-time, per-device fill of the sector table, completed before the flag is set so that contexts on other streams

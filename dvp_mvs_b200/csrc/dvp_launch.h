@@ -31,6 +31,11 @@ constexpr int kWeakThreads = DVP_WEAK_THREADS;   // WEAK sweep block = one tile 
 #ifndef DVP_K4_THREADS
 #define DVP_K4_THREADS 64
 #endif
+#ifdef DVP_WEAK_NO_SCORE_KERNEL
+constexpr int kWeakSweepKernels = 1;
+#else
+constexpr int kWeakSweepKernels = 2;             // kernels per K10 / K11 launch: k_weak_score + k_weak_sweep
+#endif
 constexpr int kK4Threads = DVP_K4_THREADS;       // K4 block = one (threads / 8) x 8 pixel tile of the WEAK list
 #ifndef DVP_WIDE_RB
 #define DVP_WIDE_RB 2
@@ -72,7 +77,7 @@ cudaError_t launch_explain_init(const KArgs& a, int red, const RaceExpected& e, 
 cudaError_t launch_explain_compare(const KArgs& a, int red, const D4Force& f, const RaceExpected& e, uint8_t* explained, cudaStream_t st);
 cudaError_t launch_explain_collect(const KArgs& a, int red, const uint8_t* explained, int* list, int* count, int cap, cudaStream_t st);
 cudaError_t launch_ransac_fit(const KArgs& a, const int* weak_list, cudaStream_t st);                                  // K9
-cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count, int iter, int red, cudaStream_t st);  // K10 / K11
+cudaError_t launch_weak_sweep(const KArgs& a, const int* colour_list, int count, int iter, int red, void* scratch, cudaStream_t st);  // K10 / K11
 cudaError_t launch_depth_normal(const KArgs& a, cudaStream_t st);                                // K12
 cudaError_t launch_filter(const KArgs& a, int red, cudaStream_t st);                             // K13 / K14
 cudaError_t launch_depth_to_weak(const KArgs& a, cudaStream_t st);                               // K15

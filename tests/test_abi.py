@@ -118,7 +118,7 @@ def test_documents_only_name_entry_points_that_exist():
     known_other = {"dvp_mvs", "dvp_mvs_b200", "dvp_ctx", "dvp_scene", "dvp_fusion", "dvp_params", "dvp_inputs", "dvp_camera", "dvp_status",
                    "dvp_fusion_view", "dvp_apd_adapter", "dvp_stage", "dvp_buffer", "dvp_api", "dvp_ncc", "dvp_strong", "dvp_weak", "dvp_common",
                    "dvp_launch", "dvp_unionfind", "dvp_io", "dvp_kernels_post", "dvp_kernels_edge", "dvp_kernels_fusion", "dvp_kernels_prep",
-                   "dvp_kernels_strong", "dvp_kernels_weak", "dvp_kernels_", "dvp_b200", "dvp_fuse"}
+                   "dvp_kernels_strong", "dvp_kernels_weak", "dvp_kernels_image", "dvp_kernels_", "dvp_b200", "dvp_fuse", "dvp_farm"}
     missing = {}
     for doc in ("INTEGRATION.md", "DESIGN.md", "README.md"):
         text = open(os.path.join(ROOT, doc)).read()

@@ -432,7 +432,7 @@ def test_full_size_properties():
     total, per_stage, launches = e.last_run_times()
     # kernels actually launched: K1, K2 (edge sweep + per-pixel pass; nothing WEAK), K3, K5, K6; K7, K8, K9 per iteration
     # (no WEAK pixel: K4, K10, K11 launch nothing); K12, K13, K14 and the fused K15+K16
-    assert launches == 6 + 2 * (2 + 2 + 1) + 4 and total > 0   # each sweep is two kernels (scoring, update)
+    assert launches == 6 + 2 * (2 + 2 + 1) + 4 and total > 0   # each strong sweep is two kernels (scoring, update); no WEAK pixel: K10 / K11 launch nothing
     assert set(np.unique(weak)) <= {WEAK, STRONG, UNKNOWN}
     border = np.ones((H, W), bool); border[6:-6, 6:-6] = False
     assert (weak[border] == UNKNOWN).all()                      # APD.cu:3907-3910
