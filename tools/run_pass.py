@@ -19,8 +19,11 @@ def main():
     ap.add_argument("--state", default="refine_iter")
     ap.add_argument("--geom", type=int, default=1)
     ap.add_argument("--derived", type=int, default=0, help="pixel states from a real previous pass instead of the painted wall")
+    ap.add_argument("--size", default="", help="WxH instead of the workload's size (small runs under compute-sanitizer)")
     a = ap.parse_args()
     a.width, a.height = bench.WORKLOADS[a.workload]
+    if a.size:
+        a.width, a.height = (int(v) for v in a.size.split("x"))
     from dvp_mvs_b200 import Engine
     sc, p, inputs, name = bench.make_workload(a, seed=0)
     if a.derived:
