@@ -275,6 +275,29 @@ def test_weak_path_stagewise_vs_reference(geom):
             assert by[(st, n)]["mismatched"] <= limit, (st, n, by[(st, n)])
 
 
+@needs_ref
+@pytest.mark.parametrize("S,rotate_time", [(8, 4), (3, 1)])
+def test_weak_path_with_many_views_and_other_rotations_vs_reference(S, rotate_time):
+    """The WEAK path away from the schedule's usual shape: 8 source views (the scoring kernel's 8 x S scratch rows, the
+    32-entry cost columns) and rotate_time 4 / 1 (32 / 8 search directions in K4, shift ranges 1 / 8 for the exact
+    multiply-based modulo), photometric: K4's anchors and RNG states, K9 and both WEAK sweeps bit for bit."""
+    W, H = 256, 192
+    q, kw, weak = _second_pass_inputs(W, H, S, 0)
+    q.rotate_time = rotate_time
+    assert (weak == WEAK).sum() > 1000
+    ref = ref_oracle.engine(W, H, S, q); prod = Engine(W, H, S, q)
+    ref.upload(**kw); prod.upload(**kw)
+    res = step_compare(ref, prod, 1)
+    by = {(r["stage"], r.get("buffer")): r for r in res}
+    assert not [r for r in res if r.get("error")], [r for r in res if r.get("error")][:2]
+    for key in [("K4_GEN_NEIGHBOURS", "neighbours"), ("K4_GEN_NEIGHBOURS", "weak_reliable"), ("K4_GEN_NEIGHBOURS", "rand"),
+                ("K9_RANSAC_FIT_PLANE", "fit_planes"), ("K9_RANSAC_FIT_PLANE", "rand"),
+                ("K10_BLACK_WEAK", "planes"), ("K10_BLACK_WEAK", "costs"), ("K10_BLACK_WEAK", "selected"), ("K10_BLACK_WEAK", "view_weight"),
+                ("K10_BLACK_WEAK", "rand"), ("K11_RED_WEAK", "planes"), ("K11_RED_WEAK", "costs"), ("K11_RED_WEAK", "selected"),
+                ("K11_RED_WEAK", "view_weight"), ("K11_RED_WEAK", "rand")]:
+        assert by[key]["not_bit_exact"] == 0, (key, by[key])
+
+
 @pytest.mark.parametrize("geom", [0, 1])
 def test_fused_k15_k16_equals_the_two_kernels(geom):
     """dvp_run issues DepthToWeak and LocalRefine as one kernel that shares the NCCs of the 11 common disparity
