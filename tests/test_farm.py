@@ -270,3 +270,74 @@ def test_library_farm_on_two_gpus_matches_the_block_gauss_seidel_order():
     fa.close()
     for s in scenes:
         s.close()
+
+
+_NCCL_FARM_SCRIPT = r'''
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["DVP_REPO_ROOT"])
+from dvp_mvs_b200 import Scene, Farm, synth
+from dvp_mvs_b200.farm import run_scene_schedule
+
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+V, L = 4, 2
+mv = synth.make_multiview(320, 240, V, L, seed=3)
+
+
+def fill(o):
+    o.set_max_iterations(0)                   # no propagation sweeps: every stage of a pass is deterministic
+    for v in range(V):
+        o.set_view(v, mv.cameras[v], mv.full_w, mv.full_h, mv.src_views[v])
+        for l in range(L):
+            o.set_level(v, l, mv.levels[l][v]["image"], None, mv.levels[l][v]["label"])
+            o.compute_edges(v, l)
+        o.set_initial_planes(v, mv.planes_init[v])
+
+
+sc = Scene(V, L, device=local); fill(sc)
+owner = run_scene_schedule(sc, V, L, seed=11)      # NCCL all-gather of the depth maps after every pass
+torch.cuda.synchronize()
+mine = {v: [np.ascontiguousarray(x) for x in sc.get_view(v)] for v in range(V) if owner[v] == rank}
+gathered = [None, None]
+dist.all_gather_object(gathered, mine)
+ok = True
+if rank == 0:
+    views = {}
+    for g in gathered:
+        views.update(g)
+    fa = Farm([0, 1], V, L); fill(fa)               # the library's farm: threads + peer copies, same dealing, same seeds
+    fa.run(seed=11)
+    for v in range(V):
+        for x, y in zip(views[v], fa.get_view(v)):
+            ok = ok and (np.asarray(x).view(np.uint8) == np.asarray(y).view(np.uint8)).all()
+    fa.close()
+open(os.path.join(os.environ["DVP_OUT_DIR"], f"rank{rank}.txt"), "w").write("RANK_OK" if ok else "MISMATCH")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.gpu
+def test_nccl_farm_on_two_gpus_equals_the_library_farm(tmp_path):
+    """ADVICE r01 (high): the NCCL exchange of farm.run_scene_schedule must be ordered against the library's own streams.
+    Two ranks under torchrun run the whole schedule with 0 iterations (deterministic) and every view's maps must equal, bit for
+    bit, what the in-library farm (threads + peer copies, same block Gauss-Seidel order) computes — a depth map read before its
+    all-gather landed, or overwritten while NCCL was still sending it, would show up here."""
+    import socket, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "nccl_farm.py"
+    script.write_text(_NCCL_FARM_SCRIPT)
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", DVP_REPO_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), DVP_OUT_DIR=str(tmp_path))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert (tmp_path / "rank0.txt").read_text() == "RANK_OK" and (tmp_path / "rank1.txt").read_text() == "RANK_OK"
