@@ -17,7 +17,7 @@
 #include <algorithm>
 #include <new>
 
-namespace dvp { cudaError_t launch_edge_inform(const KArgs& a, cudaStream_t st); }
+namespace dvp { cudaError_t launch_edge_inform(const KArgs& a, bool with_candidates, cudaStream_t st); }
 
 using namespace dvp;
 
@@ -63,6 +63,9 @@ struct dvp_ctx {
 	short2* candidate = nullptr;
 	short2* nearest_strong = nullptr;
 	uint8_t* weak_reliable = nullptr;
+	uint8_t* anchor_flag = nullptr;                 // [N] pixels named by some WEAK pixel's anchor list (dvp_run: K2's candidate records are evaluated for these only)
+	bool lazy_candidates = false;                   // inside dvp_run
+	bool last_run_lazy = false;                     // ... and whether the last dvp_run was (launch counts of dvp_last_run_times)
 	int32_t* neighbours_map = nullptr;
 	short2* neighbours = nullptr;
 	short2* label_boundary = nullptr;
@@ -174,9 +177,9 @@ BufDesc buf_desc(dvp_ctx* c, int id) {
 int stage_kernel_count(const dvp_ctx* c, int stage) {
 	const bool weak = c->weak_count > 0;
 	switch (stage) {
-	case DVP_K2_GEN_EDGE_INFORM: return (weak ? 1 : 0) + (c->prm.use_edge ? 1 : 0) + ((c->prm.use_label && weak) ? 1 : 0) + 1;
+	case DVP_K2_GEN_EDGE_INFORM: return ((weak && !c->lazy_candidates) ? 1 : 0) + (c->prm.use_edge ? 1 : 0) + ((c->prm.use_label && weak) ? 1 : 0) + 1;
 	case DVP_K3_FIND_NEAREST_STRONG: return (weak ? 1 : 0) + 1;
-	case DVP_K4_GEN_NEIGHBOURS: return weak ? 1 : 0;
+	case DVP_K4_GEN_NEIGHBOURS: return weak ? (c->lazy_candidates ? 3 : 1) : 0;   // + k_mark_anchors + k_candidate for the anchors
 	case DVP_K7_BLACK_STRONG: case DVP_K8_RED_STRONG: return 2;   // k_sweep_score + k_sweep_update
 	case DVP_K9_RANSAC_FIT_PLANE: return 1 + (weak ? 1 : 0);
 	case DVP_K10_BLACK_WEAK: return c->colour_count[0] > 0 ? kWeakSweepKernels : 0;   // k_weak_score + k_weak_sweep
@@ -189,9 +192,9 @@ cudaError_t launch_stage(dvp_ctx* c, const KArgs& a, int stage, int iter) {
 	cudaStream_t st = c->stream;
 	switch (stage) {
 	case DVP_K1_INIT_RANDOM_STATES: return launch_init_rng(a, c->seed, st);
-	case DVP_K2_GEN_EDGE_INFORM: return launch_edge_inform(a, st);
+	case DVP_K2_GEN_EDGE_INFORM: return launch_edge_inform(a, !c->lazy_candidates, st);
 	case DVP_K3_FIND_NEAREST_STRONG: return launch_nearest_strong(a, c->next_right, c->next_down, st);
-	case DVP_K4_GEN_NEIGHBOURS: return launch_gen_neighbours(a, c->weak_list, st);
+	case DVP_K4_GEN_NEIGHBOURS: return launch_gen_neighbours(a, c->weak_list, c->lazy_candidates ? c->anchor_flag : nullptr, st);
 	case DVP_K5_NEIGHBOUR_UPDATE: return launch_neighbour_update(a, st);
 	case DVP_K6_RANDOM_INITIALIZATION: return launch_random_init(a, st);
 	case DVP_K7_BLACK_STRONG:
@@ -440,6 +443,7 @@ dvp_ctx* dvp_create(int device, int width, int height, int num_src, const dvp_pa
 	ok = ok && zalloc(&c->candidate, (N + 1) * DVP_LAB_BOUNDARY_NUM * cand_views) == cudaSuccess;
 	ok = ok && zalloc(&c->nearest_strong, N) == cudaSuccess;
 	ok = ok && zalloc(&c->weak_reliable, N) == cudaSuccess;
+	ok = ok && zalloc(&c->anchor_flag, N) == cudaSuccess;
 	ok = ok && zalloc(&c->neighbours_map, N) == cudaSuccess;
 	ok = ok && zalloc(&c->neighbours, 1) == cudaSuccess;
 	ok = ok && zalloc(&c->label_boundary, 1) == cudaSuccess;
@@ -476,7 +480,7 @@ void dvp_destroy(dvp_ctx* c) {
 	cudaFree(c->d_img_tex); cudaFree(c->d_dep_tex); cudaFree(c->ref_img); cudaFree(c->cams); cudaFree(c->views);
 	cudaFree(c->planes); cudaFree(c->fit_planes); cudaFree(c->costs); cudaFree(c->selected_alloc); cudaFree(c->weak);
 	cudaFree(c->radius); cudaFree(c->view_weight); cudaFree(c->rng); cudaFree(c->edge); cudaFree(c->edge_sat); cudaFree(c->edge_dist); cudaFree(c->edge_neigh);
-	cudaFree(c->label); cudaFree(c->candidate); cudaFree(c->nearest_strong); cudaFree(c->weak_reliable);
+	cudaFree(c->label); cudaFree(c->candidate); cudaFree(c->nearest_strong); cudaFree(c->weak_reliable); cudaFree(c->anchor_flag);
 	cudaFree(c->neighbours_map); cudaFree(c->neighbours); cudaFree(c->label_boundary); cudaFree(c->complex_); cudaFree(c->weak_list); cudaFree(c->scan_blocks); cudaFree(c->scan_total); cudaFree(c->next_right); cudaFree(c->next_down); for (int k = 0; k < 2; ++k) { cudaFree(c->scan_blocks_c[k]); cudaFree(c->colour_list[k]); }
 	cudaFree(c->vis_parent); cudaFree(c->vis_count); cudaFree(c->fetch_counter); cudaFree(c->sweep_scratch);
 	cudaFree(c->sort_keys[0]); cudaFree(c->sort_keys[1]); cudaFree(c->sort_vals); cudaFree(c->sort_temp);
@@ -527,6 +531,11 @@ int dvp_run(dvp_ctx* ctx, int sync) {
 		return DVP_OK;
 	};
 	int r;
+#ifndef DVP_EAGER_CANDIDATES
+	ctx->lazy_candidates = true;   // K2's candidate records after K4, for the anchors only; stage stepping (dvp_run_stage) keeps K2 whole
+#endif
+	ctx->last_run_lazy = ctx->lazy_candidates;
+	struct Unset { dvp_ctx* c; ~Unset() { c->lazy_candidates = false; } } unset{ctx};
 	for (int s = DVP_K1_INIT_RANDOM_STATES; s <= DVP_K6_RANDOM_INITIALIZATION; ++s) if ((r = go(s, 0))) return r;
 	for (int it = 0; it < ctx->prm.max_iterations; ++it)
 		for (int s = DVP_K7_BLACK_STRONG; s <= DVP_K11_RED_WEAK; ++s) if ((r = go(s, it))) return r;
@@ -560,7 +569,10 @@ int dvp_last_run_times(dvp_ctx* ctx, float* total_ms, float* per_stage_ms, int* 
 	(void)sum;
 	if (launches) {
 		int n = 0;
+		const bool was = ctx->lazy_candidates;
+		ctx->lazy_candidates = ctx->last_run_lazy;
 		for (int i = 0; i < ctx->n_timed; ++i) n += stage_kernel_count(ctx, ctx->ev_stage[i]);
+		ctx->lazy_candidates = was;
 		*launches = n;
 	}
 	return DVP_OK;

@@ -43,7 +43,12 @@ __global__ void k_fill_sector_table() {
 // in each of 12 sectors of the 11x11 window; the 8 best sectors' offsets -> candidate[pixel][view][8].
 // Sectors without any visible pixel hold uninitialised stack data in the reference; here they
 // rank last and yield the offset (0,0), which the deformable NCC replaces by its default ring offset.
-__global__ void __launch_bounds__(256) k_candidate(const __grid_constant__ KArgs a) {
+// `only` (dvp_run): the records are read for one purpose — the deformable NCC looks up the offsets of a WEAK pixel's ANCHORS
+// (ncc_new) — and the anchors are known after K4.  Nothing the records depend on (reference image, selected views) changes
+// between K2 and K5, so dvp_run evaluates them after K4 for the pixels some anchor list names (k_mark_anchors) and skips the
+// tiles without any: the same records where they are read, 1 % of the work at the bench workload.  only == nullptr (stage
+// stepping, the parity tests): every pixel, as the reference.
+__global__ void __launch_bounds__(256) k_candidate(const __grid_constant__ KArgs a, const uint8_t* __restrict__ only) {
 	// 32x8 pixel tile + 5 px halo of the reference image and of the selected-view masks, staged once in shared
 	// memory and reused by the 120 window reads of every pixel for every view (weak_radius is 5 in every schedule
 	// of the reference; other radii fall back to global reads)
@@ -51,6 +56,12 @@ __global__ void __launch_bounds__(256) k_candidate(const __grid_constant__ KArgs
 	__shared__ float s_img[TH][TW];
 	__shared__ uint32_t s_sel[TH][TW];
 	const int W = a.W, H = a.H;
+	bool wanted = true;
+	if (only) {
+		const int qx = blockIdx.x * 32 + threadIdx.x, qy = blockIdx.y * 8 + threadIdx.y;
+		wanted = qx < W && qy < H && only[qx + qy * W] != 0;
+		if (!__syncthreads_or(wanted)) return;   // no anchor in this tile
+	}
 	const int x0 = blockIdx.x * 32 - R, y0 = blockIdx.y * 8 - R;
 	for (int i = threadIdx.y * 32 + threadIdx.x; i < TW * TH; i += 256) {
 		const int ty = i / TW, tx = i - ty * TW;
@@ -61,7 +72,7 @@ __global__ void __launch_bounds__(256) k_candidate(const __grid_constant__ KArgs
 	}
 	__syncthreads();
 	const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-	if (x >= W || y >= H) return;
+	if (x >= W || y >= H || !wanted) return;
 	const int center = x + y * W;
 	float rcp_s, rcp_c; RefPatch::sigma_rcps(a.prm, rcp_s, rcp_c);
 	const int radius = a.prm.weak_radius;
@@ -803,19 +814,39 @@ __global__ void __launch_bounds__(kWeakThreads, DVP_WEAK_MIN_BLOCKS) k_weak_swee
 #undef PROB
 
 // ------------------------------------------------------------------------------------------------------
-cudaError_t launch_edge_inform(const KArgs& a, cudaStream_t st) {
+// every pixel some WEAK pixel's anchor list names (entries 1..10; entry 0 is the pixel itself, whose record nobody reads)
+__global__ void __launch_bounds__(256) k_mark_anchors(const __grid_constant__ KArgs a, const int* weak_list, uint8_t* flag) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int wi = t / (DVP_NEIGHBOUR_NUM - 1), k = t % (DVP_NEIGHBOUR_NUM - 1) + 1;
+	if (wi >= a.weak_count) return;
+	const int center = weak_list[wi];
+	if (a.weak[center] != DVP_WEAK) return;   // demoted before K4 wrote its list: the list is stale and has no reader
+	const short2 np = a.neighbours[(size_t)a.neighbours_map[center] * DVP_NEIGHBOUR_NUM + k];
+	if (np.x >= 0 && np.y >= 0 && np.x < a.W && np.y < a.H) flag[np.x + np.y * a.W] = 1;
+}
+
+cudaError_t launch_edge_inform(const KArgs& a, bool with_candidates, cudaStream_t st) {
 	// part (a) (candidate offsets) is only ever read by the deformable NCC of WEAK pixels; with no WEAK pixel in
 	// the view it has no reader and is skipped (the reference computes it regardless: 31 % of its pass at S=4).
-	if (a.weak_count > 0) {
+	if (a.weak_count > 0 && with_candidates) {
 		dim3 b(32, 8);   // the sector table was filled by configure_weak_kernels at upload
 		dim3 g((a.W + 31) / 32, (a.H + 7) / 8, 1);
-		k_candidate<<<g, b, 0, st>>>(a);
+		k_candidate<<<g, b, 0, st>>>(a, nullptr);
 	}
 	return launch_edge_inform_prep(a, st);
 }
-cudaError_t launch_gen_neighbours(const KArgs& a, const int* weak_list, cudaStream_t st) {
+cudaError_t launch_gen_neighbours(const KArgs& a, const int* weak_list, uint8_t* anchor_flag, cudaStream_t st) {
 	if (a.weak_count == 0) return cudaSuccess;
 	k_gen_neighbours<<<(a.weak_count + kK4Threads - 1) / kK4Threads, kK4Threads, 0, st>>>(a, weak_list);
+	if (anchor_flag) {   // dvp_run: K2's candidate records, now that the anchors are known (see k_candidate)
+		cudaError_t e = cudaMemsetAsync(anchor_flag, 0, (size_t)a.N, st);
+		if (e != cudaSuccess) return e;
+		const long long pairs = (long long)a.weak_count * (DVP_NEIGHBOUR_NUM - 1);
+		k_mark_anchors<<<(int)((pairs + 255) / 256), 256, 0, st>>>(a, weak_list, anchor_flag);
+		dim3 b(32, 8);
+		dim3 g((a.W + 31) / 32, (a.H + 7) / 8, 1);
+		k_candidate<<<g, b, 0, st>>>(a, anchor_flag);
+	}
 	return cudaGetLastError();
 }
 cudaError_t launch_ransac_fit(const KArgs& a, const int* weak_list, cudaStream_t st) {

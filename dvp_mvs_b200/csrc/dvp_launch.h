@@ -54,9 +54,9 @@ cudaError_t configure_weak_kernels(int S);
 cudaError_t launch_fill_sd_table(cudaStream_t st);
 cudaError_t launch_setup_views(const dvp_camera* cams, ViewConst* views, int S, cudaStream_t st);
 cudaError_t launch_init_rng(const KArgs& a, unsigned long long seed, cudaStream_t st);          // K1
-cudaError_t launch_edge_inform(const KArgs& a, cudaStream_t st);                                 // K2
+cudaError_t launch_edge_inform(const KArgs& a, bool with_candidates, cudaStream_t st);                                 // K2
 cudaError_t launch_nearest_strong(const KArgs& a, short* next_right, short* next_down, cudaStream_t st);  // K3
-cudaError_t launch_gen_neighbours(const KArgs& a, const int* weak_list, cudaStream_t st);        // K4
+cudaError_t launch_gen_neighbours(const KArgs& a, const int* weak_list, uint8_t* anchor_flag, cudaStream_t st);        // K4
 cudaError_t launch_neighbour_update(const KArgs& a, cudaStream_t st);                            // K5
 cudaError_t launch_random_init(const KArgs& a, cudaStream_t st);                                 // K6
 size_t sweep_scratch_bytes(int W, int H, int S);                                                 // candidate costs / winners between the two kernels of a sweep

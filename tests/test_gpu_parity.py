@@ -338,6 +338,36 @@ def test_fused_k15_k16_equals_the_two_kernels(geom):
         assert same.all(), (n, int((~same).sum()))
 
 
+def test_run_equals_the_stage_by_stage_sequence_with_weak_pixels():
+    """dvp_run takes short cuts that the stage API does not: K2's candidate records are evaluated after K4 and only for the
+    pixels some anchor list names, K15 and K16 run as one kernel.  Our own sweeps are deterministic, so a whole pass through
+    dvp_run must leave every buffer bit-identical to the same stages issued one by one (each of which is what the parity
+    tests compare with the reference) — on a second pass with WEAK pixels, geometric consistency and 2 iterations."""
+    from dvp_mvs_b200 import REFINE_ITER
+    W, H, S = 320, 240, 3
+    sc = synth.make_scene(W, H, S)
+    p = c1_params(sc.depth_min, sc.depth_max, S, iters=1)
+    e = Engine(W, H, S, p)
+    e.upload(images=sc.images, cameras=sc.cameras, planes=sc.planes_init, edge=sc.edge, label=sc.label, seed=synth.SEED_RNG)
+    e.run()
+    planes, weak, sel, rad = e.download()
+    assert (weak == WEAK).sum() > 2000
+    q = c1_params(sc.depth_min, sc.depth_max, S, iters=2, use_apd=1)
+    q.state = REFINE_ITER; q.geom_consistency = 1; q.use_detail = 1; q.ransac_threshold = 0.00875; q.rotate_time = 2
+    kw = dict(images=sc.images, depths=sc.depths, cameras=sc.cameras, planes=planes, selected_views=sel, weak_info=weak, edge=sc.edge,
+              label=sc.label, radius=rad, seed=synth.SEED_RNG + 5, params=q)
+    names = ("planes", "costs", "selected", "weak", "radius", "rand", "view_weight", "fit_planes", "neighbours", "weak_reliable")
+    e.upload(**kw); e.run()
+    whole = {n: e.get(n) for n in names}
+    e.upload(**kw)
+    for st, it in sequence(2):
+        e.run_stage(st, it)
+    for n in names:
+        a, b = whole[n], e.get(n)
+        same = (a.view(np.uint32) == b.view(np.uint32)) if a.dtype == np.float32 else (a == b)
+        assert same.all(), (n, int((~same).sum()))
+
+
 @pytest.mark.parametrize("use_weak", [0, 1])
 def test_overlapped_upload_gives_the_same_results(use_weak):
     """dvp_upload_overlapped streams planes, images and depth maps on a second stream behind K1..K5; with 0 iterations
