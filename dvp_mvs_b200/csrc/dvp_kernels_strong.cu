@@ -628,10 +628,25 @@ __global__ void __launch_bounds__(128, DVP_UPDATE_MIN_BLOCKS) k_sweep_update(con
 			cum_prob += prob;
 			SCOST(8 * S + i) = cum_prob;
 		}
-		for (int sample = 0; sample < 15; ++sample) {
-			const float rand_prob = rng.uniform() - FLT_EPSILON;
-			for (int image_id = 0; image_id < S; ++image_id) {
-				if (SCOST(8 * S + image_id) > rand_prob) { vw.inc(image_id); break; }
+		if (S <= 8) {
+			// the CDF in registers: the 15 draws below would otherwise walk it in the scratch area, a dependent global load per
+			// comparison (8 % of this kernel's stall samples).  First index whose CDF exceeds the draw, as the loop below.
+			float cdf[8];
+#pragma unroll
+			for (int i = 0; i < 8; ++i) cdf[i] = i < S ? SCOST(8 * S + i) : 0.0f;
+			for (int sample = 0; sample < 15; ++sample) {
+				const float rand_prob = rng.uniform() - FLT_EPSILON;
+				int image_id = -1;
+#pragma unroll
+				for (int i = 7; i >= 0; --i) if (i < S && cdf[i] > rand_prob) image_id = i;
+				if (image_id >= 0) vw.inc(image_id);
+			}
+		} else {
+			for (int sample = 0; sample < 15; ++sample) {
+				const float rand_prob = rng.uniform() - FLT_EPSILON;
+				for (int image_id = 0; image_id < S; ++image_id) {
+					if (SCOST(8 * S + image_id) > rand_prob) { vw.inc(image_id); break; }
+				}
 			}
 		}
 	}

@@ -74,6 +74,13 @@ static __device__ __noinline__ float4 random_normal(const KArgs& a, int px, int 
 	}
 	int times = 200;
 	float4 normal;
+	// up to 5 directions (the reference view + 4 selected sources, every schedule of the reference) are tested from registers:
+	// the rejection loop below runs up to 200 times and would otherwise re-read them from the stack each time.  The test has
+	// no side effects, so evaluating all of them instead of stopping at the first failure gives the same answer.
+	constexpr int kRegDirs = 5;
+	float3 rd[kRegDirs];
+#pragma unroll
+	for (int i = 0; i < kRegDirs; ++i) rd[i] = i < index ? vdir[i] : make_float3(0.f, 0.f, 0.f);
 	while (times > 0) {
 		float q1 = 1.0f, q2 = 1.0f, s = 2.0f;
 		while (s >= 1.0f) {
@@ -87,7 +94,12 @@ static __device__ __noinline__ float4 random_normal(const KArgs& a, int px, int 
 		normal.z = 1.0f - 2.0f * s;
 		normal.w = 0;
 		bool satisfy = true;
-		for (int i = 0; i < index; i++) {
+#pragma unroll
+		for (int i = 0; i < kRegDirs; ++i) {
+			const float d = normal.x * rd[i].x + normal.y * rd[i].y + normal.z * rd[i].z;
+			if (i < index && d > 0.0f) satisfy = false;
+		}
+		for (int i = kRegDirs; i < index && satisfy; i++) {
 			const float d = normal.x * vdir[i].x + normal.y * vdir[i].y + normal.z * vdir[i].z;
 			if (d > 0.0f) { satisfy = false; break; }
 		}
