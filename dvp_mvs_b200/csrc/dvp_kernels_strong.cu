@@ -502,6 +502,7 @@ __global__ void __launch_bounds__(256, 3) k_sweep_score(const __grid_constant__ 
 			if (d < 4 && step_len % 2 == 1) step_len -= 1;
 			int min_pos = -1, min_k = 0;
 			float min_cost = FLT_MAX;
+#pragma unroll 4   // four cost reads of the ladder in flight
 			for (int step = 0; step < step_num; ++step) {
 				const int tx = x + sx + step * step_len * dx + fx, ty = y + sy + step * step_len * dy + fy;
 				if (!(tx >= 0 && ty >= 0 && tx < W && ty < H)) continue;
@@ -537,9 +538,9 @@ __global__ void __launch_bounds__(256, 3) k_sweep_score(const __grid_constant__ 
 				const float4 pl = a.planes[min_pos];
 				int good0 = 0, good1 = 0, bad0 = 0, bad1 = 0;
 				for (int v = 0; v < S; ++v) {
+					const float c0 = SCOST(d * S + v);   // read ahead of the NCC: its latency hides behind the fetches
 					const float c1 = ncc_cost<kWideRB>(a, a.views[v], a.tex_img[v + 1], x, y, pl, rp, wt, T);
 					SCOST(8 * S + v) = c1;
-					const float c0 = SCOST(d * S + v);
 					if (c0 < good_threshold) good0++;
 					if (c0 > bad_threshold) bad0++;
 					if (c1 < good_threshold) good1++;
