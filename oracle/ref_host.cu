@@ -6,6 +6,8 @@
 //   APD.cpp:501-546    Get3DPointonWorld, Get3DPoint, ProjectCamera          -> row N3
 //   APD.cpp:1797-1806  GetAngle                                               -> row N3
 //   APD.cpp:1875-1957  the fusing loop of RunFusion (ETH version)             -> row N3
+//   APD.cpp:1967-1971, 2028-2127   constants and fusing loop of RunFusion_TAT_Intermediate   -> row N3, mode 1
+//   APD.cpp:2137-2138, 2195-2276   constants and fusing loop of RunFusion_TAT_advanced       -> row N3, mode 2
 // The loops around them that cannot be cut out (they sit inside ProcessProblem between OpenCV and file calls,
 // main.cpp:322-363) are restated here in a few lines each, citing the lines they follow.
 // cv::Mat is the stub of oracle/stubs (rows, cols, at<T>(), clone()); OpenCV itself is not installed in this image.
@@ -144,3 +146,83 @@ long long refhost_run_fusion(int num_views, const refhost_view* views, float* po
 }
 
 }  // extern "C"
+
+// The two Tanks-and-Temples variants (APD.cpp:1962-2279): same set-up, their own fusing loops and thresholds.  mode 1 =
+// RunFusion_TAT_Intermediate, mode 2 = RunFusion_TAT_advanced.  Outputs as refhost_run_fusion.
+namespace {
+struct FusionInputs {
+	std::vector<Problem> problems;
+	std::vector<cv::Mat> images, depths, normals, masks, blocks, weaks;
+	std::vector<Camera> cameras;
+	std::unordered_map<int, int> imageIdToindexMap;
+	bool use_block = false;
+	FusionInputs(int num_views, const refhost_view* views) : problems(num_views) {
+		for (int i = 0; i < num_views; ++i) use_block = use_block || views[i].block != nullptr;
+		for (int i = 0; i < num_views; ++i) {
+			const refhost_view& v = views[i];
+			problems[i].index = i; problems[i].ref_image_id = i;
+			for (int k = 0; k < v.num_src; ++k) problems[i].src_image_ids.push_back(v.src_views[k]);
+			imageIdToindexMap.emplace(i, i);
+			const size_t n = (size_t)v.width * v.height;
+			cv::Mat image(v.height, v.width, CV_8UC3), depth(v.height, v.width, CV_32FC1), normal(v.height, v.width, CV_32FC3);
+			cv::Mat mask(v.height, v.width, CV_8UC1), weak(v.height, v.width, CV_8UC1), block(v.height, v.width, CV_8UC1);
+			std::memcpy(image.ptr<uchar>(0), v.image, n * 3);
+			std::memcpy(depth.ptr<float>(0), v.depth, n * 4);
+			std::memcpy(normal.ptr<float>(0), v.normal, n * 12);
+			if (v.weak) std::memcpy(weak.ptr<uchar>(0), v.weak, n); else std::memset(weak.ptr<uchar>(0), STRONG, n);
+			if (v.block) std::memcpy(block.ptr<uchar>(0), v.block, n); else std::memset(block.ptr<uchar>(0), 255, n);
+			images.push_back(image); depths.push_back(depth); normals.push_back(normal); masks.push_back(mask); weaks.push_back(weak);
+			blocks.push_back(block); cameras.push_back(v.camera);
+		}
+	}
+};
+
+long long export_points(const std::vector<PointList>& PointCloud, const FusionInputs& in, int num_views, const refhost_view* views, float* points, long long cap, uint8_t* masks_out) {
+	const long long n_pts = (long long)PointCloud.size();
+	if (points)
+		for (long long k = 0; k < n_pts && k < cap; ++k) {
+			const PointList& p = PointCloud[(size_t)k];
+			float* o = points + 6 * k;
+			o[0] = p.coord.x; o[1] = p.coord.y; o[2] = p.coord.z; o[3] = p.color.x; o[4] = p.color.y; o[5] = p.color.z;
+		}
+	if (masks_out) {
+		size_t off = 0;
+		for (int i = 0; i < num_views; ++i) {
+			const size_t n = (size_t)views[i].width * views[i].height;
+			std::memcpy(masks_out + off, in.masks[i].ptr<uchar>(0), n);
+			off += n;
+		}
+	}
+	return n_pts;
+}
+
+long long run_tat_intermediate(int num_views, const refhost_view* views, float* points, long long cap, uint8_t* masks_out) {
+	FusionInputs in(num_views, views);
+	const int num_images = num_views;
+	auto& problems = in.problems; auto& images = in.images; auto& depths = in.depths; auto& normals = in.normals; auto& masks = in.masks;
+	auto& blocks = in.blocks; auto& cameras = in.cameras; auto& imageIdToindexMap = in.imageIdToindexMap; const bool use_block = in.use_block;
+	std::vector<PointList> PointCloud;
+#include "_ref/src/apd_cpp_1967_1971.inc"
+#include "_ref/src/apd_cpp_2028_2127.inc"
+	return export_points(PointCloud, in, num_views, views, points, cap, masks_out);
+}
+
+long long run_tat_advanced(int num_views, const refhost_view* views, float* points, long long cap, uint8_t* masks_out) {
+	FusionInputs in(num_views, views);
+	const int num_images = num_views;
+	auto& problems = in.problems; auto& images = in.images; auto& depths = in.depths; auto& normals = in.normals; auto& masks = in.masks;
+	auto& blocks = in.blocks; auto& cameras = in.cameras; auto& imageIdToindexMap = in.imageIdToindexMap; const bool use_block = in.use_block;
+	std::vector<PointList> PointCloud;
+#include "_ref/src/apd_cpp_2137_2138.inc"
+#include "_ref/src/apd_cpp_2195_2276.inc"
+	return export_points(PointCloud, in, num_views, views, points, cap, masks_out);
+}
+}  // namespace
+
+extern "C" long long refhost_run_fusion_tat(int mode, int num_views, const refhost_view* views, float* points, long long cap, uint8_t* masks_out) {
+	if (num_views <= 0 || !views || (mode != 1 && mode != 2)) return -1;
+	std::cout.setstate(std::ios_base::failbit);   // the loops announce every view on std::cout
+	const long long n = mode == 1 ? run_tat_intermediate(num_views, views, points, cap, masks_out) : run_tat_advanced(num_views, views, points, cap, masks_out);
+	std::cout.clear();
+	return n;
+}

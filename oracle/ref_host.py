@@ -29,6 +29,9 @@ def _lib(fast=False):
     lib.refhost_roberts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.refhost_run_fusion.restype = C.c_longlong
     lib.refhost_run_fusion.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+    if hasattr(lib, "refhost_run_fusion_tat"):
+        lib.refhost_run_fusion_tat.restype = C.c_longlong
+        lib.refhost_run_fusion_tat.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
     return lib
 
 
@@ -69,6 +72,22 @@ def run_fusion(views: list, fast: bool = False):
     pts = np.empty((cap, 6), np.float32)
     masks = np.zeros(cap, np.uint8)
     n = _lib(fast).refhost_run_fusion(len(views), arr, pts.ctypes.data, cap, masks.ctypes.data)
+    assert n >= 0
+    out_masks, off = [], 0
+    for h, w in shapes:
+        out_masks.append(masks[off:off + h * w].reshape(h, w).copy()); off += h * w
+    return pts[:n].copy(), out_masks
+
+
+def run_fusion_tat(views: list, mode: int, fast: bool = False):
+    """The reference's own RunFusion_TAT_Intermediate (mode 1) / RunFusion_TAT_advanced (mode 2) loop -> (points [n, 6], masks)."""
+    keep = []
+    arr = (FusionView * len(views))(*[make_fusion_view(v, keep) for v in views])
+    shapes = [(fv.height, fv.width) for fv in arr]
+    cap = sum(h * w for h, w in shapes)
+    pts = np.empty((cap, 6), np.float32)
+    masks = np.zeros(cap, np.uint8)
+    n = _lib(fast).refhost_run_fusion_tat(mode, len(views), arr, pts.ctypes.data, cap, masks.ctypes.data)
     assert n >= 0
     out_masks, off = [], 0
     for h, w in shapes:

@@ -109,3 +109,36 @@ def test_reference_host_flags_do_not_change_fusion_decisions_here():
     assert abs(len(a) - len(b)) <= max(2, len(a) // 10000) and flipped <= max(8, len(a) // 2500), (len(a), len(b), flipped)
     if len(a) == len(b):
         assert np.abs(a[:, :3] - b[:, :3]).max() < 1e-3
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_tat_fusion_restatement_equals_the_reference_loops(mode):
+    """Row N3, the two Tanks-and-Temples variants: RunFusion_TAT_Intermediate (APD.cpp:2028-2127) and RunFusion_TAT_advanced
+    (APD.cpp:2195-2276) compiled from the reference vs oracle/cpu/fusion_cpu.cpp — the same points (bit for bit, same order)
+    and the same masks, including the `diff` vector the reference declares once per view and therefore carries from pixel
+    to pixel (a source a pixel cannot evaluate keeps the measures of the last pixel that could)."""
+    for level, seed in ((1, 3), (0, 5)):
+        mv = synth.make_multiview(640, 480, 4, 2, seed=seed)
+        views = synth.make_fusion_views(mv, level)
+        o = FusionOracle(views)
+        mine, _ = o.run_tat(mode)
+        want, want_masks = ref_host.run_fusion_tat(views, mode)
+        assert len(mine) == len(want) > 1000, (len(mine), len(want))
+        assert (mine.view(np.uint32) == want.view(np.uint32)).all()
+        for a, b in zip(o.masks, want_masks):
+            assert (a == b).all()
+
+
+def test_tat_fusion_restatement_with_block_masks_and_mixed_sizes():
+    """Views at different resolutions and a block mask, both T&T variants."""
+    mv = synth.make_multiview(320, 240, 3, 2, seed=9)
+    v0 = synth.make_fusion_views(mv, 0); v1 = synth.make_fusion_views(mv, 1)
+    views = [v1[0], v0[1], v1[2]]
+    blk = np.full(views[1]["depth"].shape, 255, np.uint8); blk[:30, :] = 0
+    views[1] = dict(views[1], block=blk)
+    for mode in (1, 2):
+        o = FusionOracle(views)
+        mine, _ = o.run_tat(mode)
+        want, want_masks = ref_host.run_fusion_tat(views, mode)
+        assert len(mine) == len(want) > 50 and (mine.view(np.uint32) == want.view(np.uint32)).all(), mode
+        assert all((a == b).all() for a, b in zip(o.masks, want_masks)), mode
