@@ -4,6 +4,7 @@
 // wraps them in a C ABI.  They pin the CPU restatements of the callers' rows to the reference itself:
 //   APD.cpp:120-346    Roberts, Label_Seek, Label_Update, Connect          -> row N1 (visibility restoration), N4 (labels)
 //   APD.cpp:501-546    Get3DPointonWorld, Get3DPoint, ProjectCamera          -> row N3
+//   APD.cpp:1773-1796  RescaleMatToTargetSize (swapped scale factors, B10)    -> row N2
 //   APD.cpp:1797-1806  GetAngle                                               -> row N3
 //   APD.cpp:1875-1957  the fusing loop of RunFusion (ETH version)             -> row N3
 //   APD.cpp:1967-1971, 2028-2127   constants and fusing loop of RunFusion_TAT_Intermediate   -> row N3, mode 1
@@ -21,6 +22,7 @@
 
 #include "_ref/src/apd_cpp_120_346.inc"
 #include "_ref/src/apd_cpp_501_546.inc"
+#include "_ref/src/apd_cpp_1773_1796.inc"
 #include "_ref/src/apd_cpp_1797_1806.inc"
 
 struct refhost_view {   // == dvp_fusion_view (include/dvp_mvs.h)
@@ -225,4 +227,25 @@ extern "C" long long refhost_run_fusion_tat(int mode, int num_views, const refho
 	const long long n = mode == 1 ? run_tat_intermediate(num_views, views, points, cap, masks_out) : run_tat_advanced(num_views, views, points, cap, masks_out);
 	std::cout.clear();
 	return n;
+}
+
+// RescaleMatToTargetSize<TYPE> (APD.cpp:1773-1796) as InuputInitialization / SupportInitialization instantiate it between
+// levels (APD.cpp:1162, 1178, 1437-1438, 1454, 1661): kind 0 uchar, 1 float, 2 cv::Vec3f, 3 unsigned int, 4 int.
+// Pixels the reference leaves unwritten (its source index falls outside) come back as 0.
+extern "C" int refhost_rescale(int kind, const void* src, int sw, int sh, void* dst, int dw, int dh) {
+	if (!src || !dst || sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || kind < 0 || kind > 4) return 1;
+	const int types[5] = {CV_8UC1, CV_32FC1, CV_32FC3, CV_32SC1, CV_32SC1};
+	cv::Mat in(sh, sw, types[kind]), out;
+	std::memcpy(in.ptr<uchar>(0), src, (size_t)sw * sh * in.elem_size);
+	out = in;
+	switch (kind) {
+	case 0: RescaleMatToTargetSize<uchar>(in, out, cv::Size2i(dw, dh)); break;
+	case 1: RescaleMatToTargetSize<float>(in, out, cv::Size2i(dw, dh)); break;
+	case 2: RescaleMatToTargetSize<cv::Vec3f>(in, out, cv::Size2i(dw, dh)); break;
+	case 3: RescaleMatToTargetSize<unsigned int>(in, out, cv::Size2i(dw, dh)); break;
+	default: RescaleMatToTargetSize<int>(in, out, cv::Size2i(dw, dh)); break;
+	}
+	if (out.rows != dh || out.cols != dw) return 2;
+	std::memcpy(dst, out.ptr<uchar>(0), (size_t)dw * dh * out.elem_size);
+	return 0;
 }

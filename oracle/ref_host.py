@@ -93,3 +93,16 @@ def run_fusion_tat(views: list, mode: int, fast: bool = False):
     for h, w in shapes:
         out_masks.append(masks[off:off + h * w].reshape(h, w).copy()); off += h * w
     return pts[:n].copy(), out_masks
+
+
+def rescale(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """The reference's own RescaleMatToTargetSize<TYPE> (APD.cpp:1773-1796) on a uint8 / float32 / float32x3 / uint32 / int32 map."""
+    a = np.ascontiguousarray(src)
+    kind = {("uint8", 2): 0, ("float32", 2): 1, ("float32", 3): 2, ("uint32", 2): 3, ("int32", 2): 4}[(a.dtype.name, a.ndim)]
+    assert kind != 2 or a.shape[2] == 3
+    out = np.zeros((dh, dw) + a.shape[2:], a.dtype)
+    lib = _lib()
+    lib.refhost_rescale.restype = C.c_int
+    lib.refhost_rescale.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    assert lib.refhost_rescale(kind, a.ctypes.data, a.shape[1], a.shape[0], out.ctypes.data, dw, dh) == 0
+    return out

@@ -57,15 +57,17 @@ class Mat {
 public:
 	int rows, cols;
 	size_t elem_size;
+	int type_;
 	std::vector<unsigned char> storage;
-	Mat() : rows(0), cols(0), elem_size(1) {}
+	Mat() : rows(0), cols(0), elem_size(1), type_(0) {}
 	Mat(int r, int c, int type) { create(r, c, type); }
 	void create(int r, int c, int type) {
-		rows = r; cols = c;
+		rows = r; cols = c; type_ = type;
 		elem_size = (type == CV_8U) ? 1 : (type == CV_8UC3 ? 3 : (type == CV_32FC3 ? 12 : 4));
 		storage.assign((size_t)r * c * elem_size, 0);
 	}
 	bool empty() const { return rows == 0 || cols == 0; }
+	int type() const { return type_; }   // RescaleMatToTargetSize (APD.cpp:1781) builds its destination from it
 	template <typename T> T& at(int r, int c) { return ptr<T>(r)[c]; }
 	template <typename T> const T& at(int r, int c) const { return ptr<T>(r)[c]; }
 	Mat clone() const { return *this; }   // storage is a std::vector: copying the object is a deep copy

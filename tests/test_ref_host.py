@@ -142,3 +142,21 @@ def test_tat_fusion_restatement_with_block_masks_and_mixed_sizes():
         want, want_masks = ref_host.run_fusion_tat(views, mode)
         assert len(mine) == len(want) > 50 and (mine.view(np.uint32) == want.view(np.uint32)).all(), mode
         assert all((a == b).all() for a, b in zip(o.masks, want_masks)), mode
+
+
+def test_rescale_restatement_equals_the_reference_function():
+    """Row N2: RescaleMatToTargetSize (APD.cpp:1773-1796, scale factors swapped — SURVEY B10) compiled from the reference vs
+    oracle/host_chain.rescale_ref, the restatement the scene driver's device rescale is compared with: every element type the
+    reference instantiates, up- and down-scaling at the ratios of the schedule and at awkward ones."""
+    import host_chain
+    rng = np.random.default_rng(11)
+    sizes = [((778, 518), (1555, 1037)), ((1555, 1037), (3111, 2073)), ((97, 33), (194, 67)), ((194, 67), (97, 33)), ((64, 48), (64, 48)),
+             ((31, 57), (100, 41)), ((120, 90), (37, 111)), ((5, 3), (9, 7))]
+    for (sw, sh), (dw, dh) in sizes:
+        maps = [rng.integers(0, 255, (sh, sw)).astype(np.uint8), rng.random((sh, sw), dtype=np.float32),
+                rng.random((sh, sw, 3), dtype=np.float32), rng.integers(0, 2 ** 32, (sh, sw), dtype=np.uint64).astype(np.uint32),
+                rng.integers(-50, 50, (sh, sw)).astype(np.int32)]
+        for m in maps:
+            want = ref_host.rescale(m, dw, dh)
+            mine = host_chain.rescale_ref(m, dw, dh)
+            assert mine.shape == want.shape and (mine.view(np.uint8) == want.view(np.uint8)).all(), (sw, sh, dw, dh, m.dtype)
