@@ -4,6 +4,8 @@
 // wraps them in a C ABI.  They pin the CPU restatements of the callers' rows to the reference itself:
 //   APD.cpp:120-346    Roberts, Label_Seek, Label_Update, Connect          -> row N1 (visibility restoration), N4 (labels)
 //   APD.cpp:501-546    Get3DPointonWorld, Get3DPoint, ProjectCamera          -> row N3
+//   APD.cpp:548-692    ReadBinMat, writeDepthDmb, writeNormalDmb, WriteBinMat, ReadCamera  -> row N4 (on-disk formats)
+//   APD.cpp:978-982, main.cpp:127-170   ToFormatIndex, GenerateSampleList (pair.txt)      -> row N4 (on-disk formats)
 //   APD.cpp:1773-1796  RescaleMatToTargetSize (swapped scale factors, B10)    -> row N2
 //   APD.cpp:1797-1806  GetAngle                                               -> row N3
 //   APD.cpp:1875-1957  the fusing loop of RunFusion (ETH version)             -> row N3
@@ -20,8 +22,15 @@
 #include <vector>
 #include <unordered_map>
 
+#include <fstream>
+#include <sstream>
+#include <iomanip>
+#include <iostream>
 #include "_ref/src/apd_cpp_120_346.inc"
 #include "_ref/src/apd_cpp_501_546.inc"
+#include "_ref/src/apd_cpp_548_692.inc"
+#include "_ref/src/apd_cpp_978_982.inc"
+#include "_ref/src/main_cpp_127_170.inc"
 #include "_ref/src/apd_cpp_1773_1796.inc"
 #include "_ref/src/apd_cpp_1797_1806.inc"
 
@@ -248,4 +257,53 @@ extern "C" int refhost_rescale(int kind, const void* src, int sw, int sh, void* 
 	if (out.rows != dh || out.cols != dw) return 2;
 	std::memcpy(dst, out.ptr<uchar>(0), (size_t)dw * dh * out.elem_size);
 	return 0;
+}
+
+// ---- the reference's own file readers / writers (row N4, on-disk formats) -----------------------------------------
+// kind as in refhost_rescale (0 uchar, 1 float, 2 Vec3f, 3 unsigned int, 4 int).
+extern "C" int refhost_write_binmat(const char* file, int kind, const void* src, int w, int h) {
+	if (!file || !src || kind < 0 || kind > 4) return 1;
+	const int types[5] = {CV_8UC1, CV_32FC1, CV_32FC3, CV_32SC1, CV_32SC1};
+	cv::Mat m(h, w, types[kind]);
+	std::memcpy(m.ptr<uchar>(0), src, (size_t)w * h * m.elem_size);
+	return WriteBinMat(path(file), m) ? 0 : 2;
+}
+// -> rows, cols, OpenCV type code; data copied when `dst` is given (capacity in bytes)
+extern "C" int refhost_read_binmat(const char* file, int* rows, int* cols, int* type, void* dst, long long cap) {
+	if (!file) return 1;
+	cv::Mat m;
+	std::cerr.setstate(std::ios_base::failbit);
+	const bool ok = ReadBinMat(path(file), m);
+	std::cerr.clear();
+	if (!ok) return 2;
+	if (rows) *rows = m.rows; if (cols) *cols = m.cols; if (type) *type = m.type();
+	const long long n = (long long)m.rows * m.cols * (long long)m.elem_size;
+	if (dst) { if (n > cap) return 3; std::memcpy(dst, m.ptr<uchar>(0), (size_t)n); }
+	return 0;
+}
+extern "C" int refhost_write_dmb(const char* file, int channels, const float* src, int w, int h) {
+	if (!file || !src || (channels != 1 && channels != 3)) return 1;
+	cv::Mat m(h, w, channels == 1 ? CV_32FC1 : CV_32FC3);
+	std::memcpy(m.ptr<uchar>(0), src, (size_t)w * h * m.elem_size);
+	if (channels == 1) return writeDepthDmb(path(file), cv::Mat_<float>(m));
+	return writeNormalDmb(path(file), cv::Mat_<cv::Vec3f>(m));
+}
+extern "C" int refhost_read_camera(const char* file, Camera* cam) {
+	if (!file || !cam) return 1;
+	std::memset(cam, 0, sizeof(Camera));
+	return ReadCamera(path(file), *cam) ? 0 : 2;
+}
+// pair.txt: -> number of problems; ref ids and source lists (cap_src entries per problem, -1 padded) when given
+extern "C" int refhost_read_pairs(const char* dense_folder, int* ref_ids, int* num_src, int* src_ids, int cap_problems, int cap_src) {
+	if (!dense_folder) return -1;
+	std::vector<Problem> problems;
+	GenerateSampleList(path(dense_folder), problems);
+	const int n = (int)problems.size();
+	for (int i = 0; i < n && i < cap_problems; ++i) {
+		if (ref_ids) ref_ids[i] = problems[i].ref_image_id;
+		const int ns = (int)problems[i].src_image_ids.size();
+		if (num_src) num_src[i] = ns;
+		if (src_ids) for (int k = 0; k < cap_src; ++k) src_ids[(size_t)i * cap_src + k] = k < ns ? problems[i].src_image_ids[k] : -1;
+	}
+	return n;
 }

@@ -106,3 +106,52 @@ def rescale(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
     lib.refhost_rescale.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
     assert lib.refhost_rescale(kind, a.ctypes.data, a.shape[1], a.shape[0], out.ctypes.data, dw, dh) == 0
     return out
+
+
+# ---- the reference's own file readers / writers (APD.cpp:548-692, main.cpp:127-170) ---------------------------------
+_KINDS = {("uint8", 2): 0, ("float32", 2): 1, ("float32", 3): 2, ("uint32", 2): 3, ("int32", 2): 4}
+
+
+def write_binmat(path: str, a: np.ndarray):
+    a = np.ascontiguousarray(a)
+    lib = _lib()
+    lib.refhost_write_binmat.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    assert lib.refhost_write_binmat(os.fsencode(path), _KINDS[(a.dtype.name, a.ndim)], a.ctypes.data, a.shape[1], a.shape[0]) == 0
+
+
+def read_binmat(path: str):
+    """-> (rows, cols, OpenCV type code, raw bytes) as the reference's ReadBinMat sees the file; None when it refuses it."""
+    lib = _lib()
+    lib.refhost_read_binmat.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
+    r, c, t = C.c_int(), C.c_int(), C.c_int()
+    if lib.refhost_read_binmat(os.fsencode(path), C.byref(r), C.byref(c), C.byref(t), None, 0) != 0:
+        return None
+    elem = {0: 1, 16: 3, 21: 12}.get(t.value, 4)
+    buf = np.empty(r.value * c.value * elem, np.uint8)
+    assert lib.refhost_read_binmat(os.fsencode(path), C.byref(r), C.byref(c), C.byref(t), buf.ctypes.data, buf.nbytes) == 0
+    return r.value, c.value, t.value, buf
+
+
+def write_dmb(path: str, a: np.ndarray):
+    a = np.ascontiguousarray(a, np.float32)
+    lib = _lib()
+    lib.refhost_write_dmb.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    assert lib.refhost_write_dmb(os.fsencode(path), 1 if a.ndim == 2 else 3, a.ctypes.data, a.shape[1], a.shape[0]) == 0
+
+
+def read_camera(path: str):
+    from dvp_mvs_b200.synth import CAMERA_DTYPE
+    cam = np.zeros(1, CAMERA_DTYPE)
+    lib = _lib()
+    lib.refhost_read_camera.argtypes = [C.c_char_p, C.c_void_p]
+    assert lib.refhost_read_camera(os.fsencode(path), cam.ctypes.data) == 0
+    return cam[0]
+
+
+def read_pairs(dense_folder: str, cap_src: int = 64):
+    lib = _lib()
+    lib.refhost_read_pairs.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    n = lib.refhost_read_pairs(os.fsencode(dense_folder), None, None, None, 0, 0)
+    ref = np.zeros(max(n, 1), np.int32); num = np.zeros(max(n, 1), np.int32); src = np.zeros((max(n, 1), cap_src), np.int32)
+    assert lib.refhost_read_pairs(os.fsencode(dense_folder), ref.ctypes.data, num.ctypes.data, src.ctypes.data, n, cap_src) == n
+    return [(int(ref[i]), [int(v) for v in src[i, :num[i]]]) for i in range(n)]

@@ -59,12 +59,21 @@ public:
 	size_t elem_size;
 	int type_;
 	std::vector<unsigned char> storage;
-	Mat() : rows(0), cols(0), elem_size(1), type_(0) {}
+	unsigned char* data;   // == storage.data(); `data` and `step` are what ReadBinMat / WriteBinMat touch (APD.cpp:548-650)
+	size_t step;           // bytes per row
+	Mat() : rows(0), cols(0), elem_size(1), type_(0), data(nullptr), step(0) {}
 	Mat(int r, int c, int type) { create(r, c, type); }
+	Mat(const Mat& o) : rows(o.rows), cols(o.cols), elem_size(o.elem_size), type_(o.type_), storage(o.storage) { rebind(); }
+	Mat& operator=(const Mat& o) {
+		if (this != &o) { rows = o.rows; cols = o.cols; elem_size = o.elem_size; type_ = o.type_; storage = o.storage; }
+		rebind();
+		return *this;
+	}
 	void create(int r, int c, int type) {
 		rows = r; cols = c; type_ = type;
 		elem_size = (type == CV_8U) ? 1 : (type == CV_8UC3 ? 3 : (type == CV_32FC3 ? 12 : 4));
 		storage.assign((size_t)r * c * elem_size, 0);
+		rebind();
 	}
 	bool empty() const { return rows == 0 || cols == 0; }
 	int type() const { return type_; }   // RescaleMatToTargetSize (APD.cpp:1781) builds its destination from it
@@ -73,7 +82,13 @@ public:
 	Mat clone() const { return *this; }   // storage is a std::vector: copying the object is a deep copy
 	template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(storage.data() + (size_t)r * cols * elem_size); }
 	template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(storage.data() + (size_t)r * cols * elem_size); }
+private:
+	void rebind() { data = storage.empty() ? nullptr : storage.data(); step = (size_t)cols * elem_size; }
 };
-template <typename T> class Mat_ : public Mat {};
+template <typename T> class Mat_ : public Mat {
+public:
+	Mat_() {}
+	Mat_(const Mat& m) : Mat(m) {}
+};
 }  // namespace cv
 #endif

@@ -1,6 +1,7 @@
 """Row N4, second half: the reference's on-disk exchange formats (ReadBinMat / WriteBinMat
 APD.cpp:548-648, writeDepthDmb / writeNormalDmb APD.cpp:575-628, ReadCamera APD.cpp:651-692, GenerateSampleList
-main.cpp:127-170) against files laid out by hand exactly as the reference writes / expects them.  Host code: no GPU."""
+main.cpp:127-170) against files laid out by hand exactly as the reference writes / expects them (the same entry points are
+compared with the reference's own functions, compiled from those lines, in tests/test_ref_host.py).  Host code: no GPU."""
 import struct
 
 import numpy as np

@@ -160,3 +160,44 @@ def test_rescale_restatement_equals_the_reference_function():
             want = ref_host.rescale(m, dw, dh)
             mine = host_chain.rescale_ref(m, dw, dh)
             assert mine.shape == want.shape and (mine.view(np.uint8) == want.view(np.uint8)).all(), (sw, sh, dw, dh, m.dtype)
+
+
+def test_on_disk_formats_against_the_reference_s_own_readers_and_writers(tmp_path):
+    """Row N4, on-disk formats: dvp_io_* (csrc/dvp_io.cpp) against ReadBinMat / WriteBinMat / writeDepthDmb / writeNormalDmb /
+    ReadCamera (APD.cpp:548-692) and GenerateSampleList (main.cpp:127-170) compiled from the reference: files written by one
+    side are byte-identical to the other's and read back to the same values by both."""
+    from dvp_mvs_b200 import formats
+    rng = np.random.default_rng(4)
+    mats = [rng.integers(0, 3, (37, 53)).astype(np.uint8), rng.random((19, 64), dtype=np.float32), rng.random((12, 9, 3), dtype=np.float32),
+            rng.integers(0, 2 ** 31, (8, 33)).astype(np.int32)]
+    for i, m in enumerate(mats):
+        theirs, ours = tmp_path / f"ref{i}.bin", tmp_path / f"dvp{i}.bin"
+        ref_host.write_binmat(str(theirs), m)
+        formats.write_binmat(str(ours), m)
+        assert theirs.read_bytes() == ours.read_bytes(), i
+        got = formats.read_binmat(str(theirs))                     # their file, our reader
+        assert got.dtype == m.dtype and got.shape == m.shape and (got == m).all(), i
+        r, c, t, raw = ref_host.read_binmat(str(ours))             # our file, their reader
+        assert (r, c) == m.shape[:2] and raw.tobytes() == m.tobytes(), i
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(np.array([2, 1, 1, 0], np.int32).tobytes() + b"\0")
+    assert ref_host.read_binmat(str(bad)) is None                  # "Version error" on both sides
+    with pytest.raises(Exception):
+        formats.read_binmat(str(bad))
+    depth = rng.random((23, 31), dtype=np.float32); normal = rng.random((23, 31, 3), dtype=np.float32)
+    for name, a in (("d", depth), ("n", normal)):
+        ref_host.write_dmb(str(tmp_path / f"ref_{name}.dmb"), a)
+        formats.write_dmb(str(tmp_path / f"dvp_{name}.dmb"), a)
+        assert (tmp_path / f"ref_{name}.dmb").read_bytes() == (tmp_path / f"dvp_{name}.dmb").read_bytes(), name
+    # cameras: awkward decimals, exponents, negative values; the centre -R^T t is accumulated in double by both
+    for k in range(20):
+        R = rng.normal(size=(3, 3)); t = rng.normal(size=3) * 10; K = np.array([[3000 + rng.random(), 0, 1500.123 + k], [0, 2999.5 + rng.random(), 1000.7], [0, 0, 1]])
+        txt = "extrinsic\n" + "".join(" ".join(repr(float(v)) for v in list(R[j]) + [t[j]]) + "\n" for j in range(3)) + "0.0 0.0 0.0 1.0\n\nintrinsic\n"
+        txt += "".join(" ".join(f"{v:.9e}" if k % 2 else repr(float(v)) for v in K[j]) + "\n" for j in range(3)) + f"\n{0.37 + k} {0.0123} {192} {9.5 + k}\n"
+        p = tmp_path / f"{k:08d}_cam.txt"
+        p.write_text(txt)
+        theirs, ours = ref_host.read_camera(str(p)), formats.read_camera(str(p))
+        for f in ("K", "R", "t", "c", "depth_min", "depth_max"):
+            assert (np.asarray(theirs[f]).view(np.uint32) == np.asarray(ours[f]).view(np.uint32)).all(), (k, f)
+    (tmp_path / "pair.txt").write_text("4\n0\n3 1 0.75 2 0.5 7 -1.0\n4\n2 0 2.5 2 0.0\n2\n0\n9\n10 1 1 2 1 3 1 4 1 5 1 6 1 7 1 8 1 10 1 11 0.001\n")
+    assert ref_host.read_pairs(str(tmp_path)) == formats.read_pairs(str(tmp_path / "pair.txt"))
