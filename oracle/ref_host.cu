@@ -6,6 +6,7 @@
 //   APD.cpp:501-546    Get3DPointonWorld, Get3DPoint, ProjectCamera          -> row N3
 //   APD.cpp:548-692    ReadBinMat, writeDepthDmb, writeNormalDmb, WriteBinMat, ReadCamera  -> row N4 (on-disk formats)
 //   APD.cpp:978-982, main.cpp:127-170   ToFormatIndex, GenerateSampleList (pair.txt)      -> row N4 (on-disk formats)
+//   APD.cpp:1119-1140  the level-size / camera-rescale block of InuputInitialization              -> row N2 (image pyramid)
 //   APD.cpp:1773-1796  RescaleMatToTargetSize (swapped scale factors, B10)    -> row N2
 //   APD.cpp:1797-1806  GetAngle                                               -> row N3
 //   APD.cpp:1875-1957  the fusing loop of RunFusion (ETH version)             -> row N3
@@ -306,4 +307,29 @@ extern "C" int refhost_read_pairs(const char* dense_folder, int* ref_ids, int* n
 		if (src_ids) for (int k = 0; k < cap_src; ++k) src_ids[(size_t)i * cap_src + k] = k < ns ? problems[i].src_image_ids[k] : -1;
 	}
 	return n;
+}
+
+// InuputInitialization's "scale images" block (APD.cpp:1119-1143): level size = round(size / scale_size) in float, the
+// intrinsics scaled by the ratios of the ROUNDED sizes.  cv::resize is stood in for by an allocation of the target size
+// (the pixels are row N2's image pyramid, pinned against OpenCV itself in tests/test_image.py); what is checked here is
+// the size and camera arithmetic.
+namespace cv {
+enum { INTER_LINEAR = 1 };
+inline void resize(const Mat& src, Mat& dst, Size dsize, double, double, int) { (void)src; dst.create(dsize.height, dsize.width, CV_32FC1); }
+}
+extern "C" int refhost_level_camera(const Camera* full, int full_w, int full_h, int scale_size, Camera* out, int* out_w, int* out_h) {
+	if (!full || !out || full_w <= 0 || full_h <= 0 || scale_size < 1) return 1;
+	struct { int scale_size; } problem = {scale_size};
+	int num_images = 1, width = full_w, height = full_h;
+	std::vector<cv::Mat> images(1, cv::Mat(full_h, full_w, CV_32FC1));
+	std::vector<Camera> cameras(1, *full);
+	cameras[0].width = full_w; cameras[0].height = full_h;   // APD.cpp:1087-1088, 1103-1104
+	std::cout.setstate(std::ios_base::failbit);
+	{
+#include "_ref/src/apd_cpp_1119_1143.inc"
+	}
+	std::cout.clear();
+	*out = cameras[0];
+	if (out_w) *out_w = width; if (out_h) *out_h = height;
+	return 0;
 }

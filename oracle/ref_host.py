@@ -155,3 +155,15 @@ def read_pairs(dense_folder: str, cap_src: int = 64):
     ref = np.zeros(max(n, 1), np.int32); num = np.zeros(max(n, 1), np.int32); src = np.zeros((max(n, 1), cap_src), np.int32)
     assert lib.refhost_read_pairs(os.fsencode(dense_folder), ref.ctypes.data, num.ctypes.data, src.ctypes.data, n, cap_src) == n
     return [(int(ref[i]), [int(v) for v in src[i, :num[i]]]) for i in range(n)]
+
+
+def level_camera(cam_full, full_w: int, full_h: int, scale_size: int):
+    """The reference's own level-size / camera-rescale block (APD.cpp:1119-1143) -> (camera at the level, w, h)."""
+    from dvp_mvs_b200.synth import CAMERA_DTYPE
+    src = np.array(cam_full, dtype=CAMERA_DTYPE, copy=True).reshape(1)
+    out = np.zeros(1, CAMERA_DTYPE)
+    w, h = C.c_int(), C.c_int()
+    lib = _lib()
+    lib.refhost_level_camera.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert lib.refhost_level_camera(src.ctypes.data, full_w, full_h, scale_size, out.ctypes.data, C.byref(w), C.byref(h)) == 0
+    return out[0], w.value, h.value

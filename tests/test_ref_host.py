@@ -201,3 +201,27 @@ def test_on_disk_formats_against_the_reference_s_own_readers_and_writers(tmp_pat
             assert (np.asarray(theirs[f]).view(np.uint32) == np.asarray(ours[f]).view(np.uint32)).all(), (k, f)
     (tmp_path / "pair.txt").write_text("4\n0\n3 1 0.75 2 0.5 7 -1.0\n4\n2 0 2.5 2 0.0\n2\n0\n9\n10 1 1 2 1 3 1 4 1 5 1 6 1 7 1 8 1 10 1 11 0.001\n")
     assert ref_host.read_pairs(str(tmp_path)) == formats.read_pairs(str(tmp_path / "pair.txt"))
+
+
+def test_level_sizes_and_cameras_equal_the_reference_block():
+    """Row N2: the level size (round(size / scale) in float) and the intrinsics scaled by the ratios of the ROUNDED sizes —
+    InuputInitialization's block APD.cpp:1119-1143 compiled from the reference vs the restatement (oracle/host_chain.py) and
+    vs the library's own dvp_scene_level_size, over the dataset sizes and awkward ones, scales 1 to 16."""
+    import host_chain
+    from dvp_mvs_b200 import Scene
+    rng = np.random.default_rng(2)
+    cam = np.zeros((), synth.CAMERA_DTYPE)
+    sizes = [(6221, 4146), (6048, 4032), (1920, 1080), (3111, 2073), (1555, 1037), (101, 67), (33, 35), (5, 3), (4097, 2049)]
+    for full_w, full_h in sizes:
+        cam["K"] = np.array([3409.7 + rng.random(), 0, full_w / 2 + rng.random(), 0, 3411.3 + rng.random(), full_h / 2 + rng.random(), 0, 0, 1], np.float32)
+        cam["depth_min"], cam["depth_max"] = 0.5, 9.0
+        for levels in (1, 2, 3, 4):
+            sc = Scene(2, levels, device=-1)            # host-only scene: schedule and size queries need no GPU
+            for level in range(levels):
+                scale = host_chain.level_scale(levels, level)
+                want, w, h = ref_host.level_camera(cam, full_w, full_h, scale)
+                assert (w, h) == host_chain.level_size(full_w, full_h, scale) == tuple(sc.level_size(full_w, full_h, level)), (full_w, full_h, scale)
+                mine = host_chain.level_camera(cam, full_w, full_h, w, h, scale)
+                assert (np.asarray(mine["K"]).view(np.uint32) == np.asarray(want["K"]).view(np.uint32)).all(), (full_w, full_h, scale)
+                assert int(want["width"]) == w and int(want["height"]) == h
+            sc.close()
