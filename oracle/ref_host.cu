@@ -7,6 +7,7 @@
 //   APD.cpp:548-692    ReadBinMat, writeDepthDmb, writeNormalDmb, WriteBinMat, ReadCamera  -> row N4 (on-disk formats)
 //   APD.cpp:978-982, main.cpp:127-170   ToFormatIndex, GenerateSampleList (pair.txt)      -> row N4 (on-disk formats)
 //   APD.cpp:1119-1140  the level-size / camera-rescale block of InuputInitialization              -> row N2 (image pyramid)
+//   main.cpp:450-512   the rounds x passes x views loop of main(), ProcessProblem / GetProblemEdges recorded     -> row N2 (schedule)
 //   APD.cpp:1773-1796  RescaleMatToTargetSize (swapped scale factors, B10)    -> row N2
 //   APD.cpp:1797-1806  GetAngle                                               -> row N3
 //   APD.cpp:1875-1957  the fusing loop of RunFusion (ETH version)             -> row N3
@@ -332,4 +333,46 @@ extern "C" int refhost_level_camera(const Camera* full, int full_w, int full_h, 
 	*out = cameras[0];
 	if (out_w) *out_w = width; if (out_h) *out_h = height;
 	return 0;
+}
+
+// main()'s schedule (main.cpp:450-512), compiled as it stands: ProcessProblem and GetProblemEdges are recorders here, so
+// the loop yields, call by call, which view runs at which scale with which parameters — what dvp_scene_pass_params and the
+// scene driver's order restate.  A record = 4 ints (view, iteration, scale_size, edges_requested) + the PatchMatchParams.
+namespace {
+struct ScheduleRecord { int view, iteration, scale_size, edges; PatchMatchParams params; };
+std::vector<ScheduleRecord>* g_schedule = nullptr;
+int g_edges_seen = 0;
+void GetProblemEdges(const Problem&) { g_edges_seen = 1; }
+void ProcessProblem(const Problem& p) {
+	if (g_schedule) g_schedule->push_back({p.ref_image_id, p.iteration, p.scale_size, g_edges_seen, p.params});
+	g_edges_seen = 0;
+}
+}  // namespace
+// out: [cap][27] ints / floats-as-bits in the order of dvp_params after the 4 record ints; returns the number of calls
+extern "C" int refhost_schedule(int round_num, int num_problems, int32_t* out, int cap) {
+	if (round_num < 2 || num_problems < 1) return -1;
+	std::vector<Problem> problems(num_problems);
+	for (int i = 0; i < num_problems; ++i) { problems[i].index = i; problems[i].ref_image_id = i; }
+	std::vector<ScheduleRecord> log;
+	g_schedule = &log; g_edges_seen = 0;
+	int iteration_index = 0;
+	bool flag = true;
+	std::cout.setstate(std::ios_base::failbit);
+#include "_ref/src/main_cpp_450_512.inc"
+	std::cout.clear();
+	g_schedule = nullptr;
+	(void)iteration_index;
+	for (int k = 0; k < (int)log.size() && k < cap; ++k) {
+		const ScheduleRecord& r = log[k];
+		const PatchMatchParams& q = r.params;
+		int32_t* o = out + (size_t)k * 27;
+		auto fbits = [](float f) { int32_t b; std::memcpy(&b, &f, 4); return b; };
+		o[0] = r.view; o[1] = r.iteration; o[2] = r.scale_size; o[3] = r.edges;
+		o[4] = q.max_iterations; o[5] = q.num_images; o[6] = fbits(q.sigma_spatial); o[7] = fbits(q.sigma_color); o[8] = q.top_k;
+		o[9] = fbits(q.depth_min); o[10] = fbits(q.depth_max); o[11] = q.geom_consistency; o[12] = q.strong_radius; o[13] = q.strong_increment;
+		o[14] = q.weak_radius; o[15] = q.weak_increment; o[16] = q.use_APD; o[17] = q.use_edge; o[18] = q.use_limit; o[19] = q.use_label;
+		o[20] = q.use_detail; o[21] = q.use_radius; o[22] = q.weak_peak_radius; o[23] = q.rotate_time; o[24] = fbits(q.ransac_threshold);
+		o[25] = fbits(q.geom_factor); o[26] = (int32_t)q.state;
+	}
+	return (int)log.size();
 }

@@ -167,3 +167,27 @@ def level_camera(cam_full, full_w: int, full_h: int, scale_size: int):
     lib.refhost_level_camera.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     assert lib.refhost_level_camera(src.ctypes.data, full_w, full_h, scale_size, out.ctypes.data, C.byref(w), C.byref(h)) == 0
     return out[0], w.value, h.value
+
+
+SCHEDULE_FIELDS = ("max_iterations", "num_images", "sigma_spatial", "sigma_color", "top_k", "depth_min", "depth_max", "geom_consistency",
+                   "strong_radius", "strong_increment", "weak_radius", "weak_increment", "use_APD", "use_edge", "use_limit", "use_label",
+                   "use_detail", "use_radius", "weak_peak_radius", "rotate_time", "ransac_threshold", "geom_factor", "state")
+_FLOAT_FIELDS = {"sigma_spatial", "sigma_color", "depth_min", "depth_max", "ransac_threshold", "geom_factor"}
+
+
+def schedule(round_num: int, num_problems: int):
+    """main()'s own loop (main.cpp:450-512) with ProcessProblem recorded -> [dict(view, iteration, scale_size, edges, params{...})]."""
+    lib = _lib()
+    lib.refhost_schedule.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
+    cap = (round_num - 1) * 4 * num_problems
+    out = np.zeros((cap, 27), np.int32)
+    n = lib.refhost_schedule(round_num, num_problems, out.ctypes.data, cap)
+    assert n == cap, (n, cap)
+    recs = []
+    for row in out:
+        prm = {}
+        for k, name in enumerate(SCHEDULE_FIELDS):
+            v = row[4 + k]
+            prm[name] = float(np.array([v], np.int32).view(np.float32)[0]) if name in _FLOAT_FIELDS else int(v)
+        recs.append(dict(view=int(row[0]), iteration=int(row[1]), scale_size=int(row[2]), edges=int(row[3]), params=prm))
+    return recs

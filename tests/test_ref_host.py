@@ -225,3 +225,37 @@ def test_level_sizes_and_cameras_equal_the_reference_block():
                 assert (np.asarray(mine["K"]).view(np.uint32) == np.asarray(want["K"]).view(np.uint32)).all(), (full_w, full_h, scale)
                 assert int(want["width"]) == w and int(want["height"]) == h
             sc.close()
+
+
+@pytest.mark.parametrize("num_levels", [1, 2, 3, 4])
+def test_schedule_equals_main_s_own_loop(num_levels):
+    """Row N2: main()'s rounds x passes x views loop (main.cpp:450-512) compiled from the reference, with ProcessProblem and
+    GetProblemEdges replaced by recorders, against the library's dvp_scene_pass_params / dvp_scene_run order and the
+    restatement (oracle/host_chain.py): which view runs when, at which scale, with every PatchMatchParams field — float
+    fields bit for bit (ransac_threshold is 0.01 - i * 0.00125 evaluated in double and narrowed)."""
+    import host_chain
+    from dvp_mvs_b200 import Scene
+    V = 3
+    recs = ref_host.schedule(num_levels + 1, V)
+    assert len(recs) == num_levels * 4 * V
+    sc = Scene(V, num_levels, device=-1)
+    k = 0
+    for level in range(num_levels):
+        for pass_ in range(4):
+            mine = sc.pass_params(level, pass_)
+            restated = host_chain.schedule_params(num_levels, level, pass_)
+            for v in range(V):                       # every pass visits the views in index order (Gauss-Seidel over the views)
+                r = recs[k]; k += 1
+                assert (r["view"], r["iteration"], r["scale_size"]) == (v, level * 4 + pass_, host_chain.level_scale(num_levels, level))
+                assert r["edges"] == (1 if pass_ == 0 else 0)          # GetProblemEdges precedes the INIT pass of every round
+                for name in ref_host.SCHEDULE_FIELDS:
+                    if name in ("depth_min", "depth_max", "num_images"):   # set per view by InuputInitialization, not by the schedule
+                        continue
+                    want = r["params"][name]
+                    for who, p in (("library", mine), ("restatement", restated)):
+                        got = getattr(p, name)
+                        if name in ("sigma_spatial", "sigma_color", "ransac_threshold", "geom_factor"):
+                            assert np.float32(got).view(np.uint32) == np.float32(want).view(np.uint32), (who, level, pass_, name, got, want)
+                        else:
+                            assert int(got) == int(want), (who, level, pass_, name, got, want)
+    sc.close()
