@@ -7,6 +7,7 @@
 //   APD.cpp:548-692    ReadBinMat, writeDepthDmb, writeNormalDmb, WriteBinMat, ReadCamera  -> row N4 (on-disk formats)
 //   APD.cpp:978-982, main.cpp:127-170   ToFormatIndex, GenerateSampleList (pair.txt)      -> row N4 (on-disk formats)
 //   APD.cpp:1119-1140  the level-size / camera-rescale block of InuputInitialization              -> row N2 (image pyramid)
+//   main.cpp:6-9, 282-363   setBit_YZL and ProcessProblem's post-pass: depth range check + visibility restoration        -> row N1
 //   main.cpp:450-512   the rounds x passes x views loop of main(), ProcessProblem / GetProblemEdges recorded     -> row N2 (schedule)
 //   APD.cpp:1773-1796  RescaleMatToTargetSize (swapped scale factors, B10)    -> row N2
 //   APD.cpp:1797-1806  GetAngle                                               -> row N3
@@ -375,4 +376,38 @@ extern "C" int refhost_schedule(int round_num, int num_problems, int32_t* out, i
 		o[25] = fbits(q.geom_factor); o[26] = (int32_t)q.state;
 	}
 	return (int)log.size();
+}
+
+// ProcessProblem after RunPatchMatch (main.cpp:282-363), compiled as it stands against an object that answers the APD
+// getters it calls: out-of-range depths are zeroed and their pixels become UNKNOWN; per source view the pixels that do not
+// select the view are labelled (Connect + Label_Update) and regions below 20 * (8 / scale)^2 pixels are given the view.
+// (The reference draws the kept regions' display colours with rand(): a region whose three draws all give 0 would count as
+// small — probability 2^-24 per region, and the same for anyone who runs the reference; srand(1) fixes the draws here.)
+#include "_ref/src/main_cpp_6_9.inc"
+namespace {
+struct PostPassAPD {
+	int w, h; float dmin, dmax;
+	const float4* planes; cv::Mat states; const uint32_t* sel_in; uint32_t* sel_out;
+	int GetWidth() const { return w; }
+	int GetHeight() const { return h; }
+	float GetDepthMin() const { return dmin; }
+	float GetDepthMax() const { return dmax; }
+	cv::Mat GetPixelStates() const { return states; }
+	float4 GetPlaneHypothesis(int r, int c) const { return planes[(size_t)r * w + c]; }
+	unsigned int GetPixelSelectedViews(int r, int c) const { return sel_in[(size_t)r * w + c]; }
+	void SetPixelSelectedViews(int r, int c, unsigned int v) { sel_out[(size_t)r * w + c] = v; }
+};
+}  // namespace
+extern "C" int refhost_post_pass(const float* planes /*[h][w][4]*/, const uint8_t* states_in, const uint32_t* selected_in, int w, int h, int num_src, int scale_size,
+                                 float depth_min, float depth_max, float* depth_out, uint8_t* states_out, uint32_t* selected_out) {
+	if (!planes || !states_in || !selected_in || !depth_out || !states_out || !selected_out || w <= 0 || h <= 0 || num_src < 0 || num_src > 32 || scale_size < 1) return 1;
+	struct { std::vector<int> src_image_ids; int scale_size; } problem;
+	problem.src_image_ids.assign(num_src, 0); problem.scale_size = scale_size;
+	PostPassAPD APD{w, h, depth_min, depth_max, reinterpret_cast<const float4*>(planes), cv::Mat(h, w, CV_8UC1), selected_in, selected_out};
+	std::memcpy(APD.states.ptr<uchar>(0), states_in, (size_t)w * h);
+	srand(1);
+#include "_ref/src/main_cpp_282_363.inc"
+	std::memcpy(depth_out, depth.ptr<float>(0), (size_t)w * h * 4);
+	std::memcpy(states_out, pixel_states.ptr<uchar>(0), (size_t)w * h);
+	return 0;
 }

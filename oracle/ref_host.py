@@ -191,3 +191,15 @@ def schedule(round_num: int, num_problems: int):
             prm[name] = float(np.array([v], np.int32).view(np.float32)[0]) if name in _FLOAT_FIELDS else int(v)
         recs.append(dict(view=int(row[0]), iteration=int(row[1]), scale_size=int(row[2]), edges=int(row[3]), params=prm))
     return recs
+
+
+def post_pass(planes: np.ndarray, states: np.ndarray, selected: np.ndarray, num_src: int, scale_size: int, depth_min: float, depth_max: float):
+    """ProcessProblem's own post-pass (main.cpp:282-363) -> (depth map, pixel states, selected views)."""
+    pl = np.ascontiguousarray(planes, np.float32); st = np.ascontiguousarray(states, np.uint8); se = np.ascontiguousarray(selected, np.uint32)
+    h, w = st.shape
+    depth = np.empty((h, w), np.float32); st_out = np.empty((h, w), np.uint8); se_out = np.empty((h, w), np.uint32)
+    lib = _lib()
+    lib.refhost_post_pass.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert lib.refhost_post_pass(pl.ctypes.data, st.ctypes.data, se.ctypes.data, w, h, num_src, scale_size, depth_min, depth_max,
+                                 depth.ctypes.data, st_out.ctypes.data, se_out.ctypes.data) == 0
+    return depth, st_out, se_out

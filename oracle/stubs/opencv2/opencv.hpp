@@ -44,11 +44,17 @@ struct Size2i {
 typedef Size2i Size;
 struct Vec3f {
 	float val[3];
+	Vec3f() : val{0.f, 0.f, 0.f} {}
+	Vec3f(float a, float b, float c) : val{a, b, c} {}
 	float& operator[](int i) { return val[i]; }
 	const float& operator[](int i) const { return val[i]; }
 };
 struct Vec3b {   // host code compiled from reference line ranges (oracle/ref_host.cu) reads colours through it
 	unsigned char val[3];
+	Vec3b() : val{0, 0, 0} {}
+	Vec3b(int a, int b, int c) : val{(unsigned char)a, (unsigned char)b, (unsigned char)c} {}
+	bool operator==(const Vec3b& o) const { return val[0] == o.val[0] && val[1] == o.val[1] && val[2] == o.val[2]; }
+	bool operator!=(const Vec3b& o) const { return !(*this == o); }
 	unsigned char& operator[](int i) { return val[i]; }
 	const unsigned char& operator[](int i) const { return val[i]; }
 };
@@ -89,6 +95,8 @@ template <typename T> class Mat_ : public Mat {
 public:
 	Mat_() {}
 	Mat_(const Mat& m) : Mat(m) {}
+	Mat_(int r, int c) : Mat(r, c, sizeof(T) == 1 ? CV_8UC1 : (sizeof(T) == 3 ? CV_8UC3 : (sizeof(T) == 12 ? CV_32FC3 : CV_32FC1))) {}   // main.cpp:293
+	Mat_(int r, int c, int type) : Mat(r, c, type) {}                                                                              // main.cpp:292
 };
 }  // namespace cv
 #endif

@@ -1,8 +1,11 @@
 """The CPU restatements of the callers' rows pinned to the reference ITSELF: oracle/ref_host.cu compiles line ranges cut
-out of /root/reference/APD.cpp at build time (Roberts / Connect / Label_Seek / Label_Update, APD.cpp:120-346; the geometry
-helpers and the fusing loop of RunFusion, APD.cpp:501-546, 1797-1806, 1875-1957) against the stub cv::Mat.  What is
-compared with them here is what the GPU paths are compared with in tests/test_visibility.py, test_fusion.py and
-test_labels.py, so device parity for rows N1, N3 and N4 now rests on compiled reference code, not on hand-computed cases."""
+out of /root/reference/APD.cpp and main.cpp at build time against the stub cv::Mat — Roberts / Connect / Label_Seek /
+Label_Update (APD.cpp:120-346), the geometry helpers and the three fusing loops (APD.cpp:501-546, 1797-1806, 1875-1957,
+2028-2127, 2195-2276), the file readers and writers (APD.cpp:548-692, main.cpp:127-170), the level-size block and
+RescaleMatToTargetSize (APD.cpp:1119-1143, 1773-1796), ProcessProblem's post-pass (main.cpp:282-363) and main()'s schedule
+loop (main.cpp:450-512).  What is compared with them here is what the GPU paths are compared with in tests/test_visibility.py,
+test_fusion.py, test_labels.py, test_scene.py and test_formats.py, so device parity for rows N1-N4 rests on compiled
+reference code, not on hand-computed cases."""
 import ctypes as C
 import os
 
@@ -259,3 +262,29 @@ def test_schedule_equals_main_s_own_loop(num_levels):
                         else:
                             assert int(got) == int(want), (who, level, pass_, name, got, want)
     sc.close()
+
+
+def test_post_pass_equals_process_problem_s_own_lines():
+    """Row N1 as ProcessProblem runs it: main.cpp:282-363 compiled from the reference (against an object answering the APD
+    getters it calls) — out-of-range depths zeroed and marked UNKNOWN, then per source view the visibility restoration —
+    vs the restatement the device path is compared with (oracle/cpu/visibility_cpu.cpp) and vs the hand-wrapped loop
+    (refhost_restore_visibility) the other tests of this file use."""
+    from dvp_mvs_b200 import UNKNOWN
+    rng = np.random.default_rng(21)
+    for trial in range(300):
+        H, W = int(rng.integers(4, 40)), int(rng.integers(4, 40))
+        S = int(rng.integers(1, 5))
+        scale = int(rng.choice([8, 4, 2, 1]))
+        sel = blobs(rng, H, W, S, int(rng.integers(1, 8)), 7) if trial % 2 else random_masks(rng, H, W, S, rng.choice([0.1, 0.4, 0.7, 0.9]))
+        planes = rng.normal(size=(H, W, 4)).astype(np.float32)
+        planes[..., 3] = rng.uniform(0.0, 12.0, (H, W)).astype(np.float32)
+        planes[rng.random((H, W)) < 0.05, 3] = np.float32(0.0)
+        states = rng.integers(0, 3, (H, W)).astype(np.uint8)
+        dmin, dmax = np.float32(1.5), np.float32(9.25)
+        depth, st, se = ref_host.post_pass(planes, states, sel, S, scale, dmin, dmax)
+        bad = (planes[..., 3] < dmin) | (planes[..., 3] > dmax)
+        want_depth = planes[..., 3].copy(); want_depth[bad] = 0
+        want_states = states.copy(); want_states[bad] = UNKNOWN
+        assert (depth.view(np.uint32) == want_depth.view(np.uint32)).all() and (st == want_states).all(), trial
+        assert (se == visibility_restatement(sel, S, scale, 0)).all(), (trial, H, W, S, scale)
+        assert (se == ref_host.restore_visibility(sel, S, scale)).all(), trial
