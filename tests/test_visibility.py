@@ -134,6 +134,16 @@ def test_gpu_restoration_matches_the_restatement(W, H, S):
         assert (got_planes[..., 3][bad] == 0).all() and (got_planes[..., 3][~bad] == planes[..., 3][~bad]).all()
         assert (got_planes[..., :3] == planes[..., :3]).all()
         assert (got_weak[bad] == 2).all() and (got_weak[~bad] == 1).all()
+        # ... and against ProcessProblem's own lines (main.cpp:282-363 compiled from the reference) where that build is present
+        try:
+            import ref_host
+            have_ref = ref_host.available()
+        except Exception:
+            have_ref = False
+        if have_ref and W * H <= 6000:      # Label_Seek is quadratic in the label count
+            depth_ref, weak_ref, sel_ref = ref_host.post_pass(planes, np.ones((H, W), np.uint8), sel, S, scale, p.depth_min, p.depth_max)
+            assert (got_sel == sel_ref).all() and (got_weak == weak_ref).all()
+            assert (got_planes[..., 3].view(np.uint32) == depth_ref.view(np.uint32)).all()
 
 
 @pytest.mark.gpu
