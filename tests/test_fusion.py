@@ -421,3 +421,40 @@ def test_gpu_tat_variants_vs_restatement(scene):
         assert flips <= max(4, 1e-4 * len(ref)), flips
         if flips == 0:
             np.testing.assert_array_equal(pts, ref)
+
+
+@pytest.mark.gpu
+def test_gpu_fusion_all_variants_vs_the_reference_s_own_loops(scene):
+    """The device path against the reference's fusing loops THEMSELVES (APD.cpp:1875-1957, 2028-2127, 2195-2276 compiled from
+    /root/reference by oracle/Makefile, tests/test_ref_host.py): same points in the same order, same masks.  The ETH loop and
+    T&T mode 1 go through exp / acos, where a value within an ulp of a threshold may flip a decision (bounded at 1e-4 of the
+    points); T&T mode 2 is IEEE arithmetic only and must agree bit for bit."""
+    import ref_host
+    from dvp_mvs_b200 import Fusion
+    if not ref_host.available():
+        pytest.skip("oracle/_ref/libref_host.so not built")
+    views = synth.make_fusion_views(scene, 1, seed=3)
+    want, want_masks = ref_host.run_fusion(views)
+    f = Fusion(views)
+    pts, _ = f.run()
+    a = {tuple(p) for p in np.round(pts[:, :3].astype(np.float64), 6)}
+    b = {tuple(p) for p in np.round(want[:, :3].astype(np.float64), 6)}
+    assert len(want) > 5000 and len(a ^ b) <= max(4, 1e-4 * len(b)), (len(a), len(b), len(a ^ b))
+    if len(pts) == len(want) and not (a ^ b):
+        assert (pts.view(np.uint32) == want.view(np.uint32)).all()
+    f.close()
+    tviews = synth.make_fusion_views(scene, 1, seed=2, depth_noise=0.0003, normal_noise=0.01)
+    for v in tviews:
+        v.pop("weak")
+    for mode in (2, 1):
+        want, want_masks = ref_host.run_fusion_tat(tviews, mode)
+        f = Fusion(tviews); f.set_mode(mode)
+        pts, _ = f.run()
+        assert len(want) > 1000
+        if mode == 2:
+            np.testing.assert_array_equal(pts, want)
+        else:
+            a = {tuple(p) for p in np.round(pts[:, :3].astype(np.float64), 6)}
+            b = {tuple(p) for p in np.round(want[:, :3].astype(np.float64), 6)}
+            assert len(a ^ b) <= max(4, 1e-4 * len(b)), (mode, len(a), len(b), len(a ^ b))
+        f.close()
