@@ -3,6 +3,8 @@
 // out of /root/reference/APD.cpp into oracle/_ref/src/*.inc at build time (nothing of them is committed) and this file
 // wraps them in a C ABI.  They pin the CPU restatements of the callers' rows to the reference itself:
 //   APD.cpp:120-346    Roberts, Label_Seek, Label_Update, Connect          -> row N1 (visibility restoration), N4 (labels)
+//   APD.cpp:348-499    EdgeSegment: its own glue over cv::resize / Canny / HoughLinesP / line / threshold, which are the
+//                      restated primitives of oracle/cpu (pinned against OpenCV 4.13 golden vectors)                  -> row N4, both halves
 //   APD.cpp:501-546    Get3DPointonWorld, Get3DPoint, ProjectCamera          -> row N3
 //   APD.cpp:548-692    ReadBinMat, writeDepthDmb, writeNormalDmb, WriteBinMat, ReadCamera  -> row N4 (on-disk formats)
 //   APD.cpp:978-982, main.cpp:127-170   ToFormatIndex, GenerateSampleList (pair.txt)      -> row N4 (on-disk formats)
@@ -409,5 +411,66 @@ extern "C" int refhost_post_pass(const float* planes /*[h][w][4]*/, const uint8_
 #include "_ref/src/main_cpp_282_363.inc"
 	std::memcpy(depth_out, depth.ptr<float>(0), (size_t)w * h * 4);
 	std::memcpy(states_out, pixel_states.ptr<uchar>(0), (size_t)w * h);
+	return 0;
+}
+
+// ---- EdgeSegment (APD.cpp:348-499) from the reference's own lines ---------------------------------------------------
+// OpenCV is not in this image: the five OpenCV calls EdgeSegment makes are forwarded to the restatements of oracle/cpu
+// (libapd_cpu.so), each of which is pinned against real OpenCV 4.13 output (tests/golden/edge_canny.npz, label_segment.npz,
+// tests/test_labels_oracle.py).  Everything ELSE in the function — thresholds from the histogram median, weak_tex_num, the
+// region loop, border extraction, line drawing order, the border clean-up, the final labelling rule — is the reference's code.
+extern "C" {
+void edge_cpu_canny(const uint8_t* img, int cols, int rows, double low, double high, uint8_t* dst);
+void label_cpu_resize8u(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
+void label_cpu_line(uint8_t* img, int w, int h, int x0, int y0, int x1, int y1, int value);
+int hough_cpu_lines_p(const uint8_t* image, int width, int height, float rho, float theta, int threshold, int line_length, int line_gap, int* lines, int max_lines);
+}
+namespace cv {
+inline void resize8(const Mat& src_in, Mat& dst, Size dsize) {
+	const Mat src = src_in;   // src and dst may be the same object (APD.cpp:361, 439, 445)
+	Mat out(dsize.height, dsize.width, CV_8UC1);
+	if (src.cols == dsize.width && src.rows == dsize.height) out = src;   // cv::resize to the same size copies
+	else label_cpu_resize8u(src.ptr<uchar>(0), src.cols, src.rows, out.ptr<uchar>(0), dsize.width, dsize.height);
+	dst = out;
+}
+#define DVP_REF_HOST_RESIZE8 1
+inline void threshold(const Mat& src, Mat& dst, double thresh, double maxval, int) {
+	Mat out = src;
+	for (size_t i = 0; i < out.storage.size(); ++i) out.storage[i] = out.storage[i] > thresh ? (unsigned char)maxval : 0;
+	dst = out;
+}
+inline void Canny(const Mat& image, Mat& edges, double t1, double t2, int, bool) {
+	Mat out(image.rows, image.cols, CV_8UC1);
+	edge_cpu_canny(image.ptr<uchar>(0), image.cols, image.rows, t1, t2, out.ptr<uchar>(0));
+	edges = out;
+}
+inline void HoughLinesP(const Mat& image, std::vector<Vec4i>& lines, double rho, double theta, int threshold, double min_len, double max_gap) {
+	std::vector<int> buf(4 * 65536);
+	const int n = hough_cpu_lines_p(image.ptr<uchar>(0), image.cols, image.rows, (float)rho, (float)theta, threshold, (int)min_len, (int)max_gap, buf.data(), 65536);
+	lines.clear();
+	for (int i = 0; i < n && i < 65536; ++i) lines.push_back(Vec4i{{buf[4 * i], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]}});
+}
+inline void line(Mat& img, Point a, Point b, const Scalar& color, int) {
+	label_cpu_line(img.ptr<uchar>(0), img.cols, img.rows, a.x, a.y, b.x, b.y, (int)color.val[0]);
+}
+}  // namespace cv
+namespace edge_segment_ref {
+// the cut lines call cv::resize(src, dst, Size, 0, 0, INTER_LINEAR) on 8-bit images: route it to the 8-bit restatement
+// (the float stand-in above serves the level-size block only)
+namespace cv_shadow {}
+#define resize(src, dst, size, fx, fy, interp) resize8(src, dst, size)
+#include "_ref/src/apd_cpp_348_499.inc"
+#undef resize
+}  // namespace edge_segment_ref
+
+// mode 0 (use_canny = true): edge map [rows][cols] u8.  mode 1 (use_canny = false): label map at the level size, int32.
+extern "C" int refhost_edge_segment(int scale, const uint8_t* image, int cols, int rows, int mode, int use_canny, void* out, int* out_cols, int* out_rows) {
+	if (!image || !out || cols < 4 || rows < 4 || (mode != 0 && mode != 1)) return 1;
+	cv::Mat src(rows, cols, CV_8UC1);
+	std::memcpy(src.ptr<uchar>(0), image, (size_t)cols * rows);
+	srand(1);
+	const cv::Mat r = edge_segment_ref::EdgeSegment(scale, src, mode, use_canny != 0);
+	if (out_cols) *out_cols = r.cols; if (out_rows) *out_rows = r.rows;
+	std::memcpy(out, r.ptr<uchar>(0), (size_t)r.cols * r.rows * r.elem_size);
 	return 0;
 }

@@ -203,3 +203,19 @@ def post_pass(planes: np.ndarray, states: np.ndarray, selected: np.ndarray, num_
     assert lib.refhost_post_pass(pl.ctypes.data, st.ctypes.data, se.ctypes.data, w, h, num_src, scale_size, depth_min, depth_max,
                                  depth.ctypes.data, st_out.ctypes.data, se_out.ctypes.data) == 0
     return depth, st_out, se_out
+
+
+def edge_segment(image: np.ndarray, scale: int, mode: int):
+    """The reference's own EdgeSegment (APD.cpp:348-499; its OpenCV calls forwarded to the restated primitives):
+    mode 0 (use_canny) -> edge map u8 [rows, cols]; mode 1 -> label map int32 at the level size."""
+    img = np.ascontiguousarray(image, np.uint8)
+    H, W = img.shape
+    lib = _lib()
+    lib.refhost_edge_segment.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    buf = np.zeros(H * W * 4 + 64, np.uint8)
+    oc, orows = C.c_int(), C.c_int()
+    assert lib.refhost_edge_segment(scale, img.ctypes.data, W, H, mode, 1 if mode == 0 else 0, buf.ctypes.data, C.byref(oc), C.byref(orows)) == 0
+    n = oc.value * orows.value
+    if mode == 0:
+        return buf[:n].reshape(orows.value, oc.value).copy()
+    return buf[:4 * n].view(np.int32).reshape(orows.value, oc.value).copy()

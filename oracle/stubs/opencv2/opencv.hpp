@@ -30,7 +30,18 @@ typedef unsigned char uchar;
 #define CV_32FC3 21
 #define CV_8UC3 16
 
+#define CV_PI 3.1415926535897932384626433832795
 namespace cv {
+struct Scalar {   // EdgeSegment (APD.cpp:379, 399) initialises an image with Scalar(0) and draws with Scalar(255, 0, 0)
+	double val[4];
+	Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : val{a, b, c, d} {}
+};
+struct Vec4i {
+	int val[4];
+	int& operator[](int i) { return val[i]; }
+	const int& operator[](int i) const { return val[i]; }
+};
+enum { THRESH_BINARY = 0 };
 struct Point {
 	int x, y;
 	Point() : x(0), y(0) {}
@@ -69,6 +80,7 @@ public:
 	size_t step;           // bytes per row
 	Mat() : rows(0), cols(0), elem_size(1), type_(0), data(nullptr), step(0) {}
 	Mat(int r, int c, int type) { create(r, c, type); }
+	Mat(int r, int c, int type, const Scalar& s) { create(r, c, type); if (elem_size == 1) std::memset(storage.data(), (int)s.val[0], storage.size()); }
 	Mat(const Mat& o) : rows(o.rows), cols(o.cols), elem_size(o.elem_size), type_(o.type_), storage(o.storage) { rebind(); }
 	Mat& operator=(const Mat& o) {
 		if (this != &o) { rows = o.rows; cols = o.cols; elem_size = o.elem_size; type_ = o.type_; storage = o.storage; }

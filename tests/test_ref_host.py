@@ -288,3 +288,36 @@ def test_post_pass_equals_process_problem_s_own_lines():
         assert (depth.view(np.uint32) == want_depth.view(np.uint32)).all() and (st == want_states).all(), trial
         assert (se == visibility_restatement(sel, S, scale, 0)).all(), (trial, H, W, S, scale)
         assert (se == ref_host.restore_visibility(sel, S, scale)).all(), trial
+
+
+def test_edge_segment_glue_from_the_reference_s_own_lines():
+    """Row N4, both halves: EdgeSegment (APD.cpp:348-499) compiled from the reference — histogram median and thresholds,
+    weak_tex_num, the region loop with its border extraction, the order the Hough segments are drawn in, the border clean-up
+    and the final labelling rule are the reference's code; the five OpenCV calls it makes go to the restated primitives, each
+    pinned against real OpenCV 4.13 output.  Its results equal the OpenCV-made golden vectors and the restatements the device
+    paths are compared with (edge map: oracle/cpu/edge_cpu.cpp; label map: oracle/cpu/label_cpu.cpp), label numbers included."""
+    golden = os.path.join(ROOT, "tests", "golden")
+    g = np.load(os.path.join(golden, "edge_canny.npz"))
+    k = 0
+    while f"image_{k}" in g:
+        np.testing.assert_array_equal(ref_host.edge_segment(g[f"image_{k}"], 1, 0), g[f"edge_{k}"])
+        k += 1
+    assert k >= 5
+    g = np.load(os.path.join(golden, "label_segment.npz"))
+    for i in range(int(g["count"])):
+        img = g[f"image_{int(g[f'image_of_{i}'])}"]
+        np.testing.assert_array_equal(ref_host.edge_segment(img, int(g[f"scale_{i}"]), 1), g[f"labels_{i}"])
+    # renders of the synthetic scene at other sizes and scales: against the restatements
+    CPU.label_cpu_segment.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    CPU.label_cpu_size.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    CPU.edge_cpu_segment.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    for (W, H, scale) in ((320, 240, 1), (401, 303, 2), (640, 480, 3)):
+        img = np.ascontiguousarray(np.clip(np.rint(synth.make_scene(W, H, 2, seed=W).images[0]), 0, 255).astype(np.uint8))
+        edge = np.empty((H, W), np.uint8)
+        assert CPU.edge_cpu_segment(img.ctypes.data, W, H, edge.ctypes.data, None) == 0
+        np.testing.assert_array_equal(ref_host.edge_segment(img, scale, 0), edge)
+        nc, nr = C.c_int(), C.c_int()
+        CPU.label_cpu_size(W, H, scale, C.byref(nc), C.byref(nr))
+        labels = np.empty((nr.value, nc.value), np.int32)
+        assert CPU.label_cpu_segment(img.ctypes.data, W, H, scale, labels.ctypes.data, None) == 0
+        np.testing.assert_array_equal(ref_host.edge_segment(img, scale, 1), labels)
