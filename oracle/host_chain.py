@@ -94,6 +94,25 @@ def restore_visibility(selected, S, scale):
     return out
 
 
+def assemble_inputs(own: dict, sources: list, w: int, h: int, p) -> dict:
+    """What InuputInitialization / SupportInitialization read back from the previous pass's files and how they bring it to
+    this pass's size (APD.cpp:1147-1205, 1426-1456, 1647-1667): `own` and `sources` are the per-view "files" (planes =
+    APD_normals.dmb + depths.dmb, weak = weak.bin, selected = selected_views.bin, radius = radius.bin).  None = not read.
+    (The radius map's UNKNOWN -> strong_radius rule, APD.cpp:1663-1667, is applied by the engine's upload.)
+    Pinned to the reference's own lines in tests/test_ref_host.py::test_input_assembly_equals_the_reference_s_own_lines."""
+    depths = None
+    if p.geom_consistency:
+        depths = np.stack([rescale_ref(f["planes"][..., 3], w, h) for f in [own] + list(sources)])
+    planes = rescale_ref(own["planes"], w, h)
+    if p.state == FIRST_INIT:
+        selected, weak, radius = None, None, None
+    else:
+        selected = rescale_ref(own["selected"], w, h)
+        weak = rescale_ref(own["weak"], w, h) if p.use_APD else None
+        radius = rescale_ref(own["radius"], w, h) if p.use_radius else None
+    return dict(depths=depths, planes=planes, selected=selected, weak=weak, radius=radius)
+
+
 class HostChain:
     """The reference's schedule over a dvp_mvs_b200.synth.MultiView, one Engine per (size, S); the per-view "files"
     (depths.dmb, APD_normals.dmb, weak.bin, selected_views.bin, radius.bin) are numpy arrays in `self.files`."""
@@ -127,16 +146,8 @@ class HostChain:
         cams = np.zeros(S + 1, CAMERA_DTYPE)
         for k, vv in enumerate([v] + src):
             cams[k] = level_camera(mv.cameras[vv], mv.full_w, mv.full_h, w, h, scale)
-        depths = None
-        if p.geom_consistency:
-            depths = np.stack([rescale_ref(self.files[vv]["planes"][..., 3], w, h) for vv in [v] + src])
-        planes = rescale_ref(f["planes"], w, h)
-        if p.state == FIRST_INIT:
-            selected, weak, radius = None, None, None
-        else:
-            selected = rescale_ref(f["selected"], w, h)
-            weak = rescale_ref(f["weak"], w, h) if p.use_APD else None
-            radius = rescale_ref(f["radius"], w, h) if p.use_radius else None   # + UNKNOWN -> strong_radius, done by the upload
+        a = assemble_inputs(f, [self.files[vv] for vv in src], w, h, p)
+        depths, planes, selected, weak, radius = a["depths"], a["planes"], a["selected"], a["weak"], a["radius"]
         e = self._engine(w, h, S, p)
         e.upload(images=images, depths=depths, cameras=cams, planes=planes, selected_views=selected, weak_info=weak,
                  edge=L["edge"], label=L["label"], radius=radius, seed=seed, params=p)

@@ -11,6 +11,8 @@
 //   APD.cpp:1119-1140  the level-size / camera-rescale block of InuputInitialization              -> row N2 (image pyramid)
 //   main.cpp:6-9, 282-363   setBit_YZL and ProcessProblem's post-pass: depth range check + visibility restoration        -> row N1
 //   main.cpp:450-512   the rounds x passes x views loop of main(), ProcessProblem / GetProblemEdges recorded     -> row N2 (schedule)
+//   APD.cpp:1147-1205, 1426-1493, 1615-1668   InuputInitialization's and SupportInitialization's assembly of a pass's inputs
+//                      from the previous pass's files (depths.dmb, APD_normals.dmb, weak.bin, selected_views.bin, radius.bin)   -> row N2
 //   APD.cpp:1773-1796  RescaleMatToTargetSize (swapped scale factors, B10)    -> row N2
 //   APD.cpp:1797-1806  GetAngle                                               -> row N3
 //   APD.cpp:1875-1957  the fusing loop of RunFusion (ETH version)             -> row N3
@@ -472,5 +474,72 @@ extern "C" int refhost_edge_segment(int scale, const uint8_t* image, int cols, i
 	const cv::Mat r = edge_segment_ref::EdgeSegment(scale, src, mode, use_canny != 0);
 	if (out_cols) *out_cols = r.cols; if (out_rows) *out_rows = r.rows;
 	std::memcpy(out, r.ptr<uchar>(0), (size_t)r.cols * r.rows * r.elem_size);
+	return 0;
+}
+
+// ---- how a pass's inputs are assembled from the previous pass's files (row N2) ------------------------------------------
+// InuputInitialization (APD.cpp:1147-1205: depth maps for the geometric term, pixel states; 1426-1493: plane hypotheses from
+// depths.dmb + APD_normals.dmb, selected views) and SupportInitialization (APD.cpp:1615-1668: edge map, label map, radius map)
+// compiled from the reference's lines as members of a class that has exactly the members those lines touch.  The files are
+// real files in a temporary dense folder, read by the reference's own ReadBinMat.
+namespace assembly_ref {
+class APD {
+public:
+	Problem problem;
+	PatchMatchParams params_host;
+	int width = 0, height = 0, weak_count = 0, num_images = 0;
+	std::vector<cv::Mat> depths;
+	std::vector<Camera> cameras;
+	cv::Mat weak_info_host, neighbours_map_host, selected_views_host, edge_host, label_host, radius_host;
+	float4* plane_hypotheses_host = nullptr;
+	~APD() { delete[] plane_hypotheses_host; }
+	void Assemble();
+	void SupportInitialization();
+};
+void APD::Assemble() {
+#include "_ref/src/apd_cpp_1147_1205.inc"
+	plane_hypotheses_host = new float4[(size_t)width * height]();   // APD.cpp:1209 (the FIRST_INIT prior that follows is out of scope)
+#include "_ref/src/apd_cpp_1426_1493.inc"
+}
+#include "_ref/src/apd_cpp_1615_1668.inc"
+}  // namespace assembly_ref
+
+// outputs (any may be NULL): depths [(1+S)][h][w] f32 (geom only), weak [h][w] u8, planes [h][w][4] f32 (x, y, z, w),
+// selected [h][w] u32, radius [h][w] i32, edge [eh][ew] u8 as read (its size in edge_wh), weak_count
+// flags: state, geom_consistency, use_APD, use_edge, use_limit, use_label, use_radius, strong_radius (PatchMatchParams fields)
+extern "C" int refhost_assemble(const char* dense_folder, int ref_id, int num_src, const int* src_ids, int scale_size, const int* flags,
+                                int width, int height, float* depths, uint8_t* weak, float* planes, uint32_t* selected, int32_t* radius,
+                                uint8_t* edge, int* edge_wh, int* weak_count) {
+	if (!dense_folder || !flags || width <= 0 || height <= 0 || num_src < 0) return 1;
+	PatchMatchParams prm;
+	prm.state = (RunState)flags[0]; prm.geom_consistency = flags[1] != 0; prm.use_APD = flags[2] != 0; prm.use_edge = flags[3] != 0;
+	prm.use_limit = flags[4] != 0; prm.use_label = flags[5] != 0; prm.use_radius = flags[6] != 0; prm.strong_radius = flags[7];
+	const PatchMatchParams* params = &prm;
+	assembly_ref::APD a;
+	a.problem.index = 0; a.problem.ref_image_id = ref_id; a.problem.scale_size = scale_size; a.problem.params = *params;
+	for (int k = 0; k < num_src; ++k) a.problem.src_image_ids.push_back(src_ids[k]);
+	a.problem.dense_folder = path(dense_folder);
+	a.problem.result_folder = path(dense_folder) / path("APD") / path(ToFormatIndex(ref_id));
+	a.params_host = *params;
+	a.width = width; a.height = height; a.num_images = num_src + 1;
+	a.cameras.resize(num_src + 1);
+	for (auto& c : a.cameras) { c.width = width; c.height = height; }
+	std::cout.setstate(std::ios_base::failbit); std::cerr.setstate(std::ios_base::failbit);
+	a.Assemble();
+	a.SupportInitialization();
+	std::cout.clear(); std::cerr.clear();
+	const size_t n = (size_t)width * height;
+	if (depths && params->geom_consistency)
+		for (size_t k = 0; k < a.depths.size(); ++k) {
+			if (a.depths[k].cols != width || a.depths[k].rows != height) return 2;
+			std::memcpy(depths + k * n, a.depths[k].ptr<float>(0), n * 4);
+		}
+	if (weak) { if (a.weak_info_host.cols != width || a.weak_info_host.rows != height) return 3; std::memcpy(weak, a.weak_info_host.ptr<uchar>(0), n); }
+	if (planes) std::memcpy(planes, a.plane_hypotheses_host, n * 16);
+	if (selected) { if (a.selected_views_host.cols != width || a.selected_views_host.rows != height) return 4; std::memcpy(selected, a.selected_views_host.ptr<uchar>(0), n * 4); }
+	if (radius && params->use_radius) { if (a.radius_host.cols != width || a.radius_host.rows != height) return 5; std::memcpy(radius, a.radius_host.ptr<uchar>(0), n * 4); }
+	if (edge_wh) { edge_wh[0] = a.edge_host.cols; edge_wh[1] = a.edge_host.rows; }
+	if (edge && !a.edge_host.empty() && a.edge_host.cols == width && a.edge_host.rows == height) std::memcpy(edge, a.edge_host.ptr<uchar>(0), n);
+	if (weak_count) *weak_count = a.weak_count;
 	return 0;
 }

@@ -219,3 +219,21 @@ def edge_segment(image: np.ndarray, scale: int, mode: int):
     if mode == 0:
         return buf[:n].reshape(orows.value, oc.value).copy()
     return buf[:4 * n].view(np.int32).reshape(orows.value, oc.value).copy()
+
+
+def assemble(dense_folder: str, ref_id: int, src_ids, scale_size: int, width: int, height: int, state: int, geom: int, use_apd: int,
+             use_radius: int = 1, strong_radius: int = 5):
+    """InuputInitialization's and SupportInitialization's own lines (APD.cpp:1147-1205, 1426-1493, 1615-1668) over the files of
+    `dense_folder` -> dict(depths, weak, planes, selected, radius, edge_size, weak_count)."""
+    S = len(src_ids)
+    src = (C.c_int * max(S, 1))(*src_ids)
+    flags = (C.c_int * 8)(state, geom, use_apd, 1, 1, 0, use_radius, strong_radius)   # use_label off: it reads another tool's MVS4/ depth maps
+    depths = np.zeros((S + 1, height, width), np.float32); weak = np.zeros((height, width), np.uint8)
+    planes = np.zeros((height, width, 4), np.float32); sel = np.zeros((height, width), np.uint32); rad = np.zeros((height, width), np.int32)
+    edge = np.zeros((height, width), np.uint8); ewh = (C.c_int * 2)(); wc = C.c_int()
+    lib = _lib()
+    lib.refhost_assemble.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
+    rc = lib.refhost_assemble(os.fsencode(dense_folder), ref_id, S, src, scale_size, flags, width, height, depths.ctypes.data, weak.ctypes.data,
+                              planes.ctypes.data, sel.ctypes.data, rad.ctypes.data, edge.ctypes.data, ewh, C.byref(wc))
+    assert rc == 0, rc
+    return dict(depths=depths, weak=weak, planes=planes, selected=sel, radius=rad, edge=edge, edge_size=(ewh[0], ewh[1]), weak_count=wc.value)

@@ -17,7 +17,8 @@ public:
 	operator std::string() const { return s_; }   // boost's ifstream / ofstream open a path; std::ifstream opens a string
 	friend std::ostream& operator<<(std::ostream& os, const path& p) { return os << p.s_; }
 };
-inline bool create_directory(const path&) { return true; }   // GenerateSampleList (main.cpp:152) makes its result folders; the checker does not
+inline bool create_directory(const path&) { return true; }
+inline bool exists(const path& p) { std::ifstream f(p.string().c_str()); return f.good(); }   // InuputInitialization checks weak.bin (APD.cpp:1171)   // GenerateSampleList (main.cpp:152) makes its result folders; the checker does not
 typedef std::ifstream ifstream;
 typedef std::ofstream ofstream;
 } }

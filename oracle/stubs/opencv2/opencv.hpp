@@ -94,6 +94,9 @@ public:
 		rebind();
 	}
 	bool empty() const { return rows == 0 || cols == 0; }
+	Size size() const { return Size(cols, rows); }
+	static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }          // create() zero-fills
+	static Mat zeros(Size s, int type) { return Mat(s.height, s.width, type); }
 	int type() const { return type_; }   // RescaleMatToTargetSize (APD.cpp:1781) builds its destination from it
 	template <typename T> T& at(int r, int c) { return ptr<T>(r)[c]; }
 	template <typename T> const T& at(int r, int c) const { return ptr<T>(r)[c]; }

@@ -321,3 +321,43 @@ def test_edge_segment_glue_from_the_reference_s_own_lines():
         labels = np.empty((nr.value, nc.value), np.int32)
         assert CPU.label_cpu_segment(img.ctypes.data, W, H, scale, labels.ctypes.data, None) == 0
         np.testing.assert_array_equal(ref_host.edge_segment(img, scale, 1), labels)
+
+
+def test_input_assembly_equals_the_reference_s_own_lines(tmp_path):
+    """Row N2: how a pass's inputs are put together from the previous pass's files — InuputInitialization (APD.cpp:1147-1205,
+    1426-1493) and SupportInitialization (APD.cpp:1615-1668) compiled from the reference, reading real files written by the
+    reference's own WriteBinMat — vs oracle/host_chain.assemble_inputs, which the host-chain restatement (and through it the
+    resident scene driver) is compared with: same size and level change (the swapped-factor rescale), REFINE_INIT and
+    REFINE_ITER, with and without the adaptive-patch states."""
+    import host_chain
+    from dvp_mvs_b200 import default_params, FIRST_INIT, REFINE_INIT, REFINE_ITER, WEAK, UNKNOWN
+    rng = np.random.default_rng(8)
+    src_ids = [2, 0, 3]
+    for (pw, ph), (w, h) in (((97, 61), (97, 61)), ((97, 61), (194, 122)), ((80, 60), (161, 119))):
+        files = {}
+        for vid in [1] + src_ids:
+            planes = rng.normal(size=(ph, pw, 4)).astype(np.float32); planes[..., 3] = rng.uniform(0.5, 9.0, (ph, pw)).astype(np.float32)
+            files[vid] = dict(planes=planes, weak=rng.integers(0, 3, (ph, pw)).astype(np.uint8),
+                              selected=rng.integers(0, 8, (ph, pw)).astype(np.uint32), radius=rng.integers(0, 11, (ph, pw)).astype(np.int32))
+            d = tmp_path / f"{pw}x{ph}_{w}" / "APD" / f"{vid:08d}"
+            d.mkdir(parents=True, exist_ok=True)
+            ref_host.write_binmat(str(d / "depths.dmb"), np.ascontiguousarray(planes[..., 3]))
+            ref_host.write_binmat(str(d / "APD_normals.dmb"), np.ascontiguousarray(planes[..., :3]))
+            ref_host.write_binmat(str(d / "weak.bin"), files[vid]["weak"])
+            ref_host.write_binmat(str(d / "selected_views.bin"), files[vid]["selected"])
+            ref_host.write_binmat(str(d / "radius.bin"), files[vid]["radius"])
+            ref_host.write_binmat(str(d / "edges_1.dmb"), rng.integers(0, 2, (h, w)).astype(np.uint8) * 255)
+        dense = str(tmp_path / f"{pw}x{ph}_{w}")
+        for state, geom, use_apd in ((REFINE_INIT, 0, 1), (REFINE_ITER, 1, 1), (REFINE_ITER, 1, 0)):
+            got = ref_host.assemble(dense, 1, src_ids, 2, w, h, state, geom, use_apd)
+            p = default_params(); p.state = state; p.geom_consistency = geom; p.use_APD = use_apd; p.use_radius = 1
+            mine = host_chain.assemble_inputs(files[1], [files[s] for s in src_ids], w, h, p)
+            assert (mine["planes"].view(np.uint32) == got["planes"].view(np.uint32)).all(), (pw, w, state)
+            assert (mine["selected"] == got["selected"]).all()
+            if geom:
+                assert (mine["depths"].view(np.uint32) == got["depths"].view(np.uint32)).all()
+            weak = mine["weak"] if use_apd else np.ones((h, w), np.uint8)      # no adaptive patches: every pixel STRONG (APD.cpp:1196-1204)
+            assert (weak == got["weak"]).all() and got["weak_count"] == (int((weak == WEAK).sum()) if use_apd else 0)
+            want_radius = mine["radius"].copy(); want_radius[weak == UNKNOWN] = p.strong_radius     # APD.cpp:1663-1667 (the engine's upload)
+            assert (want_radius == got["radius"]).all()
+            assert got["edge_size"] == (w, h)                                 # edges_<scale>.dmb is taken as it is, at the pass's size
