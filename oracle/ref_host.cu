@@ -10,6 +10,7 @@
 //   APD.cpp:978-982, main.cpp:127-170   ToFormatIndex, GenerateSampleList (pair.txt)      -> row N4 (on-disk formats)
 //   APD.cpp:1119-1140  the level-size / camera-rescale block of InuputInitialization              -> row N2 (image pyramid)
 //   main.cpp:6-9, 282-363   setBit_YZL and ProcessProblem's post-pass: depth range check + visibility restoration        -> row N1
+//   main.cpp:193-246, 248-265   GetProblemEdges (which image, at which scale, through which EdgeSegment mode, into which file) and ComputeRoundNum   -> rows N2 / N4
 //   main.cpp:450-512   the rounds x passes x views loop of main(), ProcessProblem / GetProblemEdges recorded     -> row N2 (schedule)
 //   APD.cpp:1147-1205, 1426-1493, 1615-1668   InuputInitialization's and SupportInitialization's assembly of a pass's inputs
 //                      from the previous pass's files (depths.dmb, APD_normals.dmb, weak.bin, selected_views.bin, radius.bin)   -> row N2
@@ -320,8 +321,41 @@ extern "C" int refhost_read_pairs(const char* dense_folder, int* ref_ids, int* n
 // (the pixels are row N2's image pyramid, pinned against OpenCV itself in tests/test_image.py); what is checked here is
 // the size and camera arithmetic.
 namespace cv {
-enum { INTER_LINEAR = 1 };
-inline void resize(const Mat& src, Mat& dst, Size dsize, double, double, int) { (void)src; dst.create(dsize.height, dsize.width, CV_32FC1); }
+enum { INTER_LINEAR = 1, IMREAD_GRAYSCALE = 0 };
+// cv::resize(.., INTER_LINEAR) for CV_32FC1: OpenCV's generic path (imgproc/src/resize.cpp, resizeGeneric_ with HResizeLinear /
+// VResizeLinear) as oracle/image_oracle.py restates it and tests/golden/resize_f32.npz pins it against OpenCV 4.13 without IPP:
+// fx = (float)((dx + 0.5) * scale - 0.5) with scale = 1 / (dst / src) in double, taps clamped (columns: weight zeroed at the
+// borders; rows: clipped), a row pass then a column pass, every product and sum rounded to float (this file is built with
+// -ffp-contract=off).  The level-size block above only needs the size of the result.
+inline void resize(const Mat& src_in, Mat& dst, Size dsize, double, double, int) {
+	const Mat src = src_in;
+	const int sw = src.cols, sh = src.rows, dw = dsize.width, dh = dsize.height;
+	Mat out(dh, dw, CV_32FC1);
+	if (src.type() != CV_32FC1 || sw <= 0 || sh <= 0) { dst = out; return; }
+	std::vector<int> x0(dw), x1(dw); std::vector<float> fx(dw);
+	const double scale_x = 1.0 / ((double)dw / sw), scale_y = 1.0 / ((double)dh / sh);
+	for (int dx = 0; dx < dw; ++dx) {
+		float f = (float)((dx + 0.5) * scale_x - 0.5);
+		int s = (int)std::floor(f); f -= (float)s;
+		if (s < 0) { f = 0.f; s = 0; }
+		if (s >= sw - 1) { f = 0.f; s = sw - 1; }
+		x0[dx] = s; x1[dx] = s + 1 < sw ? s + 1 : sw - 1; fx[dx] = f;
+	}
+	std::vector<float> rows((size_t)sh * dw);
+	for (int y = 0; y < sh; ++y) {
+		const float* r = src.ptr<float>(y);
+		for (int dx = 0; dx < dw; ++dx) { const float a0 = 1.0f - fx[dx]; const float p0 = r[x0[dx]] * a0, p1 = r[x1[dx]] * fx[dx]; rows[(size_t)y * dw + dx] = p0 + p1; }
+	}
+	for (int dy = 0; dy < dh; ++dy) {
+		float f = (float)((dy + 0.5) * scale_y - 0.5);
+		const int s = (int)std::floor(f); f -= (float)s;
+		const int y0 = s < 0 ? 0 : (s > sh - 1 ? sh - 1 : s), y1 = s + 1 < 0 ? 0 : (s + 1 > sh - 1 ? sh - 1 : s + 1);
+		const float b0 = 1.0f - f;
+		float* o = out.ptr<float>(dy);
+		for (int dx = 0; dx < dw; ++dx) { const float p0 = rows[(size_t)y0 * dw + dx] * b0, p1 = rows[(size_t)y1 * dw + dx] * f; o[dx] = p0 + p1; }
+	}
+	dst = out;
+}
 }
 extern "C" int refhost_level_camera(const Camera* full, int full_w, int full_h, int scale_size, Camera* out, int* out_w, int* out_h) {
 	if (!full || !out || full_w <= 0 || full_h <= 0 || scale_size < 1) return 1;
@@ -542,4 +576,42 @@ extern "C" int refhost_assemble(const char* dense_folder, int ref_id, int num_sr
 	if (edge && !a.edge_host.empty() && a.edge_host.cols == width && a.edge_host.rows == height) std::memcpy(edge, a.edge_host.ptr<uchar>(0), n);
 	if (weak_count) *weak_count = a.weak_count;
 	return 0;
+}
+
+// ---- GetProblemEdges (main.cpp:193-246) and ComputeRoundNum (main.cpp:248-265) from the reference's own lines --------------
+// cv::imread hands back the image the caller supplied; cv::imwrite is a no-op (show_medium_result is switched off).
+namespace cv {
+static Mat g_imread_image;
+inline Mat imread(const std::string&, int = 1) { return g_imread_image; }
+inline bool imwrite(const std::string&, const Mat&) { return true; }
+}
+namespace problem_edges_ref {
+cv::Mat EdgeSegment(const int scale, const cv::Mat& srcImage, int mode = 0, bool useCanny = false) { return edge_segment_ref::EdgeSegment(scale, srcImage, mode, useCanny); }
+#include "_ref/src/main_cpp_193_246.inc"
+#include "_ref/src/main_cpp_248_265.inc"
+}  // namespace problem_edges_ref
+#include <chrono>
+extern "C" int refhost_get_problem_edges(const char* dense_folder, int ref_id, int scale_size, const uint8_t* image, int cols, int rows) {
+	if (!dense_folder || !image || cols < 16 || rows < 16 || scale_size < 1) return 1;
+	cv::g_imread_image = cv::Mat(rows, cols, CV_8UC1);
+	std::memcpy(cv::g_imread_image.ptr<uchar>(0), image, (size_t)cols * rows);
+	Problem problem;
+	problem.index = 0; problem.ref_image_id = ref_id; problem.scale_size = scale_size; problem.show_medium_result = false;
+	problem.dense_folder = path(dense_folder);
+	problem.result_folder = path(dense_folder) / path("APD") / path(ToFormatIndex(ref_id));
+	srand(1);
+	std::cout.setstate(std::ios_base::failbit);
+	problem_edges_ref::GetProblemEdges(problem);
+	std::cout.clear();
+	return 0;
+}
+// ComputeRoundNum over `n` problems whose images all have the given size (it reads the first image's size through cv::imread)
+extern "C" int refhost_compute_round_num(const char* dense_folder, int n, int cols, int rows) {
+	cv::g_imread_image = cv::Mat(rows, cols, CV_8UC1);
+	std::vector<Problem> problems((size_t)(n > 0 ? n : 0));
+	for (int i = 0; i < n; ++i) { problems[i].index = i; problems[i].ref_image_id = i; problems[i].dense_folder = path(dense_folder ? dense_folder : "."); }
+	std::cout.setstate(std::ios_base::failbit);
+	const int r = problem_edges_ref::ComputeRoundNum(problems);
+	std::cout.clear();
+	return r;
 }

@@ -237,3 +237,18 @@ def assemble(dense_folder: str, ref_id: int, src_ids, scale_size: int, width: in
                               planes.ctypes.data, sel.ctypes.data, rad.ctypes.data, edge.ctypes.data, ewh, C.byref(wc))
     assert rc == 0, rc
     return dict(depths=depths, weak=weak, planes=planes, selected=sel, radius=rad, edge=edge, edge_size=(ewh[0], ewh[1]), weak_count=wc.value)
+
+
+def get_problem_edges(dense_folder: str, ref_id: int, scale_size: int, image_u8: np.ndarray):
+    """The reference's own GetProblemEdges (main.cpp:193-246) on `image_u8` (what cv::imread(.., IMREAD_GRAYSCALE) would return):
+    writes APD/<id>/edges_<scale>.dmb and labels_<scale>.dmb under dense_folder."""
+    img = np.ascontiguousarray(image_u8, np.uint8)
+    lib = _lib()
+    lib.refhost_get_problem_edges.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    assert lib.refhost_get_problem_edges(os.fsencode(dense_folder), ref_id, scale_size, img.ctypes.data, img.shape[1], img.shape[0]) == 0
+
+
+def compute_round_num(n: int, cols: int, rows: int) -> int:
+    lib = _lib()
+    lib.refhost_compute_round_num.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
+    return int(lib.refhost_compute_round_num(b".", n, cols, rows))

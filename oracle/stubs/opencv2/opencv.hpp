@@ -95,6 +95,16 @@ public:
 	}
 	bool empty() const { return rows == 0 || cols == 0; }
 	Size size() const { return Size(cols, rows); }
+	// convertTo between CV_8UC1 and CV_32FC1 (GetProblemEdges, main.cpp:202, 209): to float exactly, to 8 bits with
+	// cv::saturate_cast<uchar>(float) = clamp(cvRound(v)), cvRound rounding halves to even
+	void convertTo(Mat& dst, int type) const {
+		Mat out(rows, cols, type);
+		const size_t n = (size_t)rows * cols;
+		if (type_ == CV_8UC1 && type == CV_32FC1) { for (size_t i = 0; i < n; ++i) reinterpret_cast<float*>(out.storage.data())[i] = (float)storage[i]; }
+		else if (type_ == CV_32FC1 && type == CV_8UC1) { for (size_t i = 0; i < n; ++i) { const long v = std::lrint(reinterpret_cast<const float*>(storage.data())[i]); out.storage[i] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v)); } }
+		else out = *this;
+		dst = out;
+	}
 	static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }          // create() zero-fills
 	static Mat zeros(Size s, int type) { return Mat(s.height, s.width, type); }
 	int type() const { return type_; }   // RescaleMatToTargetSize (APD.cpp:1781) builds its destination from it

@@ -361,3 +361,35 @@ def test_input_assembly_equals_the_reference_s_own_lines(tmp_path):
             want_radius = mine["radius"].copy(); want_radius[weak == UNKNOWN] = p.strong_radius     # APD.cpp:1663-1667 (the engine's upload)
             assert (want_radius == got["radius"]).all()
             assert got["edge_size"] == (w, h)                                 # edges_<scale>.dmb is taken as it is, at the pass's size
+
+
+def test_get_problem_edges_from_the_reference_s_own_lines(tmp_path):
+    """Rows N2 / N4 as main() prepares them: GetProblemEdges (main.cpp:193-246) compiled from the reference — the grey image
+    goes to float, is resized to the level with cv::resize(INTER_LINEAR), comes back to 8 bits (saturate_cast), and THAT image
+    goes through EdgeSegment(scale, ., 0, true) into edges_<scale>.dmb, while the FULL image goes through
+    EdgeSegment(scale, ., 1) into labels_<scale>.dmb — vs the restatements dvp_scene_set_image is compared with
+    (oracle/image_oracle.py, edge_cpu.cpp, label_cpu.cpp).  ComputeRoundNum (main.cpp:248-265) rides along."""
+    import image_oracle
+    from dvp_mvs_b200 import formats
+    CPU.label_cpu_segment.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    CPU.label_cpu_size.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    CPU.edge_cpu_segment.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    for (W, H, scale_size) in ((640, 480, 2), (801, 603, 4), (333, 250, 2), (640, 480, 1)):
+        img = np.ascontiguousarray(np.clip(np.rint(synth.make_scene(W, H, 2, seed=H).images[0]), 0, 255).astype(np.uint8))
+        dense = tmp_path / f"{W}x{H}_{scale_size}"
+        (dense / "APD" / "00000007").mkdir(parents=True)
+        ref_host.get_problem_edges(str(dense), 7, scale_size, img)
+        scale = {1: 0, 2: 1, 4: 2}[scale_size]
+        lw, lh = image_oracle.level_size(W, H, scale_size)
+        level = np.rint(image_oracle.resize_linear_f32(img.astype(np.float32), lw, lh)).clip(0, 255).astype(np.uint8) if scale_size != 1 else img
+        edge = np.empty((lh, lw), np.uint8)
+        assert CPU.edge_cpu_segment(np.ascontiguousarray(level).ctypes.data, lw, lh, edge.ctypes.data, None) == 0
+        np.testing.assert_array_equal(formats.read_binmat(str(dense / "APD" / "00000007" / f"edges_{scale}.dmb")), edge)
+        nc, nr = C.c_int(), C.c_int()
+        CPU.label_cpu_size(W, H, scale, C.byref(nc), C.byref(nr))
+        labels = np.empty((nr.value, nc.value), np.int32)
+        assert CPU.label_cpu_segment(img.ctypes.data, W, H, scale, labels.ctypes.data, None) == 0
+        np.testing.assert_array_equal(formats.read_binmat(str(dense / "APD" / "00000007" / f"labels_{scale}.dmb")), labels)
+    for (cols, rows), want in (((6221, 4146), 4), ((3111, 2073), 3), ((1920, 1080), 3), ((800, 600), 1), ((801, 600), 2), ((1601, 40), 2), ((600, 3300), 4)):
+        assert ref_host.compute_round_num(3, cols, rows) == want, (cols, rows)        # halve the longer side until it is <= 800
+    assert ref_host.compute_round_num(0, 640, 480) == 0

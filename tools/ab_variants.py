@@ -16,6 +16,8 @@ def main():
     ap.add_argument("--derived", type=int, default=0)
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--state", default="refine_iter")
+    ap.add_argument("--geom", type=int, default=1)
     ap.add_argument("libs", nargs="+")
     a = ap.parse_args()
     rows = {}
@@ -23,7 +25,7 @@ def main():
         name, path = spec.split("=", 1)
         env = dict(os.environ, DVP_MVS_LIB=os.path.abspath(path))
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_pass.py"), "--workload", a.workload, "--passes", str(a.passes),
-                            "--iters", str(a.iters), "--derived", str(a.derived)], capture_output=True, text=True, env=env)
+                            "--iters", str(a.iters), "--derived", str(a.derived), "--state", a.state, "--geom", str(a.geom)], capture_output=True, text=True, env=env)
         line = (r.stdout.strip().splitlines() or [r.stderr[-300:]])[-1]
         rows[name] = line
         print(f"{name:28s} {line}", flush=True)
