@@ -202,4 +202,62 @@ __device__ __forceinline__ int is_set(uint32_t v, int n) { return (v >> n) & 1; 
 // reference APD.cu:186-189 — clears bit n AND every lower bit (bug B1, reproduced on purpose)
 __device__ __forceinline__ void unset_bit_ref(uint32_t* v, int n) { (*v) &= (uint32_t)(0xFFFFFFFEu << n); }
 
+// ---- thread -> pixel maps of the NCC kernels ----
+// The texture unit retires the four lanes of a quad in one clock only when their four bilinear footprints fall in a
+// small texel window (profiles/r01_tex_coherence_ubench.txt).  With one image row per warp a quad is 4 x 1 pixels —
+// on a checkerboard colour a 4 x 2 zigzag — whose footprints span 3 s + 2 texels at source scale s.  These maps give
+// every quad a compact pixel set instead; the work per pixel is unchanged, so results are bit-identical (same SHA-1
+// over every output buffer of a pass, tools/ab_variants.py).  Measured on B200 (profiles/r02_quad_maps.txt):
+//   full-grid kernels, 2 x 2 quads: fused K15+K16 51.1 -> 49.0 ms at 3111x2073, 205.2 -> 197.1 ms at 6221x4146; K6 1.25 -> 1.17
+//     (a 16 x 2 and an 8 x 4 tile per warp measure the same)                                          -> default 1
+//   checkerboard kernels: both compact maps LOSE 4 % (K7 113.7 -> 118.9 ms at 6221x4146): the scratch rows a warp
+//     writes and reads stop being one 128-byte line                                                   -> default 0
+#ifndef DVP_QUAD_FULL
+#define DVP_QUAD_FULL 1     // full-grid kernels (K6, K15+K16): 0 = a row of 32 pixels per warp, 1 = a 16 x 2 tile per warp (quads 2 x 2), 2 = an 8 x 4 tile
+#endif
+#ifndef DVP_QUAD_SWEEP
+#define DVP_QUAD_SWEEP 0    // checkerboard kernels (K7/K8): 0 = zigzag row, 1 = 2 x 2 in (x, y / 2), 2 = diamonds (3 x 3 pixels per quad)
+#endif
+// 32 x (T / 32) pixel block, T = 128 or 256 threads: warp w owns the 16 x 2 tile (w & 1, w >> 1), lane l the pixel
+// (2 (l >> 2) + (l & 1), (l >> 1) & 1) of it.
+__device__ __forceinline__ void quad_tile_xy(int tid, int& lx, int& ly) {
+	const int lane = tid & 31, w = tid >> 5;
+#if DVP_QUAD_FULL == 2   // 8 x 4 tile per warp (quads 4 x 2), warps 4 x 2 in the block
+	const int q = lane >> 2;
+	lx = (w & 3) * 8 + 2 * (q & 3) + (lane & 1);
+	ly = (w >> 2) * 4 + 2 * (q >> 2) + ((lane >> 1) & 1);
+#else
+	lx = (w & 1) * 16 + 2 * (lane >> 2) + (lane & 1);
+	ly = (w >> 1) * 2 + ((lane >> 1) & 1);
+#endif
+}
+__device__ __forceinline__ void full_grid_pixel(int& x, int& y) {
+#if DVP_QUAD_FULL
+	int lx, ly; quad_tile_xy(threadIdx.y * blockDim.x + threadIdx.x, lx, ly);
+	x = blockIdx.x * 32 + lx; y = blockIdx.y * (blockDim.x * blockDim.y / 32) + ly;
+#else
+	x = blockIdx.x * blockDim.x + threadIdx.x; y = blockIdx.y * blockDim.y + threadIdx.y;
+#endif
+}
+// Pixel of colour `red` ((x + y) & 1 == red) owned by this thread of a checkerboard launch; y = 2 yy + ((x & 1) ^ red).
+// Mode 2 tiles the colour's lattice with diamonds {(xa, ya), (xa + 1, ya - 1), (xa + 1, ya + 1), (xa + 2, ya)} laid like
+// bricks: diamond row r sits at ya = 2 r - 2 + red (row 0 reaches y = 0 through its lower pixel) and starts at xa = 4 k - 2 (r & 1); every pixel of the colour belongs to
+// exactly one diamond (tests/test_host_logic.py enumerates it).  x or y may come out negative: callers bounds-check.
+__device__ __forceinline__ void sweep_pixel(int red, int& x, int& y) {
+	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+#if DVP_QUAD_SWEEP == 2
+	const int rows = blockDim.x * blockDim.y / 32;
+	const int k = blockIdx.x * 8 + ((tid >> 2) & 7), r = blockIdx.y * rows + (tid >> 5), q = tid & 3;
+	x = 4 * k - 2 * (r & 1) + ((q + 1) >> 1);
+	y = 2 * r - 2 + red + ((q == 1) ? -1 : (q == 2) ? 1 : 0);
+#elif DVP_QUAD_SWEEP == 1
+	int lx, ly; quad_tile_xy(tid, lx, ly);
+	x = blockIdx.x * 32 + lx;
+	y = 2 * (blockIdx.y * (blockDim.x * blockDim.y / 32) + ly) + ((x & 1) ^ red);
+#else
+	x = blockIdx.x * blockDim.x + threadIdx.x;
+	y = 2 * (blockIdx.y * blockDim.y + threadIdx.y) + ((x & 1) ^ red);
+#endif
+}
+
 }  // namespace dvp

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256, 3) k_random_init(const __grid_constant__ 
 	constexpr int T = 256;   // compile-time stride: shared-memory offsets become immediates
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
 	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
-	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	int x, y; full_grid_pixel(x, y);
 	if (x >= a.W || y >= a.H) return;
 	const int center = y * a.W + x;
 	RefPatch rp;
@@ -449,10 +449,9 @@ __global__ void __launch_bounds__(256, 3) k_sweep_score(const __grid_constant__ 
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
 	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
 	const int S = a.S, W = a.W, H = a.H;
-	const int x = blockIdx.x * blockDim.x + threadIdx.x;
-	const int yy = blockIdx.y * blockDim.y + threadIdx.y;
-	const int y = 2 * yy + ((x & 1) ^ red);
-	if (x >= W || y >= H || yy >= yy_limit) return;
+	int x, y; sweep_pixel(red, x, y);
+	const int yy = y >> 1;
+	if (x < 0 || y < 0 || x >= W || y >= H || yy >= yy_limit) return;
 	const int center = y * W + x;
 	if (a.weak[center] == DVP_WEAK) return;
 	const size_t slot = (size_t)yy * W + x;
@@ -569,10 +568,9 @@ __global__ void __launch_bounds__(128, DVP_UPDATE_MIN_BLOCKS) k_sweep_update(con
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
 	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
 	const int S = a.S, W = a.W, H = a.H;
-	const int x = blockIdx.x * blockDim.x + threadIdx.x;
-	const int yy = blockIdx.y * blockDim.y + threadIdx.y;
-	const int y = 2 * yy + ((x & 1) ^ red);
-	if (x >= W || y >= H || yy >= yy_limit) return;
+	int x, y; sweep_pixel(red, x, y);
+	const int yy = y >> 1;
+	if (x < 0 || y < 0 || x >= W || y >= H || yy >= yy_limit) return;
 	const int center = y * W + x;
 	if (a.weak[center] == DVP_WEAK) return;
 	const size_t slot = (size_t)yy * W + x;
@@ -1009,12 +1007,15 @@ __global__ void __launch_bounds__(256, 3) k_local_refine(const __grid_constant__
 // (sum += ncc*w; sum += f*geom*w, APD.cu:4121-4129).  12*S_sel of the 73*S_sel NCCs of the two kernels remain as
 // S_sel (the cost of the current depth, which only LocalRefine uses).  The 6-pixel margin DepthToWeak skips is
 // refined by the stand-alone LocalRefine code.  Bit-exact against K15 followed by K16 (tests/test_gpu_parity.py).
-__global__ void __launch_bounds__(256, 3) k_depth_to_weak_refine(const __grid_constant__ KArgs a) {
+#ifndef DVP_K15_MIN_BLOCKS
+#define DVP_K15_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, DVP_K15_MIN_BLOCKS) k_depth_to_weak_refine(const __grid_constant__ KArgs a) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	constexpr int T = 256;
 	const int tid = threadIdx.y * blockDim.x + threadIdx.x;
 	float2* wt = reinterpret_cast<float2*>(smem_raw) + tid;
-	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	int x, y; full_grid_pixel(x, y);
 	if (x >= a.W || y >= a.H) return;
 	const int min_margin = 6;
 	const int center = x + y * a.W;
@@ -1167,12 +1168,19 @@ cudaError_t launch_strong_sweep(const KArgs& a, int iter, int red, void* scratch
 	sc.pos = reinterpret_cast<uint4*>(base);                base += (size_t)sc.slots * sizeof(uint4);
 	sc.cost = reinterpret_cast<float*>(base);               base += (size_t)sc.slots * 9 * a.S * sizeof(float);
 	sc.flag = reinterpret_cast<uint32_t*>(base);
+#if DVP_QUAD_SWEEP == 2
+	// diamond rows r = 0 .. H / 2 + 1 (ya = 2 r - 2 + red from -2 to H: the first and last image rows are reached through a quad's lower / upper pixel), 8 diamonds of a
+	// row per warp, k = 0 .. (W + 1) / 4 + 1 so that xa = 4 k - 2 (r & 1) reaches W - 1
+	const int gx = ((a.W + 1) / 4 + 2 + 7) / 8, rows = a.H / 2 + 2;
+#else
+	const int gx = (a.W + 31) / 32, rows = yy_limit;
+#endif
 	{
-		dim3 b(32, 8), g((a.W + 31) / 32, (yy_limit + 7) / 8, 1);
+		dim3 b(32, 8), g(gx, (rows + 7) / 8, 1);
 		k_sweep_score<<<g, b, patch_smem_bytes(256), st>>>(a, iter, red, yy_limit, sc);
 	}
 	{
-		dim3 b(32, 4), g((a.W + 31) / 32, (yy_limit + 3) / 4, 1);
+		dim3 b(32, 4), g(gx, (rows + 3) / 4, 1);
 		k_sweep_update<<<g, b, patch_smem_bytes(128), st>>>(a, iter, red, yy_limit, sc);
 	}
 	return cudaGetLastError();

@@ -265,3 +265,41 @@ def test_fast_modulo_of_the_neighbour_search_is_exact():
         r = np.where(r >= m, r - np.uint64(m), r)
         r = np.where(r >= m, r - np.uint64(m), r)
         assert (r == x % np.uint64(m)).all(), m
+
+
+def _sweep_pixel(mode, red, bx, by, tid, threads):
+    """Python mirror of sweep_pixel (csrc/dvp_common.cuh): the pixel a thread of a checkerboard launch owns."""
+    rows = threads // 32
+    if mode == 2:
+        k, r, q = bx * 8 + ((tid >> 2) & 7), by * rows + (tid >> 5), tid & 3
+        return 4 * k - 2 * (r & 1) + ((q + 1) >> 1), 2 * r - 2 + red + (-1 if q == 1 else 1 if q == 2 else 0)
+    if mode == 1:
+        lane, w = tid & 31, tid >> 5
+        x = bx * 32 + (w & 1) * 16 + 2 * (lane >> 2) + (lane & 1)
+        return x, 2 * (by * rows + (w >> 1) * 2 + ((lane >> 1) & 1)) + ((x & 1) ^ red)
+    x = bx * 32 + (tid & 31)
+    return x, 2 * (by * rows + (tid >> 5)) + ((x & 1) ^ red)
+
+
+def test_every_thread_to_pixel_map_of_the_sweep_covers_each_pixel_of_the_colour_once():
+    """The quad-compact maps of the K7/K8 kernels (zigzag row, 2 x 2 in (x, y / 2), diamonds laid like bricks) with the grids
+    launch_sweep_split gives them: every pixel of the colour the reference's half grid reaches exactly once, for both block sizes, odd and even sizes."""
+    for W, H in ((67, 33), (64, 48), (33, 35), (130, 97), (5, 4), (1, 1)):
+        yy_limit = (((H // 2) + 15) // 16) * 16
+        for mode in (0, 1, 2):
+            for threads in (128, 256):
+                rows = threads // 32
+                gx, nrows = (((W + 1) // 4 + 2 + 7) // 8, H // 2 + 2) if mode == 2 else ((W + 31) // 32, yy_limit)
+                gy = (nrows + rows - 1) // rows
+                for red in (0, 1):
+                    seen = np.zeros((H, W), np.int32)
+                    for by in range(gy):
+                        for bx in range(gx):
+                            for tid in range(threads):
+                                x, y = _sweep_pixel(mode, red, bx, by, tid, threads)
+                                if 0 <= x < W and 0 <= y < H and (y >> 1) < yy_limit:
+                                    assert (x + y) & 1 == red
+                                    seen[y, x] += 1
+                    yy, xx = np.mgrid[0:H, 0:W]
+                    # the reference's half grid stops at yy_limit row pairs (APD.cu:4421-4424): with H = 33 the last row is never swept
+                    assert (seen == ((((xx + yy) & 1) == red) & ((yy >> 1) < yy_limit))).all(), (W, H, mode, threads, red)

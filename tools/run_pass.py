@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--state", default="refine_iter")
     ap.add_argument("--geom", type=int, default=1)
     ap.add_argument("--derived", type=int, default=0, help="pixel states from a real previous pass instead of the painted wall")
+    ap.add_argument("--digest", type=int, default=1, help="print a SHA-1 over every output buffer of the last pass")
     ap.add_argument("--size", default="", help="WxH instead of the workload's size (small runs under compute-sanitizer)")
     a = ap.parse_args()
     a.width, a.height = bench.WORKLOADS[a.workload]
@@ -34,7 +35,14 @@ def main():
         e.upload(**inputs)
         e.run()
     total, per_stage, launches = e.last_run_times()
-    print(name, f"{total:.2f} ms", [round(v, 2) for v in per_stage], launches, "launches")
+    digest = ""
+    if a.digest:   # our launches are deterministic: two builds that compute the same thing print the same digest
+        import hashlib
+        h = hashlib.sha1()
+        for k, v in sorted(e.snapshot().items()):
+            h.update(k.encode()); h.update(v.tobytes())
+        digest = " sha1=" + h.hexdigest()[:16]
+    print(name, f"{total:.2f} ms", [round(v, 2) for v in per_stage], launches, "launches" + digest)
 
 
 if __name__ == "__main__":
