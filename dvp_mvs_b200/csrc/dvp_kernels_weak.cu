@@ -382,6 +382,92 @@ __global__ void __launch_bounds__(kK4Threads, DVP_K4_MIN_BLOCKS) k_gen_neighbour
 			}
 			return e;
 		};
+		// The reference's loop (APD.cu:3569-3678) makes 200 tries — `iteration` starts at 300 and falls by one per
+		// evaluated triple, so `max_iter` alone ends it — and a try is: three draws, the triple's tests (distinct,
+		// pixel inside the triangle, no edge between the corners, a usable normal, a proper plane), and for the ~25 % of
+		// the triples that pass, an inlier count over all anchors and the running-best update.  As one loop a warp pays
+		// the inlier count in nearly every iteration with a quarter of its lanes (some lane's triple passes almost every
+		// time).  It is split where the data flow splits: the tests consume the RNG and fill the edge-test cache in try
+		// order but never read the running best; the running best never feeds back into the tests.  Pass A runs the 200
+		// tries' draws and tests and records the triples that pass (with the one bit the tests hand on: is_strong_plane);
+		// pass B walks the record in try order.  Same arithmetic on the same operands in the same order per pixel.
+#ifndef DVP_K4_FUSED_RANSAC
+		uint32_t passed[200];   // a | b << 8 | c << 16 | is_strong_plane << 24 (indices < kMaxPts = 160)
+		int n_passed = 0;
+		const FastMod count_mod((unsigned int)valid_count);   // x % valid_count for the 600 draws: exact (tests/test_host_logic.py)
+		const bool label_rule = a.prm.use_label && my_label > 0;
+		auto plane_of = [&](int ia, int ib, int ic, float4& cross_vec) -> bool {
+			const float3 A = valid_3d[ia], B = valid_3d[ib], C = valid_3d[ic];
+			const float3 A_C = make_float3(A.x - C.x, A.y - C.y, A.z - C.z);
+			const float3 B_C = make_float3(B.x - C.x, B.y - C.y, B.z - C.z);
+			cross_vec.x = A_C.y * B_C.z - B_C.y * A_C.z;
+			cross_vec.y = -(A_C.x * B_C.z - B_C.x * A_C.z);
+			cross_vec.z = A_C.x * B_C.y - B_C.x * A_C.y;
+			if ((cross_vec.x == 0 && cross_vec.y == 0 && cross_vec.z == 0) || isnan(cross_vec.x) || isnan(cross_vec.y) || isnan(cross_vec.z)) return false;
+			normalize3(&cross_vec);
+			cross_vec.w = -(cross_vec.x * A.x + cross_vec.y * A.y + cross_vec.z * A.z);
+			return true;
+		};
+		for (int tries = 0; tries < max_iter; ++tries) {
+			const int a_index = (int)count_mod.mod(rng.next());
+			const int b_index = (int)count_mod.mod(rng.next());
+			const int c_index = (int)count_mod.mod(rng.next());
+			if (a_index == b_index || b_index == c_index || a_index == c_index) continue;
+			if (!point_in_triangle(valid_pts[a_index], valid_pts[b_index], valid_pts[c_index], px, py)) continue;
+			if (edge_limit) {
+				const int e_ab = crossing(a_index, b_index);
+				const int e_bc = crossing(b_index, c_index);
+				const int e_ca = crossing(c_index, a_index);
+				if (e_ab == 1 || e_bc == 1 || e_ca == 1) continue;
+			}
+			const float3 AN = anchor_normal(a_index);   // B8: the reference compares normal A with itself
+			const float nn = AN.x * AN.x + AN.y * AN.y + AN.z * AN.z;
+			if (nn < 0.9f || nn < 0.9f || nn < 0.9f) continue;
+			float4 cross_vec;
+			if (!plane_of(a_index, b_index, c_index, cross_vec)) continue;
+			bool is_strong_plane = true;
+			const float dn = fabs(AN.x * cross_vec.x + AN.y * cross_vec.y + AN.z * cross_vec.z);
+			if (label_rule && dn < 0.9f && dn < 0.9f && dn < 0.9f) is_strong_plane = false;
+			passed[n_passed++] = (uint32_t)a_index | ((uint32_t)b_index << 8) | ((uint32_t)c_index << 16) | ((uint32_t)is_strong_plane << 24);
+		}
+		(void)iteration; (void)min_cost;
+		bool has_strong_plane = false;
+		const float factor_x = __fmul_rn(__fadd_rn((float)px, -a.ref.K[2]), rcp_approx(a.ref.K[0]));
+		const float factor_y = __fmul_rn(__fadd_rn((float)py, -a.ref.K[5]), rcp_approx(a.ref.K[4]));
+		const float rcp_depth_diff = rcp_approx(depth_diff);
+		float best_center_distance = FLT_MAX;
+		for (int q = 0; q < n_passed; ++q) {
+			const uint32_t rec = passed[q];
+			const bool is_strong_plane = (rec >> 24) & 1;
+			if (has_strong_plane && !is_strong_plane) continue;
+			float4 cross_vec;
+			plane_of((int)(rec & 255), (int)((rec >> 8) & 255), (int)((rec >> 16) & 255), cross_vec);
+			// |fit_depth - z| with fit_depth = -w / (x fx + y fy + z) exactly as the reference build evaluates it (SASS of
+			// GenNeighbours and of the single-loop form here): the y product is rounded, the x product fused onto it, z added,
+			// and the quotient fused with the subtraction — fma(-w, rcp(den), -z).  Written out because under
+			// --use_fast_math the compiler picks the order of the two products per context.
+			auto depth_gap = [&](float fx, float fy, float z) -> float {
+				const float den = __fadd_rn(cross_vec.z, __fmaf_rn(cross_vec.x, fx, __fmul_rn(cross_vec.y, fy)));
+				return fabsf(__fmaf_rn(-cross_vec.w, rcp_approx(den), -z));
+			};
+			int temp_count = 0;
+			for (int si = 0; si < valid_count; ++si) {
+				const float distance = depth_gap(valid_factor[si].x, valid_factor[si].y, valid_3d[si].z);
+				if (__fmul_rn(distance, rcp_depth_diff) < ransac_threshold) temp_count++;   // (the reference also sums the distances; the sum is never read)
+			}
+			if (temp_count < 6) continue;
+			if (temp_count > max_count || (!has_strong_plane && is_strong_plane)) {
+				if (!has_strong_plane && is_strong_plane) has_strong_plane = true;
+				best_center_distance = depth_gap(factor_x, factor_y, center_z);
+				best_plane = cross_vec;
+				max_count = temp_count;
+				has_valid_plane = true;
+			} else if (temp_count == max_count) {
+				const float center_distance = depth_gap(factor_x, factor_y, center_z);
+				if (center_distance < best_center_distance) { best_plane = cross_vec; max_count = temp_count; best_center_distance = center_distance; }
+			}
+		}
+#else
 		bool has_strong_plane = false;
 		while (iteration > 0 && max_iter > 0) {
 			max_iter--;
@@ -440,6 +526,7 @@ __global__ void __launch_bounds__(kK4Threads, DVP_K4_MIN_BLOCKS) k_gen_neighbour
 				if (center_distance < min_cost) { best_plane = cross_vec; max_count = temp_count; min_cost = center_distance; }
 			}
 		}
+#endif
 	}
 	rng.store(a.rng, a.N, center);
 	if (!has_valid_plane) { *weak_reliable = 0; return; }
