@@ -388,9 +388,9 @@ __global__ void __launch_bounds__(kK4Threads, DVP_K4_MIN_BLOCKS) k_gen_neighbour
 		// the triples that pass, an inlier count over all anchors and the running-best update.  As one loop a warp pays
 		// the inlier count in nearly every iteration with a quarter of its lanes (some lane's triple passes almost every
 		// time).  It is split where the data flow splits: the tests consume the RNG and fill the edge-test cache in try
-		// order but never read the running best; the running best never feeds back into the tests.  Pass A runs the 200
-		// tries' draws and tests and records the triples that pass (with the one bit the tests hand on: is_strong_plane);
-		// pass B walks the record in try order.  Same arithmetic on the same operands in the same order per pixel.
+		// order but never read the running best; the running best never feeds back into the tests.  Pass A (in two steps, below)
+		// runs the 200 tries' draws and tests and records the triples that pass (with the one bit the tests hand on:
+		// is_strong_plane); pass B walks the record in try order.  Same arithmetic on the same operands in the same order per pixel.
 #ifndef DVP_K4_FUSED_RANSAC
 		uint32_t passed[200];   // a | b << 8 | c << 16 | is_strong_plane << 24 (indices < kMaxPts = 160)
 		int n_passed = 0;
@@ -408,12 +408,20 @@ __global__ void __launch_bounds__(kK4Threads, DVP_K4_MIN_BLOCKS) k_gen_neighbour
 			cross_vec.w = -(cross_vec.x * A.x + cross_vec.y * A.y + cross_vec.z * A.z);
 			return true;
 		};
+		// pass A1: the draws and the two tests without side effects (a quarter of the triples survive)
 		for (int tries = 0; tries < max_iter; ++tries) {
 			const int a_index = (int)count_mod.mod(rng.next());
 			const int b_index = (int)count_mod.mod(rng.next());
 			const int c_index = (int)count_mod.mod(rng.next());
 			if (a_index == b_index || b_index == c_index || a_index == c_index) continue;
 			if (!point_in_triangle(valid_pts[a_index], valid_pts[b_index], valid_pts[c_index], px, py)) continue;
+			passed[n_passed++] = (uint32_t)a_index | ((uint32_t)b_index << 8) | ((uint32_t)c_index << 16);
+		}
+		// pass A2: the remaining tests in try order (the edge-test cache is filled by whichever try asks first), compacting in place
+		const int n_inside = n_passed;
+		n_passed = 0;
+		for (int q = 0; q < n_inside; ++q) {
+			const int a_index = (int)(passed[q] & 255), b_index = (int)((passed[q] >> 8) & 255), c_index = (int)((passed[q] >> 16) & 255);
 			if (edge_limit) {
 				const int e_ab = crossing(a_index, b_index);
 				const int e_bc = crossing(b_index, c_index);
