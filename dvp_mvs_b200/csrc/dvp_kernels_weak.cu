@@ -199,6 +199,11 @@ __global__ void __launch_bounds__(kK4Threads, DVP_K4_MIN_BLOCKS) k_gen_neighbour
 		}
 	}
 
+	// (Flattening the three nested loops below into one loop whose iteration is one rung of the lane's own current direction —
+	// so that a lane starts its next direction as soon as its own search ends — was measured on B200, bit-identical, and is
+	// SLOWER: 14.2 -> 17.3 ms at 3111x2073, 23.5 -> 25.9 on derived states.  Lanes of a tile walk the same direction at the
+	// same radius, so their probe gathers land next to each other; once the lanes drift apart the gathers scatter, and that
+	// costs more than the idle lanes did.  profiles/r02_k4_restructure.txt)
 	for (int ox = -1; ox <= 1; ++ox) {
 		for (int oy = -1; oy <= 1; ++oy) {
 			if (ox == 0 && oy == 0) continue;
