@@ -260,14 +260,16 @@ __device__ __forceinline__ float ncc_new(const KArgs& a, int px, int py, int v /
 #pragma unroll
 			for (int q = 0; q < 9; q++) {
 				const float w = weight_colour(ref_pix[q], ref_center_pix, rcp_c);
-				// each "row" is one sample: row = fma(x, y, 0), total += row -> product rounded, then added (SASS of the reference)
+				// each "row" is one sample: row = fma(x, y, 0), total += row -> product rounded, then added (SASS of the reference).
+				// The reference's `0 + t`, `0 + u`, `0 + w` are not issued: w = ex2(.) > 0, the grey values are >= +0 and every
+				// product is already flushed (FTZ), so none of the three can be -0 or denormal and 0 + x == x bit for bit.
 				const float t = __fmul_rn(ref_pix[q], w), u = __fmul_rn(src_pix[q], w);
-				s_r = __fadd_rn(__fadd_rn(0.f, t), s_r);
-				s_rr = __fadd_rn(__fmaf_rn(ref_pix[q], t, 0.f), s_rr);
-				s_s = __fadd_rn(__fadd_rn(0.f, u), s_s);
-				s_ss = __fadd_rn(__fmaf_rn(src_pix[q], u, 0.f), s_ss);
-				s_rs = __fadd_rn(__fmaf_rn(src_pix[q], t, 0.f), s_rs);
-				s_w = __fadd_rn(__fadd_rn(0.f, w), s_w);
+				s_r = __fadd_rn(t, s_r);
+				s_rr = __fadd_rn(__fmul_rn(ref_pix[q], t), s_rr);
+				s_s = __fadd_rn(u, s_s);
+				s_ss = __fadd_rn(__fmul_rn(src_pix[q], u), s_ss);
+				s_rs = __fadd_rn(__fmul_rn(src_pix[q], t), s_rs);
+				s_w = __fadd_rn(w, s_w);
 			}
 		}
 		const float temp_cost = ncc_tail(s_w, s_r, s_rr, s_s, s_ss, s_rs);
