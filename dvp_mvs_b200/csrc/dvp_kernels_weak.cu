@@ -174,9 +174,15 @@ __global__ void __launch_bounds__(kK4Threads, DVP_K4_MIN_BLOCKS) k_gen_neighbour
 	// appended by the label-boundary extension and are all valid.  Nothing above extend_index is ever read, so only the
 	// direction slots are initialised (the reference initialises, and later scans, all 160: 1.4 KB of stack writes per pixel).
 	constexpr int kDirSlots = 32;
-	short2 strong_points[kMaxPts];
+	// Anchor slots as packed 32-bit words (x in the low half, y in the high half; (-1, -1) = 0xffffffff), 16-byte aligned: the
+	// two duplicate scans below compare four slots per 128-bit local load without a branch per slot.  They were the top two
+	// stall sites of this kernel (ncu, profiles/r02_final_kernels_ncu.txt: 19 % of the samples): a dependent 16-bit load,
+	// compare and branch per slot.
+	__align__(16) uint32_t strong_points[kMaxPts];
+	auto pack_pt = [](short2 p) -> uint32_t { return (uint32_t)(uint16_t)p.x | ((uint32_t)(uint16_t)p.y << 16); };
+	auto unpack_pt = [](uint32_t v) -> short2 { return make_short2((short)(v & 0xffffu), (short)(v >> 16)); };
 	uint32_t dir_valid = 0;
-	for (int i = 0; i < kDirSlots; ++i) strong_points[i] = make_short2(-1, -1);
+	for (int i = 0; i < kDirSlots; ++i) strong_points[i] = 0xffffffffu;
 	int origin_direction_index = -1;
 	int strong_point_size = 0;
 
@@ -259,12 +265,21 @@ __global__ void __launch_bounds__(kK4Threads, DVP_K4_MIN_BLOCKS) k_gen_neighbour
 						normalize2(&test_direction);
 						const float cosv = test_direction.x * origin_direction.x + test_direction.y * origin_direction.y;
 						if (!(cosv > threshhold)) continue;
+						// the reference scans slots 0 .. dir_index - 1; slots from dir_index on still hold (-1, -1), which no probe can equal
+						// (both coordinates of np are >= 0 here), so all 32 direction slots are compared
 						bool has_same_pt = false;
-						for (int k = 0; k < dir_index; k++)
-							if (strong_points[k].x == np.x && strong_points[k].y == np.y) { has_same_pt = true; break; }
+						{
+							const uint32_t np32 = pack_pt(np);
+							const uint4* sp4 = reinterpret_cast<const uint4*>(strong_points);
+#pragma unroll
+							for (int c = 0; c < kDirSlots / 4; ++c) {
+								const uint4 v = sp4[c];
+								has_same_pt |= (v.x == np32) | (v.y == np32) | (v.z == np32) | (v.w == np32);
+							}
+						}
 						if (has_same_pt) continue;
 						if (!edge_limit || !bresenham_crosses_edge(a, px, py, np.x, np.y)) {
-							strong_points[dir_index] = np;
+							strong_points[dir_index] = pack_pt(np);
 							dir_valid |= 1u << dir_index;
 							strong_point_size++;
 							rng.restore(after[radius_iter]);
@@ -327,13 +342,21 @@ __global__ void __launch_bounds__(kK4Threads, DVP_K4_MIN_BLOCKS) k_gen_neighbour
 					if (np.x == -1 || np.y == -1) continue;
 					npc = np.x + np.y * W;
 				}
-				bool has_same_pt = false;
-				for (int k = 0; k <= extend_index; k++)
-					if (strong_points[k].x == np.x && strong_points[k].y == np.y) { has_same_pt = true; break; }
+				bool has_same_pt = false;   // any of slots 0 .. extend_index (slots above it are not initialised: masked)
+				{
+					const uint32_t np32 = pack_pt(np);
+					const uint4* sp4 = reinterpret_cast<const uint4*>(strong_points);
+					const int n_slots = extend_index + 1;
+					for (int c = 0; 4 * c < n_slots; ++c) {
+						const uint4 v = sp4[c];
+						const int left = n_slots - 4 * c;   // >= 1
+						has_same_pt |= (v.x == np32) | ((left > 1) & (v.y == np32)) | ((left > 2) & (v.z == np32)) | ((left > 3) & (v.w == np32));
+					}
+				}
 				if (has_same_pt) continue;
 				if (extend_index + 1 >= kMaxPts) continue;  // cannot happen with rotate_time <= 4 (31 + 128 slots)
 				extend_index++;
-				strong_points[extend_index] = np;
+				strong_points[extend_index] = pack_pt(np);
 				strong_point_size++;
 			}
 		}
@@ -354,7 +377,7 @@ __global__ void __launch_bounds__(kK4Threads, DVP_K4_MIN_BLOCKS) k_gen_neighbour
 	for (int i = 0; i < DVP_NEIGHBOUR_NUM - 1; ++i) valid_pts[i] = make_short2(-1, -1);   // read back below even when fewer anchors survive
 	for (int i = 0; i <= extend_index; ++i) {
 		if (i >= kDirSlots || ((dir_valid >> i) & 1)) {
-			const short2 sp = strong_points[i];
+			const short2 sp = unpack_pt(strong_points[i]);
 			const int spc = sp.x + sp.y * W;
 			valid_pts[valid_count] = sp;
 			get_3d_point(a.ref, sp.x, sp.y, a.planes[spc].w, X);
@@ -544,22 +567,54 @@ __global__ void __launch_bounds__(kK4Threads, DVP_K4_MIN_BLOCKS) k_gen_neighbour
 	rng.store(a.rng, a.N, center);
 	if (!has_valid_plane) { *weak_reliable = 0; return; }
 
+	// Distance of every anchor to the winning plane, outliers last, the DVP_NEIGHBOUR_NUM - 1 best kept (APD.cu:3680-3708).
+	// The reference insertion-sorts all anchors (sort_small_weighted, APD.cu:125-138: ~n^2 / 4 dependent moves through local
+	// memory, 9 % of this kernel's stall samples) and then reads the first 11.  A stable ascending sort's first 11 are kept
+	// here in a sorted register list instead — an anchor goes in front of the first kept one that is strictly heavier, i.e.
+	// behind its equals, as the insertion sort leaves it.  NaN weights make the reference's loop order-dependent (`<` is false
+	// both ways, a NaN stops every later element): those pixels take the reference's loop.
+	constexpr int K = DVP_NEIGHBOUR_NUM - 1;
+	float top_w[K]; uint32_t top_pt[K];
+#pragma unroll
+	for (int j = 0; j < K; ++j) { top_w[j] = __int_as_float(0x7f800000); top_pt[j] = 0xffffffffu; }   // +inf: behind every anchor (outliers weigh FLT_MAX)
 	float weight[kMaxPts];
-	for (int i = 0; i < valid_count; ++i) {
-		const float factor_x = valid_factor[i].x, factor_y = valid_factor[i].y;
-		const float fit_depth = -best_plane.w / (best_plane.x * factor_x + best_plane.y * factor_y + best_plane.z);
-		const float distance = fabs(fit_depth - valid_3d[i].z);
-		if (distance / depth_diff >= ransac_threshold) { valid_pts[i] = make_short2(-1, -1); weight[i] = FLT_MAX; continue; }
-		weight[i] = distance;
+	bool any_nan = false;
+	{
+		const float rcp_dd = rcp_approx(depth_diff);
+		for (int i = 0; i < valid_count; ++i) {
+			// |fit_depth - z| in the rounding order of the reference build (see depth_gap above)
+			const float den = __fadd_rn(best_plane.z, __fmaf_rn(best_plane.x, valid_factor[i].x, __fmul_rn(best_plane.y, valid_factor[i].y)));
+			const float distance = fabsf(__fmaf_rn(-best_plane.w, rcp_approx(den), -valid_3d[i].z));
+			const bool outlier = __fmul_rn(distance, rcp_dd) >= ransac_threshold;
+			const float w = outlier ? FLT_MAX : distance;
+			if (outlier) valid_pts[i] = make_short2(-1, -1);
+			weight[i] = w;
+			any_nan |= (w != w);
+			const uint32_t pt = outlier ? 0xffffffffu : pack_pt(valid_pts[i]);
+			if (w < top_w[K - 1]) {
+#pragma unroll
+				for (int j = K - 1; j >= 1; --j) {
+					const bool shift = w < top_w[j - 1], here = w < top_w[j];
+					top_pt[j] = shift ? top_pt[j - 1] : (here ? pt : top_pt[j]);
+					top_w[j] = shift ? top_w[j - 1] : (here ? w : top_w[j]);
+				}
+				if (w < top_w[0]) { top_w[0] = w; top_pt[0] = pt; }
+			}
+		}
 	}
-	for (int i = 1; i < valid_count; i++) {   // sort_small_weighted, APD.cu:125-138
-		const short2 tmp = valid_pts[i];
-		const float tmp_w = weight[i];
-		int j;
-		for (j = i; j >= 1 && tmp_w < weight[j - 1]; j--) { valid_pts[j] = valid_pts[j - 1]; weight[j] = weight[j - 1]; }
-		valid_pts[j] = tmp; weight[j] = tmp_w;
+	if (!any_nan) {
+#pragma unroll
+		for (int i = 1; i < DVP_NEIGHBOUR_NUM; ++i) neighbours[i] = unpack_pt(top_pt[i - 1]);
+	} else {
+		for (int i = 1; i < valid_count; i++) {   // sort_small_weighted, APD.cu:125-138
+			const short2 tmp = valid_pts[i];
+			const float tmp_w = weight[i];
+			int j;
+			for (j = i; j >= 1 && tmp_w < weight[j - 1]; j--) { valid_pts[j] = valid_pts[j - 1]; weight[j] = weight[j - 1]; }
+			valid_pts[j] = tmp; weight[j] = tmp_w;
+		}
+		for (int i = 1; i < DVP_NEIGHBOUR_NUM; ++i) neighbours[i] = valid_pts[i - 1];
 	}
-	for (int i = 1; i < DVP_NEIGHBOUR_NUM; ++i) neighbours[i] = valid_pts[i - 1];
 	*weak_reliable = 1;
 }
 
