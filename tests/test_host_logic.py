@@ -303,3 +303,42 @@ def test_every_thread_to_pixel_map_of_the_sweep_covers_each_pixel_of_the_colour_
                     yy, xx = np.mgrid[0:H, 0:W]
                     # the reference's half grid stops at yy_limit row pairs (APD.cu:4421-4424): with H = 33 the last row is never swept
                     assert (seen == ((((xx + yy) & 1) == red) & ((yy >> 1) < yy_limit))).all(), (W, H, mode, threads, red)
+
+
+def test_sorted_register_list_of_k4_equals_the_reference_insertion_sort():
+    """k_gen_neighbours keeps the DVP_NEIGHBOUR_NUM - 1 lightest anchors in a sorted list (an anchor goes in front of the first
+    kept one that is strictly heavier) instead of insertion-sorting all anchors as the reference does (sort_small_weighted,
+    APD.cu:125-138) and reading the first 11.  Same anchors in the same order, ties and FLT_MAX outliers included, whenever no
+    weight is NaN (the kernel takes the reference's loop otherwise)."""
+    K = 11
+    rng = np.random.default_rng(5)
+    fmax = np.float32(np.finfo(np.float32).max)
+    for trial in range(400):
+        n = int(rng.integers(0, 60))
+        w = rng.choice(np.array([0.0, 0.25, 0.5, 1.0, 3.0], np.float32), n) if trial % 2 else rng.random(n).astype(np.float32)
+        pts = np.arange(1, n + 1)
+        out = rng.random(n) < 0.3
+        w = np.where(out, fmax, w).astype(np.float32)
+        pts = np.where(out, -1, pts)
+        # the reference: insertion sort of (weight, point) over a list pre-filled with -1, first K read back
+        rw, rp = list(w), list(pts) + [-1] * K
+        for i in range(1, n):
+            tw, tp = rw[i], rp[i]
+            j = i
+            while j >= 1 and tw < rw[j - 1]:
+                rw[j], rp[j] = rw[j - 1], rp[j - 1]
+                j -= 1
+            rw[j], rp[j] = tw, tp
+        want = rp[:K]
+        # the kernel: sorted list of K, +inf sentinels, branch-free insertion evaluated from the back
+        tw_, tp_ = [np.float32(np.inf)] * K, [-1] * K
+        for i in range(n):
+            x, p = w[i], pts[i]
+            if x < tw_[K - 1]:
+                for j in range(K - 1, 0, -1):
+                    shift, here = x < tw_[j - 1], x < tw_[j]
+                    tp_[j] = tp_[j - 1] if shift else (p if here else tp_[j])
+                    tw_[j] = tw_[j - 1] if shift else (x if here else tw_[j])
+                if x < tw_[0]:
+                    tw_[0], tp_[0] = x, p
+        assert [int(v) for v in tp_] == [int(v) for v in want], (trial, n)
