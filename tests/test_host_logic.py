@@ -342,3 +342,62 @@ def test_sorted_register_list_of_k4_equals_the_reference_insertion_sort():
                 if x < tw_[0]:
                     tw_[0], tp_[0] = x, p
         assert [int(v) for v in tp_] == [int(v) for v in want], (trial, n)
+
+
+def test_three_pass_ransac_of_k4_equals_the_reference_single_loop():
+    """k_gen_neighbours splits GenNeighbours' RANSAC loop (APD.cu:3569-3678) into pass A1 (draws, distinct, pixel inside the
+    triangle), pass A2 (edge tests through a symmetric cache that is filled by whichever try asks first, with a walk that
+    depends on its direction; normal and plane tests; the is_strong_plane bit) and pass B (inlier count, running best).  A model
+    of both forms on random instances — asymmetric edge walks, strong / weak planes, ties in the inlier count and in the centre
+    distance — must reach the same best try, the same cache and the same number of draws."""
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        n = int(rng.integers(4, 14))
+        walk = rng.random((n, n)) < 0.25                     # walk[i, j]: the walk from i to j crosses an edge (asymmetric)
+        inside = rng.random((n, n, n)) < 0.3                 # pixel inside triangle (a, b, c)
+        normal_ok = rng.random(n) < 0.9
+        strong = rng.random((n, n, n)) < 0.5
+        inliers = rng.integers(3, 10, (n, n, n))
+        centre = rng.integers(0, 4, (n, n, n)).astype(np.float32)
+        draws = rng.integers(0, n, (200, 3))
+
+        def tests_without_side_effects(t):
+            a, b, c = draws[t]
+            return a != b and b != c and a != c and inside[a, b, c]
+
+        def tests_with_side_effects(t, cache):
+            a, b, c = draws[t]
+            for i, j in ((a, b), (b, c), (c, a)):
+                if (i, j) not in cache:
+                    cache[(i, j)] = cache[(j, i)] = bool(walk[i, j])
+            if cache[(a, b)] or cache[(b, c)] or cache[(c, a)]:
+                return False
+            return bool(normal_ok[a])
+
+        def running_best(state, t):
+            a, b, c = draws[t]
+            is_strong = bool(strong[a, b, c])
+            if state["has_strong"] and not is_strong:
+                return
+            cnt = int(inliers[a, b, c])
+            if cnt < 6:
+                return
+            if cnt > state["max_count"] or (not state["has_strong"] and is_strong):
+                if not state["has_strong"] and is_strong:
+                    state["has_strong"] = True
+                state.update(best=t, max_count=cnt, min_cost=float(centre[a, b, c]))
+            elif cnt == state["max_count"] and float(centre[a, b, c]) < state["min_cost"]:
+                state.update(best=t, max_count=cnt, min_cost=float(centre[a, b, c]))
+
+        # the reference: one loop
+        s1, cache1 = dict(has_strong=False, max_count=3, min_cost=np.inf, best=-1), {}
+        for t in range(200):
+            if tests_without_side_effects(t) and tests_with_side_effects(t, cache1):
+                running_best(s1, t)
+        # the kernel: three passes
+        s2, cache2 = dict(has_strong=False, max_count=3, min_cost=np.inf, best=-1), {}
+        survivors = [t for t in range(200) if tests_without_side_effects(t)]
+        passed = [t for t in survivors if tests_with_side_effects(t, cache2)]
+        for t in passed:
+            running_best(s2, t)
+        assert s1 == s2 and cache1 == cache2, trial
